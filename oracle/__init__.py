@@ -1,0 +1,123 @@
+"""Python loader of the CPU oracle (oracle/zts_oracle.c). TEST INFRASTRUCTURE ONLY:
+only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+PARITY UNPINNED (no JS engine in this image; see zts_oracle.h)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libzts_oracle.so")
+
+NONE, FIXED, DYNAMIC = 0, 1, 2
+ERR_TEXT = {
+    1: "input buffer is broken", 2: "unknown BTYPE: 3", 3: "invalid code length", 4: "output overflow",
+    5: "invalid uncompressed block header: LEN", 6: "invalid compression type", 7: "out of memory",
+    8: "undefined behaviour in the reference (incomplete code / distance before start)",
+}
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = ctypes.CDLL(LIB_PATH)
+        vp, sz, u32, i32 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_int
+        L.zo_crc32_update.argtypes = [vp, sz, u32]
+        L.zo_crc32_update.restype = u32
+        L.zo_adler32_update.argtypes = [u32, vp, sz]
+        L.zo_adler32_update.restype = u32
+        L.zo_lz77_encode.argtypes = [vp, sz, i32, vp, ctypes.POINTER(sz), vp, vp]
+        L.zo_lz77_encode.restype = i32
+        L.zo_get_lengths.argtypes = [vp, i32, i32, vp]
+        L.zo_get_lengths.restype = i32
+        L.zo_raw_deflate.argtypes = [vp, sz, i32, i32, vp, sz, sz, ctypes.POINTER(sz)]
+        L.zo_raw_deflate.restype = i32
+        L.zo_raw_deflate_bound.argtypes = [sz]
+        L.zo_raw_deflate_bound.restype = sz
+        L.zo_raw_inflate.argtypes = [vp, sz, sz, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(sz), i32]
+        L.zo_raw_inflate.restype = i32
+        L.zo_diag_rpm_freq_oob.restype = ctypes.c_uint64
+        _lib = L
+    return _lib
+
+
+class OracleError(Exception):
+    def __init__(self, code):
+        super().__init__(ERR_TEXT.get(code, f"oracle error {code}"))
+        self.code = code
+
+
+def _u8(data):
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+def crc32(data, crc=0):
+    a = _u8(data)
+    return int(lib().zo_crc32_update(a.ctypes.data, a.size, crc))
+
+
+def adler32(data, adler=1):
+    a = _u8(data)
+    return int(lib().zo_adler32_update(adler, a.ctypes.data, a.size))
+
+
+def raw_deflate(data, compression_type=DYNAMIC, lazy=0, prefix=b""):
+    """new RawDeflate(data, {compressionType, lazy, outputBuffer: prefix.., outputIndex}).compress()"""
+    a = _u8(data)
+    cap = int(lib().zo_raw_deflate_bound(a.size)) + len(prefix)
+    out = np.zeros(cap, dtype=np.uint8)
+    out[:len(prefix)] = np.frombuffer(bytes(prefix), dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    rc = lib().zo_raw_deflate(a.ctypes.data, a.size, compression_type, lazy, out.ctypes.data, cap, len(prefix),
+                              ctypes.byref(n))
+    if rc:
+        raise OracleError(rc)
+    return out[:n.value].tobytes()
+
+
+def raw_inflate(data, index=0, out_cap=None, mirror_readbits_quirk=False):
+    """new RawInflate(data, {index}).decompress() -> (output bytes, ip)"""
+    a = _u8(data)
+    cap = out_cap if out_cap is not None else max(1 << 16, a.size * 64)
+    out = np.zeros(max(cap, 1), dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    ip = ctypes.c_size_t(0)
+    rc = lib().zo_raw_inflate(a.ctypes.data, a.size, index, out.ctypes.data, cap, ctypes.byref(n), ctypes.byref(ip),
+                              1 if mirror_readbits_quirk else 0)
+    if rc:
+        raise OracleError(rc)
+    return out[:n.value].tobytes(), ip.value
+
+
+def lz77(data, lazy=0):
+    """LZ77.encode() -> (Uint16 token array, litlen freqs[286], dist freqs[30])"""
+    a = _u8(data)
+    tok = np.zeros(2 * a.size + 2, dtype=np.uint16)
+    fl = np.zeros(286, dtype=np.uint32)
+    fd = np.zeros(30, dtype=np.uint32)
+    n = ctypes.c_size_t(0)
+    rc = lib().zo_lz77_encode(a.ctypes.data, a.size, lazy, tok.ctypes.data, ctypes.byref(n), fl.ctypes.data,
+                              fd.ctypes.data)
+    if rc:
+        raise OracleError(rc)
+    return tok[:n.value], fl, fd
+
+
+def get_lengths(freqs, limit):
+    f = np.ascontiguousarray(freqs, dtype=np.uint32)
+    out = np.zeros(f.size, dtype=np.uint8)
+    rc = lib().zo_get_lengths(f.ctypes.data, f.size, limit, out.ctypes.data)
+    if rc:
+        raise OracleError(rc)
+    return out

@@ -1,0 +1,103 @@
+"""GPU: warp-per-stream inflate vs the oracle's RawInflate (src/RawInflate.ts:127-516) and the source data.
+
+Streams come from (a) the oracle's RawDeflate (reference encoder: one dynamic / fixed / stored block)
+and (b) CPython zlib at levels 0/1/6/9 (multi-block, stored, fixed and dynamic blocks)."""
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import gpu_inflate_many, rand_bytes, zlib_raw
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(engine, datas, streams, trailer=b"\0\0\0\0"):
+    outs, res = gpu_inflate_many(engine, streams, [len(d) for d in datas], trailer=trailer)
+    for i, (d, s, o, r) in enumerate(zip(datas, streams, outs, res)):
+        assert int(r["status"]) == 0, (i, r)
+        assert o == bytes(d), i
+        assert int(r["in_used"]) == len(s), (i, int(r["in_used"]), len(s))
+        ref_out, ref_ip = oracle.raw_inflate(bytes(s) + trailer, 0, out_cap=len(d))
+        assert ref_out == o and ref_ip == int(r["in_used"])
+
+
+def test_reference_encoder_streams(engine):
+    from zlibts_b200 import synth
+    datas = [b"a", b"abc", b"aaaaaaaaaa", b"abcabcabcabc", b"hello hello hello hello", bytes(range(256))]
+    datas += [synth.text(65536, 1).tobytes(), synth.mixed(65536, 2).tobytes(), synth.text(5000, 9).tobytes()]
+    for ctype in (oracle.DYNAMIC, oracle.FIXED, oracle.NONE):
+        streams = [oracle.raw_deflate(d, ctype) for d in datas]
+        _check(engine, datas, streams)
+
+
+def test_zlib_streams_fuzz(engine):
+    rng = np.random.default_rng(3)
+    datas, streams = [], []
+    for i in range(600):
+        n = int(rng.integers(1, 3000))
+        alpha = int(rng.choice([1, 2, 3, 4, 16, 64, 256]))
+        d = rand_bytes(rng, n, alpha).tobytes()
+        level = int(rng.choice([0, 1, 6, 9]))
+        strat = int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE]))
+        datas.append(d)
+        streams.append(zlib_raw(d, level, strat))
+    _check(engine, datas, streams)
+
+
+def test_multiblock_and_long_codes(engine):
+    """zlib splits big inputs into several blocks; skewed histograms give 13..15-bit codes (slow path)."""
+    rng = np.random.default_rng(4)
+    datas = []
+    # geometric-ish symbol distribution -> long Huffman codes
+    p = 0.5 ** np.arange(1, 40)
+    p = np.concatenate([p, np.full(216, p[-1] / 300)])
+    p /= p.sum()
+    datas.append(rng.choice(256, size=300000, p=p).astype(np.uint8).tobytes())
+    datas.append(rand_bytes(rng, 400000, 256).tobytes())
+    datas.append((b"0123456789abcdef" * 40000))
+    from zlibts_b200 import synth
+    datas.append(synth.mixed(1 << 20, 11).tobytes())
+    streams = [zlib_raw(d, 6) for d in datas] + [zlib_raw(d, 1) for d in datas]
+    _check(engine, datas + datas, streams)
+
+
+def test_sync_flush_joined_stream(engine):
+    """SURVEY App. A.7 layout: blocks joined by empty stored blocks (what chunk-parallel deflate emits)."""
+    rng = np.random.default_rng(5)
+    parts = [rand_bytes(rng, int(rng.integers(1, 5000)), 8).tobytes() for _ in range(7)]
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    s = b"".join(co.compress(p) + co.flush(zlib.Z_SYNC_FLUSH) for p in parts[:-1])
+    s += co.compress(parts[-1]) + co.flush()
+    _check(engine, [b"".join(parts)], [s])
+
+
+def test_error_statuses(engine):
+    import zlibts_b200 as z
+    good = zlib_raw(b"hello hello hello hello hello", 6)
+    # truncated input
+    outs, res = gpu_inflate_many(engine, [good[:3]], [100])
+    assert int(res["status"][0]) in (z.ST_INPUT_BROKEN, z.ST_BAD_CODE)
+    # BTYPE 3
+    outs, res = gpu_inflate_many(engine, [b"\x07\x00\x00"], [100])
+    assert int(res["status"][0]) == z.ST_BTYPE
+    # output too small
+    outs, res = gpu_inflate_many(engine, [zlib_raw(b"x" * 1000, 6)], [10])
+    assert int(res["status"][0]) == z.ST_OUT_OVERFLOW
+    # distance before start of output: fixed block, match len 3 dist 1 with no prior byte
+    # bits: BFINAL=1 BTYPE=01, code 257 (0000001), dist code 0 (00000), EOB (0000000)
+    outs, res = gpu_inflate_many(engine, [bytes([0b00000011, 0b00000010, 0, 0])], [100])
+    assert int(res["status"][0]) == z.ST_BAD_CODE
+
+
+def test_checksums_of_output(engine):
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    datas = [synth.text(65536, 1000 + i).tobytes() for i in range(4)] + [b"", b"q"]
+    streams = [oracle.raw_deflate(d) if d else zlib_raw(d) for d in datas]
+    outs, res = gpu_inflate_many(engine, streams, [len(d) for d in datas],
+                                 flags=z.INFLATE_WANT_CRC32 | z.INFLATE_WANT_ADLER32, trailer=b"\0\0\0\0", slack=7)
+    for d, o, r in zip(datas, outs, res):
+        assert o == d and int(r["status"]) == 0
+        assert int(r["crc32"]) == zlib.crc32(d) and int(r["adler32"]) == zlib.adler32(d)

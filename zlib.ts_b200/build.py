@@ -1,0 +1,47 @@
+"""Builds the native libraries in-tree (sm_100a only; nvcc cross-compiles without a GPU).
+
+    libzlibts_b200.so  -- the C-ABI engine (include/zlibts_b200.h): CUDA kernels + host glue
+    libzts_synth.so    -- synthetic input generators, plain C
+"""
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libzlibts_b200.so")
+SYNTH_LIB = os.path.join(HERE, "libzts_synth.so")
+
+CU_SOURCES = ["zts_ctx.cu", "zts_checksum.cu", "zts_inflate.cu", "zts_deflate.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def build(force=False, verbose=False):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    deps.append(os.path.join(HERE, "..", "include", "zlibts_b200.h"))
+    if force or not _newer(LIB, deps):
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+        subprocess.run(cmd, check=True, cwd=CSRC)
+    synth_src = os.path.join(CSRC, "zts_synth.c")
+    if force or not _newer(SYNTH_LIB, [synth_src]):
+        gcc = shutil.which("gcc") or "gcc"
+        subprocess.run([gcc, "-O2", "-fPIC", "-shared", "-std=c11", "-o", SYNTH_LIB, synth_src], check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,105 @@
+// zts_common.cuh -- shared host/device plumbing for libzlibts_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/zlibts_b200.h"
+
+// ---- kernel slots for the per-kernel event timers (zlb_profile_*) ---------------------------
+enum ZtsKernelSlot {
+    ZK_INFLATE = 0,
+    ZK_CHECKSUM_SLICES,
+    ZK_CHECKSUM_COMBINE,
+    ZK_LZ77,
+    ZK_HUFFMAN,
+    ZK_SCAN,
+    ZK_BITPACK,
+    ZK_STORED,
+    ZK_FINALIZE,
+    ZK_COUNT
+};
+
+static const char* const kZtsKernelNames[ZK_COUNT] = {
+    "inflate_warp_kernel", "checksum_slices_kernel", "checksum_combine_kernel",
+    "lz77_chunk_kernel",   "huffman_build_kernel",   "chunk_scan_kernel",
+    "bitpack_kernel",      "stored_block_kernel",    "deflate_finalize_kernel"};
+
+struct ZtsDevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct ZtsProfRec {
+    int slot;
+    cudaEvent_t a, b;
+};
+
+struct zlb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    char err[512] = {0};
+
+    // device arenas (grow-only, freed in zlb_destroy)
+    ZtsDevBuf d_items, d_results, d_chunks, d_chunk_info, d_tokens, d_spec, d_hist, d_codes, d_sortT,
+        d_sums, d_misc, d_stage_in, d_stage_out;
+    // pinned host staging for the small tables
+    void* h_pin = nullptr;
+    size_t h_pin_cap = 0;
+
+    // profiling
+    bool prof = false;
+    std::vector<ZtsProfRec> pending;
+    std::vector<cudaEvent_t> ev_pool;
+    double slot_ms[ZK_COUNT] = {0};
+    uint64_t slot_launches[ZK_COUNT] = {0};
+    uint64_t launches = 0;
+};
+
+int zts_fail(zlb_ctx* ctx, int code, const char* fmt, ...);
+int zts_reserve(zlb_ctx* ctx, ZtsDevBuf* b, size_t bytes);
+int zts_reserve_pinned(zlb_ctx* ctx, size_t bytes);
+void zts_prof_begin(zlb_ctx* ctx, int slot);
+void zts_prof_end(zlb_ctx* ctx, int slot);
+
+#define ZTS_CUDA(ctx, call)                                                                       \
+    do {                                                                                          \
+        cudaError_t _e = (call);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return zts_fail((ctx), ZLB_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), \
+                            __FILE__, __LINE__);                                                  \
+    } while (0)
+
+// Launch wrapper: counts the launch, brackets it with events when profiling, checks the launch.
+#define ZTS_LAUNCH(ctx, slot, ...)                                                                \
+    do {                                                                                          \
+        zts_prof_begin((ctx), (slot));                                                            \
+        __VA_ARGS__;                                                                              \
+        zts_prof_end((ctx), (slot));                                                              \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess)                                                                    \
+            return zts_fail((ctx), ZLB_E_CUDA, "launch %s failed: %s", kZtsKernelNames[(slot)],   \
+                            cudaGetErrorString(_e));                                              \
+    } while (0)
+
+// ---- cross-file entry points (device buffers, async on ctx->stream) ---------------------------
+// checksums of n items; writes crc32/adler32 into d_results[i] (fields selected by kinds)
+int zts_checksum_device(zlb_ctx* ctx, const uint8_t* d_in, const zlb_item* d_items, zlb_result* d_results,
+                        const zlb_item* h_items, size_t n, uint32_t kinds, int use_out_len);
+
+// ---- small device helpers ----------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned zts_lane() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned zts_lanemask_lt()
+{
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+#endif

@@ -1,0 +1,532 @@
+// zts_inflate.cu -- batched RFC-1951 decoder, one warp per independent stream
+// (replaces RawInflate.decompress / parseBlock / parseDynamicHuffmanBlock / decodeHuffmanAdaptive,
+//  src/RawInflate.ts:127-516, and buildHuffmanTable, src/Huffman.ts:8-68).
+//
+// Design (B200): the decode state is warp-uniform -- every lane tracks the same bit buffer and
+// output cursor, so table look-ups are shared-memory broadcasts and there is no divergence; the
+// lanes differ only where they cooperate:
+//   * input: the warp keeps a 128-byte window of the stream in registers (one coalesced 4-byte
+//     load per lane), words are handed to the bit reader with a shuffle;
+//   * LZ77 copies: lane k copies byte k, k+32, ... of the match; overlapping matches (dist < len,
+//     src/RawInflate.ts:506-508) read the periodic source out[op - dist + k mod dist], which lies
+//     entirely before the match, so no intra-copy ordering is needed;
+//   * table construction: canonical code assignment with ballots, no atomics.
+// Tables per warp in shared memory: a 10-bit root for literal/length codes and an 8-bit root for
+// distance codes (entry = base << 16 | kind << 8 | extra_bits << 4 | code_bits); codes longer than
+// the root are resolved canonically (first_code / count per length + symbols sorted by code), which
+// replaces the reference's 2^15-entry single-level table.
+//
+// Algorithmic bytes per stream: C (compressed, read once) + N (output, written once).
+#include "zts_common.cuh"
+
+#define INF_WARPS_PER_CTA 4
+#define LIT_ROOT_BITS 10
+#define DIST_ROOT_BITS 8
+#define CL_ROOT_BITS 7
+
+#define KIND_LITERAL 0u
+#define KIND_BASE 1u   // length or distance base + extra bits
+#define KIND_EOB 2u
+#define KIND_INVALID 3u
+
+struct HuffTab {
+    uint16_t first_code[16];  // canonical (MSB-first) first code of each length
+    uint16_t first_idx[16];   // index into sorted[] of the first symbol of each length
+    uint16_t count[16];
+};
+
+struct InfWarpSmem {
+    uint32_t lit_root[1 << LIT_ROOT_BITS];
+    uint32_t dist_root[1 << DIST_ROOT_BITS];
+    uint32_t cl_root[1 << CL_ROOT_BITS];
+    uint16_t lit_sorted[288];
+    uint16_t dist_sorted[32];
+    uint16_t cl_sorted[20];
+    HuffTab lit, dist, cl;
+    uint8_t lens[32 + 288 + 32 + 16];  // [0,19) code-length code; [32, 32+hlit+hdist) litlen ++ dist
+};
+
+// LengthCodeTable / LengthExtraTable (src/RawInflate.ts:17-28; symbols 286/287 decode as 258 there)
+__constant__ uint16_t c_len_base[31] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23,  27, 31,
+                                        35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258, 258, 258};
+__constant__ uint8_t c_len_extra[31] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2,
+                                        3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0, 0, 0};
+// DistCodeTable / DistExtraTable (src/RawInflate.ts:31-42)
+__constant__ uint16_t c_dist_base[30] = {1,    2,    3,    4,    5,    7,    9,    13,    17,    25,
+                                         33,   49,   65,   97,   129,  193,  257,  385,   513,   769,
+                                         1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+__constant__ uint8_t c_dist_extra[30] = {0, 0, 0, 0, 1, 1, 2, 2,  3,  3,  4,  4,  5,  5,  6,
+                                         6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+// HuffmanOrder (src/RawInflate.ts:14)
+__constant__ uint8_t c_huff_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+enum { TAB_LITLEN = 0, TAB_DIST = 1, TAB_CL = 2 };
+
+__device__ __forceinline__ uint32_t make_entry(int which, uint32_t sym, uint32_t nbits)
+{
+    if (which == TAB_LITLEN) {
+        if (sym < 256) return (sym << 16) | (KIND_LITERAL << 8) | nbits;
+        if (sym == 256) return (KIND_EOB << 8) | nbits;
+        if (sym < 288) return ((uint32_t)c_len_base[sym - 257] << 16) | (KIND_BASE << 8) |
+                              ((uint32_t)c_len_extra[sym - 257] << 4) | nbits;
+        return (KIND_INVALID << 8) | nbits;
+    }
+    if (which == TAB_DIST) {
+        if (sym < 30) return ((uint32_t)c_dist_base[sym] << 16) | (KIND_BASE << 8) |
+                             ((uint32_t)c_dist_extra[sym] << 4) | nbits;
+        return (KIND_INVALID << 8) | nbits;  // DistCodeTable[30..31] is undefined in the reference
+    }
+    return (sym << 16) | (KIND_LITERAL << 8) | nbits;
+}
+
+// Canonical decoder construction for one code (warp-cooperative, all lanes call it).
+// Mirrors what buildHuffmanTable (src/Huffman.ts:8-68) produces for complete or incomplete codes:
+// shorter lengths first, ascending symbol order inside a length. Returns false when the lengths
+// are over-subscribed (the reference would silently overwrite table slots).
+__device__ bool build_table(int which, const uint8_t* lens, int n, int root_bits, uint32_t* root,
+                            uint16_t* sorted, HuffTab* tab)
+{
+    const unsigned lane = zts_lane();
+    const unsigned lt = zts_lanemask_lt();
+    // count per length: lane L accumulates count[L]
+    uint32_t mycount = 0;
+    for (int base = 0; base < n; base += 32) {
+        int s = base + (int)lane;
+        uint32_t l = s < n ? lens[s] : 0;
+#pragma unroll
+        for (uint32_t L = 1; L <= 15; ++L) {
+            unsigned m = __ballot_sync(0xFFFFFFFFu, l == L);
+            if (lane == L) mycount += __popc(m);
+        }
+    }
+    if (lane < 16) tab->count[lane] = (uint16_t)(lane ? mycount : 0);
+    __syncwarp();
+    // first codes / first indices, Kraft check (every lane computes the same values)
+    uint32_t code = 0, idx = 0, kraft = 0;
+    uint32_t my_first_idx = 0;
+#pragma unroll
+    for (uint32_t L = 1; L <= 15; ++L) {
+        uint32_t c = tab->count[L];
+        if (lane == L) {
+            tab->first_code[L] = (uint16_t)code;
+            tab->first_idx[L] = (uint16_t)idx;
+        }
+        if (lane == L) my_first_idx = idx;
+        code = (code + c) << 1;
+        idx += c;
+        kraft += c << (15 - L);
+    }
+    (void)my_first_idx;
+    if (kraft > (1u << 15)) return false;
+    // root table: 0 = "not resolved here" (long code or unused pattern)
+    for (int i = (int)lane; i < (1 << root_bits); i += 32) root[i] = 0;
+    __syncwarp();
+    // assign codes in (length, symbol) order; running offset per length kept uniformly in registers
+    uint32_t offs[16];
+#pragma unroll
+    for (int L = 0; L < 16; ++L) offs[L] = 0;
+    for (int base = 0; base < n; base += 32) {
+        int s = base + (int)lane;
+        uint32_t l = s < n ? lens[s] : 0;
+        uint32_t my_rank = 0;
+#pragma unroll
+        for (uint32_t L = 1; L <= 15; ++L) {
+            unsigned m = __ballot_sync(0xFFFFFFFFu, l == L);
+            if (l == L) my_rank = offs[L] + __popc(m & lt);
+            offs[L] += __popc(m);
+        }
+        if (l) {
+            uint32_t slot = tab->first_idx[l] + my_rank;
+            sorted[slot] = (uint16_t)s;
+            uint32_t c = tab->first_code[l] + my_rank;  // MSB-first canonical code
+            if ((int)l <= root_bits) {
+                uint32_t r = __brev(c) >> (32 - l);  // as it appears in the LSB-first bit buffer
+                uint32_t e = make_entry(which, (uint32_t)s, l);
+                for (uint32_t j = r; j < (1u << root_bits); j += (1u << l)) root[j] = e;
+            }
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// canonical resolution of a code that the root table did not resolve; `bits` = bit buffer (LSB first)
+__device__ __forceinline__ uint32_t slow_decode(int which, uint32_t bits, int root_bits, const uint16_t* sorted,
+                                                const HuffTab* tab)
+{
+    uint32_t v = __brev(bits) >> 17;  // first 15 stream bits, MSB-first
+    for (int L = root_bits + 1; L <= 15; ++L) {
+        uint32_t c = v >> (15 - L);
+        uint32_t d = c - tab->first_code[L];
+        if (d < tab->count[L]) return make_entry(which, sorted[tab->first_idx[L] + d], (uint32_t)L);
+    }
+    return 0;  // undefined code
+}
+
+struct BitReader {
+    const uint32_t* win_base;  // aligned address of the current 128-byte window
+    const uint8_t* end;        // one past the last readable input byte
+    uint32_t win;              // this lane's word of the window
+    uint32_t win_pos;          // next word of the window to consume (0..32)
+    unsigned long long buf;
+    int cnt;                   // valid bits in buf
+    unsigned long long words_taken;  // words moved into buf since the last (re)start
+    unsigned long long base_bits;    // stream bits consumed before the last (re)start
+    uint32_t skip_bits;        // bits of the first word that precede the (re)start point
+};
+
+__device__ __forceinline__ void br_load_window(BitReader& br)
+{
+    const uint32_t* p = br.win_base + zts_lane();
+    // a word is readable if it overlaps [.., end); bytes past `end` inside that word are never
+    // consumed as data because every consumer checks the consumed-bit count against the item length
+    br.win = ((const uint8_t*)p < br.end) ? __ldg(p) : 0u;
+    br.win_pos = 0;
+}
+
+__device__ __forceinline__ void br_init(BitReader& br, const uint8_t* src, const uint8_t* end,
+                                        unsigned long long base_bits)
+{
+    uintptr_t a = (uintptr_t)src;
+    br.win_base = (const uint32_t*)(a & ~(uintptr_t)3);
+    br.end = end;
+    br.base_bits = base_bits;
+    br.skip_bits = (uint32_t)(a & 3) * 8;
+    br.buf = 0;
+    br.cnt = 0;
+    br.words_taken = 0;
+    br_load_window(br);
+    // first word: drop the bytes before the stream
+    uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, 0);
+    br.win_pos = 1;
+    br.words_taken = 1;
+    br.buf = (unsigned long long)(w >> br.skip_bits);
+    br.cnt = 32 - (int)br.skip_bits;
+}
+
+__device__ __forceinline__ void br_refill(BitReader& br)
+{
+    if (br.cnt <= 32) {
+        if (br.win_pos == 32) {
+            br.win_base += 32;
+            br_load_window(br);
+        }
+        uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, br.win_pos);
+        br.win_pos++;
+        br.words_taken++;
+        br.buf |= (unsigned long long)w << br.cnt;
+        br.cnt += 32;
+    }
+}
+
+__device__ __forceinline__ uint32_t br_take(BitReader& br, int n)
+{
+    uint32_t v = (uint32_t)br.buf & ((1u << n) - 1u);
+    br.buf >>= n;
+    br.cnt -= n;
+    return v;
+}
+
+// stream bits consumed so far
+__device__ __forceinline__ unsigned long long br_bits_used(const BitReader& br)
+{
+    return br.base_bits + br.words_taken * 32ull - br.skip_bits - (unsigned long long)br.cnt;
+}
+
+__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
+inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const zlb_item* __restrict__ items,
+                    zlb_result* __restrict__ results, uint32_t n_items, uint32_t flags)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned lane = zts_lane();
+    const unsigned warp = threadIdx.x >> 5;
+    InfWarpSmem* S = reinterpret_cast<InfWarpSmem*>(smem_raw) + warp;
+    const uint32_t item = blockIdx.x * INF_WARPS_PER_CTA + warp;
+    if (item >= n_items) return;
+
+    const zlb_item it = items[item];
+    const uint8_t* src = in + it.in_off;
+    uint8_t* dst = out + it.out_off;
+    const unsigned long long in_bits = it.in_len * 8ull;
+    const unsigned long long cap = it.out_cap;
+
+    BitReader br;
+    br_init(br, src, src + it.in_len, 0);
+
+    unsigned long long op = 0;
+    uint32_t status = ZLB_ST_OK;
+    uint32_t blocks = 0;
+    int have_fixed = 0;
+    bool bfinal = false;
+
+    while (!bfinal && status == ZLB_ST_OK) {
+        br_refill(br);
+        if (br_bits_used(br) + 3 > in_bits) {
+            status = ZLB_ST_INPUT_BROKEN;
+            break;
+        }
+        uint32_t hdr = br_take(br, 3);  // src/RawInflate.ts:146-152
+        bfinal = hdr & 1u;
+        uint32_t btype = hdr >> 1;
+        blocks++;
+
+        if (btype == 0) {
+            // ---- stored block (src/RawInflate.ts:251-318): drop to the byte boundary, LEN, NLEN
+            unsigned long long used = br_bits_used(br);
+            unsigned long long byte_pos = (used + 7) >> 3;
+            if (byte_pos + 4 > it.in_len) {
+                status = ZLB_ST_STORED_LEN;
+                break;
+            }
+            const uint8_t* p = src + byte_pos;
+            uint32_t len = (uint32_t)p[0] | ((uint32_t)p[1] << 8);
+            uint32_t nlen = (uint32_t)p[2] | ((uint32_t)p[3] << 8);
+            if ((flags & ZLB_INFLATE_CHECK_NLEN) && ((len ^ nlen) != 0xFFFFu)) {
+                status = ZLB_ST_STORED_LEN;
+                break;
+            }
+            byte_pos += 4;
+            if (byte_pos + len > it.in_len) {
+                status = ZLB_ST_INPUT_BROKEN;
+                break;
+            }
+            if (op + len > cap) {
+                status = ZLB_ST_OUT_OVERFLOW;
+                break;
+            }
+            for (uint32_t k = lane; k < len; k += 32) dst[op + k] = src[byte_pos + k];
+            op += len;
+            br_init(br, src + byte_pos + len, src + it.in_len, (byte_pos + len) * 8ull);
+            __syncwarp();
+            continue;
+        }
+        if (btype == 3) {
+            status = ZLB_ST_BTYPE;  // src/RawInflate.ts:168
+            break;
+        }
+
+        if (btype == 1) {
+            // ---- fixed Huffman tables (src/RawInflate.ts:45-61)
+            if (have_fixed != 1) {
+                for (int i = (int)lane; i < 288; i += 32) S->lens[32 + i] = i <= 143 ? 8 : i <= 255 ? 9 : i <= 279 ? 7 : 8;
+                for (int i = (int)lane; i < 30; i += 32) S->lens[32 + 288 + i] = 5;
+                __syncwarp();
+                build_table(TAB_LITLEN, S->lens + 32, 288, LIT_ROOT_BITS, S->lit_root, S->lit_sorted, &S->lit);
+                build_table(TAB_DIST, S->lens + 32 + 288, 30, DIST_ROOT_BITS, S->dist_root, S->dist_sorted, &S->dist);
+                have_fixed = 1;
+            }
+        } else {
+            // ---- dynamic Huffman header (src/RawInflate.ts:345-388)
+            have_fixed = 0;
+            br_refill(br);
+            uint32_t hlit = br_take(br, 5) + 257;
+            uint32_t hdist = br_take(br, 5) + 1;
+            uint32_t hclen = br_take(br, 4) + 4;
+            if (lane < 19) S->lens[lane] = 0;
+            __syncwarp();
+            for (uint32_t i = 0; i < hclen; ++i) {
+                br_refill(br);
+                uint32_t v = br_take(br, 3);
+                if (lane == 0) S->lens[c_huff_order[i]] = (uint8_t)v;
+            }
+            __syncwarp();
+            if (br_bits_used(br) > in_bits) {
+                status = ZLB_ST_INPUT_BROKEN;
+                break;
+            }
+            if (!build_table(TAB_CL, S->lens, 19, CL_ROOT_BITS, S->cl_root, S->cl_sorted, &S->cl)) {
+                status = ZLB_ST_BAD_LENGTHS;
+                break;
+            }
+            // code lengths with repeat codes 16/17/18 (:361-383); over-long repeats are clipped like
+            // the reference's out-of-range typed-array stores
+            const uint32_t total = hlit + hdist;
+            uint32_t i = 0, prev = 0;
+            while (i < total && status == ZLB_ST_OK) {
+                br_refill(br);
+                uint32_t e = S->cl_root[(uint32_t)br.buf & ((1u << CL_ROOT_BITS) - 1u)];
+                uint32_t nb = e & 15u;
+                if (nb == 0) {
+                    status = ZLB_ST_BAD_CODE;
+                    break;
+                }
+                br_take(br, (int)nb);
+                uint32_t sym = e >> 16;
+                uint32_t rep = 1, val = sym;
+                if (sym == 16) {
+                    rep = 3 + br_take(br, 2);
+                    val = prev;
+                } else if (sym == 17) {
+                    rep = 3 + br_take(br, 3);
+                    val = 0;
+                } else if (sym == 18) {
+                    rep = 11 + br_take(br, 7);
+                    val = 0;
+                }
+                // lanes store the run cooperatively (rep <= 138)
+                for (uint32_t k = lane; k < rep; k += 32)
+                    if (i + k < total) S->lens[32 + i + k] = (uint8_t)val;  // staging above the CL lengths
+                i += rep;
+                prev = val;
+                if (br_bits_used(br) > in_bits) status = ZLB_ST_INPUT_BROKEN;
+            }
+            if (status != ZLB_ST_OK) break;
+            __syncwarp();
+            // lens[32 .. 32+total) holds litlen then dist lengths
+            if (!build_table(TAB_LITLEN, S->lens + 32, (int)hlit, LIT_ROOT_BITS, S->lit_root, S->lit_sorted, &S->lit) ||
+                !build_table(TAB_DIST, S->lens + 32 + hlit, (int)hdist, DIST_ROOT_BITS, S->dist_root, S->dist_sorted,
+                             &S->dist)) {
+                status = ZLB_ST_BAD_LENGTHS;
+                break;
+            }
+        }
+
+        // ---- symbol loop (src/RawInflate.ts:466-516)
+        for (;;) {
+            br_refill(br);
+            uint32_t e = S->lit_root[(uint32_t)br.buf & ((1u << LIT_ROOT_BITS) - 1u)];
+            if ((e & 15u) == 0) {
+                e = slow_decode(TAB_LITLEN, (uint32_t)br.buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit);
+                if (e == 0) {
+                    status = ZLB_ST_BAD_CODE;
+                    break;
+                }
+            }
+            br_take(br, (int)(e & 15u));
+            const uint32_t kind = (e >> 8) & 3u;
+            if (kind == KIND_LITERAL) {
+                if (op >= cap) {
+                    status = ZLB_ST_OUT_OVERFLOW;
+                    break;
+                }
+                if (lane == 0) dst[op] = (uint8_t)(e >> 16);
+                op++;
+                continue;
+            }
+            if (kind == KIND_EOB) break;
+            if (kind == KIND_INVALID) {
+                status = ZLB_ST_BAD_CODE;
+                break;
+            }
+            uint32_t len = (e >> 16) + br_take(br, (int)((e >> 4) & 15u));
+            br_refill(br);
+            uint32_t d = S->dist_root[(uint32_t)br.buf & ((1u << DIST_ROOT_BITS) - 1u)];
+            if ((d & 15u) == 0) {
+                d = slow_decode(TAB_DIST, (uint32_t)br.buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist);
+                if (d == 0) {
+                    status = ZLB_ST_BAD_CODE;
+                    break;
+                }
+            }
+            br_take(br, (int)(d & 15u));
+            if (((d >> 8) & 3u) != KIND_BASE) {
+                status = ZLB_ST_BAD_CODE;
+                break;
+            }
+            uint32_t dist = (d >> 16) + br_take(br, (int)((d >> 4) & 15u));
+            if (br_bits_used(br) > in_bits) {
+                status = ZLB_ST_INPUT_BROKEN;
+                break;
+            }
+            if ((unsigned long long)dist > op) {
+                status = ZLB_ST_BAD_CODE;  // the reference would copy `undefined` -> 0 here
+                break;
+            }
+            if (op + len > cap) {
+                status = ZLB_ST_OUT_OVERFLOW;
+                break;
+            }
+            __syncwarp();  // earlier literal / match stores of other lanes become visible
+            {
+                uint8_t* o = dst + op;
+                const uint8_t* s0 = o - dist;
+                if (dist >= len) {
+                    for (uint32_t k = lane; k < len; k += 32) o[k] = s0[k];
+                } else {
+                    // periodic source: byte k comes from s0[k mod dist]
+                    uint32_t r = lane % dist;
+                    const uint32_t step = 32u % dist;
+                    for (uint32_t k = lane; k < len; k += 32) {
+                        o[k] = s0[r];
+                        r += step;
+                        if (r >= dist) r -= dist;
+                    }
+                }
+            }
+            op += len;
+        }
+        if (status == ZLB_ST_OK && br_bits_used(br) > in_bits) status = ZLB_ST_INPUT_BROKEN;
+    }
+
+    if (lane == 0) {
+        zlb_result r = results[item];
+        r.status = status;
+        r.blocks = blocks;
+        r.out_len = op;
+        r.in_used = (br_bits_used(br) + 7) >> 3;  // whole unread bytes are given back (:511-514)
+        results[item] = r;
+    }
+}
+
+static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item* h_items,
+                          zlb_result* h_results, size_t n, uint32_t flags)
+{
+    int rc = zts_reserve(ctx, &ctx->d_items, n * sizeof(zlb_item) + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_results, n * sizeof(zlb_result) + 64);
+    if (rc) return rc;
+    zlb_item* d_items = (zlb_item*)ctx->d_items.p;
+    zlb_result* d_results = (zlb_result*)ctx->d_results.p;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(d_items, h_items, n * sizeof(zlb_item), cudaMemcpyHostToDevice, ctx->stream));
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_results, 0, n * sizeof(zlb_result), ctx->stream));
+    const size_t smem = sizeof(InfWarpSmem) * INF_WARPS_PER_CTA;
+    ZTS_CUDA(ctx, cudaFuncSetAttribute(inflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((n + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA);
+    ZTS_LAUNCH(ctx, ZK_INFLATE,
+               inflate_warp_kernel<<<grid, INF_WARPS_PER_CTA * 32, smem, ctx->stream>>>(d_in, d_out, d_items, d_results,
+                                                                                        (uint32_t)n, flags));
+    uint32_t kinds = 0;
+    if (flags & ZLB_INFLATE_WANT_CRC32) kinds |= ZLB_SUM_CRC32;
+    if (flags & ZLB_INFLATE_WANT_ADLER32) kinds |= ZLB_SUM_ADLER32;
+    if (kinds) {
+        rc = zts_checksum_device(ctx, d_out, d_items, d_results, h_items, n, kinds, 1);
+        if (rc) return rc;
+    }
+    ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+    return ZLB_OK;
+}
+
+extern "C" int zlb_inflate_batch(zlb_ctx* ctx, const void* d_in, void* d_out, const zlb_item* items,
+                                 zlb_result* results, size_t n, uint32_t flags)
+{
+    if (!ctx || (!items && n) || (!results && n) || (!d_in && n) || (!d_out && n)) return ZLB_E_ARG;
+    if (n == 0) return ZLB_OK;
+    if (n > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many items");
+    ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = inflate_device(ctx, (const uint8_t*)d_in, (uint8_t*)d_out, items, results, n, flags);
+    if (rc) return rc;
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZLB_OK;
+}
+
+extern "C" int zlb_inflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_bytes, void* h_out, size_t out_bytes,
+                                      const zlb_item* items, zlb_result* results, size_t n, uint32_t flags)
+{
+    if (!ctx || (!items && n) || (!results && n) || (!h_in && in_bytes) || (!h_out && out_bytes)) return ZLB_E_ARG;
+    if (n == 0) return ZLB_OK;
+    ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n; ++i) {
+        if (items[i].in_off + items[i].in_len > in_bytes || items[i].out_off + items[i].out_cap > out_bytes)
+            return zts_fail(ctx, ZLB_E_ARG, "item %zu out of range", i);
+    }
+    int rc = zts_reserve(ctx, &ctx->d_stage_in, in_bytes + 256);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_stage_out, out_bytes + 256);
+    if (rc) return rc;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = inflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, flags);
+    if (rc) return rc;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_stage_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZLB_OK;
+}
