@@ -1,0 +1,211 @@
+"""GPU: chunk-parallel deflate vs the oracle (reference RawDeflate restatement).
+
+Stage parity: LZ77 tokens + histograms (src/LZ77.ts), code lengths (src/RawDeflate.ts:440-571).
+End to end:   compat bytes == oracle RawDeflate(chunk) per chunk; joined multi-chunk streams decode
+              with the oracle's RawInflate and with CPython zlib."""
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import pack, rand_bytes
+
+pytestmark = pytest.mark.gpu
+
+LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163,
+            195, 227, 258]
+DIST_BASE = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073,
+             4097, 6145, 8193, 12289, 16385, 24577]
+
+
+def oracle_tokens(data):
+    """oracle LZ77 Uint16 stream -> engine token words (literal byte | 0x80000000 | (len-3)<<16 | (dist-1))."""
+    tok, fl, fd = oracle.lz77(data)
+    out, i = [], 0
+    t = tok.tolist()
+    while i < len(t):
+        s = t[i]
+        if s < 256:
+            out.append(s)
+            i += 1
+        elif s == 256:
+            break
+        else:
+            ln = LEN_BASE[s - 257] + t[i + 1]
+            ds = DIST_BASE[t[i + 3]] + t[i + 4]
+            out.append(0x80000000 | ((ln - 3) << 16) | (ds - 1))
+            i += 6
+    return np.array(out, dtype=np.uint32), np.concatenate([fl, fd])
+
+
+def sample_inputs():
+    from zlibts_b200 import synth
+    rng = np.random.default_rng(11)
+    ins = [b"a", b"ab", b"abc", b"abcd", b"aaaaaaaaaa", b"abcabcabcabc", b"hello hello hello hello", bytes(range(256))]
+    ins += [rand_bytes(rng, n, a).tobytes() for n, a in
+            [(5, 2), (300, 2), (5000, 2), (65536, 2), (65536, 3), (40000, 4), (65536, 16), (65536, 256), (2049, 5),
+             (2048, 7), (4097, 3), (65535, 64)]]
+    ins += [b"\0" * 65536, b"xy" * 30000, (b"0123456789abcdefghijklmnopqrstuvwxyz" * 2000)[:65536]]
+    ins += [synth.text(65536, 1).tobytes(), synth.mixed(65536, 2).tobytes(), synth.mixed(65536, 3, 512).tobytes(),
+            synth.text(30000, 5).tobytes(), synth.mixed(50001, 6).tobytes()]
+    # a 1000-byte block repeated: many equally long candidates (ties -> nearest)
+    blk = rand_bytes(rng, 1000, 256).tobytes()
+    ins.append((blk * 66)[:65536])
+    return ins
+
+
+def test_lz77_tokens_and_histograms(engine):
+    import torch
+    for data in sample_inputs():
+        d = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+        tok, hist = engine.debug_lz77(d, len(data))
+        want_tok, want_hist = oracle_tokens(data)
+        assert len(tok) == len(want_tok), (len(data), len(tok), len(want_tok))
+        bad = np.nonzero(tok != want_tok)[0]
+        assert bad.size == 0, (len(data), int(bad[0]), hex(int(tok[bad[0]])), hex(int(want_tok[bad[0]])))
+        assert np.array_equal(hist, want_hist), len(data)
+
+
+def test_code_lengths_match_reference_heap_and_package_merge(engine):
+    rng = np.random.default_rng(12)
+    cases = []
+    for _ in range(60):
+        nsym, limit = [(286, 15), (30, 7), (19, 7)][int(rng.integers(0, 3))]
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            f = rng.integers(0, 4, nsym)
+        elif kind == 1:
+            f = rng.integers(0, 60000, nsym)
+        elif kind == 2:
+            f = (rng.geometric(0.02, nsym) * (rng.random(nsym) < 0.5)).astype(np.int64)
+        elif kind == 3:
+            f = np.zeros(nsym, dtype=np.int64)
+            f[rng.integers(0, nsym, int(rng.integers(1, 4)))] = rng.integers(1, 100)
+        else:
+            f = np.floor(2.0 ** (np.arange(nsym) % 24) * rng.random()).astype(np.int64) % 65536  # skew: limit binds
+        cases.append((f.astype(np.uint32), limit))
+    for f, limit in cases:
+        got = engine.debug_code_lengths(f, limit)
+        want = oracle.get_lengths(f, limit)
+        assert np.array_equal(got, want), (f.tolist(), limit, got.tolist(), want.tolist())
+
+
+def _deflate_items(engine, datas, block_type=2, chunk_bytes=0, flags=0, align=1, host=False):
+    import torch
+    import zlibts_b200 as z
+    blob, offs, lens = pack(datas, align)
+    caps = [z.deflate_bound(n, chunk_bytes, block_type) for n in lens]
+    ooffs = np.concatenate([[0], np.cumsum(caps)]).astype(np.uint64)
+    items = z.make_items(len(datas))
+    items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = offs, lens, ooffs[:-1], caps
+    if host:
+        h_out = np.zeros(int(ooffs[-1]), dtype=np.uint8)
+        res = engine.deflate_batch_host(blob, h_out, items, block_type, chunk_bytes, flags)
+    else:
+        d_out = torch.zeros(int(ooffs[-1]), dtype=torch.uint8, device="cuda")
+        res = engine.deflate_batch(torch.from_numpy(blob).cuda(), d_out, items, block_type, chunk_bytes, flags)
+        h_out = d_out.cpu().numpy()
+    outs = [h_out[int(o):int(o) + int(r["out_len"])].tobytes() for o, r in zip(ooffs[:-1], res)]
+    return outs, res
+
+
+def test_single_chunk_bytes_identical_to_reference(engine):
+    datas = sample_inputs()
+    for btype in (oracle.DYNAMIC, oracle.FIXED, oracle.NONE):
+        outs, res = _deflate_items(engine, datas, btype, align=1)
+        for d, o, r in zip(datas, outs, res):
+            assert int(r["status"]) == 0
+            want = oracle.raw_deflate(d, btype)
+            assert o == want, (btype, len(d), len(o), len(want))
+            assert zlib.decompress(o, -15) == d
+
+
+def test_multi_chunk_join_roundtrip_and_per_chunk_identity(engine):
+    from zlibts_b200 import synth
+    rng = np.random.default_rng(13)
+    datas = [synth.mixed(300000, 21).tobytes(), synth.text(200001, 22).tobytes(), rand_bytes(rng, 70000, 3).tobytes(),
+             b"z" * 131072, rand_bytes(rng, 131073, 256).tobytes()]
+    for chunk in (0, 4096, 1000):
+        outs, res = _deflate_items(engine, datas, oracle.DYNAMIC, chunk)
+        cb = chunk or 65536
+        for d, o, r in zip(datas, outs, res):
+            assert int(r["status"]) == 0 and int(r["blocks"]) == -(-len(d) // cb)
+            assert zlib.decompress(o, -15) == d                           # RFC-valid single stream
+            ref, ip = oracle.raw_inflate(o + b"\0\0\0\0", 0, out_cap=len(d))  # reference decoder accepts the joins
+            assert ref == d and ip == len(o)
+            # compat: chunk k's bytes == reference RawDeflate(chunk k) with BFINAL masked
+            pos = 0
+            nchunks = -(-len(d) // cb)
+            for k in range(nchunks):
+                want = bytearray(oracle.raw_deflate(d[k * cb:(k + 1) * cb]))
+                if k + 1 < nchunks:
+                    want[0] &= 0xFE
+                got = o[pos:pos + len(want)]
+                assert got == bytes(want), (chunk, k)
+                pos += len(want)
+                if k + 1 < nchunks:  # join marker: [00] 00 00 FF FF
+                    if o[pos:pos + 4] == b"\x00\x00\xff\xff":
+                        pos += 4
+                    else:
+                        assert o[pos:pos + 5] == b"\x00\x00\x00\xff\xff", (chunk, k)
+                        pos += 5
+            assert pos == len(o)
+
+
+def test_batch_of_entries_host_path_and_checksums(engine):
+    """zip-like batch: many small independent items through the host-buffer entry point."""
+    import zlibts_b200 as z
+    rng = np.random.default_rng(14)
+    datas = [rand_bytes(rng, int(n), int(a)).tobytes()
+             for n, a in zip(rng.integers(1, 9000, 300), rng.choice([2, 4, 26, 256], 300))]
+    datas += [b"", b"x"]
+    outs, res = _deflate_items(engine, datas, oracle.DYNAMIC, flags=z.DEFLATE_WANT_CRC32 | z.DEFLATE_WANT_ADLER32,
+                               host=True)
+    for d, o, r in zip(datas, outs, res):
+        assert int(r["status"]) == 0
+        assert zlib.decompress(o, -15) == d
+        if d:
+            assert o == oracle.raw_deflate(d)
+        assert int(r["crc32"]) == zlib.crc32(d) and int(r["adler32"]) == zlib.adler32(d)
+
+
+def test_output_overflow_status(engine):
+    import torch
+    import zlibts_b200 as z
+    rng = np.random.default_rng(15)
+    data = rand_bytes(rng, 100000, 256)
+    items = z.make_items(1)
+    items["in_len"], items["out_cap"] = data.size, 50000
+    d_out = torch.zeros(60000, dtype=torch.uint8, device="cuda")
+    res = engine.deflate_batch(torch.from_numpy(data).cuda(), d_out, items)
+    assert int(res["status"][0]) == z.ST_OUT_OVERFLOW
+    assert int(d_out[50000:].max()) == 0  # nothing written past the slot
+
+
+def test_gpu_roundtrip_large_property(engine):
+    """C2-shaped property test at 64 MiB: GPU deflate -> GPU inflate reproduces the input bit-exactly."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    n = 64 << 20
+    data = synth.mixed(n, 2)
+    d_in = torch.from_numpy(data).cuda()
+    cap = z.deflate_bound(n)
+    d_z = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    items = z.make_items(1)
+    items["in_len"], items["out_cap"] = n, cap
+    r = engine.deflate_batch(d_in, d_z, items, flags=z.DEFLATE_WANT_CRC32)
+    assert int(r["status"][0]) == 0 and int(r["blocks"][0]) == n // 65536
+    clen = int(r["out_len"][0])
+    d_o = torch.empty(n, dtype=torch.uint8, device="cuda")
+    it2 = z.make_items(1)
+    it2["in_len"], it2["out_cap"] = clen, n
+    r2 = engine.inflate_batch(d_z, d_o, it2, flags=z.INFLATE_WANT_CRC32)
+    assert int(r2["status"][0]) == 0 and int(r2["out_len"][0]) == n and int(r2["in_used"][0]) == clen
+    assert torch.equal(d_o, d_in)
+    assert int(r2["crc32"][0]) == int(r["crc32"][0]) == zlib.crc32(data)
+    # first chunk equals the reference's bytes for that chunk (BFINAL masked)
+    want = bytearray(oracle.raw_deflate(data[:65536]))
+    want[0] &= 0xFE
+    assert bytes(d_z[:len(want)].cpu().numpy()) == bytes(want)

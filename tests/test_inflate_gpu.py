@@ -52,7 +52,7 @@ def test_multiblock_and_long_codes(engine):
     datas = []
     # geometric-ish symbol distribution -> long Huffman codes
     p = 0.5 ** np.arange(1, 40)
-    p = np.concatenate([p, np.full(216, p[-1] / 300)])
+    p = np.concatenate([p, np.full(256 - p.size, p[-1] / 300)])
     p /= p.sum()
     datas.append(rng.choice(256, size=300000, p=p).astype(np.uint8).tobytes())
     datas.append(rand_bytes(rng, 400000, 256).tobytes())

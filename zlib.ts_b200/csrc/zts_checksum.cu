@@ -255,6 +255,8 @@ int zts_checksum_device(zlb_ctx* ctx, const uint8_t* d_in, const zlb_item* d_ite
     }
     ZTS_CUDA(ctx, cudaMemcpyToSymbolAsync(c_xinv_bytes, h_xinv_bytes, sizeof h_xinv_bytes, 0,
                                           cudaMemcpyHostToDevice, ctx->stream));
+    // the pinned staging area is shared with other tables that may still be in flight on the stream
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // slice table from the host copy of the items. With use_out_len the true lengths are only on
     // the device; out_cap bounds them, empty trailing slices contribute nothing.
     size_t n_slices = 0;

@@ -1,11 +1,572 @@
-// placeholder: replaced by the real pipeline
-#include "zts_common.cuh"
-extern "C" {
-int zlb_deflate_batch(zlb_ctx* ctx, const void*, void*, const zlb_item*, zlb_result*, size_t, int, int, uint32_t, uint32_t)
-{ return zts_fail(ctx, ZLB_E_UNSUPPORTED, "deflate not built yet"); }
-int zlb_deflate_batch_host(zlb_ctx* ctx, const void*, size_t, void*, size_t, const zlb_item*, zlb_result*, size_t, int, int, uint32_t, uint32_t)
-{ return zts_fail(ctx, ZLB_E_UNSUPPORTED, "deflate not built yet"); }
-uint64_t zlb_deflate_bound(uint64_t n, uint32_t, int) { return n * 2 + 1024; }
-int zlb_debug_lz77(zlb_ctx* ctx, const void*, uint32_t, uint32_t*, uint32_t*, uint32_t*) { return zts_fail(ctx, ZLB_E_UNSUPPORTED, "n/a"); }
-int zlb_debug_code_lengths(zlb_ctx* ctx, const uint32_t*, int, int, uint8_t*) { return zts_fail(ctx, ZLB_E_UNSUPPORTED, "n/a"); }
+// zts_deflate.cu -- chunk-parallel raw deflate: output-offset scan, bit packing, stored blocks, host
+// orchestration (replaces RawDeflate.compress / dynamicHuffman / fixedHuffman / makeNocompressBlock,
+// src/RawDeflate.ts:87-173,262-330, and BitStream.writeBits / finish, src/Bitstream.ts:62-130).
+//
+// Pipeline per wave of chunks (all on ctx->stream, no host round trip in between):
+//   lz77_chunk_kernel    tokens + histograms                      (zts_lz77.cu)
+//   huffman_build_kernel code tables, header bits, exact block size (zts_huffman.cu)
+//   chunk_scan_kernel    exclusive scan of block sizes -> byte offset of every chunk in its item
+//   bitpack_kernel       prefix sum over code lengths, bits OR-ed into a shared-memory image of the
+//                        block, image copied out with aligned word stores (byte stores at the edges)
+// Chunks of one item are joined by an empty stored block that byte-aligns; the
+// reference's RawInflate accepts this (src/RawInflate.ts:128-130,261-262,311).
+#include "zts_deflate.cuh"
+
+size_t zts_lz77_smem_bytes();
+int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
+                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint16_t* d_sortT,
+                    uint32_t* d_counter, uint32_t grid);
+int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
+                       ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type);
+int zts_huffman_lengths_debug(zlb_ctx* ctx, const uint32_t* d_freqs, int nsym, int limit, uint8_t* d_lengths);
+
+#define WAVE_CHUNKS 2048u
+#define PACK_THREADS 512
+#define PACK_STAGE_WORDS 31744u  // 124 KiB image: 64 Ki literals * 15 bits + header + join marker
+
+// ---- exclusive scan of chunk sizes (single CTA; a wave has <= 2048 chunks) --------------------------
+__global__ void __launch_bounds__(1024)
+chunk_scan_kernel(const ZtsChunk* __restrict__ chunks, ZtsChunkInfo* __restrict__ info, uint32_t n_chunks,
+                  const zlb_item* __restrict__ items, unsigned long long* __restrict__ item_running,
+                  unsigned long long* __restrict__ gpos)
+{
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t tile_total;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long carry = 0;
+    for (uint32_t base = 0; base < n_chunks; base += 1024) {
+        const uint32_t c = base + tid;
+        const uint32_t v = c < n_chunks ? info[c].out_bytes : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (unsigned)d) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = warp_tot[lane], winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+                if (lane >= (unsigned)d) winc += t;
+            }
+            warp_tot[lane] = winc - w;
+            if (lane == 31) tile_total = winc;
+        }
+        __syncthreads();
+        if (c < n_chunks) gpos[c] = carry + warp_tot[warp] + inc - v;
+        carry += tile_total;
+        __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+    // offset inside the item = running total of earlier waves + distance from the item's first chunk
+    for (uint32_t c = tid; c < n_chunks; c += 1024) {
+        const ZtsChunk ch = chunks[c];
+        const unsigned long long rel = item_running[ch.item] + (gpos[c] - gpos[ch.seg_first]);
+        info[c].out_off = items[ch.item].out_off + rel;
+    }
+    __syncthreads();
+    for (uint32_t c = tid; c < n_chunks; c += 1024) {
+        const ZtsChunk ch = chunks[c];
+        const bool last_in_wave = (c + 1 == n_chunks) || (chunks[c + 1].item != ch.item);
+        if (last_in_wave)
+            item_running[ch.item] = (info[c].out_off - items[ch.item].out_off) + info[c].out_bytes;
+    }
+}
+
+__global__ void deflate_finalize_kernel(const zlb_item* __restrict__ items, zlb_result* __restrict__ results,
+                                        const unsigned long long* __restrict__ item_running,
+                                        const uint32_t* __restrict__ item_blocks, uint32_t n_items)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const unsigned long long total = item_running[i];
+    results[i].out_len = total;
+    results[i].blocks = item_blocks[i];
+    results[i].in_used = items[i].in_len;
+    results[i].status = total > items[i].out_cap ? ZLB_ST_OUT_OVERFLOW : ZLB_ST_OK;
+}
+
+// ---- bit packer: one CTA per chunk ------------------------------------------------------------------------
+struct PackSeg {
+    uint32_t prefix;      // tokens before this segment
+    uint32_t src;         // index into the fix (bit 31 clear) or spec (bit 31 set) token buffer
+};
+
+__global__ void __launch_bounds__(PACK_THREADS)
+bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restrict__ info,
+               const ZtsChunkCodes* __restrict__ codes, const uint32_t* __restrict__ spec_tok,
+               const uint32_t* __restrict__ fix_tok, const zlb_item* __restrict__ items, uint8_t* __restrict__ out)
+{
+    extern __shared__ __align__(16) uint32_t stage[];  // PACK_STAGE_WORDS
+    __shared__ uint32_t s_ll[286];
+    __shared__ uint32_t s_d[30];
+    __shared__ PackSeg s_seg[2 * LZ_WARPS + 1];
+    __shared__ uint32_t s_nseg;
+    __shared__ uint32_t warp_tot[PACK_THREADS / 32];
+    __shared__ uint32_t tile_total;
+
+    const uint32_t c = blockIdx.x;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const ZtsChunk ch = chunks[c];
+    const ZtsChunkInfo* ci = info + c;
+    const zlb_item it = items[ch.item];
+    const uint32_t out_bytes = ci->out_bytes;
+    const unsigned long long rel = ci->out_off - it.out_off;
+    if (rel + out_bytes > it.out_cap) return;  // item overflows its slot: status is set by the finalize kernel
+    uint8_t* dst = out + ci->out_off;
+    const uint32_t shift = (uint32_t)((uintptr_t)dst & 3u);  // image word j <-> aligned global word j
+    const uint32_t n_words = (shift + out_bytes + 3) >> 2;
+    if (n_words > PACK_STAGE_WORDS) return;  // cannot happen for <= 64 KiB chunks (optimal codes)
+
+    for (uint32_t i = tid; i < n_words; i += PACK_THREADS) stage[i] = 0;
+    for (uint32_t i = tid; i < 286; i += PACK_THREADS) s_ll[i] = codes[c].ll[i];
+    if (tid < 30) s_d[tid] = codes[c].d[tid];
+    if (tid == 0) {
+        // token segments in stream order: per tile the re-parsed tokens, then the reused speculative ones
+        uint32_t ns = 0, pre = 0;
+        for (uint32_t w = 0; w < LZ_WARPS; ++w) {
+            const ZtsTile t = ci->tiles[w];
+            if (t.fix_count) {
+                s_seg[ns].prefix = pre;
+                s_seg[ns].src = w * LZ_TOK_STRIDE;
+                ns++;
+                pre += t.fix_count;
+            }
+            if (t.spec_count > t.spec_from) {
+                s_seg[ns].prefix = pre;
+                s_seg[ns].src = 0x80000000u | (w * LZ_TOK_STRIDE + t.spec_from);
+                ns++;
+                pre += t.spec_count - t.spec_from;
+            }
+        }
+        s_seg[ns].prefix = pre;  // == n_tokens
+        s_seg[ns].src = 0;
+        s_nseg = ns;
+    }
+    __syncthreads();
+    // header bits
+    const uint32_t hdr_bits = ci->hdr_bits;
+    const uint32_t base_bit = shift * 8;
+    for (uint32_t i = tid; i < (hdr_bits + 7) / 8; i += PACK_THREADS) {
+        const uint32_t b = codes[c].hdr[i];
+        const uint32_t bit = base_bit + i * 8;
+        if (b) atomicOr(&stage[bit >> 5], b << (bit & 31));  // byte-aligned inside a word: never straddles
+    }
+    const uint32_t n_tok = ci->n_tokens;
+    const uint32_t nseg = s_nseg;
+    const uint32_t* sp = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
+    const uint32_t* fx = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
+    unsigned long long bitpos = (unsigned long long)base_bit + hdr_bits;
+
+    // tokens 0 .. n_tok-1, then the end-of-block symbol
+    for (uint32_t base = 0; base <= n_tok; base += PACK_THREADS) {
+        const uint32_t g = base + tid;
+        unsigned long long bits = 0;
+        uint32_t nb = 0;
+        if (g < n_tok) {
+            // segment lookup: last segment with prefix <= g
+            uint32_t lo = 0, hi = nseg;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (s_seg[mid].prefix <= g)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const uint32_t src = s_seg[lo].src;
+            const uint32_t idx = (src & 0x7FFFFFFFu) + (g - s_seg[lo].prefix);
+            const uint32_t tok = (src & 0x80000000u) ? sp[idx] : fx[idx];
+            if (tok & TOK_MATCH) {
+                uint32_t ls, lb, lv, ds, db, dv;
+                zts_len_code(((tok >> 16) & 0xFF) + 3, ls, lb, lv);
+                zts_dist_code((tok & 0xFFFF) + 1, ds, db, dv);
+                const uint32_t le = s_ll[257 + ls], de = s_d[ds];
+                // litlen code, length extra, distance code, distance extra (src/RawDeflate.ts:279-289)
+                bits = le & 0xFFFF;
+                nb = le >> 16;
+                bits |= (unsigned long long)lv << nb;
+                nb += lb;
+                bits |= (unsigned long long)(de & 0xFFFF) << nb;
+                nb += de >> 16;
+                bits |= (unsigned long long)dv << nb;
+                nb += db;
+            } else {
+                const uint32_t le = s_ll[tok & 0xFF];
+                bits = le & 0xFFFF;
+                nb = le >> 16;
+            }
+        } else if (g == n_tok) {
+            const uint32_t le = s_ll[256];
+            bits = le & 0xFFFF;
+            nb = le >> 16;
+        }
+        // exclusive prefix sum of the bit counts of this batch
+        uint32_t inc = nb;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (unsigned)d) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = lane < PACK_THREADS / 32 ? warp_tot[lane] : 0u, winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+                if (lane >= (unsigned)d) winc += t;
+            }
+            if (lane < PACK_THREADS / 32) warp_tot[lane] = winc - w;
+            if (lane == 31) tile_total = winc;
+        }
+        __syncthreads();
+        if (nb) {
+            const unsigned long long bp = bitpos + warp_tot[warp] + inc - nb;
+            const uint32_t w0 = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
+            // up to 48 + 31 bits -> three words
+            const unsigned long long lo64 = bits << sh;
+            atomicOr(&stage[w0], (uint32_t)lo64);
+            const uint32_t mid = (uint32_t)(lo64 >> 32);
+            if (mid) atomicOr(&stage[w0 + 1], mid);
+            if (sh && nb + sh > 64) {
+                const uint32_t hi32 = (uint32_t)(bits >> (64 - sh));
+                if (hi32) atomicOr(&stage[w0 + 2], hi32);
+            }
+        }
+        bitpos += tile_total;
+        __syncthreads();
+    }
+    // join marker: (byte align incl. the 3 header bits of an empty stored block) 00 00 FF FF
+    if (tid == 0 && !(ch.flags & CHUNK_LAST)) {
+        const uint32_t b0 = shift + out_bytes - 2;  // the two 0xFF bytes are the last two of the chunk
+        atomicOr(&stage[b0 >> 2], 0xFFu << ((b0 & 3) * 8));
+        atomicOr(&stage[(b0 + 1) >> 2], 0xFFu << (((b0 + 1) & 3) * 8));
+    }
+    __syncthreads();
+    // copy the image out: whole aligned words in the middle, own bytes only at the two edges
+    uint32_t* gw = reinterpret_cast<uint32_t*>(dst - shift);
+    const uint32_t end_byte = shift + out_bytes;
+    for (uint32_t j = tid; j < n_words; j += PACK_THREADS) {
+        const uint32_t w = stage[j];
+        const uint32_t b_lo = j * 4, b_hi = b_lo + 4;
+        if (b_lo >= shift && b_hi <= end_byte) {
+            gw[j] = w;
+        } else {
+            uint8_t* gb = reinterpret_cast<uint8_t*>(gw + j);
+            for (uint32_t k = 0; k < 4; ++k)
+                if (b_lo + k >= shift && b_lo + k < end_byte) gb[k] = (uint8_t)(w >> (8 * k));
+        }
+    }
+}
+
+// ---- stored blocks (CompressionType.NONE, src/RawDeflate.ts:93-100,122-153): 65535-byte pieces ----------
+__global__ void __launch_bounds__(256)
+stored_block_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const zlb_item* __restrict__ items,
+                    const uint32_t* __restrict__ blk_item, const uint32_t* __restrict__ blk_index)
+{
+    const uint32_t b = blockIdx.x;
+    const zlb_item it = items[blk_item[b]];
+    const uint64_t k = blk_index[b];
+    const uint64_t n_blocks = (it.in_len + 0xFFFEull) / 0xFFFFull;
+    const uint64_t o = k * (0xFFFFull + 5ull);
+    const uint64_t pos = k * 0xFFFFull;
+    const uint32_t len = (uint32_t)min((uint64_t)0xFFFF, it.in_len - pos);
+    if (o + 5 + len > it.out_cap) return;
+    const uint8_t* s = in + it.in_off + pos;
+    uint8_t* d = out + it.out_off + o;
+    if (threadIdx.x == 0) {
+        d[0] = (k + 1 == n_blocks) ? 1 : 0;  // bfinal | btype(0) << 1
+        d[1] = len & 0xFF;
+        d[2] = len >> 8;
+        d[3] = (len ^ 0xFFFFu) & 0xFF;
+        d[4] = (len ^ 0xFFFFu) >> 8;
+    }
+    for (uint32_t i = threadIdx.x; i < len; i += 256) d[5 + i] = s[i];
+}
+
+extern "C" uint64_t zlb_deflate_bound(uint64_t in_len, uint32_t chunk_bytes, int block_type)
+{
+    if (block_type == ZLB_NONE) return in_len + 5 * ((in_len + 0xFFFE) / 0xFFFF) + 8;
+    uint64_t cb = (chunk_bytes == 0 || chunk_bytes > LZ_MAX_CHUNK) ? LZ_MAX_CHUNK : chunk_bytes;
+    uint64_t n_chunks = in_len ? (in_len + cb - 1) / cb : 1;
+    // <= 15 bits per literal, <= 4498 header bits, end-of-block, join marker
+    return (in_len * 15 + 7) / 8 + n_chunks * (ZTS_HDR_BYTES + 8) + 16;
+}
+
+static int deflate_stored(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item* h_items,
+                          zlb_result* h_results, size_t n, zlb_item* d_items)
+{
+    size_t n_blocks = 0;
+    for (size_t i = 0; i < n; ++i) n_blocks += (h_items[i].in_len + 0xFFFE) / 0xFFFF;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t nb = (h_items[i].in_len + 0xFFFE) / 0xFFFF;
+        uint64_t total = h_items[i].in_len + 5 * nb;
+        h_results[i].status = total > h_items[i].out_cap ? ZLB_ST_OUT_OVERFLOW : ZLB_ST_OK;
+        h_results[i].out_len = total;
+        h_results[i].in_used = h_items[i].in_len;
+        h_results[i].blocks = (uint32_t)nb;
+    }
+    if (n_blocks == 0) return ZLB_OK;
+    if (n_blocks > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many stored blocks");
+    int rc = zts_reserve_pinned(ctx, n_blocks * 8);
+    if (rc) return rc;
+    uint32_t* h_bi = (uint32_t*)ctx->h_pin;
+    uint32_t* h_bk = h_bi + n_blocks;
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t nb = (h_items[i].in_len + 0xFFFE) / 0xFFFF;
+        for (uint64_t j = 0; j < nb; ++j) {
+            h_bi[k] = (uint32_t)i;
+            h_bk[k] = (uint32_t)j;
+            ++k;
+        }
+    }
+    rc = zts_reserve(ctx, &ctx->d_misc, n_blocks * 8 + 64);
+    if (rc) return rc;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_misc.p, h_bi, n_blocks * 8, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* d_bi = (uint32_t*)ctx->d_misc.p;
+    ZTS_LAUNCH(ctx, ZK_STORED,
+               stored_block_kernel<<<(unsigned)n_blocks, 256, 0, ctx->stream>>>(d_in, d_out, d_items, d_bi,
+                                                                                d_bi + n_blocks));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZLB_OK;
+}
+
+struct DeflatePlan {
+    size_t n_chunks = 0;
+};
+
+// Runs the pipeline on device buffers. Results land in h_results after the final synchronise.
+static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item* h_items,
+                          zlb_result* h_results, size_t n, int mode, int block_type, uint32_t chunk_bytes,
+                          uint32_t flags)
+{
+    if (mode != ZLB_MODE_COMPAT) return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
+    if (block_type != ZLB_NONE && block_type != ZLB_FIXED && block_type != ZLB_DYNAMIC)
+        return zts_fail(ctx, ZLB_E_ARG, "invalid compression type");  // src/RawDeflate.ts:110
+    const uint32_t cb = (chunk_bytes == 0 || chunk_bytes > LZ_MAX_CHUNK) ? LZ_MAX_CHUNK : chunk_bytes;
+    if (n > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many items");
+
+    int rc = zts_reserve(ctx, &ctx->d_items, n * sizeof(zlb_item) + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_results, n * sizeof(zlb_result) + 64);
+    if (rc) return rc;
+    zlb_item* d_items = (zlb_item*)ctx->d_items.p;
+    zlb_result* d_results = (zlb_result*)ctx->d_results.p;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(d_items, h_items, n * sizeof(zlb_item), cudaMemcpyHostToDevice, ctx->stream));
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_results, 0, n * sizeof(zlb_result), ctx->stream));
+    memset(h_results, 0, n * sizeof(zlb_result));
+
+    uint32_t kinds = 0;
+    if (flags & ZLB_DEFLATE_WANT_CRC32) kinds |= ZLB_SUM_CRC32;
+    if (flags & ZLB_DEFLATE_WANT_ADLER32) kinds |= ZLB_SUM_ADLER32;
+
+    if (block_type == ZLB_NONE) {
+        rc = deflate_stored(ctx, d_in, d_out, h_items, h_results, n, d_items);
+        if (rc) return rc;
+        if (kinds) {
+            rc = zts_checksum_device(ctx, d_in, d_items, d_results, h_items, n, kinds, 0);
+            if (rc) return rc;
+            zlb_result* tmp = nullptr;
+            rc = zts_reserve_pinned(ctx, n * sizeof(zlb_result));
+            if (rc) return rc;
+            tmp = (zlb_result*)ctx->h_pin;
+            ZTS_CUDA(ctx, cudaMemcpyAsync(tmp, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+            ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            for (size_t i = 0; i < n; ++i) {
+                h_results[i].crc32 = tmp[i].crc32;
+                h_results[i].adler32 = tmp[i].adler32;
+            }
+        }
+        return ZLB_OK;
+    }
+
+    // ---- chunk table
+    size_t n_chunks = 0;
+    for (size_t i = 0; i < n; ++i) n_chunks += h_items[i].in_len ? (h_items[i].in_len + cb - 1) / cb : 1;
+    if (n_chunks > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many chunks");
+    const size_t wave = n_chunks < WAVE_CHUNKS ? n_chunks : WAVE_CHUNKS;
+    rc = zts_reserve_pinned(ctx, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t));
+    if (rc) return rc;
+    ZtsChunk* h_chunks = (ZtsChunk*)ctx->h_pin;
+    uint32_t* h_blocks = (uint32_t*)(h_chunks + n_chunks);
+    {
+        size_t k = 0;
+        for (size_t i = 0; i < n; ++i) {
+            const uint64_t len = h_items[i].in_len;
+            const uint64_t nc = len ? (len + cb - 1) / cb : 1;
+            h_blocks[i] = (uint32_t)nc;
+            for (uint64_t j = 0; j < nc; ++j, ++k) {
+                ZtsChunk& c = h_chunks[k];
+                c.in_off = h_items[i].in_off + j * cb;
+                c.len = (uint32_t)(len - j * cb < cb ? len - j * cb : cb);
+                c.item = (uint32_t)i;
+                c.flags = (j + 1 == nc) ? CHUNK_LAST : 0u;
+                c.pad0 = c.pad1 = 0;
+                // first chunk of this item inside the chunk's wave
+                const size_t wave_base = (k / wave) * wave;
+                const size_t item_first = k - j;
+                c.seg_first = (uint32_t)((item_first > wave_base ? item_first : wave_base) - wave_base);
+            }
+        }
+    }
+    const uint32_t grid = (uint32_t)(wave < (size_t)ctx->sm_count ? wave : (size_t)ctx->sm_count);
+    rc = zts_reserve(ctx, &ctx->d_chunks, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t) + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_chunk_info, wave * sizeof(ZtsChunkInfo) + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_tokens, wave * (size_t)LZ_TOK_PER_CHUNK * 4 + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_spec, wave * (size_t)LZ_TOK_PER_CHUNK * 4 + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_hist, wave * 316 * 4 + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_codes, wave * sizeof(ZtsChunkCodes) + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 2 + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_misc, n * 8 + wave * 8 + 256);
+    if (rc) return rc;
+    ZtsChunk* d_chunks = (ZtsChunk*)ctx->d_chunks.p;
+    uint32_t* d_blocks = (uint32_t*)(d_chunks + n_chunks);
+    ZtsChunkInfo* d_info = (ZtsChunkInfo*)ctx->d_chunk_info.p;
+    uint32_t* d_fix = (uint32_t*)ctx->d_tokens.p;
+    uint32_t* d_spec = (uint32_t*)ctx->d_spec.p;
+    uint32_t* d_hist = (uint32_t*)ctx->d_hist.p;
+    ZtsChunkCodes* d_codes = (ZtsChunkCodes*)ctx->d_codes.p;
+    unsigned long long* d_running = (unsigned long long*)ctx->d_misc.p;
+    unsigned long long* d_gpos = d_running + n;
+    uint32_t* d_counter = (uint32_t*)(d_gpos + wave);
+    ZTS_CUDA(ctx, cudaMemcpyAsync(d_chunks, h_chunks, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_running, 0, n * 8, ctx->stream));
+    ZTS_CUDA(ctx, cudaFuncSetAttribute(bitpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(PACK_STAGE_WORDS * 4)));
+
+    for (size_t w0 = 0; w0 < n_chunks; w0 += wave) {
+        const uint32_t wn = (uint32_t)(n_chunks - w0 < wave ? n_chunks - w0 : wave);
+        const uint32_t g = wn < grid ? wn : grid;
+        rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist, (uint16_t*)ctx->d_sortT.p,
+                             d_counter, g);
+        if (rc) return rc;
+        rc = zts_huffman_launch(ctx, d_chunks + w0, wn, d_hist, d_info, d_codes, block_type);
+        if (rc) return rc;
+        ZTS_LAUNCH(ctx, ZK_SCAN,
+                   chunk_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_chunks + w0, d_info, wn, d_items, d_running, d_gpos));
+        ZTS_LAUNCH(ctx, ZK_BITPACK,
+                   bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, ctx->stream>>>(
+                       d_chunks + w0, d_info, d_codes, d_spec, d_fix, d_items, d_out));
+    }
+    ZTS_LAUNCH(ctx, ZK_FINALIZE,
+               deflate_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_items, d_results,
+                                                                                             d_running, d_blocks,
+                                                                                             (uint32_t)n));
+    if (kinds) {
+        rc = zts_checksum_device(ctx, d_in, d_items, d_results, h_items, n, kinds, 0);
+        if (rc) return rc;
+    }
+    ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZLB_OK;
+}
+
+extern "C" int zlb_deflate_batch(zlb_ctx* ctx, const void* d_in, void* d_out, const zlb_item* items,
+                                 zlb_result* results, size_t n, int mode, int block_type, uint32_t chunk_bytes,
+                                 uint32_t flags)
+{
+    if (!ctx || (!items && n) || (!results && n) || (!d_out && n)) return ZLB_E_ARG;
+    if (n == 0) return ZLB_OK;
+    ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return deflate_device(ctx, (const uint8_t*)d_in, (uint8_t*)d_out, items, results, n, mode, block_type,
+                          chunk_bytes, flags);
+}
+
+extern "C" int zlb_deflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_bytes, void* h_out, size_t out_bytes,
+                                      const zlb_item* items, zlb_result* results, size_t n, int mode, int block_type,
+                                      uint32_t chunk_bytes, uint32_t flags)
+{
+    if (!ctx || (!items && n) || (!results && n) || (!h_in && in_bytes) || (!h_out && out_bytes)) return ZLB_E_ARG;
+    if (n == 0) return ZLB_OK;
+    ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (size_t i = 0; i < n; ++i) {
+        if (items[i].in_off + items[i].in_len > in_bytes || items[i].out_off + items[i].out_cap > out_bytes)
+            return zts_fail(ctx, ZLB_E_ARG, "item %zu out of range", i);
+    }
+    int rc = zts_reserve(ctx, &ctx->d_stage_in, in_bytes + 256);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_stage_out, out_bytes + 256);
+    if (rc) return rc;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    rc = deflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, mode,
+                        block_type, chunk_bytes, flags);
+    if (rc) return rc;
+    // copy back only what was produced: the span up to the furthest written byte
+    uint64_t hi = 0;
+    for (size_t i = 0; i < n; ++i) {
+        uint64_t e = items[i].out_off + (results[i].status == ZLB_ST_OK ? results[i].out_len : 0);
+        if (e > hi) hi = e;
+    }
+    if (hi)
+        ZTS_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_stage_out.p, hi, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZLB_OK;
+}
+
+// ---- test hooks ---------------------------------------------------------------------------------------
+extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32_t* h_tokens_out, uint32_t* n_tokens,
+                              uint32_t* h_hist_out)
+{
+    if (!ctx || !h_tokens_out || !n_tokens || !h_hist_out || n > LZ_MAX_CHUNK) return ZLB_E_ARG;
+    ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_chunks, sizeof(ZtsChunk) + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_chunk_info, sizeof(ZtsChunkInfo) + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_tokens, (size_t)LZ_TOK_PER_CHUNK * 4 + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_spec, (size_t)LZ_TOK_PER_CHUNK * 4 + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_hist, 316 * 4 + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 2 + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_misc, 256))) return rc;
+    ZtsChunk ch = {0, n, 0, 0, CHUNK_LAST, 0, 0};
+    ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunks.p, &ch, sizeof ch, cudaMemcpyHostToDevice, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    rc = zts_lz77_launch(ctx, (const uint8_t*)d_in, (const ZtsChunk*)ctx->d_chunks.p, 1, (ZtsChunkInfo*)ctx->d_chunk_info.p,
+                         (uint32_t*)ctx->d_spec.p, (uint32_t*)ctx->d_tokens.p, (uint32_t*)ctx->d_hist.p,
+                         (uint16_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1);
+    if (rc) return rc;
+    std::vector<uint32_t> spec(LZ_TOK_PER_CHUNK), fix(LZ_TOK_PER_CHUNK);
+    ZtsChunkInfo ci;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(spec.data(), ctx->d_spec.p, spec.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaMemcpyAsync(fix.data(), ctx->d_tokens.p, fix.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaMemcpyAsync(&ci, ctx->d_chunk_info.p, sizeof ci, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaMemcpyAsync(h_hist_out, ctx->d_hist.p, 316 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t k = 0;
+    for (uint32_t w = 0; w < LZ_WARPS; ++w) {
+        const ZtsTile t = ci.tiles[w];
+        for (uint32_t i = 0; i < t.fix_count && k <= n; ++i) h_tokens_out[k++] = fix[w * LZ_TOK_STRIDE + i];
+        for (uint32_t i = t.spec_from; i < t.spec_count && k <= n; ++i) h_tokens_out[k++] = spec[w * LZ_TOK_STRIDE + i];
+    }
+    *n_tokens = k;
+    if (k != ci.n_tokens) return zts_fail(ctx, ZLB_E_CUDA, "token count mismatch %u vs %u", k, ci.n_tokens);
+    return ZLB_OK;
+}
+
+extern "C" int zlb_debug_code_lengths(zlb_ctx* ctx, const uint32_t* h_freqs, int nsym, int limit, uint8_t* h_lengths)
+{
+    if (!ctx || !h_freqs || !h_lengths || nsym < 1 || nsym > 286 || limit < 1 || limit > 15) return ZLB_E_ARG;
+    ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = zts_reserve(ctx, &ctx->d_hist, 316 * 4 + 64);
+    if (rc) return rc;
+    rc = zts_reserve(ctx, &ctx->d_misc, 1024);
+    if (rc) return rc;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_hist.p, h_freqs, (size_t)nsym * 4, cudaMemcpyHostToDevice, ctx->stream));
+    rc = zts_huffman_lengths_debug(ctx, (const uint32_t*)ctx->d_hist.p, nsym, limit, (uint8_t*)ctx->d_misc.p);
+    if (rc) return rc;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(h_lengths, ctx->d_misc.p, (size_t)nsym, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ZLB_OK;
 }

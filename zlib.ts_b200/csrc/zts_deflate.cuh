@@ -1,0 +1,96 @@
+// zts_deflate.cuh -- shared definitions of the chunk-parallel deflate pipeline.
+#pragma once
+#include "zts_common.cuh"
+
+#define LZ_THREADS 1024
+#define LZ_WARPS 32
+#define LZ_TILE 2048                    // positions parsed by one warp
+#define LZ_MAX_CHUNK 65536u
+#define LZ_HASH_BITS 13
+#define LZ_NB (1u << LZ_HASH_BITS)
+#define LZ_WINDOW 32768u                // WindowSize, src/LZ77.ts:8
+#define LZ_MAXLEN 258u                  // LZ77MaxLength, src/LZ77.ts:5
+#define LZ_TOK_STRIDE (LZ_TILE + 8)     // token slots per tile in the spec / fix buffers
+#define LZ_TOK_PER_CHUNK (LZ_WARPS * LZ_TOK_STRIDE)
+
+#define TOK_MATCH 0x80000000u           // literal: byte ; match: TOK_MATCH | (len-3) << 16 | (dist-1)
+
+#define ZTS_HDR_BYTES 576               // 3 + 14 + 19*3 + 316*14 bits = 4498 bits = 563 bytes
+
+#define CHUNK_LAST 1u                   // last chunk of its item: BFINAL = 1, no join marker
+
+struct ZtsChunk {      // host-built, one per chunk
+    uint64_t in_off;   // absolute offset of the chunk in d_in
+    uint32_t len;      // <= 65536
+    uint32_t item;
+    uint32_t seg_first;  // index (within the wave) of the first chunk of the same item
+    uint32_t flags;
+    uint32_t pad0, pad1;
+};
+
+struct ZtsTile {
+    uint32_t fix_count;   // tokens re-parsed from the true entry point until it met the speculative parse
+    uint32_t spec_from;   // first speculative token that belongs to the true parse
+    uint32_t spec_count;  // speculative tokens of the tile
+    uint32_t pad;
+};
+
+struct ZtsChunkInfo {  // device-produced, one per chunk
+    ZtsTile tiles[LZ_WARPS];
+    uint32_t n_tokens;   // tokens of the true parse (without end-of-block)
+    uint32_t hdr_bits;   // block header bits incl. BFINAL/BTYPE
+    unsigned long long body_bits;  // token bits incl. end-of-block
+    uint32_t out_bytes;  // bytes this chunk contributes (incl. the join marker)
+    uint32_t pad;
+    unsigned long long out_off;    // absolute offset in d_out
+};
+
+struct ZtsChunkCodes {  // device-produced by the Huffman kernel
+    uint32_t ll[286];   // (bit-reversed code) | len << 16
+    uint32_t d[30];
+    uint8_t hdr[ZTS_HDR_BYTES];
+};
+
+// length (3..258) -> litlen symbol index (0..28), extra bit count and value  (src/LZ77.ts:20-53)
+__host__ __device__ __forceinline__ void zts_len_code(uint32_t len, uint32_t& sym, uint32_t& ebits, uint32_t& eval)
+{
+    uint32_t l = len - 3;
+    if (l < 8) {
+        sym = l;
+        ebits = 0;
+        eval = 0;
+    } else if (l == 255) {
+        sym = 28;
+        ebits = 0;
+        eval = 0;
+    } else {
+#ifdef __CUDA_ARCH__
+        uint32_t nb = (31 - __clz(l)) - 2;
+#else
+        uint32_t nb = (31 - __builtin_clz(l)) - 2;
+#endif
+        sym = 4 * nb + 4 + ((l >> nb) & 3);
+        ebits = nb;
+        eval = l & ((1u << nb) - 1);
+    }
+}
+
+// distance (1..32768) -> distance symbol (0..29), extra bit count and value  (src/LZ77.ts:56-90)
+__host__ __device__ __forceinline__ void zts_dist_code(uint32_t dist, uint32_t& sym, uint32_t& ebits, uint32_t& eval)
+{
+    uint32_t d = dist - 1;
+    if (d < 4) {
+        sym = d;
+        ebits = 0;
+        eval = 0;
+    } else {
+#ifdef __CUDA_ARCH__
+        uint32_t nb = (31 - __clz(d)) - 1;
+#else
+        uint32_t nb = (31 - __builtin_clz(d)) - 1;
+#endif
+        sym = 2 * nb + 2 + ((d >> nb) & 1);
+        ebits = nb;
+        eval = d & ((1u << nb) - 1);
+    }
+}

@@ -1,0 +1,494 @@
+// zts_lz77.cu -- exact LZ77 tokenisation of one chunk per CTA
+// (replaces LZ77.encode / searchLongestMatch / maxMatchTest, src/LZ77.ts:149-283, lazy = 0).
+//
+// What the reference computes: at every parse position p (p + 3 < n) take ALL
+// earlier positions q with the same 3 bytes and p - q <= 32768, the longest match wins (<= 258,
+// <= n - p), ties go to the nearest q; greedy: p += len, else literal. The reference walks
+// per-key JS arrays newest-first; here the same function is evaluated as:
+//
+//   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
+//   2. all positions are radix-sorted (stable, 2 LSD passes, warp match.any ranking, no atomics)
+//      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
+//   3. 32 warps parse 32 tiles of 2048 positions speculatively, each from its tile start; a search
+//      is warp-cooperative: 32 candidates per step (newest first), exact-key filter, tail-byte
+//      filter against the best so far, word-wise extension, REDUX.MAX over (len << 16 | q);
+//   4. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
+//      of the previous one and is re-parsed only until it meets a speculatively parsed position
+//      (a visited-bit per position); the remainder of the speculative tokens is reused;
+//   5. litlen / dist histograms are taken over the surviving tokens.
+//
+// Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 8 KiB scratch.
+#include "zts_deflate.cuh"
+
+struct LzSmem {
+    // byte offsets into dynamic shared memory
+    static constexpr uint32_t S_OFF = 0;                          // chunk bytes (+ shift, + slack)
+    static constexpr uint32_t S_BYTES = LZ_MAX_CHUNK + 64;
+    static constexpr uint32_t SORTED_OFF = S_OFF + S_BYTES;       // u16[65536]
+    static constexpr uint32_t SORTED_BYTES = LZ_MAX_CHUNK * 2;
+    static constexpr uint32_t BSTART_OFF = SORTED_OFF + SORTED_BYTES;  // u16[LZ_NB + 2]
+    static constexpr uint32_t BSTART_BYTES = (LZ_NB + 8) * 2;
+    static constexpr uint32_t AUX_OFF = BSTART_OFF + BSTART_BYTES;     // 8 KiB: radix counters | visited bits
+    static constexpr uint32_t AUX_BYTES = 8192;
+    static constexpr uint32_t MISC_OFF = AUX_OFF + AUX_BYTES;
+    static constexpr uint32_t MISC_BYTES = 2048;
+    static constexpr uint32_t TOTAL = MISC_OFF + MISC_BYTES;
+};
+
+struct LzMisc {
+    unsigned long long mbar;
+    uint32_t chunk;
+    uint32_t warp_tot[32];
+    uint32_t warp_min[32];
+    uint32_t spec_exit[32];
+    uint32_t spec_count[32];
+    uint32_t tile_tot[33];
+    uint32_t hist[316];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 4 bytes at byte offset i of S. S = (128-byte aligned shared buffer) + shift, so the misalignment of
+// S + i is (shift + i) & 3; pointer arithmetic stays on S so the loads compile to LDS, not generic LD.
+// >= 8 readable bytes follow any i <= n.
+struct LzS {
+    const uint8_t* S;
+    uint32_t shift;
+    __device__ __forceinline__ uint8_t operator[](uint32_t i) const { return S[i]; }
+};
+__device__ __forceinline__ uint32_t ld_u32(const LzS& V, uint32_t i)
+{
+    const uint32_t mis = (V.shift + i) & 3u;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(V.S + i - mis);
+    return __funnelshift_r(w[0], w[1], mis * 8);
+}
+
+__device__ __forceinline__ uint32_t hash13(uint32_t key3) { return (key3 * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
+
+// exclusive block scan (sum) over 1024 threads
+__device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* warp_tot, uint32_t* total)
+{
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+        if (lane >= (unsigned)d) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane], winc = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+            if (lane >= (unsigned)d) winc += t;
+        }
+        warp_tot[lane] = winc - w;
+        if (lane == 31 && total) *total = winc;
+    }
+    __syncthreads();
+    uint32_t r = warp_tot[warp] + inc - v;
+    __syncthreads();
+    return r;
+}
+
+// ---- warp-cooperative longest/nearest match search at position p (requires p + 3 < n) ----------
+// returns (len << 16) | dist, or 0 when no candidate exists (src/LZ77.ts:157-194 + :242)
+__device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __restrict__ sorted,
+                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n)
+{
+    const unsigned lane = zts_lane();
+    const uint32_t pw = ld_u32(S, p);
+    const uint32_t h = hash13(pw & 0xFFFFFFu);
+    const uint32_t lo = bstart[h];
+    uint32_t a = lo, b = bstart[h + 1];
+    // slot of p inside its bucket (positions ascending): 32-way search
+    while (b - a > 32) {
+        const uint32_t step = (b - a + 31) >> 5;
+        const uint32_t s = a + lane * step;
+        const bool less = (s < b) && (sorted[s] < p);
+        const uint32_t k = __popc(__ballot_sync(0xFFFFFFFFu, less));
+        if (k == 0) {
+            b = a;
+            break;
+        }
+        const uint32_t na = a + (k - 1) * step + 1;
+        const uint32_t nb = min(b, a + k * step);
+        a = na;
+        b = nb;
+    }
+    uint32_t cur;
+    {
+        const uint32_t s = a + lane;
+        const bool less = (s < b) && (sorted[s] < p);
+        cur = a + __popc(__ballot_sync(0xFFFFFFFFu, less));
+    }
+    const uint32_t maxlen = min(LZ_MAXLEN, n - p);
+    uint32_t best = 0, best_len = 0;
+    while (cur > lo) {
+        const uint32_t cnt = min(32u, cur - lo);
+        const bool act = lane < cnt;
+        const uint32_t q = act ? sorted[cur - 1 - lane] : 0u;  // lane 0 = newest candidate
+        const bool inwin = act && (p - q <= LZ_WINDOW);
+        uint32_t len = 0;
+        if (inwin) {
+            const uint32_t x0 = ld_u32(S, q) ^ pw;
+            if ((x0 & 0xFFFFFFu) == 0) {  // same table[] key (src/LZ77.ts:204-214)
+                // only a strictly longer match can replace the best of the nearer blocks (:183)
+                bool ok = true;
+                if (best_len >= 3) ok = S[q + best_len] == S[p + best_len];
+                if (ok) {
+                    uint32_t k = 3;
+                    if (x0 == 0) {
+                        k = 4;
+                        while (k < maxlen) {
+                            const uint32_t x = ld_u32(S, q + k) ^ ld_u32(S, p + k);
+                            if (x) {
+                                k += (uint32_t)(__ffs((int)x) - 1) >> 3;
+                                break;
+                            }
+                            k += 4;
+                        }
+                    }
+                    len = min(k, maxlen);
+                }
+            }
+        }
+        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, (len << 16) | q);  // longest, then nearest
+        if ((m >> 16) > best_len) {
+            best_len = m >> 16;
+            best = m;
+        }
+        if (best_len >= maxlen) break;                          // :189 (258) or capped by the input end
+        if (__any_sync(0xFFFFFFFFu, act && !inwin)) break;      // older ones are outside the window (:223)
+        cur -= cnt;
+    }
+    if (best_len < 3) return 0;
+    return (best_len << 16) | (p - (best & 0xFFFFu));
+}
+
+// one greedy step at parse position p: emits the token, returns the next parse position
+__device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
+                                            uint32_t p, uint32_t n, uint32_t* tok_out)
+{
+    uint32_t r = 0;
+    if (p + 3 < n) r = lz_search(S, sorted, bstart, p, n);  // src/LZ77.ts:228: no search in the last 3 bytes
+    if (r) {
+        const uint32_t len = r >> 16, dist = r & 0xFFFFu;
+        *tok_out = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
+        return p + len;
+    }
+    *tok_out = S[p];
+    return p + 1;
+}
+
+__device__ __forceinline__ void hist_token(uint32_t tok, uint32_t* hist)
+{
+    if (tok & TOK_MATCH) {
+        uint32_t ls, lb, lv, ds, db, dv;
+        zts_len_code(((tok >> 16) & 0xFF) + 3, ls, lb, lv);
+        zts_dist_code((tok & 0xFFFF) + 1, ds, db, dv);
+        atomicAdd(&hist[257 + ls], 1u);
+        atomicAdd(&hist[286 + ds], 1u);
+    } else {
+        atomicAdd(&hist[tok & 0xFF], 1u);
+    }
+}
+
+__global__ void __launch_bounds__(LZ_THREADS, 1)
+lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ chunks, uint32_t n_chunks,
+                  ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ spec_tok, uint32_t* __restrict__ fix_tok,
+                  uint32_t* __restrict__ hist_out, uint16_t* __restrict__ sortT, uint32_t* __restrict__ work_counter)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint8_t* Sbuf = smem + LzSmem::S_OFF;
+    uint16_t* sorted = reinterpret_cast<uint16_t*>(smem + LzSmem::SORTED_OFF);
+    uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);
+    uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::AUX_OFF);   // [32 warps][128 digits]
+    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position
+    LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint16_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;  // per-CTA radix temp (L2 resident)
+    uint32_t phase = 0;
+
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&M->mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    for (;;) {
+        if (tid == 0) M->chunk = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t c = M->chunk;
+        if (c >= n_chunks) break;
+        const ZtsChunk ch = chunks[c];
+        const uint32_t n = ch.len;
+        const uint8_t* src = in + ch.in_off;
+
+        // ---- 1. stage the chunk: 16-byte aligned body by TMA bulk copy, ragged ends by plain loads
+        const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)src & 15u)) & 15u));
+        const uint32_t body = (n - head) & ~15u;
+        const uint32_t tail = n - head - body;
+        uint8_t* S = Sbuf + ((16u - head) & 15u);  // S + head is 16-byte aligned
+        const LzS SV = {S, (16u - head) & 15u};
+        if (tid == 0 && body) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&M->mbar)), "r"(body)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                    smem_u32(S + head)),
+                "l"(src + head), "r"(body), "r"(smem_u32(&M->mbar))
+                : "memory");
+        }
+        if (tid < head) S[tid] = src[tid];
+        if (tid < tail) S[head + body + tid] = src[head + body + tid];
+        if (tid < 32) S[n + tid] = 0;  // slack read by the word-wise compares
+        if (body) {
+            uint32_t done = 0, spins = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done)
+                    : "r"(smem_u32(&M->mbar)), "r"(phase)
+                    : "memory");
+                if (!done && ++spins > (1u << 26)) __trap();  // never hang the device
+            }
+            phase ^= 1;
+        }
+        __syncthreads();
+
+        const uint32_t m = n >= 3 ? n - 2 : 0;  // positions that own a 3-byte key
+
+        // ---- 2. stable LSD radix sort of positions by hash13(key): pass 1 (low 7 bits) -> T (global)
+        for (int pass = 0; pass < 2; ++pass) {
+            const uint32_t ndig = pass == 0 ? 128u : 64u;
+            for (uint32_t i = tid; i < 32u * 128u; i += LZ_THREADS) cnt16[i] = 0;
+            __syncthreads();
+            const uint32_t w_begin = warp * LZ_TILE;
+            uint16_t* wc = cnt16 + warp * ndig;
+            // count
+            if (w_begin < m) {
+                for (uint32_t it = 0; it < LZ_TILE / 32; ++it) {
+                    const uint32_t i = w_begin + it * 32 + lane;
+                    const bool v = i < m;
+                    uint32_t d = 0xFFFFFFFFu;
+                    if (v) {
+                        const uint32_t q = pass == 0 ? i : (uint32_t)__ldcg(&T[i]);
+                        const uint32_t hh = hash13(ld_u32(SV, q) & 0xFFFFFFu);
+                        d = pass == 0 ? (hh & 127u) : (hh >> 7);
+                    }
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+                    if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+            // exclusive scan in (digit major, warp minor) order: entry e = d * 32 + w
+            {
+                const uint32_t per = (ndig * 32u) / LZ_THREADS;  // 4 or 2
+                uint32_t vals[4];
+                uint32_t sum = 0;
+                for (uint32_t k = 0; k < per; ++k) {
+                    const uint32_t e = tid * per + k;
+                    const uint32_t d = e >> 5, w = e & 31u;
+                    vals[k] = cnt16[w * ndig + d];
+                    sum += vals[k];
+                }
+                uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
+                for (uint32_t k = 0; k < per; ++k) {
+                    const uint32_t e = tid * per + k;
+                    const uint32_t d = e >> 5, w = e & 31u;
+                    cnt16[w * ndig + d] = (uint16_t)base;
+                    base += vals[k];
+                }
+            }
+            __syncthreads();
+            // scatter
+            if (w_begin < m) {
+                for (uint32_t it = 0; it < LZ_TILE / 32; ++it) {
+                    const uint32_t i = w_begin + it * 32 + lane;
+                    const bool v = i < m;
+                    uint32_t d = 0xFFFFFFFFu, q = 0;
+                    if (v) {
+                        q = pass == 0 ? i : (uint32_t)__ldcg(&T[i]);
+                        const uint32_t hh = hash13(ld_u32(SV, q) & 0xFFFFFFu);
+                        d = pass == 0 ? (hh & 127u) : (hh >> 7);
+                    }
+                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+                    uint32_t dst = 0;
+                    if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
+                    __syncwarp();
+                    if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                    if (v) {
+                        if (pass == 0)
+                            __stcg(&T[dst], (uint16_t)q);
+                        else
+                            sorted[dst] = (uint16_t)q;
+                    }
+                    __syncwarp();
+                }
+            }
+            __threadfence_block();
+            __syncthreads();
+        }
+
+        // ---- bucket starts: first slot of every hash, empty buckets point at the next one
+        for (uint32_t i = tid; i < LZ_NB + 1; i += LZ_THREADS) bstart[i] = 0xFFFF;
+        __syncthreads();
+        for (uint32_t i = tid; i < m; i += LZ_THREADS) {
+            const uint32_t hcur = hash13(ld_u32(SV, sorted[i]) & 0xFFFFFFu);
+            const uint32_t hprev = i ? hash13(ld_u32(SV, sorted[i - 1]) & 0xFFFFFFu) : 0xFFFFFFFFu;
+            if (hcur != hprev) bstart[hcur] = (uint16_t)i;
+        }
+        if (tid == 0) bstart[LZ_NB] = (uint16_t)m;
+        __syncthreads();
+        {
+            // suffix-min over bstart[0 .. LZ_NB]: thread t owns 8 consecutive entries
+            uint32_t v[8];
+            uint32_t mn = 0xFFFFu;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                v[k] = bstart[tid * 8 + k];
+                mn = min(mn, v[k]);
+            }
+            // suffix-min across threads (exclusive: the minimum of everything to the right)
+            uint32_t inc = mn;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_down_sync(0xFFFFFFFFu, inc, d);
+                if (lane + d < 32) inc = min(inc, t);
+            }
+            if (lane == 0) M->warp_min[warp] = inc;
+            __syncthreads();
+            uint32_t right = m;  // bstart[LZ_NB]
+            for (uint32_t w = warp + 1; w < 32; ++w) right = min(right, M->warp_min[w]);
+            uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, inc, 1);
+            if (lane < 31) right = min(right, nxt);
+            uint32_t run = right;
+#pragma unroll
+            for (int k = 7; k >= 0; --k) {
+                run = min(run, v[k]);
+                bstart[tid * 8 + k] = (uint16_t)run;
+            }
+        }
+        __syncthreads();
+
+        // ---- 3. speculative parse: warp w parses tile w from its first position
+        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
+        __syncthreads();
+        const uint32_t n_tiles = (n + LZ_TILE - 1) / LZ_TILE;
+        uint32_t* my_spec = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK + warp * LZ_TOK_STRIDE;
+        if (warp < n_tiles) {
+            const uint32_t t_begin = warp * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+            uint32_t p = t_begin, ntok = 0;
+            while (p < t_end) {
+                uint32_t tok;
+                const uint32_t np = lz_step(SV, sorted, bstart, p, n, &tok);
+                if (lane == 0) {
+                    visited[p >> 5] |= 1u << (p & 31);
+                    my_spec[ntok] = tok;
+                }
+                ntok++;
+                p = np;
+            }
+            if (lane == 0) {
+                M->spec_exit[warp] = p;
+                M->spec_count[warp] = ntok;
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. true parse: re-enter every tile at the true exit of its predecessor (warp 0)
+        ZtsChunkInfo* ci = info + c;
+        if (warp == 0) {
+            uint32_t entry = n_tiles ? M->spec_exit[0] : 0;
+            if (lane == 0 && n_tiles) {
+                ZtsTile t0 = {0u, 0u, M->spec_count[0], 0u};
+                ci->tiles[0] = t0;
+                M->tile_tot[0] = M->spec_count[0];
+            }
+            for (uint32_t w = 1; w < n_tiles; ++w) {
+                const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+                const uint32_t sc = M->spec_count[w];
+                uint32_t nfix = 0, from = sc;
+                uint32_t* my_fix = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK + w * LZ_TOK_STRIDE;
+                uint32_t p = entry;
+                while (p < t_end) {
+                    if ((visited[p >> 5] >> (p & 31)) & 1u) {
+                        // met the speculative parse: its tokens from this position on are the true ones
+                        uint32_t idx = 0;
+                        for (uint32_t wd = (t_begin >> 5) + lane; wd <= (p >> 5); wd += 32) {
+                            uint32_t bits = visited[wd];
+                            if (wd == (p >> 5)) bits &= (1u << (p & 31)) - 1u;
+                            idx += __popc(bits);
+                        }
+                        from = __reduce_add_sync(0xFFFFFFFFu, idx);
+                        p = M->spec_exit[w];
+                        break;
+                    }
+                    uint32_t tok;
+                    const uint32_t np = lz_step(SV, sorted, bstart, p, n, &tok);
+                    if (lane == 0) my_fix[nfix] = tok;
+                    nfix++;
+                    p = np;
+                }
+                entry = max(entry, p);
+                if (lane == 0) {
+                    ZtsTile t = {nfix, from, sc, 0u};
+                    ci->tiles[w] = t;
+                    M->tile_tot[w] = nfix + (sc - from);
+                }
+            }
+            if (lane == 0)
+                for (uint32_t w = n_tiles; w < LZ_WARPS; ++w) {
+                    ZtsTile t = {0u, 0u, 0u, 0u};
+                    ci->tiles[w] = t;
+                    M->tile_tot[w] = 0;
+                }
+        }
+        for (uint32_t i = tid; i < 316; i += LZ_THREADS) M->hist[i] = 0;
+        __threadfence_block();
+        __syncthreads();
+
+        // ---- 5. histograms over the surviving tokens (src/LZ77.ts:126-128,141-142,236,251,271,279)
+        {
+            const ZtsTile t = ci->tiles[warp];
+            const uint32_t* fx = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK + warp * LZ_TOK_STRIDE;
+            const uint32_t* sp = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK + warp * LZ_TOK_STRIDE;
+            for (uint32_t k = lane; k < t.fix_count; k += 32) hist_token(fx[k], M->hist);
+            for (uint32_t k = t.spec_from + lane; k < t.spec_count; k += 32) hist_token(sp[k], M->hist);
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < 316; i += LZ_THREADS)
+            hist_out[(size_t)c * 316 + i] = M->hist[i] + (i == 256 ? 2u : 0u);  // freqsLitLen[256] ends at 2
+        if (tid == 0) {
+            uint32_t tot = 0;
+            for (uint32_t w = 0; w < LZ_WARPS; ++w) tot += M->tile_tot[w];
+            ci->n_tokens = tot;
+        }
+        __syncthreads();
+    }
+}
+
+size_t zts_lz77_smem_bytes() { return LzSmem::TOTAL; }
+
+int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
+                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint16_t* d_sortT,
+                    uint32_t* d_counter, uint32_t grid)
+{
+    static_assert(sizeof(LzMisc) <= LzSmem::MISC_BYTES, "misc area too small");
+    static_assert(LzSmem::TOTAL <= 232448, "exceeds 227 KiB of dynamic shared memory");
+    ZTS_CUDA(ctx, cudaFuncSetAttribute(lz77_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)LzSmem::TOTAL));
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->stream));
+    ZTS_LAUNCH(ctx, ZK_LZ77,
+               lz77_chunk_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->stream>>>(
+                   d_in, d_chunks, n_chunks, d_info, d_spec, d_fix, d_hist, d_sortT, d_counter));
+    return ZLB_OK;
+}
