@@ -46,6 +46,10 @@ def lib():
         L.zo_raw_inflate.argtypes = [vp, sz, sz, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(sz), i32]
         L.zo_raw_inflate.restype = i32
         L.zo_diag_rpm_freq_oob.restype = ctypes.c_uint64
+        L.zo_deflate_chunks_mt.argtypes = [vp, sz, sz, i32, i32, ctypes.POINTER(ctypes.c_uint64)]
+        L.zo_deflate_chunks_mt.restype = i32
+        L.zo_inflate_streams_mt.argtypes = [vp, vp, vp, sz, vp, sz, i32, ctypes.POINTER(ctypes.c_uint64)]
+        L.zo_inflate_streams_mt.restype = i32
         _lib = L
     return _lib
 
@@ -121,3 +125,27 @@ def get_lengths(freqs, limit):
     if rc:
         raise OracleError(rc)
     return out
+
+
+def deflate_chunks_mt(data, chunk=65536, compression_type=DYNAMIC, threads=1):
+    """RawDeflate of every chunk on `threads` host threads (baseline timing). Returns total compressed bytes."""
+    a = _u8(data)
+    total = ctypes.c_uint64(0)
+    rc = lib().zo_deflate_chunks_mt(a.ctypes.data, a.size, chunk, compression_type, threads, ctypes.byref(total))
+    if rc:
+        raise OracleError(rc)
+    return int(total.value)
+
+
+def inflate_streams_mt(comp, offs, lens, out_stride, threads=1):
+    """RawInflate of independent streams on `threads` host threads. Returns (output array, total bytes)."""
+    c = _u8(comp)
+    o = np.ascontiguousarray(offs, dtype=np.uint64)
+    l = np.ascontiguousarray(lens, dtype=np.uint64)
+    out = np.zeros(len(o) * out_stride, dtype=np.uint8)
+    total = ctypes.c_uint64(0)
+    rc = lib().zo_inflate_streams_mt(c.ctypes.data, o.ctypes.data, l.ctypes.data, len(o), out.ctypes.data, out_stride,
+                                     threads, ctypes.byref(total))
+    if rc:
+        raise OracleError(rc)
+    return out, int(total.value)

@@ -1,0 +1,126 @@
+/*
+ * zts_oracle_mt.c -- multi-threaded batch drivers over the CPU oracle (TEST / BASELINE INFRASTRUCTURE).
+ * Used only by bench.py's cpu_baseline and --impl reference legs: the reference is single-threaded
+ * JavaScript; north_star asks for it on 1 thread and on all host cores (worker_threads), i.e. independent
+ * chunks / streams sharded over threads, which is what these drivers do with the C restatement.
+ */
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "zts_oracle.h"
+
+typedef struct {
+    const uint8_t* in;
+    size_t n, chunk;
+    int type;
+    volatile long* next;   /* shared work counter */
+    size_t n_chunks;
+    uint64_t out_bytes;
+    int rc;
+    /* inflate */
+    const uint8_t* comp;
+    const uint64_t* offs;
+    const uint64_t* lens;
+    uint8_t* out;
+    size_t out_stride;
+} mt_job;
+
+static void* deflate_worker(void* arg)
+{
+    mt_job* j = (mt_job*)arg;
+    size_t cap = zo_raw_deflate_bound(j->chunk);
+    uint8_t* buf = (uint8_t*)malloc(cap);
+    if (!buf) {
+        j->rc = ZO_E_NOMEM;
+        return NULL;
+    }
+    for (;;) {
+        long k = __sync_fetch_and_add(j->next, 1);
+        if ((size_t)k >= j->n_chunks) break;
+        size_t off = (size_t)k * j->chunk;
+        size_t len = j->n - off < j->chunk ? j->n - off : j->chunk;
+        size_t olen = 0;
+        int rc = zo_raw_deflate(j->in + off, len, j->type, 0, buf, cap, 0, &olen);
+        if (rc) j->rc = rc;
+        j->out_bytes += olen;
+    }
+    free(buf);
+    return NULL;
+}
+
+/* RawDeflate of every `chunk`-byte piece of in[0..n), `threads` workers. Returns total compressed bytes. */
+int zo_deflate_chunks_mt(const uint8_t* in, size_t n, size_t chunk, int type, int threads, uint64_t* total_out)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    mt_job jobs[256];
+    volatile long next = 0;
+    size_t n_chunks = (n + chunk - 1) / chunk;
+    for (int t = 0; t < threads; ++t) {
+        memset(&jobs[t], 0, sizeof(mt_job));
+        jobs[t].in = in;
+        jobs[t].n = n;
+        jobs[t].chunk = chunk;
+        jobs[t].type = type;
+        jobs[t].next = &next;
+        jobs[t].n_chunks = n_chunks;
+        pthread_create(&th[t], NULL, deflate_worker, &jobs[t]);
+    }
+    uint64_t total = 0;
+    int rc = 0;
+    for (int t = 0; t < threads; ++t) {
+        pthread_join(th[t], NULL);
+        total += jobs[t].out_bytes;
+        if (jobs[t].rc) rc = jobs[t].rc;
+    }
+    *total_out = total;
+    return rc;
+}
+
+static void* inflate_worker(void* arg)
+{
+    mt_job* j = (mt_job*)arg;
+    for (;;) {
+        long k = __sync_fetch_and_add(j->next, 1);
+        if ((size_t)k >= j->n_chunks) break;
+        size_t olen = 0, ip = 0;
+        int rc = zo_raw_inflate(j->comp + j->offs[k], j->lens[k], 0, j->out + (size_t)k * j->out_stride, j->out_stride,
+                                &olen, &ip, 0);
+        if (rc) j->rc = rc;
+        j->out_bytes += olen;
+    }
+    return NULL;
+}
+
+/* RawInflate of n_streams independent streams (offs/lens into comp) into out + k*out_stride. */
+int zo_inflate_streams_mt(const uint8_t* comp, const uint64_t* offs, const uint64_t* lens, size_t n_streams,
+                          uint8_t* out, size_t out_stride, int threads, uint64_t* total_out)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    mt_job jobs[256];
+    volatile long next = 0;
+    for (int t = 0; t < threads; ++t) {
+        memset(&jobs[t], 0, sizeof(mt_job));
+        jobs[t].comp = comp;
+        jobs[t].offs = offs;
+        jobs[t].lens = lens;
+        jobs[t].out = out;
+        jobs[t].out_stride = out_stride;
+        jobs[t].next = &next;
+        jobs[t].n_chunks = n_streams;
+        pthread_create(&th[t], NULL, inflate_worker, &jobs[t]);
+    }
+    uint64_t total = 0;
+    int rc = 0;
+    for (int t = 0; t < threads; ++t) {
+        pthread_join(th[t], NULL);
+        total += jobs[t].out_bytes;
+        if (jobs[t].rc) rc = jobs[t].rc;
+    }
+    *total_out = total;
+    return rc;
+}
