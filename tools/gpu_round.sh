@@ -1,0 +1,21 @@
+#!/bin/bash
+# One gpurun call: GPU tests, bench, ncu launch list, ncu full capture of the hot kernels.
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
+tag=${1:-r01}
+mkdir -p gpurun_out
+nvidia-smi -L
+nproc
+python -m pytest tests -x -q -m gpu 2>&1 | tail -15
+python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; cat gpurun_out/bench_$tag.json; tail -5 gpurun_out/bench_$tag.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>&1; cat gpurun_out/bench_ref_$tag.json
+SMALL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --bytes 67108864"
+$SMALL > gpurun_out/plain_$tag.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $SMALL > gpurun_out/ncu_launch_$tag.log 2>&1
+echo "ncu launches rc=$?"
+$SMALL > gpurun_out/plain2_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"lz77_chunk|huffman_build|bitpack" -s 3 -c 3 -f -o gpurun_out/prof_deflate_$tag $SMALL > gpurun_out/ncu_full_$tag.log 2>&1
+echo "ncu deflate rc=$?"
+$SMALL > gpurun_out/plain3_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"inflate_warp" -s 1 -c 1 -f -o gpurun_out/prof_inflate_$tag $SMALL > gpurun_out/ncu_full_inf_$tag.log 2>&1
+echo "ncu inflate rc=$?"
+ls -la gpurun_out

@@ -33,12 +33,16 @@ def build(force=False, verbose=False):
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(HERE, "..", "include", "zlibts_b200.h"))
     if force or not _newer(LIB, deps):
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
+        tmp = LIB + ".tmp%d" % os.getpid()  # built aside and renamed: concurrent ranks never see a partial file
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
         subprocess.run(cmd, check=True, cwd=CSRC)
+        os.replace(tmp, LIB)
     synth_src = os.path.join(CSRC, "zts_synth.c")
     if force or not _newer(SYNTH_LIB, [synth_src]):
         gcc = shutil.which("gcc") or "gcc"
-        subprocess.run([gcc, "-O2", "-fPIC", "-shared", "-std=c11", "-o", SYNTH_LIB, synth_src], check=True)
+        tmp = SYNTH_LIB + ".tmp%d" % os.getpid()
+        subprocess.run([gcc, "-O2", "-fPIC", "-shared", "-std=c11", "-o", tmp, synth_src], check=True)
+        os.replace(tmp, SYNTH_LIB)
     return LIB
 
 
