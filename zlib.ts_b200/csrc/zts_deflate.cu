@@ -104,7 +104,7 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     extern __shared__ __align__(16) uint32_t stage[];  // PACK_STAGE_WORDS
     __shared__ uint32_t s_ll[286];
     __shared__ uint32_t s_d[30];
-    __shared__ PackSeg s_seg[2 * LZ_WARPS + 1];
+    __shared__ PackSeg s_seg[2 * LZ_NTILES + 1];
     __shared__ uint32_t s_nseg;
     __shared__ uint32_t warp_tot[PACK_THREADS / 32];
     __shared__ uint32_t tile_total;
@@ -125,27 +125,48 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     for (uint32_t i = tid; i < n_words; i += PACK_THREADS) stage[i] = 0;
     for (uint32_t i = tid; i < 286; i += PACK_THREADS) s_ll[i] = codes[c].ll[i];
     if (tid < 30) s_d[tid] = codes[c].d[tid];
-    if (tid == 0) {
-        // token segments in stream order: per tile the re-parsed tokens, then the reused speculative ones
-        uint32_t ns = 0, pre = 0;
-        for (uint32_t w = 0; w < LZ_WARPS; ++w) {
-            const ZtsTile t = ci->tiles[w];
-            if (t.fix_count) {
-                s_seg[ns].prefix = pre;
-                s_seg[ns].src = w * LZ_TOK_STRIDE;
-                ns++;
-                pre += t.fix_count;
-            }
-            if (t.spec_count > t.spec_from) {
-                s_seg[ns].prefix = pre;
-                s_seg[ns].src = 0x80000000u | (w * LZ_TOK_STRIDE + t.spec_from);
-                ns++;
-                pre += t.spec_count - t.spec_from;
+    // token segments in stream order: per tile the re-parsed tokens, then the reused speculative ones.
+    // Slot 2w = fix tokens of tile w, slot 2w+1 = its speculative tail; empty slots share the prefix of
+    // their successor, so "last slot with prefix <= g" always lands on a non-empty one.
+    {
+        uint32_t cnt = 0, src = 0;
+        if (tid < 2 * LZ_NTILES) {
+            const ZtsTile t = ci->tiles[tid >> 1];
+            if (tid & 1) {
+                cnt = (uint32_t)t.spec_count - t.spec_from;
+                src = 0x80000000u | ((tid >> 1) * LZ_TOK_STRIDE + t.spec_from);
+            } else {
+                cnt = t.fix_count;
+                src = (tid >> 1) * LZ_TOK_STRIDE;
             }
         }
-        s_seg[ns].prefix = pre;  // == n_tokens
-        s_seg[ns].src = 0;
-        s_nseg = ns;
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= (unsigned)d) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = lane < PACK_THREADS / 32 ? warp_tot[lane] : 0u, winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
+                if (lane >= (unsigned)d) winc += t;
+            }
+            if (lane < PACK_THREADS / 32) warp_tot[lane] = winc - w;
+        }
+        __syncthreads();
+        if (tid < 2 * LZ_NTILES) {
+            s_seg[tid].prefix = warp_tot[warp] + inc - cnt;
+            s_seg[tid].src = src;
+        }
+        if (tid == 2 * LZ_NTILES) {
+            s_seg[tid].prefix = ci->n_tokens;
+            s_seg[tid].src = 0;
+            s_nseg = 2 * LZ_NTILES;
+        }
     }
     __syncthreads();
     // header bits
@@ -545,7 +566,7 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
     ZTS_CUDA(ctx, cudaMemcpyAsync(h_hist_out, ctx->d_hist.p, 316 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     uint32_t k = 0;
-    for (uint32_t w = 0; w < LZ_WARPS; ++w) {
+    for (uint32_t w = 0; w < LZ_NTILES; ++w) {
         const ZtsTile t = ci.tiles[w];
         for (uint32_t i = 0; i < t.fix_count && k <= n; ++i) h_tokens_out[k++] = fix[w * LZ_TOK_STRIDE + i];
         for (uint32_t i = t.spec_from; i < t.spec_count && k <= n; ++i) h_tokens_out[k++] = spec[w * LZ_TOK_STRIDE + i];

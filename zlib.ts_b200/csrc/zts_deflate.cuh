@@ -4,14 +4,16 @@
 
 #define LZ_THREADS 1024
 #define LZ_WARPS 32
-#define LZ_TILE 2048                    // positions parsed by one warp
 #define LZ_MAX_CHUNK 65536u
+#define LZ_TILE 512u                    // positions of one speculative parse tile (warps take tiles dynamically)
+#define LZ_NTILES (LZ_MAX_CHUNK / LZ_TILE)
+#define LZ_SORT_TILE 2048u              // positions ranked by one warp in a radix pass
 #define LZ_HASH_BITS 13
 #define LZ_NB (1u << LZ_HASH_BITS)
 #define LZ_WINDOW 32768u                // WindowSize, src/LZ77.ts:8
 #define LZ_MAXLEN 258u                  // LZ77MaxLength, src/LZ77.ts:5
 #define LZ_TOK_STRIDE (LZ_TILE + 8)     // token slots per tile in the spec / fix buffers
-#define LZ_TOK_PER_CHUNK (LZ_WARPS * LZ_TOK_STRIDE)
+#define LZ_TOK_PER_CHUNK (LZ_NTILES * LZ_TOK_STRIDE)
 
 #define TOK_MATCH 0x80000000u           // literal: byte ; match: TOK_MATCH | (len-3) << 16 | (dist-1)
 
@@ -29,14 +31,14 @@ struct ZtsChunk {      // host-built, one per chunk
 };
 
 struct ZtsTile {
-    uint32_t fix_count;   // tokens re-parsed from the true entry point until it met the speculative parse
-    uint32_t spec_from;   // first speculative token that belongs to the true parse
-    uint32_t spec_count;  // speculative tokens of the tile
-    uint32_t pad;
+    uint16_t fix_count;   // tokens re-parsed from the true entry point until it met the speculative parse
+    uint16_t spec_from;   // first speculative token that belongs to the true parse
+    uint16_t spec_count;  // speculative tokens of the tile
+    uint16_t pad;
 };
 
 struct ZtsChunkInfo {  // device-produced, one per chunk
-    ZtsTile tiles[LZ_WARPS];
+    ZtsTile tiles[LZ_NTILES];
     uint32_t n_tokens;   // tokens of the true parse (without end-of-block)
     uint32_t hdr_bits;   // block header bits incl. BFINAL/BTYPE
     unsigned long long body_bits;  // token bits incl. end-of-block

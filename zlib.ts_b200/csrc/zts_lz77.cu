@@ -9,15 +9,21 @@
 //   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
 //   2. all positions are radix-sorted (stable, 2 LSD passes, warp match.any ranking, no atomics)
 //      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
-//   3. 32 warps parse 32 tiles of 2048 positions speculatively, each from its tile start; a search
-//      is warp-cooperative: 32 candidates per step (newest first), exact-key filter, tail-byte
-//      filter against the best so far, word-wise extension, REDUX.MAX over (len << 16 | q);
+//   3. the chunk is cut into 128 tiles of 512 positions which the 32 warps take from a shared counter
+//      (segments of different entropy cost very different time) and parse speculatively, each from
+//      its tile start. A parse step first probes 32 positions at once, one per lane, for "has any
+//      earlier position with the same 3 bytes": runs of positions without one are literals and are
+//      emitted together. A position that may have candidates gets the warp-cooperative search:
+//      32 candidates per step (newest first), exact-key filter, tail-byte filter against the best
+//      so far, word-wise extension, REDUX.MAX over (len << 16 | q);
 //   4. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
 //      of the previous one and is re-parsed only until it meets a speculatively parsed position
-//      (a visited-bit per position); the remainder of the speculative tokens is reused;
+//      (a visited-bit per position); the remainder of the speculative tokens is reused. All tiles
+//      re-enter in parallel assuming their predecessor exits where its speculative parse did; one
+//      warp then walks the chain and redoes the few tiles whose assumption was wrong;
 //   5. litlen / dist histograms are taken over the surviving tokens.
 //
-// Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 8 KiB scratch.
+// Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 14 KiB scratch.
 #include "zts_deflate.cuh"
 
 struct LzSmem {
@@ -31,19 +37,23 @@ struct LzSmem {
     static constexpr uint32_t AUX_OFF = BSTART_OFF + BSTART_BYTES;     // 8 KiB: radix counters | visited bits
     static constexpr uint32_t AUX_BYTES = 8192;
     static constexpr uint32_t MISC_OFF = AUX_OFF + AUX_BYTES;
-    static constexpr uint32_t MISC_BYTES = 2048;
+    static constexpr uint32_t MISC_BYTES = 6144;
     static constexpr uint32_t TOTAL = MISC_OFF + MISC_BYTES;
 };
 
 struct LzMisc {
     unsigned long long mbar;
     uint32_t chunk;
+    uint32_t tile_next;              // next tile of the speculative parse
     uint32_t warp_tot[32];
     uint32_t warp_min[32];
-    uint32_t spec_exit[32];
-    uint32_t spec_count[32];
-    uint32_t tile_tot[33];
+    uint32_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)
+    uint32_t fix_exit[LZ_NTILES];    // exit of the tile when entered at its predecessor's speculative exit
+    uint16_t spec_count[LZ_NTILES];
+    uint16_t fix_count[LZ_NTILES];
+    uint16_t spec_from[LZ_NTILES];
     uint32_t hist[316];
+    uint32_t n_tokens;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,6 +71,19 @@ __device__ __forceinline__ uint32_t ld_u32(const LzS& V, uint32_t i)
     const uint32_t mis = (V.shift + i) & 3u;
     const uint32_t* w = reinterpret_cast<const uint32_t*>(V.S + i - mis);
     return __funnelshift_r(w[0], w[1], mis * 8);
+}
+
+// 16 bytes at byte offset i of S as four little-endian words (>= 24 readable bytes follow any i <= n)
+__device__ __forceinline__ void ld_u128(const LzS& V, uint32_t i, uint32_t (&o)[4])
+{
+    const uint32_t mis = (V.shift + i) & 3u;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(V.S + i - mis);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+    const uint32_t sh = mis * 8;
+    o[0] = __funnelshift_r(w0, w1, sh);
+    o[1] = __funnelshift_r(w1, w2, sh);
+    o[2] = __funnelshift_r(w2, w3, sh);
+    o[3] = __funnelshift_r(w3, w4, sh);
 }
 
 __device__ __forceinline__ uint32_t hash13(uint32_t key3) { return (key3 * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
@@ -142,13 +165,26 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
                     uint32_t k = 3;
                     if (x0 == 0) {
                         k = 4;
-                        while (k < maxlen) {
-                            const uint32_t x = ld_u32(S, q + k) ^ ld_u32(S, p + k);
-                            if (x) {
-                                k += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                                break;
+                        // most matches end within the next word; long ones continue 16 bytes per step
+                        const uint32_t x1 = ld_u32(S, q + 4) ^ ld_u32(S, p + 4);
+                        if (x1) {
+                            k += (uint32_t)(__ffs((int)x1) - 1) >> 3;
+                        } else {
+                            k = 8;
+                            while (k < maxlen) {
+                                uint32_t a4[4], b4[4];
+                                ld_u128(S, q + k, a4);
+                                ld_u128(S, p + k, b4);
+                                const uint32_t y0 = a4[0] ^ b4[0], y1 = a4[1] ^ b4[1], y2 = a4[2] ^ b4[2],
+                                               y3 = a4[3] ^ b4[3];
+                                if (y0 | y1 | y2 | y3) {
+                                    const uint32_t y = y0 ? y0 : y1 ? y1 : y2 ? y2 : y3;
+                                    const uint32_t wsel = y0 ? 0u : y1 ? 4u : y2 ? 8u : 12u;
+                                    k += wsel + ((uint32_t)(__ffs((int)y) - 1) >> 3);
+                                    break;
+                                }
+                                k += 16;
                             }
-                            k += 4;
                         }
                     }
                     len = min(k, maxlen);
@@ -181,6 +217,111 @@ __device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted
     }
     *tok_out = S[p];
     return p + 1;
+}
+
+// Lane-private probe: may position pl (pl + 3 < n) have a candidate, i.e. an earlier position inside the
+// window with the same 3 bytes (a non-empty table[key] list after pruning, src/LZ77.ts:211-225,242)?
+// Exact for buckets of at most LZ_PROBE_MAX entries, "maybe" (true) for longer ones.
+#define LZ_PROBE_MAX 12u
+__device__ __forceinline__ bool lz_probe(const LzS& S, const uint16_t* __restrict__ sorted,
+                                         const uint16_t* __restrict__ bstart, uint32_t pl)
+{
+    const uint32_t pw = ld_u32(S, pl) & 0xFFFFFFu;
+    const uint32_t h = hash13(pw);
+    const uint32_t lo = bstart[h], hi = bstart[h + 1];
+    if (hi - lo > LZ_PROBE_MAX) return true;
+    for (uint32_t s = lo; s < hi; ++s) {
+        const uint32_t q = sorted[s];
+        if (q >= pl) break;  // ascending positions: the rest is not earlier
+        if (pl - q <= LZ_WINDOW && (ld_u32(S, q) & 0xFFFFFFu) == pw) return true;
+    }
+    return false;
+}
+
+// Speculative parse of tile [t_begin, t_end): tokens to tok_out, visited bit per parsed position.
+// Returns the exit position (>= t_end); *count_out = tokens written.
+__device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
+                                                  uint32_t t_begin, uint32_t t_end, uint32_t n,
+                                                  uint32_t* __restrict__ tok_out, uint32_t* visited,
+                                                  uint32_t* count_out)
+{
+    const unsigned lane = zts_lane();
+    uint32_t p = t_begin, ntok = 0;
+    uint32_t wbase = 0, wmask = 0;
+    bool have = false;
+    while (p < t_end) {
+        if (!have || p >= wbase + 32) {
+            // probe the next 32 positions, one per lane
+            wbase = p;
+            const uint32_t pl = p + lane;
+            bool hc = false;
+            if (pl < t_end && pl + 3 < n) hc = lz_probe(S, sorted, bstart, pl);
+            wmask = __ballot_sync(0xFFFFFFFFu, hc);
+            have = true;
+        }
+        const uint32_t off = p - wbase;
+        const uint32_t m = wmask >> off;  // bit 0 <-> position p
+        const uint32_t avail = min(32u - off, t_end - p);
+        const uint32_t k = m ? min((uint32_t)__ffs((int)m) - 1u, avail) : avail;
+        if (k) {
+            // k positions without any candidate: k literals (src/LZ77.ts:267-272)
+            if (lane < k) tok_out[ntok + lane] = S[p + lane];
+            if (lane == 0) {
+                const unsigned long long bits = ((1ull << k) - 1ull) << (p & 31);
+                visited[p >> 5] |= (uint32_t)bits;
+                if (bits >> 32) visited[(p >> 5) + 1] |= (uint32_t)(bits >> 32);
+            }
+            ntok += k;
+            p += k;
+            continue;
+        }
+        uint32_t tok;
+        const uint32_t np = lz_step(S, sorted, bstart, p, n, &tok);
+        if (lane == 0) {
+            visited[p >> 5] |= 1u << (p & 31);
+            tok_out[ntok] = tok;
+        }
+        ntok++;
+        p = np;
+    }
+    *count_out = ntok;
+    return p;
+}
+
+// True parse of a tile entered at `entry` (>= the tile's begin is not required: entry may lie past it):
+// re-parse until a position the speculative parse visited, from there its tokens are reused.
+// Writes fix tokens, returns the exit; *nfix_out / *from_out describe the splice.
+__device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
+                                                   uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
+                                                   uint32_t* __restrict__ fix_out, const uint32_t* visited,
+                                                   uint32_t spec_count, uint32_t spec_exit, uint32_t* nfix_out,
+                                                   uint32_t* from_out)
+{
+    const unsigned lane = zts_lane();
+    uint32_t nfix = 0, from = spec_count;
+    uint32_t p = entry;
+    while (p < t_end) {
+        if ((visited[p >> 5] >> (p & 31)) & 1u) {
+            // met the speculative parse: its tokens from this position on are the true ones
+            uint32_t idx = 0;
+            for (uint32_t wd = (t_begin >> 5) + lane; wd <= (p >> 5); wd += 32) {
+                uint32_t bits = visited[wd];
+                if (wd == (p >> 5)) bits &= (1u << (p & 31)) - 1u;
+                idx += __popc(bits);
+            }
+            from = __reduce_add_sync(0xFFFFFFFFu, idx);
+            p = spec_exit;
+            break;
+        }
+        uint32_t tok;
+        const uint32_t np = lz_step(S, sorted, bstart, p, n, &tok);
+        if (lane == 0) fix_out[nfix] = tok;
+        nfix++;
+        p = np;
+    }
+    *nfix_out = nfix;
+    *from_out = from;
+    return p;
 }
 
 __device__ __forceinline__ void hist_token(uint32_t tok, uint32_t* hist)
@@ -270,11 +411,11 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             const uint32_t ndig = pass == 0 ? 128u : 64u;
             for (uint32_t i = tid; i < 32u * 128u; i += LZ_THREADS) cnt16[i] = 0;
             __syncthreads();
-            const uint32_t w_begin = warp * LZ_TILE;
+            const uint32_t w_begin = warp * LZ_SORT_TILE;
             uint16_t* wc = cnt16 + warp * ndig;
             // count
             if (w_begin < m) {
-                for (uint32_t it = 0; it < LZ_TILE / 32; ++it) {
+                for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
                     const uint32_t i = w_begin + it * 32 + lane;
                     const bool v = i < m;
                     uint32_t d = 0xFFFFFFFFu;
@@ -311,7 +452,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             __syncthreads();
             // scatter
             if (w_begin < m) {
-                for (uint32_t it = 0; it < LZ_TILE / 32; ++it) {
+                for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
                     const uint32_t i = w_begin + it * 32 + lane;
                     const bool v = i < m;
                     uint32_t d = 0xFFFFFFFFu, q = 0;
@@ -379,99 +520,91 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         }
         __syncthreads();
 
-        // ---- 3. speculative parse: warp w parses tile w from its first position
+        // ---- 3. speculative parse: warps take tiles from a shared counter
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
+        if (tid == 0) M->tile_next = 0;
         __syncthreads();
         const uint32_t n_tiles = (n + LZ_TILE - 1) / LZ_TILE;
-        uint32_t* my_spec = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK + warp * LZ_TOK_STRIDE;
-        if (warp < n_tiles) {
-            const uint32_t t_begin = warp * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
-            uint32_t p = t_begin, ntok = 0;
-            while (p < t_end) {
-                uint32_t tok;
-                const uint32_t np = lz_step(SV, sorted, bstart, p, n, &tok);
-                if (lane == 0) {
-                    visited[p >> 5] |= 1u << (p & 31);
-                    my_spec[ntok] = tok;
-                }
-                ntok++;
-                p = np;
-            }
+        uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
+        uint32_t* fix_c = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
+        for (;;) {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(&M->tile_next, 1u);
+            t = __shfl_sync(0xFFFFFFFFu, t, 0);
+            if (t >= n_tiles) break;
+            const uint32_t t_begin = t * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+            uint32_t cnt;
+            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, n, spec_c + t * LZ_TOK_STRIDE,
+                                              visited, &cnt);
             if (lane == 0) {
-                M->spec_exit[warp] = p;
-                M->spec_count[warp] = ntok;
+                M->spec_exit[t] = ex;
+                M->spec_count[t] = (uint16_t)cnt;
             }
         }
         __syncthreads();
 
-        // ---- 4. true parse: re-enter every tile at the true exit of its predecessor (warp 0)
-        ZtsChunkInfo* ci = info + c;
-        if (warp == 0) {
-            uint32_t entry = n_tiles ? M->spec_exit[0] : 0;
-            if (lane == 0 && n_tiles) {
-                ZtsTile t0 = {0u, 0u, M->spec_count[0], 0u};
-                ci->tiles[0] = t0;
-                M->tile_tot[0] = M->spec_count[0];
-            }
-            for (uint32_t w = 1; w < n_tiles; ++w) {
+        // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel)
+        for (uint32_t w = warp; w < n_tiles; w += LZ_WARPS) {
+            uint32_t nfix = 0, from = 0, ex = M->spec_exit[w];
+            if (w) {
                 const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
-                const uint32_t sc = M->spec_count[w];
-                uint32_t nfix = 0, from = sc;
-                uint32_t* my_fix = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK + w * LZ_TOK_STRIDE;
-                uint32_t p = entry;
-                while (p < t_end) {
-                    if ((visited[p >> 5] >> (p & 31)) & 1u) {
-                        // met the speculative parse: its tokens from this position on are the true ones
-                        uint32_t idx = 0;
-                        for (uint32_t wd = (t_begin >> 5) + lane; wd <= (p >> 5); wd += 32) {
-                            uint32_t bits = visited[wd];
-                            if (wd == (p >> 5)) bits &= (1u << (p & 31)) - 1u;
-                            idx += __popc(bits);
-                        }
-                        from = __reduce_add_sync(0xFFFFFFFFu, idx);
-                        p = M->spec_exit[w];
-                        break;
-                    }
-                    uint32_t tok;
-                    const uint32_t np = lz_step(SV, sorted, bstart, p, n, &tok);
-                    if (lane == 0) my_fix[nfix] = tok;
-                    nfix++;
-                    p = np;
+                ex = lz_resync_tile(SV, sorted, bstart, M->spec_exit[w - 1], t_begin, t_end, n,
+                                    fix_c + w * LZ_TOK_STRIDE, visited, M->spec_count[w], M->spec_exit[w], &nfix,
+                                    &from);
+            }
+            if (lane == 0) {
+                M->fix_exit[w] = ex;
+                M->fix_count[w] = (uint16_t)nfix;
+                M->spec_from[w] = (uint16_t)from;
+            }
+        }
+        __syncthreads();
+
+        // ---- 4b. walk the chain of true exits; redo the tiles whose assumed entry was wrong (warp 0)
+        ZtsChunkInfo* ci = info + c;
+        if (warp == 0 && n_tiles) {
+            uint32_t true_exit = M->spec_exit[0];
+            for (uint32_t w = 1; w < n_tiles; ++w) {
+                if (true_exit == M->spec_exit[w - 1]) {
+                    true_exit = M->fix_exit[w];
+                    continue;
                 }
-                entry = max(entry, p);
+                const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+                uint32_t nfix, from;
+                true_exit = lz_resync_tile(SV, sorted, bstart, true_exit, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE,
+                                           visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
-                    ZtsTile t = {nfix, from, sc, 0u};
-                    ci->tiles[w] = t;
-                    M->tile_tot[w] = nfix + (sc - from);
+                    M->fix_count[w] = (uint16_t)nfix;
+                    M->spec_from[w] = (uint16_t)from;
                 }
             }
-            if (lane == 0)
-                for (uint32_t w = n_tiles; w < LZ_WARPS; ++w) {
-                    ZtsTile t = {0u, 0u, 0u, 0u};
-                    ci->tiles[w] = t;
-                    M->tile_tot[w] = 0;
-                }
         }
         for (uint32_t i = tid; i < 316; i += LZ_THREADS) M->hist[i] = 0;
+        if (tid == 0) M->n_tokens = 0;
         __threadfence_block();
         __syncthreads();
 
-        // ---- 5. histograms over the surviving tokens (src/LZ77.ts:126-128,141-142,236,251,271,279)
-        {
-            const ZtsTile t = ci->tiles[warp];
-            const uint32_t* fx = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK + warp * LZ_TOK_STRIDE;
-            const uint32_t* sp = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK + warp * LZ_TOK_STRIDE;
+        // ---- 5. tile table + histograms over the surviving tokens (src/LZ77.ts:126-128,141-142,236,251,271,279)
+        for (uint32_t w = warp; w < LZ_NTILES; w += LZ_WARPS) {
+            ZtsTile t = {0, 0, 0, 0};
+            if (w < n_tiles) {
+                t.fix_count = M->fix_count[w];
+                t.spec_from = M->spec_from[w];
+                t.spec_count = M->spec_count[w];
+            }
+            if (lane == 0) {
+                ci->tiles[w] = t;
+                atomicAdd(&M->n_tokens, (uint32_t)t.fix_count + (t.spec_count - t.spec_from));
+            }
+            const uint32_t* fx = fix_c + w * LZ_TOK_STRIDE;
+            const uint32_t* sp = spec_c + w * LZ_TOK_STRIDE;
             for (uint32_t k = lane; k < t.fix_count; k += 32) hist_token(fx[k], M->hist);
             for (uint32_t k = t.spec_from + lane; k < t.spec_count; k += 32) hist_token(sp[k], M->hist);
         }
         __syncthreads();
         for (uint32_t i = tid; i < 316; i += LZ_THREADS)
             hist_out[(size_t)c * 316 + i] = M->hist[i] + (i == 256 ? 2u : 0u);  // freqsLitLen[256] ends at 2
-        if (tid == 0) {
-            uint32_t tot = 0;
-            for (uint32_t w = 0; w < LZ_WARPS; ++w) tot += M->tile_tot[w];
-            ci->n_tokens = tot;
-        }
+        if (tid == 0) ci->n_tokens = M->n_tokens;
         __syncthreads();
     }
 }
