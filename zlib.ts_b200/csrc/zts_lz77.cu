@@ -19,8 +19,9 @@
 //   4. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
 //      of the previous one and is re-parsed only until it meets a speculatively parsed position
 //      (a visited-bit per position); the remainder of the speculative tokens is reused. All tiles
-//      re-enter in parallel assuming their predecessor exits where its speculative parse did; one
-//      warp then walks the chain and redoes the few tiles whose assumption was wrong;
+//      re-enter in parallel assuming their predecessor exits where its speculative parse did; the
+//      few whose predecessor exits elsewhere (chains inside long runs) are redone chain by chain,
+//      one warp per chain, and a final walk over the true exits verifies every splice;
 //   5. litlen / dist histograms are taken over the surviving tokens.
 //
 // Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 14 KiB scratch.
@@ -48,7 +49,9 @@ struct LzMisc {
     uint32_t warp_tot[32];
     uint32_t warp_min[32];
     uint32_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)
-    uint32_t fix_exit[LZ_NTILES];    // exit of the tile when entered at its predecessor's speculative exit
+    uint32_t fix_exit[LZ_NTILES];    // exit of the tile for the entry it was last parsed from
+    uint32_t entry_used[LZ_NTILES];  // that entry
+    uint32_t start_mask[LZ_NTILES / 32];  // tiles that start a chain of wrongly entered tiles
     uint16_t spec_count[LZ_NTILES];
     uint16_t fix_count[LZ_NTILES];
     uint16_t spec_from[LZ_NTILES];
@@ -543,37 +546,74 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         }
         __syncthreads();
 
-        // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel)
+        // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel); this is already
+        //          the true parse wherever the predecessor did converge to its speculative parse
+        ZtsChunkInfo* ci = info + c;
+        if (tid < LZ_NTILES / 32) M->start_mask[tid] = 0;
         for (uint32_t w = warp; w < n_tiles; w += LZ_WARPS) {
-            uint32_t nfix = 0, from = 0, ex = M->spec_exit[w];
+            uint32_t nfix = 0, from = 0, ex = M->spec_exit[w], entry = 0;
             if (w) {
                 const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
-                ex = lz_resync_tile(SV, sorted, bstart, M->spec_exit[w - 1], t_begin, t_end, n,
-                                    fix_c + w * LZ_TOK_STRIDE, visited, M->spec_count[w], M->spec_exit[w], &nfix,
-                                    &from);
+                entry = M->spec_exit[w - 1];
+                ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE, visited,
+                                    M->spec_count[w], M->spec_exit[w], &nfix, &from);
             }
             if (lane == 0) {
+                M->entry_used[w] = entry;
                 M->fix_exit[w] = ex;
                 M->fix_count[w] = (uint16_t)nfix;
                 M->spec_from[w] = (uint16_t)from;
             }
         }
         __syncthreads();
-
-        // ---- 4b. walk the chain of true exits; redo the tiles whose assumed entry was wrong (warp 0)
-        ZtsChunkInfo* ci = info + c;
+        // ---- 4b. tiles entered at the wrong place form chains (consecutive tiles inside one long run of
+        //          matches that never meets the speculative parse); chains are independent, one warp each
+        for (uint32_t w = tid + 1; w < n_tiles; w += LZ_THREADS) {
+            const bool bad = M->fix_exit[w - 1] != M->entry_used[w];
+            const bool bad_prev = w >= 2 && M->fix_exit[w - 2] != M->entry_used[w - 1];
+            if (bad && !bad_prev) atomicOr(&M->start_mask[w >> 5], 1u << (w & 31));
+        }
+        __syncthreads();
+        for (uint32_t w = warp + 1; w < n_tiles; w += LZ_WARPS) {
+            if (!((M->start_mask[w >> 5] >> (w & 31)) & 1u)) continue;
+            uint32_t end = w + 1;  // next chain start (or the end of the chunk)
+            while (end < n_tiles && !((M->start_mask[end >> 5] >> (end & 31)) & 1u)) ++end;
+            uint32_t entry = M->fix_exit[w - 1];
+            for (uint32_t t = w; t < end; ++t) {
+                if (entry == M->entry_used[t]) break;
+                const uint32_t t_begin = t * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+                uint32_t nfix, from;
+                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n,
+                                                   fix_c + t * LZ_TOK_STRIDE, visited, M->spec_count[t],
+                                                   M->spec_exit[t], &nfix, &from);
+                if (lane == 0) {
+                    M->entry_used[t] = entry;
+                    M->fix_exit[t] = ex;
+                    M->fix_count[t] = (uint16_t)nfix;
+                    M->spec_from[t] = (uint16_t)from;
+                }
+                __syncwarp();
+                entry = ex;
+            }
+        }
+        __syncthreads();
+        // ---- 4c. walk the chain of true exits once; anything still entered at the wrong place is redone here
+        //          (normally nothing: this pass is what makes 4a/4b safe to run optimistically)
         if (warp == 0 && n_tiles) {
-            uint32_t true_exit = M->spec_exit[0];
+            uint32_t true_exit = M->fix_exit[0];
             for (uint32_t w = 1; w < n_tiles; ++w) {
-                if (true_exit == M->spec_exit[w - 1]) {
+                if (true_exit == M->entry_used[w]) {
                     true_exit = M->fix_exit[w];
                     continue;
                 }
                 const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
                 uint32_t nfix, from;
-                true_exit = lz_resync_tile(SV, sorted, bstart, true_exit, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE,
+                const uint32_t entry = true_exit;
+                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE,
                                            visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
+                    M->entry_used[w] = entry;
+                    M->fix_exit[w] = true_exit;
                     M->fix_count[w] = (uint16_t)nfix;
                     M->spec_from[w] = (uint16_t)from;
                 }
