@@ -12,19 +12,19 @@
 #include "zts_deflate.cuh"
 
 #define HUF_MAXSYM 288
-#define HUF_LVL 576  // >= 2 * symbols
+#define HUF_LVL 576  // >= 2 * symbols: a level holds at most symbols + symbols packages
 #define HUF_UNDEF 0xFFFFFFFFu
-#define HUF_TUNDEF 0xFFFFu
+#define HUF_PKW (HUF_LVL / 32)
 
 struct HufWork {
-    uint32_t val[2][HUF_LVL];       // value[j+1], value[j]
-    uint16_t type[15][HUF_LVL];
-    uint16_t heap[2 * HUF_MAXSYM];
-    uint32_t nval[HUF_MAXSYM];
-    uint16_t nidx[HUF_MAXSYM];
+    // val[0] doubles as the histogram being coded (read only while the heap is filled) and val[1] as
+    // the heap (dead once everything is popped): both are free again when the level lists are built
+    uint32_t val[2][HUF_LVL];        // value[j+1], value[j] of reversePackageMerge
+    uint32_t pkbits[15][HUF_PKW];    // per level: bit t set <=> item t is a package (type[j][t] === symbols)
+    uint32_t nval[HUF_MAXSYM];       // frequencies in heap pop order (descending)
+    uint16_t nidx[HUF_MAXSYM];       // their symbols
     uint8_t clen[HUF_MAXSYM];
-    uint32_t freq[HUF_MAXSYM];
-    uint32_t tree_sym[2 * (286 + 30)];
+    uint8_t tree_sym[2 * (286 + 30)];
     uint16_t code_tmp[HUF_MAXSYM];
     uint8_t ll_len[HUF_MAXSYM];
     uint8_t d_len[32];
@@ -81,143 +81,204 @@ __device__ void heap_pop(uint16_t* heap, int& length, uint16_t& index, uint16_t&
     }
 }
 
-// ---- reversePackageMerge (src/RawDeflate.ts:484-571) ------------------------------------------------
-// HUF_UNDEF plays JS `undefined`: undefined + x = NaN and every comparison with NaN is false.
-__device__ void rpm(const uint32_t* freqs, int symbols, int limit, uint8_t* code_length, HufWork* W)
+// ---- reversePackageMerge (src/RawDeflate.ts:484-571), warp-cooperative ---------------------------------
+// The reference builds, from the deepest level up, value[j] = the first minimumCost[j] items of the merge
+// of the symbols (descending freqs) with the packages value[j+1][next] + value[j+1][next+1], "package
+// first iff weight > freqs[i]" (:553), and interleaves the recursive takePackage (:496-507). Two facts
+// make this data-parallel without changing a single result (checked against the statement-by-statement
+// model on 14 000 cases incl. ties, tests/test_oracle.py + tests/test_deflate_gpu.py):
+//   1. when level j is built, currentPosition[j+1] is just flag[j+1]: takePackage only ever descends, so
+//      the levels do not depend on the recursion, and a level is a plain merge of two sorted lists:
+//      symbol i lands at i + #{k : W_k > f_i}, package k at k + #{i : f_i >= W_k} (two binary searches);
+//   2. the items taken from a level are always a prefix of it: T[0] = flag[0], and with P[j] packages
+//      among the first T[j] items of level j, T[j+1] = flag[j+1] + 2 P[j]; the S[j] = T[j] - P[j] symbols
+//      taken there are symbols 0 .. S[j]-1, so codeLength[i] = limit - #{j : i < S[j]}.
+// JS `undefined` (App. B-6): a sum with an out-of-range value[][] is NaN and compares false, i.e. "no
+// package left"; once the symbols are exhausted too the reference stores undefined items, which can
+// never be decremented -- modelled by HUF_UNDEF tail entries and the `defined` count.
+__device__ void rpm_warp(const uint32_t* freqs, int symbols, int limit, uint8_t* code_length, HufWork* W)
 {
-    uint16_t minimum_cost[16];
-    int flag[16], size[16], cur[16];
-    for (int i = 0; i < symbols; ++i) code_length[i] = (uint8_t)limit;
-    for (int j = 0; j < 16; ++j) {
-        minimum_cost[j] = 0;
-        cur[j] = 0;
-    }
-    minimum_cost[limit - 1] = (uint16_t)symbols;
-    int excess = (1 << limit) - symbols;
-    const int half = 1 << (limit - 1);
-    for (int j = 0; j < limit; ++j) {
-        if (excess < half) {
-            flag[j] = 0;
-        } else {
-            flag[j] = 1;
-            excess -= half;
+    const int lane = (int)zts_lane();
+    int flag[16], size[16];
+    {
+        uint16_t mc[16];
+        for (int j = 0; j < 16; ++j) mc[j] = 0;
+        mc[limit - 1] = (uint16_t)symbols;
+        int excess = (1 << limit) - symbols;
+        const int half = 1 << (limit - 1);
+        for (int j = 0; j < limit; ++j) {
+            if (excess < half) {
+                flag[j] = 0;
+            } else {
+                flag[j] = 1;
+                excess -= half;
+            }
+            excess <<= 1;
+            if (limit - 2 - j >= 0) mc[limit - 2 - j] = (uint16_t)((mc[limit - 1 - j] >> 1) + symbols);
         }
-        excess <<= 1;
-        if (limit - 2 - j >= 0) minimum_cost[limit - 2 - j] = (uint16_t)((minimum_cost[limit - 1 - j] >> 1) + symbols);
+        mc[0] = (uint16_t)flag[0];
+        for (int j = 1; j < limit; ++j)
+            if (mc[j] > 2 * mc[j - 1] + flag[j]) mc[j] = (uint16_t)(2 * mc[j - 1] + flag[j]);
+        for (int j = 0; j < limit; ++j) size[j] = mc[j];
     }
-    minimum_cost[0] = (uint16_t)flag[0];
-    for (int j = 1; j < limit; ++j)
-        if (minimum_cost[j] > 2 * minimum_cost[j - 1] + flag[j])
-            minimum_cost[j] = (uint16_t)(2 * minimum_cost[j - 1] + flag[j]);
-    for (int j = 0; j < limit; ++j) size[j] = minimum_cost[j];
-
     // deepest level: the symbols themselves
     {
         uint32_t* v = W->val[(limit - 1) & 1];
-        uint16_t* ty = W->type[limit - 1];
-        for (int t = 0; t < size[limit - 1]; ++t) {
-            v[t] = t < symbols ? freqs[t] : HUF_UNDEF;
-            ty[t] = (uint16_t)t;
-        }
+        for (int t = lane; t < size[limit - 1]; t += 32) v[t] = t < symbols ? freqs[t] : HUF_UNDEF;
+        for (int w = lane; w < HUF_PKW; w += 32) W->pkbits[limit - 1][w] = 0;
     }
-    if (flag[limit - 1]) {
-        if (symbols > 0) code_length[0]--;
-        cur[limit - 1]++;
-    }
+    int defined = min(size[limit - 1], symbols);
+    const uint32_t fmin = freqs[symbols - 1];
+    __syncwarp();
     for (int j = limit - 2; j >= 0; --j) {
         const uint32_t* pv = W->val[(j + 1) & 1];
         uint32_t* v = W->val[j & 1];
-        uint16_t* ty = W->type[j];
-        const int psize = size[j + 1];
-        int i = 0, next = cur[j + 1];
-        for (int t = 0; t < size[j]; ++t) {
-            const uint32_t a = next < psize ? pv[next] : HUF_UNDEF;
-            const uint32_t b = next + 1 < psize ? pv[next + 1] : HUF_UNDEF;
-            const uint32_t fi = i < symbols ? freqs[i] : HUF_UNDEF;
-            const bool pkg = a != HUF_UNDEF && b != HUF_UNDEF && fi != HUF_UNDEF && (a + b) > fi;
-            if (pkg) {
-                v[t] = a + b;
-                ty[t] = (uint16_t)symbols;
-                next += 2;
-            } else {
-                v[t] = fi;
-                ty[t] = (uint16_t)(i < 0xFFFF ? i : 0xFFFE);
-                i++;
+        uint32_t* bits = W->pkbits[j];
+        const int n0 = flag[j + 1];
+        const int K = defined > n0 ? (defined - n0) >> 1 : 0;  // packages that have two defined halves
+        const int sz = size[j];
+        for (int t = lane; t < sz; t += 32) v[t] = HUF_UNDEF;
+        for (int w = lane; w < HUF_PKW; w += 32) bits[w] = 0;
+        __syncwarp();
+        for (int i = lane; i < symbols; i += 32) {
+            const uint32_t fi = freqs[i];
+            int lo = 0, hi = K;  // first package whose weight is not > f_i (weights descend)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (pv[n0 + 2 * mid] + pv[n0 + 2 * mid + 1] > fi)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            if (i + lo < sz) v[i + lo] = fi;
+        }
+        for (int k = lane; k < K; k += 32) {
+            const uint32_t wk = pv[n0 + 2 * k] + pv[n0 + 2 * k + 1];
+            int lo = 0, hi = symbols;  // first symbol with f_i < W_k (freqs descend)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (freqs[mid] >= wk)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            // lo == symbols: every symbol precedes it, and past the last symbol the reference compares
+            // against freqs[symbols] === undefined and never takes a package again
+            if (lo < symbols && k + lo < sz) {
+                v[k + lo] = wk;
+                atomicOr(&bits[(k + lo) >> 5], 1u << ((k + lo) & 31));
             }
         }
-        cur[j] = 0;
-        if (flag[j]) {
-            // takePackage(j), recursion replaced by an explicit stack (:496-507)
-            int stack[40], sp = 0;
-            stack[sp++] = j;
-            while (sp > 0) {
-                const int lv = stack[--sp];
-                const int cp = cur[lv];
-                const uint32_t x = (cp < size[lv]) ? W->type[lv][cp] : HUF_TUNDEF;
-                cur[lv]++;
-                if (x == (uint32_t)symbols && lv + 1 < limit) {
-                    stack[sp++] = lv + 1;
-                    stack[sp++] = lv + 1;
-                } else if (x < (uint32_t)symbols) {
-                    code_length[x]--;
-                }
+        {
+            int lo = 0, hi = K;  // packages heavier than the lightest symbol = packages that get placed
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (pv[n0 + 2 * mid] + pv[n0 + 2 * mid + 1] > fmin)
+                    lo = mid + 1;
+                else
+                    hi = mid;
             }
+            defined = min(sz, symbols + lo);
         }
+        __syncwarp();
     }
+    // items taken per level, top down
+    int S[16];
+    int T = flag[0];
+    for (int j = 0; j < limit; ++j) {
+        const int t = min(T, size[j]);
+        int pc = 0;
+        if (lane < HUF_PKW) {
+            uint32_t b = W->pkbits[j][lane];
+            const int lo_bit = lane * 32;
+            if (t <= lo_bit)
+                b = 0;
+            else if (t < lo_bit + 32)
+                b &= (1u << (t - lo_bit)) - 1u;
+            pc = __popc(b);
+        }
+        const int P = (int)__reduce_add_sync(0xFFFFFFFFu, (unsigned)pc);
+        S[j] = t - P;
+        T = (j + 1 < limit ? flag[j + 1] : 0) + 2 * P;
+    }
+    for (int i = lane; i < symbols; i += 32) {
+        int l = limit;
+        for (int j = 0; j < limit; ++j) l -= (i < S[j]) ? 1 : 0;
+        code_length[i] = (uint8_t)l;
+    }
+    __syncwarp();
 }
 
-// ---- getLengths (src/RawDeflate.ts:440-474) ----------------------------------------------------------
-__device__ void get_lengths(const uint32_t* freqs, int nsym, int limit, uint8_t* lengths, HufWork* W)
+// ---- getLengths (src/RawDeflate.ts:440-474): all lanes call it; freqs / lengths in shared memory ----------
+__device__ void get_lengths(const uint32_t* freqs_in, int nsym, int limit, uint8_t* lengths, HufWork* W)
 {
-    int hlen = 0, nodes = 0;
-    for (int i = 0; i < nsym; ++i) lengths[i] = 0;
-    for (int i = 0; i < nsym; ++i)
-        if (freqs[i] > 0) {
-            heap_push(W->heap, hlen, (uint16_t)i, (uint16_t)freqs[i]);  // Uint16Array store: mod 65536
-            nodes++;
+    const int lane = (int)zts_lane();
+    uint32_t* freq = W->val[0];
+    uint16_t* heap = reinterpret_cast<uint16_t*>(W->val[1]);
+    for (int i = lane; i < nsym; i += 32) {
+        freq[i] = freqs_in[i];
+        lengths[i] = 0;
+    }
+    __syncwarp();
+    int nodes = 0;
+    if (lane == 0) {
+        int hlen = 0;
+        for (int i = 0; i < nsym; ++i)
+            if (freq[i] > 0) {
+                heap_push(heap, hlen, (uint16_t)i, (uint16_t)freq[i]);  // Uint16Array store: mod 65536
+                nodes++;
+            }
+        if (nodes == 1) {
+            uint16_t idx, val;
+            heap_pop(heap, hlen, idx, val);
+            lengths[idx] = 1;
+        } else {
+            for (int i = 0; i < nodes; ++i) {
+                uint16_t idx, val;
+                heap_pop(heap, hlen, idx, val);
+                W->nidx[i] = idx;
+                W->nval[i] = val;
+            }
         }
-    if (nodes == 0) return;
-    if (nodes == 1) {
-        uint16_t idx, val;
-        heap_pop(W->heap, hlen, idx, val);
-        lengths[idx] = 1;
-        return;
     }
-    for (int i = 0; i < nodes; ++i) {
-        uint16_t idx, val;
-        heap_pop(W->heap, hlen, idx, val);
-        W->nidx[i] = idx;
-        W->nval[i] = val;
-    }
-    rpm(W->nval, nodes, limit, W->clen, W);
-    for (int i = 0; i < nodes; ++i) lengths[W->nidx[i]] = W->clen[i];
+    nodes = __shfl_sync(0xFFFFFFFFu, nodes, 0);
+    __syncwarp();
+    if (nodes < 2) return;
+    rpm_warp(W->nval, nodes, limit, W->clen, W);
+    for (int i = lane; i < nodes; i += 32) lengths[W->nidx[i]] = W->clen[i];
+    __syncwarp();
 }
 
 // ---- getCodesFromLengths (src/RawDeflate.ts:580-611): canonical codes stored bit-reversed -------------
+// warp-cooperative: lane L assigns the codes of length L in ascending symbol order
 __device__ void codes_from_lengths(const uint8_t* lengths, int n, uint16_t* codes)
 {
-    uint32_t count[17], start_code[17];
-    for (int i = 0; i <= 16; ++i) count[i] = 0;
-    for (int i = 0; i < n; ++i) count[lengths[i]]++;
-    uint32_t code = 0;
-    for (int i = 1; i <= 16; ++i) {
-        start_code[i] = code;
-        code += count[i];
-        code <<= 1;
+    const uint32_t lane = zts_lane();
+    uint32_t mine = 0;  // count[lane]
+    for (int i = 0; i < n; ++i) mine += (lengths[i] == lane) ? 1u : 0u;
+    if (lane == 0 || lane > 16) mine = 0;
+    // startCode[L] = (startCode[L-1] + count[L-1]) << 1
+    uint32_t start = 0, code = 0;
+    for (uint32_t L = 1; L <= 16; ++L) {
+        const uint32_t cL = __shfl_sync(0xFFFFFFFFu, mine, (int)L);
+        if (lane == L) start = code;
+        code = (code + cL) << 1;
     }
-    for (int i = 0; i < n; ++i) {
-        const uint32_t l = lengths[i];
-        uint32_t r = 0;
-        if (l) {
-            const uint32_t c = start_code[l]++;
-            r = __brev(c) >> (32 - l);
-        }
-        codes[i] = (uint16_t)r;
+    if (lane == 0)
+        for (int i = 0; i < n; ++i)
+            if (lengths[i] == 0) codes[i] = 0;
+    if (lane >= 1 && lane <= 16) {
+        for (int i = 0; i < n; ++i)
+            if (lengths[i] == lane) {
+                codes[i] = (uint16_t)(__brev(start) >> (32 - lane));
+                start++;
+            }
     }
+    __syncwarp();
 }
 
-// ---- getTreeSymbols (src/RawDeflate.ts:341-431) ----------------------------------------------------------
-__device__ int tree_symbols(int hlit, const uint8_t* ll, int hdist, const uint8_t* dl, uint32_t* result, uint8_t* freqs)
+// ---- getTreeSymbols (src/RawDeflate.ts:341-431); serial (<= 316 lengths), result entries fit a byte ------
+__device__ int tree_symbols(int hlit, const uint8_t* ll, int hdist, const uint8_t* dl, uint8_t* result, uint8_t* freqs)
 {
     const int l = hlit + hdist;
     int n_result = 0, j;
@@ -240,23 +301,23 @@ __device__ int tree_symbols(int hlit, const uint8_t* ll, int hdist, const uint8_
                     if (rpt > run_length - 3 && rpt < run_length) rpt = run_length - 3;
                     if (rpt <= 10) {
                         result[n_result++] = 17;
-                        result[n_result++] = (uint32_t)(rpt - 3);
+                        result[n_result++] = (uint8_t)(rpt - 3);
                         freqs[17]++;
                     } else {
                         result[n_result++] = 18;
-                        result[n_result++] = (uint32_t)(rpt - 11);
+                        result[n_result++] = (uint8_t)(rpt - 11);
                         freqs[18]++;
                     }
                     run_length -= rpt;
                 }
             }
         } else {
-            result[n_result++] = v;
+            result[n_result++] = (uint8_t)v;
             freqs[v]++;
             run_length--;
             if (run_length < 3) {
                 while (run_length-- > 0) {
-                    result[n_result++] = v;
+                    result[n_result++] = (uint8_t)v;
                     freqs[v]++;
                 }
             } else {
@@ -264,7 +325,7 @@ __device__ int tree_symbols(int hlit, const uint8_t* ll, int hdist, const uint8_
                     int rpt = run_length < 6 ? run_length : 6;
                     if (rpt > run_length - 3 && rpt < run_length) rpt = run_length - 3;
                     result[n_result++] = 16;
-                    result[n_result++] = (uint32_t)(rpt - 3);
+                    result[n_result++] = (uint8_t)(rpt - 3);
                     freqs[16]++;
                     run_length -= rpt;
                 }
@@ -275,14 +336,30 @@ __device__ int tree_symbols(int hlit, const uint8_t* ll, int hdist, const uint8_
     return n_result;
 }
 
-// LSB-first bit append (BitStream.writeBits with reverse=true, src/Bitstream.ts:62-106)
-__device__ __forceinline__ void put_bits(uint8_t* buf, uint32_t& bitpos, uint32_t value, uint32_t nbits)
-{
-    for (uint32_t k = 0; k < nbits; ++k) {
-        if ((value >> k) & 1u) buf[bitpos >> 3] |= (uint8_t)(1u << (bitpos & 7));
-        bitpos++;
+// LSB-first bit writer (BitStream.writeBits with reverse=true, src/Bitstream.ts:62-106): a 64-bit
+// accumulator flushed a byte at a time into a zeroed buffer
+struct HdrBits {
+    uint8_t* buf;
+    unsigned long long acc;
+    uint32_t nacc;   // bits in acc
+    uint32_t nbyte;  // bytes flushed
+    __device__ __forceinline__ void put(uint32_t value, uint32_t nbits)
+    {
+        acc |= (unsigned long long)value << nacc;
+        nacc += nbits;
+        while (nacc >= 8) {
+            buf[nbyte++] = (uint8_t)acc;
+            acc >>= 8;
+            nacc -= 8;
+        }
     }
-}
+    __device__ __forceinline__ uint32_t finish()
+    {
+        const uint32_t total = nbyte * 8 + nacc;
+        if (nacc) buf[nbyte] = (uint8_t)acc;
+        return total;
+    }
+};
 
 __constant__ uint8_t c_huff_order_enc[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 __constant__ uint8_t c_lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -298,53 +375,60 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, int bl
         if (i < 32) W->d_len[i] = 0;
     }
     __syncwarp();
-    if (lane == 0) {
-        uint32_t bp = 0;
-        put_bits(W->hdr, bp, (chunk_flags & CHUNK_LAST) ? 1u : 0u, 1);  // BFINAL
-        put_bits(W->hdr, bp, (uint32_t)block_type, 2);                  // BTYPE
-        if (block_type == ZLB_FIXED) {
-            // FixedHuffmanTable (src/RawDeflate.ts:26-41) = canonical code of these lengths; 5-bit distances
-            for (int i = 0; i < 288; ++i) W->ll_len[i] = i <= 143 ? 8 : i <= 255 ? 9 : i <= 279 ? 7 : 8;
-            for (int i = 0; i < 30; ++i) W->d_len[i] = 5;
-        } else {
-            for (int i = 0; i < 286; ++i) W->freq[i] = hist_g[i];
-            get_lengths(W->freq, 286, 15, W->ll_len, W);  // :192
-            for (int i = 0; i < 30; ++i) W->freq[i] = hist_g[286 + i];
-            get_lengths(W->freq, 30, 7, W->d_len, W);     // :194
-            int hlit, hdist, hclen;
-            for (hlit = 286; hlit > 257 && W->ll_len[hlit - 1] == 0; hlit--) {
-            }
-            for (hdist = 30; hdist > 1 && W->d_len[hdist - 1] == 0; hdist--) {
-            }
-            uint8_t tf8[19];
-            const int nsyms = tree_symbols(hlit, W->ll_len, hdist, W->d_len, W->tree_sym, tf8);  // :203
-            for (int i = 0; i < 19; ++i) W->freq[i] = tf8[i];  // Uint8Array histogram (:346)
-            get_lengths(W->freq, 19, 7, W->t_len, W);          // :204
+    HdrBits hb = {W->hdr, 0ull, 0u, 0u};
+    hb.put((chunk_flags & CHUNK_LAST) ? 1u : 0u, 1);  // BFINAL
+    hb.put((uint32_t)block_type, 2);                  // BTYPE
+    if (block_type == ZLB_FIXED) {
+        // FixedHuffmanTable (src/RawDeflate.ts:26-41) = canonical code of these lengths; 5-bit distances
+        for (int i = (int)lane; i < 288; i += 32) W->ll_len[i] = i <= 143 ? 8 : i <= 255 ? 9 : i <= 279 ? 7 : 8;
+        if (lane < 30) W->d_len[lane] = 5;
+        __syncwarp();
+        if (lane == 0) W->hdr_bits = hb.finish();
+    } else {
+        get_lengths(hist_g, 286, 15, W->ll_len, W);        // :192
+        get_lengths(hist_g + 286, 30, 7, W->d_len, W);     // :194
+        int hlit, hdist, hclen;
+        for (hlit = 286; hlit > 257 && W->ll_len[hlit - 1] == 0; hlit--) {
+        }
+        for (hdist = 30; hdist > 1 && W->d_len[hdist - 1] == 0; hdist--) {
+        }
+        int nsyms = 0;
+        // the 19 code-length-symbol counts are staged in code_tmp (free until the codes are assigned);
+        // get_lengths copies its input before it touches anything else
+        uint32_t* tf = reinterpret_cast<uint32_t*>(W->code_tmp);
+        if (lane == 0) {
+            uint8_t tf8[19];  // Uint8Array histogram (:346)
+            nsyms = tree_symbols(hlit, W->ll_len, hdist, W->d_len, W->tree_sym, tf8);  // :203
+            for (int i = 0; i < 19; ++i) tf[i] = tf8[i];
+        }
+        nsyms = __shfl_sync(0xFFFFFFFFu, nsyms, 0);
+        __syncwarp();
+        get_lengths(tf, 19, 7, W->t_len, W);               // :204
+        codes_from_lengths(W->t_len, 19, W->code_tmp);
+        if (lane == 0) {
             uint8_t trans[19];
             for (int i = 0; i < 19; ++i) trans[i] = W->t_len[c_huff_order_enc[i]];
             for (hclen = 19; hclen > 4 && trans[hclen - 1] == 0; hclen--) {
             }
-            codes_from_lengths(W->t_len, 19, W->code_tmp);
-            put_bits(W->hdr, bp, (uint32_t)(hlit - 257), 5);  // :214-216
-            put_bits(W->hdr, bp, (uint32_t)(hdist - 1), 5);
-            put_bits(W->hdr, bp, (uint32_t)(hclen - 4), 4);
-            for (int i = 0; i < hclen; ++i) put_bits(W->hdr, bp, trans[i], 3);
+            hb.put((uint32_t)(hlit - 257), 5);  // :214-216
+            hb.put((uint32_t)(hdist - 1), 5);
+            hb.put((uint32_t)(hclen - 4), 4);
+            for (int i = 0; i < hclen; ++i) hb.put(trans[i], 3);
             for (int i = 0; i < nsyms; ++i) {  // :222-241
                 const uint32_t code = W->tree_sym[i];
-                put_bits(W->hdr, bp, W->code_tmp[code], W->t_len[code]);
+                hb.put(W->code_tmp[code], W->t_len[code]);
                 if (code >= 16) {
                     const uint32_t bl = code == 16 ? 2 : code == 17 ? 3 : 7;
                     i++;
-                    put_bits(W->hdr, bp, W->tree_sym[i], bl);
+                    hb.put(W->tree_sym[i], bl);
                 }
             }
+            W->hdr_bits = hb.finish();
         }
-        W->hdr_bits = bp;
     }
     __syncwarp();
     // code tables for the packer + exact body size
-    if (lane == 0) codes_from_lengths(W->ll_len, block_type == ZLB_FIXED ? 288 : 286, W->code_tmp);
-    __syncwarp();
+    codes_from_lengths(W->ll_len, block_type == ZLB_FIXED ? 288 : 286, W->code_tmp);
     unsigned long long bits = 0;
     for (int i = (int)lane; i < 286; i += 32) {
         const uint32_t l = W->ll_len[i];
@@ -355,8 +439,7 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, int bl
         bits += (unsigned long long)f * (l + ex);
     }
     __syncwarp();
-    if (lane == 0) codes_from_lengths(W->d_len, 30, W->code_tmp);
-    __syncwarp();
+    codes_from_lengths(W->d_len, 30, W->code_tmp);
     if (lane < 30) {
         const uint32_t l = W->d_len[lane];
         cc->d[lane] = (uint32_t)W->code_tmp[lane] | (l << 16);
@@ -366,10 +449,10 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, int bl
     for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
     for (int i = (int)lane; i < ZTS_HDR_BYTES; i += 32) cc->hdr[i] = W->hdr[i];
     if (lane == 0) {
-        const uint32_t hb = W->hdr_bits;
-        ci->hdr_bits = hb;
+        const uint32_t hbits = W->hdr_bits;
+        ci->hdr_bits = hbits;
         ci->body_bits = bits;
-        const unsigned long long total = hb + bits;
+        const unsigned long long total = hbits + bits;
         unsigned long long nbytes = (total + 7) >> 3;
         if (!(chunk_flags & CHUNK_LAST)) {
             // join: empty stored block that byte-aligns
@@ -384,42 +467,32 @@ __global__ void __launch_bounds__(32)
 huffman_build_kernel(const ZtsChunk* __restrict__ chunks, uint32_t n_chunks, const uint32_t* __restrict__ hist,
                      ZtsChunkInfo* __restrict__ info, ZtsChunkCodes* __restrict__ codes, int block_type)
 {
-    extern __shared__ __align__(16) unsigned char hsm[];
-    HufWork* W = reinterpret_cast<HufWork*>(hsm);
+    __shared__ HufWork W;
     const uint32_t c = blockIdx.x;
     if (c >= n_chunks) return;
-    build_chunk(hist + (size_t)c * 316, chunks[c].flags, block_type, info + c, codes + c, W);
+    build_chunk(hist + (size_t)c * 316, chunks[c].flags, block_type, info + c, codes + c, &W);
 }
 
 // test hook: code lengths of one histogram
 __global__ void __launch_bounds__(32)
 huffman_lengths_kernel(const uint32_t* __restrict__ freqs, int nsym, int limit, uint8_t* __restrict__ lengths)
 {
-    extern __shared__ __align__(16) unsigned char hsm[];
-    HufWork* W = reinterpret_cast<HufWork*>(hsm);
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < nsym; ++i) W->freq[i] = freqs[i];
-        get_lengths(W->freq, nsym, limit, W->ll_len, W);
-        for (int i = 0; i < nsym; ++i) lengths[i] = W->ll_len[i];
-    }
+    __shared__ HufWork W;
+    get_lengths(freqs, nsym, limit, W.ll_len, &W);
+    for (int i = (int)threadIdx.x; i < nsym; i += 32) lengths[i] = W.ll_len[i];
 }
 
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type)
 {
-    ZTS_CUDA(ctx, cudaFuncSetAttribute(huffman_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(HufWork)));
     ZTS_LAUNCH(ctx, ZK_HUFFMAN,
-               huffman_build_kernel<<<n_chunks, 32, sizeof(HufWork), ctx->stream>>>(d_chunks, n_chunks, d_hist, d_info,
-                                                                                    d_codes, block_type));
+               huffman_build_kernel<<<n_chunks, 32, 0, ctx->stream>>>(d_chunks, n_chunks, d_hist, d_info, d_codes,
+                                                                       block_type));
     return ZLB_OK;
 }
 
 int zts_huffman_lengths_debug(zlb_ctx* ctx, const uint32_t* d_freqs, int nsym, int limit, uint8_t* d_lengths)
 {
-    ZTS_CUDA(ctx, cudaFuncSetAttribute(huffman_lengths_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(HufWork)));
-    ZTS_LAUNCH(ctx, ZK_HUFFMAN,
-               huffman_lengths_kernel<<<1, 32, sizeof(HufWork), ctx->stream>>>(d_freqs, nsym, limit, d_lengths));
+    ZTS_LAUNCH(ctx, ZK_HUFFMAN, huffman_lengths_kernel<<<1, 32, 0, ctx->stream>>>(d_freqs, nsym, limit, d_lengths));
     return ZLB_OK;
 }
