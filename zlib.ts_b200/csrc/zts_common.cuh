@@ -52,6 +52,11 @@ struct zlb_ctx {
     // pinned host staging for the small tables
     void* h_pin = nullptr;
     size_t h_pin_cap = 0;
+    void* h_pin2 = nullptr;  // read-back area of the pipelined host paths
+    size_t h_pin2_cap = 0;
+    // copy / second compute streams of the pipelined host paths (created on first use)
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_aux[3] = {nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> sync_events;  // disable-timing events, reused across calls
 
     // profiling
     bool prof = false;
@@ -65,6 +70,9 @@ struct zlb_ctx {
 int zts_fail(zlb_ctx* ctx, int code, const char* fmt, ...);
 int zts_reserve(zlb_ctx* ctx, ZtsDevBuf* b, size_t bytes);
 int zts_reserve_pinned(zlb_ctx* ctx, size_t bytes);
+int zts_reserve_pinned2(zlb_ctx* ctx, size_t bytes);
+int zts_host_streams(zlb_ctx* ctx);                 // creates s_in / s_out / s_aux
+cudaEvent_t zts_sync_event(zlb_ctx* ctx, size_t k);  // k-th reusable ordering event (nullptr on failure)
 void zts_prof_begin(zlb_ctx* ctx, int slot);
 void zts_prof_end(zlb_ctx* ctx, int slot);
 

@@ -48,6 +48,39 @@ int zts_reserve_pinned(zlb_ctx* ctx, size_t bytes)
     return ZLB_OK;
 }
 
+int zts_reserve_pinned2(zlb_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->h_pin2_cap) return ZLB_OK;
+    size_t want = bytes + bytes / 4 + 4096;
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
+    ctx->h_pin2 = nullptr;
+    ctx->h_pin2_cap = 0;
+    cudaError_t e = cudaMallocHost(&ctx->h_pin2, want);
+    if (e != cudaSuccess) return zts_fail(ctx, ZLB_E_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    ctx->h_pin2_cap = want;
+    return ZLB_OK;
+}
+
+int zts_host_streams(zlb_ctx* ctx)
+{
+    if (ctx->s_in) return ZLB_OK;
+    ZTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+    ZTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 3; ++i) ZTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux[i], cudaStreamNonBlocking));
+    return ZLB_OK;
+}
+
+cudaEvent_t zts_sync_event(zlb_ctx* ctx, size_t k)
+{
+    while (ctx->sync_events.size() <= k) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ctx->sync_events.push_back(e);
+    }
+    return ctx->sync_events[k];
+}
+
 static cudaEvent_t prof_event(zlb_ctx* ctx)
 {
     if (!ctx->ev_pool.empty()) {
@@ -130,12 +163,22 @@ void zlb_destroy(zlb_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->s_in) cudaStreamSynchronize(ctx->s_in);
+    if (ctx->s_out) cudaStreamSynchronize(ctx->s_out);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->s_aux[i]) cudaStreamSynchronize(ctx->s_aux[i]);
     ZtsDevBuf* bufs[] = {&ctx->d_items, &ctx->d_results, &ctx->d_chunks, &ctx->d_chunk_info, &ctx->d_tokens,
                          &ctx->d_spec,  &ctx->d_hist,    &ctx->d_codes,  &ctx->d_sortT,      &ctx->d_sums,
                          &ctx->d_misc,  &ctx->d_stage_in, &ctx->d_stage_out};
     for (ZtsDevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+    if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
+    for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    for (int i = 0; i < 3; ++i)
+        if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
     for (const ZtsProfRec& r : ctx->pending) {
         cudaEventDestroy(r.a);
         cudaEventDestroy(r.b);

@@ -357,14 +357,20 @@ static int deflate_stored(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     return ZLB_OK;
 }
 
-struct DeflatePlan {
-    size_t n_chunks = 0;
+// Host buffers of the "_host" entry point. The device path below then also moves the data: the input of
+// wave k+1 travels while wave k is compressed, and what wave k produced travels while wave k+1 runs.
+struct HostIO {
+    const uint8_t* h_in;
+    uint8_t* h_out;
+    size_t in_bytes, out_bytes;
+    bool out_done;  // set when the output has already been copied wave by wave
 };
+#define HOST_DELTA_MAX_ITEMS 256u  // per-wave output read-back is done item by item up to this many items
 
 // Runs the pipeline on device buffers. Results land in h_results after the final synchronise.
 static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item* h_items,
                           zlb_result* h_results, size_t n, int mode, int block_type, uint32_t chunk_bytes,
-                          uint32_t flags)
+                          uint32_t flags, HostIO* hio)
 {
     if (mode != ZLB_MODE_COMPAT) return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
     if (block_type != ZLB_NONE && block_type != ZLB_FIXED && block_type != ZLB_DYNAMIC)
@@ -386,6 +392,8 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (flags & ZLB_DEFLATE_WANT_CRC32) kinds |= ZLB_SUM_CRC32;
     if (flags & ZLB_DEFLATE_WANT_ADLER32) kinds |= ZLB_SUM_ADLER32;
 
+    if (hio && block_type == ZLB_NONE)
+        ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     if (block_type == ZLB_NONE) {
         rc = deflate_stored(ctx, d_in, d_out, h_items, h_results, n, d_items);
         if (rc) return rc;
@@ -410,7 +418,15 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     size_t n_chunks = 0;
     for (size_t i = 0; i < n; ++i) n_chunks += h_items[i].in_len ? (h_items[i].in_len + cb - 1) / cb : 1;
     if (n_chunks > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many chunks");
-    const size_t wave = n_chunks < WAVE_CHUNKS ? n_chunks : WAVE_CHUNKS;
+    size_t wave = n_chunks < WAVE_CHUNKS ? n_chunks : WAVE_CHUNKS;
+    if (hio && n_chunks > 4u * (size_t)ctx->sm_count) {
+        // host path: about four waves so that the copies overlap the kernels, but never so small that the
+        // tail of the persistent LZ77 kernel (one chunk time per wave) starts to matter
+        size_t w4 = (n_chunks + 3) / 4;
+        const size_t lo = 4u * (size_t)ctx->sm_count;
+        if (w4 < lo) w4 = lo;
+        if (w4 < wave) wave = w4;
+    }
     rc = zts_reserve_pinned(ctx, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t));
     if (rc) return rc;
     ZtsChunk* h_chunks = (ZtsChunk*)ctx->h_pin;
@@ -468,9 +484,59 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     ZTS_CUDA(ctx, cudaFuncSetAttribute(bitpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(PACK_STAGE_WORDS * 4)));
 
-    for (size_t w0 = 0; w0 < n_chunks; w0 += wave) {
+    // ---- host path: copy plan
+    const size_t n_waves = (n_chunks + wave - 1) / wave;
+    bool pipe_in = false, delta_out = false;
+    unsigned long long* h_run = nullptr;      // [n_waves][n] running totals read back after each wave
+    std::vector<unsigned long long> copied;   // bytes of every item already copied to the host
+    if (hio) {
+        rc = zts_host_streams(ctx);
+        if (rc) return rc;
+        pipe_in = n_waves > 1;
+        for (size_t k = 1; k < n_chunks && pipe_in; ++k)
+            if (h_chunks[k].in_off < h_chunks[k - 1].in_off + h_chunks[k - 1].len) pipe_in = false;  // not laid out in order
+        delta_out = n <= HOST_DELTA_MAX_ITEMS;
+        if (delta_out) {
+            rc = zts_reserve_pinned2(ctx, n_waves * n * sizeof(unsigned long long));
+            if (rc) return rc;
+            h_run = (unsigned long long*)ctx->h_pin2;
+            copied.assign(n, 0ull);
+        }
+        if (!pipe_in)
+            ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    auto wave_in_copy = [&](size_t k) -> int {  // input bytes of wave k: one contiguous hull (chunks are in order)
+        const size_t a = k * wave, b = (a + wave < n_chunks ? a + wave : n_chunks) - 1;
+        const uint64_t lo = h_chunks[a].in_off, hi = h_chunks[b].in_off + h_chunks[b].len;
+        if (hi > lo)
+            ZTS_CUDA(ctx, cudaMemcpyAsync((void*)(d_in + lo), hio->h_in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_in));
+        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * k), ctx->s_in));
+        return ZLB_OK;
+    };
+    auto wave_out_copy = [&](size_t k) -> int {  // what wave k appended to the items it touched
+        ZTS_CUDA(ctx, cudaEventSynchronize(zts_sync_event(ctx, 2 * k + 1)));
+        const size_t a = k * wave, b = (a + wave < n_chunks ? a + wave : n_chunks) - 1;
+        for (uint32_t i = h_chunks[a].item; i <= h_chunks[b].item; ++i) {
+            unsigned long long now = h_run[k * n + i];
+            if (now > h_items[i].out_cap) now = copied[i];  // overflowed item: nothing more was written
+            if (now > copied[i]) {
+                const uint64_t off = h_items[i].out_off + copied[i];
+                ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out + off, d_out + off, now - copied[i], cudaMemcpyDeviceToHost,
+                                              ctx->s_out));
+                copied[i] = now;
+            }
+        }
+        return ZLB_OK;
+    };
+    if (pipe_in && (rc = wave_in_copy(0))) return rc;
+
+    for (size_t w0 = 0, k = 0; w0 < n_chunks; w0 += wave, ++k) {
         const uint32_t wn = (uint32_t)(n_chunks - w0 < wave ? n_chunks - w0 : wave);
         const uint32_t g = wn < grid ? wn : grid;
+        if (pipe_in) {
+            if (k + 1 < n_waves && (rc = wave_in_copy(k + 1))) return rc;
+            ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 * k), 0));
+        }
         rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist, (uint16_t*)ctx->d_sortT.p,
                              d_counter, g);
         if (rc) return rc;
@@ -481,6 +547,16 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         ZTS_LAUNCH(ctx, ZK_BITPACK,
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, ctx->stream>>>(
                        d_chunks + w0, d_info, d_codes, d_spec, d_fix, d_items, d_out));
+        if (delta_out) {
+            ZTS_CUDA(ctx, cudaMemcpyAsync(h_run + k * n, d_running, n * sizeof(unsigned long long),
+                                          cudaMemcpyDeviceToHost, ctx->stream));
+            ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * k + 1), ctx->stream));
+            if (k > 0 && (rc = wave_out_copy(k - 1))) return rc;  // wave k is queued: now wait for wave k-1
+        }
+    }
+    if (delta_out) {
+        if ((rc = wave_out_copy(n_waves - 1))) return rc;
+        hio->out_done = true;
     }
     ZTS_LAUNCH(ctx, ZK_FINALIZE,
                deflate_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_items, d_results,
@@ -492,6 +568,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     }
     ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (delta_out) ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return ZLB_OK;
 }
 
@@ -503,7 +580,7 @@ extern "C" int zlb_deflate_batch(zlb_ctx* ctx, const void* d_in, void* d_out, co
     if (n == 0) return ZLB_OK;
     ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
     return deflate_device(ctx, (const uint8_t*)d_in, (uint8_t*)d_out, items, results, n, mode, block_type,
-                          chunk_bytes, flags);
+                          chunk_bytes, flags, nullptr);
 }
 
 extern "C" int zlb_deflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_bytes, void* h_out, size_t out_bytes,
@@ -521,11 +598,12 @@ extern "C" int zlb_deflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_stage_out, out_bytes + 256);
     if (rc) return rc;
-    ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HostIO hio = {(const uint8_t*)h_in, (uint8_t*)h_out, in_bytes, out_bytes, false};
     rc = deflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, mode,
-                        block_type, chunk_bytes, flags);
+                        block_type, chunk_bytes, flags, &hio);
     if (rc) return rc;
-    // copy back only what was produced: the span up to the furthest written byte
+    if (hio.out_done) return ZLB_OK;
+    // many items: copy back the span up to the furthest written byte in one piece
     uint64_t hi = 0;
     for (size_t i = 0; i < n; ++i) {
         uint64_t e = items[i].out_off + (results[i].status == ZLB_ST_OK ? results[i].out_len : 0);

@@ -468,8 +468,29 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
     }
 }
 
+static int inflate_launch(zlb_ctx* ctx, cudaStream_t st, const uint8_t* d_in, uint8_t* d_out, const zlb_item* d_items,
+                          zlb_result* d_results, size_t n, uint32_t flags)
+{
+    const size_t smem = sizeof(InfWarpSmem) * INF_WARPS_PER_CTA;
+    ZTS_CUDA(ctx, cudaFuncSetAttribute(inflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    unsigned grid = (unsigned)((n + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA);
+    ZTS_LAUNCH(ctx, ZK_INFLATE,
+               inflate_warp_kernel<<<grid, INF_WARPS_PER_CTA * 32, smem, st>>>(d_in, d_out, d_items, d_results,
+                                                                              (uint32_t)n, flags));
+    return ZLB_OK;
+}
+
+// Host buffers of the "_host" entry point: items are cut into a few waves; the input of a wave travels while the
+// previous waves are decoded (one compute stream per wave: a wave is latency-bound, so the waves run side by side) and its output
+// travels back as soon as it is done.
+struct InfHostIO {
+    const uint8_t* h_in;
+    uint8_t* h_out;
+    size_t in_bytes, out_bytes;
+};
+
 static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item* h_items,
-                          zlb_result* h_results, size_t n, uint32_t flags)
+                          zlb_result* h_results, size_t n, uint32_t flags, const InfHostIO* hio)
 {
     int rc = zts_reserve(ctx, &ctx->d_items, n * sizeof(zlb_item) + 64);
     if (rc) return rc;
@@ -479,20 +500,66 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     zlb_result* d_results = (zlb_result*)ctx->d_results.p;
     ZTS_CUDA(ctx, cudaMemcpyAsync(d_items, h_items, n * sizeof(zlb_item), cudaMemcpyHostToDevice, ctx->stream));
     ZTS_CUDA(ctx, cudaMemsetAsync(d_results, 0, n * sizeof(zlb_result), ctx->stream));
-    const size_t smem = sizeof(InfWarpSmem) * INF_WARPS_PER_CTA;
-    ZTS_CUDA(ctx, cudaFuncSetAttribute(inflate_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    unsigned grid = (unsigned)((n + INF_WARPS_PER_CTA - 1) / INF_WARPS_PER_CTA);
-    ZTS_LAUNCH(ctx, ZK_INFLATE,
-               inflate_warp_kernel<<<grid, INF_WARPS_PER_CTA * 32, smem, ctx->stream>>>(d_in, d_out, d_items, d_results,
-                                                                                        (uint32_t)n, flags));
     uint32_t kinds = 0;
     if (flags & ZLB_INFLATE_WANT_CRC32) kinds |= ZLB_SUM_CRC32;
     if (flags & ZLB_INFLATE_WANT_ADLER32) kinds |= ZLB_SUM_ADLER32;
+
+    // waves only pay when the items are laid out in order on both sides (then a wave is one contiguous copy each way)
+    size_t n_waves = 1;
+    if (hio && n >= 1024) {
+        n_waves = 4;
+        for (size_t i = 1; i < n && n_waves > 1; ++i)
+            if (h_items[i].in_off < h_items[i - 1].in_off + h_items[i - 1].in_len ||
+                h_items[i].out_off < h_items[i - 1].out_off + h_items[i - 1].out_cap)
+                n_waves = 1;
+    }
+    if (!hio || n_waves == 1) {
+        if (hio)
+            ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        rc = inflate_launch(ctx, ctx->stream, d_in, d_out, d_items, d_results, n, flags);
+        if (rc) return rc;
+        if (kinds) {
+            rc = zts_checksum_device(ctx, d_out, d_items, d_results, h_items, n, kinds, 1);
+            if (rc) return rc;
+        }
+        if (hio)
+            ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out, d_out, hio->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+        return ZLB_OK;
+    }
+
+    rc = zts_host_streams(ctx);
+    if (rc) return rc;
+    // event 0: item table is on the device; 1+3k: input of wave k arrived; 2+3k: wave k decoded; 3+3k: spare
+    cudaEvent_t ev_tab = zts_sync_event(ctx, 0);
+    ZTS_CUDA(ctx, cudaEventRecord(ev_tab, ctx->stream));
+    for (int i = 0; i < 3; ++i) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux[i], ev_tab, 0));
+    const size_t per = (n + n_waves - 1) / n_waves;
+    for (size_t k = 0; k < n_waves; ++k) {
+        const size_t a = k * per, b = (a + per < n ? a + per : n);
+        if (a >= b) break;
+        const uint64_t ilo = h_items[a].in_off, ihi = h_items[b - 1].in_off + h_items[b - 1].in_len;
+        const uint64_t olo = h_items[a].out_off, ohi = h_items[b - 1].out_off + h_items[b - 1].out_cap;
+        cudaEvent_t ev_in = zts_sync_event(ctx, 1 + 3 * k), ev_done = zts_sync_event(ctx, 2 + 3 * k);
+        if (ihi > ilo)
+            ZTS_CUDA(ctx, cudaMemcpyAsync((void*)(d_in + ilo), hio->h_in + ilo, ihi - ilo, cudaMemcpyHostToDevice, ctx->s_in));
+        ZTS_CUDA(ctx, cudaEventRecord(ev_in, ctx->s_in));
+        cudaStream_t st = k ? ctx->s_aux[(k - 1) % 3] : ctx->stream;  // all waves may be in flight together
+        ZTS_CUDA(ctx, cudaStreamWaitEvent(st, ev_in, 0));
+        rc = inflate_launch(ctx, st, d_in, d_out, d_items + a, d_results + a, b - a, flags);
+        if (rc) return rc;
+        ZTS_CUDA(ctx, cudaEventRecord(ev_done, st));
+        ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ev_done, 0));
+        if (ohi > olo)
+            ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out + olo, d_out + olo, ohi - olo, cudaMemcpyDeviceToHost, ctx->s_out));
+        if (st != ctx->stream) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_done, 0));  // results / checksums follow on ctx->stream
+    }
     if (kinds) {
         rc = zts_checksum_device(ctx, d_out, d_items, d_results, h_items, n, kinds, 1);
         if (rc) return rc;
     }
     ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return ZLB_OK;
 }
 
@@ -503,7 +570,7 @@ extern "C" int zlb_inflate_batch(zlb_ctx* ctx, const void* d_in, void* d_out, co
     if (n == 0) return ZLB_OK;
     if (n > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many items");
     ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
-    int rc = inflate_device(ctx, (const uint8_t*)d_in, (uint8_t*)d_out, items, results, n, flags);
+    int rc = inflate_device(ctx, (const uint8_t*)d_in, (uint8_t*)d_out, items, results, n, flags, nullptr);
     if (rc) return rc;
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ZLB_OK;
@@ -514,6 +581,7 @@ extern "C" int zlb_inflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_
 {
     if (!ctx || (!items && n) || (!results && n) || (!h_in && in_bytes) || (!h_out && out_bytes)) return ZLB_E_ARG;
     if (n == 0) return ZLB_OK;
+    if (n > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many items");
     ZTS_CUDA(ctx, cudaSetDevice(ctx->device));
     for (size_t i = 0; i < n; ++i) {
         if (items[i].in_off + items[i].in_len > in_bytes || items[i].out_off + items[i].out_cap > out_bytes)
@@ -523,10 +591,10 @@ extern "C" int zlb_inflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_stage_out, out_bytes + 256);
     if (rc) return rc;
-    ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_stage_in.p, h_in, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    rc = inflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, flags);
+    InfHostIO hio = {(const uint8_t*)h_in, (uint8_t*)h_out, in_bytes, out_bytes};
+    rc = inflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, flags,
+                        &hio);
     if (rc) return rc;
-    ZTS_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_stage_out.p, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return ZLB_OK;
 }
