@@ -7,9 +7,14 @@
 // lanes differ only where they cooperate:
 //   * input: the warp keeps a 128-byte window of the stream in registers (one coalesced 4-byte
 //     load per lane), words are handed to the bit reader with a shuffle;
-//   * LZ77 copies: lane k copies byte k, k+32, ... of the match; overlapping matches (dist < len,
-//     src/RawInflate.ts:506-508) read the periodic source out[op - dist + k mod dist], which lies
-//     entirely before the match, so no intra-copy ordering is needed;
+//   * decode and copy are split: up to 32 symbols are decoded back to back into one token per lane
+//     without touching the output (the serial part is then only bit-buffer arithmetic and shared-
+//     memory look-ups), then the batch is written: all literals with one store, all short matches
+//     side by side (one per lane), long matches cooperatively (lane k copies byte k, k+32, ...).
+//     A match that reads bytes produced inside the same batch cuts the batch into sub-batches that
+//     run one after the other, so memory latency is paid per sub-batch, not per symbol;
+//   * overlapping matches (dist < len, src/RawInflate.ts:506-508) read the periodic source
+//     out[op - dist + k mod dist], which lies entirely before the match;
 //   * table construction: canonical code assignment with ballots, no atomics.
 // Tables per warp in shared memory: a 10-bit root for literal/length codes and an 8-bit root for
 // distance codes (entry = base << 16 | kind << 8 | extra_bits << 4 | code_bits); codes longer than
@@ -167,6 +172,7 @@ struct BitReader {
     const uint32_t* win_base;  // aligned address of the current 128-byte window
     const uint8_t* end;        // one past the last readable input byte
     uint32_t win;              // this lane's word of the window
+    uint32_t win_next;         // this lane's word of the following window (prefetched)
     uint32_t win_pos;          // next word of the window to consume (0..32)
     unsigned long long buf;
     int cnt;                   // valid bits in buf
@@ -175,12 +181,28 @@ struct BitReader {
     uint32_t skip_bits;        // bits of the first word that precede the (re)start point
 };
 
-__device__ __forceinline__ void br_load_window(BitReader& br)
+__device__ __forceinline__ uint32_t br_fetch(const BitReader& br, const uint32_t* base)
 {
-    const uint32_t* p = br.win_base + zts_lane();
+    const uint32_t* p = base + zts_lane();
     // a word is readable if it overlaps [.., end); bytes past `end` inside that word are never
     // consumed as data because every consumer checks the consumed-bit count against the item length
-    br.win = ((const uint8_t*)p < br.end) ? __ldg(p) : 0u;
+    return ((const uint8_t*)p < br.end) ? __ldg(p) : 0u;
+}
+
+__device__ __forceinline__ void br_load_window(BitReader& br)
+{
+    br.win = br_fetch(br, br.win_base);
+    br.win_next = br_fetch(br, br.win_base + 32);
+    br.win_pos = 0;
+}
+
+// next window: the prefetched words become current, the one after is requested now and is not
+// needed before another 128 bytes have been consumed
+__device__ __forceinline__ void br_advance_window(BitReader& br)
+{
+    br.win_base += 32;
+    br.win = br.win_next;
+    br.win_next = br_fetch(br, br.win_base + 32);
     br.win_pos = 0;
 }
 
@@ -207,10 +229,7 @@ __device__ __forceinline__ void br_init(BitReader& br, const uint8_t* src, const
 __device__ __forceinline__ void br_refill(BitReader& br)
 {
     if (br.cnt <= 32) {
-        if (br.win_pos == 32) {
-            br.win_base += 32;
-            br_load_window(br);
-        }
+        if (br.win_pos == 32) br_advance_window(br);
         uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, br.win_pos);
         br.win_pos++;
         br.words_taken++;
@@ -381,79 +400,182 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             }
         }
 
-        // ---- symbol loop (src/RawInflate.ts:466-516)
-        for (;;) {
-            br_refill(br);
-            uint32_t e = S->lit_root[(uint32_t)br.buf & ((1u << LIT_ROOT_BITS) - 1u)];
-            if ((e & 15u) == 0) {
-                e = slow_decode(TAB_LITLEN, (uint32_t)br.buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit);
-                if (e == 0) {
-                    status = ZLB_ST_BAD_CODE;
-                    break;
-                }
+        // ---- symbol loop (src/RawInflate.ts:466-516), 32 symbols per batch
+        bool eob = false;
+        while (!eob && status == ZLB_ST_OK) {
+            // -- decode: token of symbol i ends up in lane i: literal = byte << 16, match = len << 16 | dist.
+            //    The tables are addressed through 32-bit shared-window addresses held in registers (a generic
+            //    pointer to the per-warp slice gets rematerialised from %tid on every look-up otherwise).
+            uint32_t mytok = 0, ntok = 0;
+            uint32_t stop = 0;  // 1 = end of block, 2 = undefined code / symbol
+            {
+                const uint32_t lit_s = (uint32_t)__cvta_generic_to_shared(S->lit_root);
+                const uint32_t dist_s = (uint32_t)__cvta_generic_to_shared(S->dist_root);
+                unsigned long long buf = br.buf;
+                int cnt = br.cnt;
+                uint32_t wpos = br.win_pos, wtaken = 0;
+                do {
+                    if (cnt <= 32) {
+                        if (wpos == 32) {
+                            br_advance_window(br);
+                            wpos = 0;
+                        }
+                        const uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, (int)wpos);
+                        wpos++;
+                        wtaken++;
+                        buf |= (unsigned long long)w << cnt;
+                        cnt += 32;
+                    }
+                    uint32_t e;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_s + (((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)) << 2)) : "memory");
+                    if ((e & 15u) == 0) {
+                        e = slow_decode(TAB_LITLEN, (uint32_t)buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit);
+                        if (e == 0) {
+                            stop = 2;
+                            break;
+                        }
+                    }
+                    buf >>= (e & 15u);
+                    cnt -= (int)(e & 15u);
+                    uint32_t tokv = e & 0x00FF0000u;  // literal
+                    if (e & 0x300u) {
+                        if (!(e & 0x100u)) {  // KIND_EOB (2); KIND_INVALID is 3
+                            stop = 1;
+                            break;
+                        }
+                        if (e & 0x200u) {
+                            stop = 2;
+                            break;
+                        }
+                        const uint32_t xb = (e >> 4) & 15u;
+                        const uint32_t len = (e >> 16) + ((uint32_t)buf & ((1u << xb) - 1u));
+                        buf >>= xb;
+                        cnt -= (int)xb;
+                        if (cnt <= 32) {
+                            if (wpos == 32) {
+                                br_advance_window(br);
+                                wpos = 0;
+                            }
+                            const uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, (int)wpos);
+                            wpos++;
+                            wtaken++;
+                            buf |= (unsigned long long)w << cnt;
+                            cnt += 32;
+                        }
+                        uint32_t d;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(dist_s + (((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)) << 2)) : "memory");
+                        if ((d & 15u) == 0) {
+                            d = slow_decode(TAB_DIST, (uint32_t)buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist);
+                            if (d == 0) {
+                                stop = 2;
+                                break;
+                            }
+                        }
+                        buf >>= (d & 15u);
+                        cnt -= (int)(d & 15u);
+                        if ((d & 0x300u) != (KIND_BASE << 8)) {
+                            stop = 2;
+                            break;
+                        }
+                        const uint32_t db = (d >> 4) & 15u;
+                        const uint32_t dist = (d >> 16) + ((uint32_t)buf & ((1u << db) - 1u));
+                        buf >>= db;
+                        cnt -= (int)db;
+                        tokv = (len << 16) | dist;
+                    }
+                    mytok = lane == ntok ? tokv : mytok;
+                    ntok++;
+                } while (ntok < 32);
+                br.buf = buf;
+                br.cnt = cnt;
+                br.win_pos = wpos;
+                br.words_taken += wtaken;
             }
-            br_take(br, (int)(e & 15u));
-            const uint32_t kind = (e >> 8) & 3u;
-            if (kind == KIND_LITERAL) {
-                if (op >= cap) {
-                    status = ZLB_ST_OUT_OVERFLOW;
-                    break;
-                }
-                if (lane == 0) dst[op] = (uint8_t)(e >> 16);
-                op++;
-                continue;
-            }
-            if (kind == KIND_EOB) break;
-            if (kind == KIND_INVALID) {
-                status = ZLB_ST_BAD_CODE;
-                break;
-            }
-            uint32_t len = (e >> 16) + br_take(br, (int)((e >> 4) & 15u));
-            br_refill(br);
-            uint32_t d = S->dist_root[(uint32_t)br.buf & ((1u << DIST_ROOT_BITS) - 1u)];
-            if ((d & 15u) == 0) {
-                d = slow_decode(TAB_DIST, (uint32_t)br.buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist);
-                if (d == 0) {
-                    status = ZLB_ST_BAD_CODE;
-                    break;
-                }
-            }
-            br_take(br, (int)(d & 15u));
-            if (((d >> 8) & 3u) != KIND_BASE) {
-                status = ZLB_ST_BAD_CODE;
-                break;
-            }
-            uint32_t dist = (d >> 16) + br_take(br, (int)((d >> 4) & 15u));
+            if (stop == 1) eob = true;
+            if (stop == 2) status = ZLB_ST_BAD_CODE;
             if (br_bits_used(br) > in_bits) {
+                // the batch ran past the end of the input: nothing of it is trusted
                 status = ZLB_ST_INPUT_BROKEN;
                 break;
             }
-            if ((unsigned long long)dist > op) {
-                status = ZLB_ST_BAD_CODE;  // the reference would copy `undefined` -> 0 here
-                break;
+            // -- output positions: exclusive prefix sum of the token lengths
+            const bool mine = lane < ntok;
+            const uint32_t dist = mytok & 0xFFFFu;
+            const bool is_match = mine && dist != 0;
+            const uint32_t len = !mine ? 0u : (dist ? (mytok >> 16) : 1u);
+            uint32_t inc = len;
+#pragma unroll
+            for (int sft = 1; sft < 32; sft <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, sft);
+                if (lane >= (unsigned)sft) inc += t;
             }
-            if (op + len > cap) {
-                status = ZLB_ST_OUT_OVERFLOW;
-                break;
+            const unsigned long long pos = op + (inc - len);  // where this token's bytes start
+            // a distance beyond the start of the output (the reference would copy `undefined` -> 0) or an
+            // output slot that is too small ends the batch before the offending token
+            const bool bad_dist = is_match && (unsigned long long)dist > pos;
+            const bool over = mine && pos + len > cap;
+            const unsigned bad_mask = __ballot_sync(0xFFFFFFFFu, bad_dist || over);
+            uint32_t nvalid = ntok;
+            if (bad_mask) {
+                nvalid = (uint32_t)__ffs((int)bad_mask) - 1u;
+                const bool first_is_dist = __shfl_sync(0xFFFFFFFFu, (int)bad_dist, (int)nvalid) != 0;
+                status = first_is_dist ? ZLB_ST_BAD_CODE : ZLB_ST_OUT_OVERFLOW;
             }
-            __syncwarp();  // earlier literal / match stores of other lanes become visible
-            {
-                uint8_t* o = dst + op;
-                const uint8_t* s0 = o - dist;
-                if (dist >= len) {
-                    for (uint32_t k = lane; k < len; k += 32) o[k] = s0[k];
-                } else {
-                    // periodic source: byte k comes from s0[k mod dist]
-                    uint32_t r = lane % dist;
-                    const uint32_t step = 32u % dist;
-                    for (uint32_t k = lane; k < len; k += 32) {
-                        o[k] = s0[r];
-                        r += step;
-                        if (r >= dist) r -= dist;
+            const bool live = lane < nvalid;
+            // -- literals: one store
+            if (live && !is_match) dst[pos] = (uint8_t)(mytok >> 16);
+            // -- matches, sub-batch by sub-batch
+            uint32_t start = 0;
+            unsigned match_mask = __ballot_sync(0xFFFFFFFFu, live && is_match);
+            while (match_mask) {
+                const unsigned long long sub_start = __shfl_sync(0xFFFFFFFFu, pos, (int)start);
+                // reads bytes written by this very sub-batch? (source end beyond its first byte)
+                const bool dep = live && is_match && lane >= start &&
+                                 pos - dist + (len < dist ? len : dist) > sub_start;
+                const unsigned dep_mask = __ballot_sync(0xFFFFFFFFu, dep);
+                const uint32_t cut = dep_mask ? (uint32_t)__ffs((int)dep_mask) - 1u : 32u;  // > start always
+                const bool in_sub = live && is_match && lane >= start && lane < cut;
+                const bool small = in_sub && len <= 8u && dist >= len;
+                if (__any_sync(0xFFFFFFFFu, small)) {
+                    // short non-overlapping matches: every lane copies its own, loads first, then stores
+                    uint8_t v[8];
+                    const uint8_t* sp = dst + (pos - dist);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = (small && (uint32_t)k < len) ? sp[k] : (uint8_t)0;
+                    uint8_t* dp = dst + pos;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (small && (uint32_t)k < len) dp[k] = v[k];
+                }
+                unsigned big_mask = __ballot_sync(0xFFFFFFFFu, in_sub && !small);
+                while (big_mask) {
+                    const int j = __ffs((int)big_mask) - 1;
+                    big_mask &= big_mask - 1;
+                    const uint32_t jl = __shfl_sync(0xFFFFFFFFu, len, j);
+                    const uint32_t jd = __shfl_sync(0xFFFFFFFFu, dist, j);
+                    const unsigned long long jp = __shfl_sync(0xFFFFFFFFu, pos, j);
+                    uint8_t* o = dst + jp;
+                    const uint8_t* s0 = o - jd;
+                    if (jd >= jl) {
+                        for (uint32_t k = lane; k < jl; k += 32) o[k] = s0[k];
+                    } else {
+                        // periodic source: byte k comes from s0[k mod dist]
+                        uint32_t r = lane % jd;
+                        const uint32_t step = 32u % jd;
+                        for (uint32_t k = lane; k < jl; k += 32) {
+                            o[k] = s0[r];
+                            r += step;
+                            if (r >= jd) r -= jd;
+                        }
                     }
                 }
+                __syncwarp();  // the next sub-batch reads what this one wrote
+                start = cut;
+                match_mask = cut < 32u ? (match_mask >> cut) << cut : 0u;
             }
-            op += len;
+            // bytes of the tokens that were written (all of them unless the batch was cut short)
+            op += nvalid ? __shfl_sync(0xFFFFFFFFu, inc, (int)nvalid - 1) : 0u;
+            __syncwarp();
         }
         if (status == ZLB_ST_OK && br_bits_used(br) > in_bits) status = ZLB_ST_INPUT_BROKEN;
     }
