@@ -8,3 +8,8 @@ from ._native import (  # noqa: F401
     ST_OK, ST_INPUT_BROKEN, ST_BTYPE, ST_CODE_LENGTH, ST_OUT_OVERFLOW, ST_STORED_LEN, ST_BAD_CODE, ST_BAD_LENGTHS,
 )
 from . import synth  # noqa: F401
+from . import api  # noqa: F401,E402
+from .api import (  # noqa: F401,E402
+    Zlib, Deflate, Inflate, GZip, GUnzip, Zip, Unzip, RawDeflate, RawInflate, CRC32, Adler32, ZlibError,
+    CompressionType, BufferType, ZipCompressionMethod, deflate_many, inflate_many, inflate_blob, checksum_many,
+)

@@ -1,0 +1,624 @@
+"""Host-side mirror of the zlib.ts public surface over the C-ABI engine.
+
+The reference is TypeScript (`window.Zlib = {GZip, GUnzip, Zip, Unzip, Deflate, Inflate}`, src/index.ts:8-12) and
+no Node toolchain exists in this image, so the glue that stays on the host -- container headers and trailers,
+option handling, error texts -- is restated here in Python with the reference's class names, option names and
+thrown messages, and every call that the reference makes into RawDeflate / RawInflate / CRC32 / Adler32 goes to
+the GPU through zlibts_b200._native.Engine (no CPU fallback). napi/ holds the same glue as the N-API addon +
+TypeScript shim a maintainer would ship.
+
+Deviations from the reference, all deliberate:
+  * inputs larger than one chunk (64 KiB) are emitted as several blocks joined by sync-flush markers instead of
+    one block; the result is a valid stream that the reference's own Inflate / GUnzip / Unzip decodes.
+  * Deflate.compress does not raise the reference's RangeError for outputs > 32 KiB (B-1): it returns header +
+    body + Adler-32 as evidently intended.
+  * `lazy` > 0 is refused: the reference corrupts data with it (B-2).
+  * corrupt streams that make the reference loop or emit zeros (B-8) raise ZlibError instead.
+  * ZipCrypto (password) is out of scope (serial byte cipher, broken upstream).
+"""
+import datetime
+import struct
+
+import numpy as np
+
+from . import _native as N
+
+
+class ZlibError(Exception):
+    """`throw new Error(msg)` of the reference; str(e) is the reference's message text."""
+
+
+class CompressionType:  # src/RawDeflate.ts:12-17
+    NONE, FIXED, DYNAMIC, RESERVED = 0, 1, 2, 3
+
+
+class BufferType:  # src/RawInflate.ts:5-8 (accepted, irrelevant on the GPU: output slots are sized up front)
+    BLOCK, ADAPTIVE = 0, 1
+
+
+class ZipCompressionMethod:  # src/Zip.ts:7-10
+    STORE, DEFLATE = 0, 8
+
+
+_STATUS_TEXT = {  # zlb_result.status -> reference message (include/zlibts_b200.h)
+    N.ST_INPUT_BROKEN: "input buffer is broken",
+    N.ST_BTYPE: "unknown BTYPE: 3",
+    N.ST_CODE_LENGTH: "invalid code length",
+    N.ST_STORED_LEN: "invalid uncompressed block header: LEN",
+    N.ST_BAD_CODE: "invalid deflate stream: undefined code or distance",
+    N.ST_BAD_LENGTHS: "invalid deflate stream: over-subscribed code lengths",
+}
+
+_engine = None
+
+
+def set_engine(engine):
+    """Use this Engine for every call made through this module (default: one engine on device 0)."""
+    global _engine
+    _engine = engine
+
+
+def engine():
+    global _engine
+    if _engine is None:
+        _engine = N.default_engine(0)
+    return _engine
+
+
+def _u8(data):
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+    if isinstance(data, (bytes, bytearray, memoryview)):
+        return np.frombuffer(data, dtype=np.uint8)
+    return np.asarray(list(data), dtype=np.uint8)  # number[]
+
+
+def _opt(opts, key, default):
+    v = (opts or {}).get(key)
+    return default if v is None else v  # the reference's `??`
+
+
+def _b200(opts):
+    return (opts or {}).get("b200") or {}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# batch entry points (what the N-API addon exposes below the classes)
+# ------------------------------------------------------------------------------------------------------------
+def deflate_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0, want_crc32=False,
+                 want_adler32=False, prefixes=None):
+    """Raw-deflates every input in one GPU batch. Returns (list of uint8 arrays, results table). With `prefixes`
+    each output starts with its prefix bytes (RawDeflate's outputBuffer / outputIndex contract)."""
+    arrs = [_u8(x) for x in inputs]
+    n = len(arrs)
+    if n == 0:
+        return [], np.zeros(0, dtype=N.RESULT_DTYPE)
+    if compression_type not in (0, 1, 2):
+        raise ZlibError("invalid compression type")  # src/RawDeflate.ts:110 (a thrown string there)
+    lens = np.array([a.size for a in arrs], dtype=np.uint64)
+    in_off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    blob = np.concatenate(arrs) if int(lens.sum()) else np.zeros(1, dtype=np.uint8)
+    caps = np.array([N.deflate_bound(int(l), chunk_bytes, compression_type) for l in lens], dtype=np.uint64)
+    out_off = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.uint64)
+    out = np.zeros(int(caps.sum()), dtype=np.uint8)
+    items = N.make_items(n)
+    items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = in_off, lens, out_off, caps
+    flags = (N.DEFLATE_WANT_CRC32 if want_crc32 else 0) | (N.DEFLATE_WANT_ADLER32 if want_adler32 else 0)
+    res = engine().deflate_batch_host(blob, out, items, compression_type, chunk_bytes, flags)
+    outs = []
+    for i in range(n):
+        if int(res["status"][i]) != N.ST_OK:
+            raise ZlibError("deflate failed with status %d" % int(res["status"][i]))
+        body = out[int(out_off[i]):int(out_off[i]) + int(res["out_len"][i])]
+        if prefixes is not None and len(prefixes[i]):
+            body = np.concatenate([_u8(prefixes[i]), body])
+        outs.append(body)
+    return outs, res
+
+
+def inflate_blob(blob, offs, lens, size_hints=None, want_crc32=False, want_adler32=False):
+    """Raw-inflates the streams blob[offs[i] : offs[i] + lens[i]] in one GPU batch; output slots that turn out
+    too small are retried larger (the reference grows its buffer instead, src/RawInflate.ts:550-581).
+    Returns (list of uint8 arrays, results table); raises ZlibError with the reference's text on corrupt input."""
+    blob = _u8(blob)
+    n = len(offs)
+    if n == 0:
+        return [], np.zeros(0, dtype=N.RESULT_DTYPE)
+    offs = np.asarray(offs, dtype=np.uint64)
+    lens = np.asarray(lens, dtype=np.uint64)
+    caps = np.zeros(n, dtype=np.uint64)
+    for i in range(n):
+        hint = None if size_hints is None else size_hints[i]
+        caps[i] = int(hint) if hint is not None else max(0x8000, 4 * int(lens[i]))  # DefaultInflateBufferSize
+    flags = (N.INFLATE_WANT_CRC32 if want_crc32 else 0) | (N.INFLATE_WANT_ADLER32 if want_adler32 else 0)
+    if blob.size == 0:
+        blob = np.zeros(1, dtype=np.uint8)
+    outs = [None] * n
+    final = np.zeros(n, dtype=N.RESULT_DTYPE)
+    todo = np.arange(n)
+    for _ in range(12):
+        m = len(todo)
+        out_off = np.concatenate([[0], np.cumsum(caps[todo])[:-1]]).astype(np.uint64)
+        out = np.zeros(max(1, int(caps[todo].sum())), dtype=np.uint8)
+        items = N.make_items(m)
+        items["in_off"], items["in_len"] = offs[todo], lens[todo]
+        items["out_off"], items["out_cap"] = out_off, caps[todo]
+        res = engine().inflate_batch_host(blob, out, items, flags)
+        again = []
+        for k, i in enumerate(todo):
+            st = int(res["status"][k])
+            if st == N.ST_OUT_OVERFLOW:
+                caps[i] = max(int(caps[i]) * 4, 1 << 16)
+                again.append(i)
+                continue
+            if st != N.ST_OK:
+                raise ZlibError(_STATUS_TEXT.get(st, "inflate failed with status %d" % st))
+            outs[i] = out[int(out_off[k]):int(out_off[k]) + int(res["out_len"][k])]
+            final[i] = res[k]
+        if not again:
+            return outs, final
+        todo = np.array(again)
+    raise ZlibError("inflate output does not fit")
+
+
+def inflate_many(buffers, indices=None, size_hints=None, want_crc32=False, want_adler32=False):
+    """One stream per buffer, starting at indices[i] (RawInflate's `index` option)."""
+    arrs = [_u8(x) for x in buffers]
+    n = len(arrs)
+    if n == 0:
+        return [], np.zeros(0, dtype=N.RESULT_DTYPE)
+    idx = np.zeros(n, dtype=np.uint64) if indices is None else np.asarray(indices, dtype=np.uint64)
+    lens = np.array([a.size for a in arrs], dtype=np.uint64)
+    base = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    blob = np.concatenate(arrs) if int(lens.sum()) else np.zeros(1, dtype=np.uint8)
+    idx = np.minimum(idx, lens)
+    return inflate_blob(blob, base + idx, lens - idx, size_hints, want_crc32, want_adler32)
+
+
+def checksum_many(buffers, crc32=True, adler32=True):
+    arrs = [_u8(x) for x in buffers]
+    n = len(arrs)
+    if n == 0:
+        return np.zeros(0, dtype=N.RESULT_DTYPE)
+    lens = np.array([a.size for a in arrs], dtype=np.uint64)
+    off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    blob = np.concatenate(arrs) if int(lens.sum()) else np.zeros(1, dtype=np.uint8)
+    items = N.make_items(n)
+    items["in_off"], items["in_len"] = off, lens
+    return engine().checksum_batch_host(blob, items, (N.SUM_CRC32 if crc32 else 0) | (N.SUM_ADLER32 if adler32 else 0))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CRC32 / Adler32 (src/CRC32.ts, src/Adler32.ts)
+# ------------------------------------------------------------------------------------------------------------
+class CRC32:
+    @staticmethod
+    def create(data, pos=None, length=None):  # src/CRC32.ts:13
+        return CRC32.update(data, 0, pos, length)
+
+    @staticmethod
+    def update(data, crc, pos=None, length=None):  # src/CRC32.ts:25: CRC of data[pos, pos+length) continued from crc
+        a = _u8(data)
+        pos = 0 if pos is None else pos
+        length = a.size if length is None else length  # `length ?? data.length`, exactly as the reference
+        piece = a[pos:pos + length]
+        c = int(checksum_many([piece], True, False)["crc32"][0])
+        return N.crc32_combine(crc & 0xFFFFFFFF, c, piece.size) if crc else c
+
+
+class Adler32:
+    @staticmethod
+    def create(array):  # src/Adler32.ts:13
+        if isinstance(array, str):
+            array = bytes(ord(c) & 0xFF for c in array)  # stringToByteArray, src/Util.ts:5
+        return Adler32.update(1, array)
+
+    @staticmethod
+    def update(adler, array, length=None, pos=0):  # src/Adler32.ts:28
+        a = _u8(array)
+        length = a.size if length is None else length
+        piece = a[pos:pos + length]
+        c = int(checksum_many([piece], False, True)["adler32"][0])
+        return c if adler == 1 else N.adler32_combine(adler & 0xFFFFFFFF, c, piece.size)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# RawDeflate / RawInflate (src/RawDeflate.ts:50-114, src/RawInflate.ts:70-140)
+# ------------------------------------------------------------------------------------------------------------
+class RawDeflate:
+    def __init__(self, input, opts=None):
+        self.input = _u8(input)
+        self.lazy = _opt(opts, "lazy", 0)
+        self.compressionType = _opt(opts, "compressionType", CompressionType.DYNAMIC)
+        ob = (opts or {}).get("outputBuffer")
+        self.output = _u8(ob) if ob is not None else np.zeros(0, dtype=np.uint8)
+        self.op = _opt(opts, "outputIndex", 0)
+        self.chunkBytes = _b200(opts).get("chunkBytes", 0)
+        if self.lazy:
+            raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
+
+    def compress(self):
+        prefix = self.output[:self.op]
+        if prefix.size < self.op:  # outputIndex beyond the given buffer: the reference doubles it, zero filled
+            prefix = np.concatenate([prefix, np.zeros(self.op - prefix.size, dtype=np.uint8)])
+        outs, _ = deflate_many([self.input], self.compressionType, self.chunkBytes, prefixes=[prefix])
+        self.output = outs[0]
+        self.op = int(self.output.size)
+        return self.output
+
+
+class RawInflate:
+    def __init__(self, input, opts=None):
+        self.input = _u8(input)
+        self.ip = _opt(opts, "index", 0)
+        self.bufferSize = (opts or {}).get("bufferSize")
+        self.bufferType = _opt(opts, "bufferType", BufferType.ADAPTIVE)
+        self.resize = _opt(opts, "resize", False)
+        self.buffer = None
+        self.op = 0
+
+    def decompress(self):
+        outs, res = inflate_many([self.input], [self.ip], [self.bufferSize])
+        self.ip += int(res["in_used"][0])  # first byte after the deflate data (src/RawInflate.ts:511-514)
+        self.buffer = outs[0]
+        self.op = int(outs[0].size)
+        return self.buffer
+
+
+# ------------------------------------------------------------------------------------------------------------
+# zlib container (src/Deflate.ts, src/Inflate.ts)
+# ------------------------------------------------------------------------------------------------------------
+def _zlib_header(compression_type):  # src/Deflate.ts:67-78
+    cmf = 120
+    flg = (compression_type << 6) | (0 << 5)
+    flg |= 31 - ((cmf << 8) + flg) % 31
+    return bytes([cmf, flg & 0xFF])
+
+
+class Deflate:
+    def __init__(self, input, opts=None):
+        self.input = _u8(input)
+        self.compressionType = _opt(opts, "compressionType", CompressionType.DYNAMIC)
+        self.opts = dict(opts or {})
+        self.adler32 = None
+        self.output = None
+        if _opt(opts, "lazy", 0):
+            raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
+
+    @staticmethod
+    def compress_static(input, opts=None):  # `Deflate.compress(input, opts)`, src/Deflate.ts:52
+        return Deflate(input, opts).compress()
+
+    def compress(self):
+        hdr = _zlib_header(self.compressionType)
+        outs, res = deflate_many([self.input], self.compressionType, _b200(self.opts).get("chunkBytes", 0),
+                                 want_adler32=True, prefixes=[hdr])
+        self.adler32 = int(res["adler32"][0])
+        self.output = np.concatenate([outs[0], _u8(struct.pack(">I", self.adler32))])  # writeUintBE, :95
+        return self.output
+
+
+class Inflate:
+    def __init__(self, input, opts=None):
+        self.input = _u8(input)
+        self.ip = _opt(opts, "index", 0)
+        self.verify = _opt(opts, "verify", False)
+        self.adler32 = None
+        cmf, flg = int(self.input[self.ip]), int(self.input[self.ip + 1])
+        self.ip += 2
+        if (cmf & 0x0F) != 8:
+            raise ZlibError("unsupported compression method")  # src/Inflate.ts:47
+        if ((cmf << 8) + flg) % 31 != 0:
+            raise ZlibError("invalid fcheck flag:%d" % (((cmf << 8) + flg) % 31))  # :52
+        if flg & 0x20:
+            raise ZlibError("fdict flag is not supported")  # :57
+        self.rawinflate = RawInflate(self.input, {"index": self.ip, "bufferSize": (opts or {}).get("bufferSize"),
+                                                  "bufferType": (opts or {}).get("bufferType"),
+                                                  "resize": (opts or {}).get("resize")})
+
+    def decompress(self):
+        r = self.rawinflate
+        outs, res = inflate_many([r.input], [r.ip], [r.bufferSize], want_adler32=self.verify)
+        r.ip += int(res["in_used"][0])
+        self.ip = r.ip
+        buf = outs[0]
+        if self.verify:  # src/Inflate.ts:81-90
+            self.adler32 = int(res["adler32"][0])
+            stored = struct.unpack(">I", self.input[self.ip:self.ip + 4].tobytes().ljust(4, b"\0"))[0]
+            if self.adler32 != stored:
+                raise ZlibError("invalid adler-32 checksum")
+        return buf
+
+
+# ------------------------------------------------------------------------------------------------------------
+# gzip container (src/GZip.ts, src/GUnzip.ts)
+# ------------------------------------------------------------------------------------------------------------
+def _gzip_string(s):  # src/GZip.ts:133-150: chars > 0xFF are written as two bytes, NUL terminated
+    out = bytearray()
+    for ch in s:
+        c = ord(ch)
+        out += struct.pack("<H", c & 0xFFFF) if c > 0xFF else bytes([c])
+    return bytes(out) + b"\0"
+
+
+class GZip:
+    def __init__(self, input, opts=None):
+        self.input = _u8(input)
+        self.filename = _opt(opts, "filename", "")
+        self.comment = _opt(opts, "comment", "")
+        self.flags = {"fname": bool(self.filename), "fcomment": bool(self.comment), "fhcrc": bool(_opt(opts, "hcrc", False))}
+        self.deflateOptions = dict(_opt(opts, "deflateOptions", {}))
+        self.mtime = _b200(opts).get("mtime")  # engine-only knob: fixed MTIME for reproducible output
+        self.crc32 = None
+        self.output = None
+
+    def header(self):
+        flg = (0x08 if self.flags["fname"] else 0) | (0x10 if self.flags["fcomment"] else 0) | (0x02 if self.flags["fhcrc"] else 0)
+        mtime = int(datetime.datetime.now().timestamp()) if self.mtime is None else int(self.mtime)  # Date.now()/1000, :121
+        h = b"\x1f\x8b\x08" + bytes([flg]) + struct.pack("<I", mtime & 0xFFFFFFFF) + b"\x00\x03"  # XFL 0, OS Unix
+        if self.flags["fname"]:
+            h += _gzip_string(self.filename)
+        if self.flags["fcomment"]:
+            h += _gzip_string(self.comment)
+        if self.flags["fhcrc"]:
+            h += struct.pack("<H", CRC32.create(h) & 0xFFFF)  # :153-156
+        return h
+
+    def compress(self):
+        hdr = self.header()
+        ctype = _opt(self.deflateOptions, "compressionType", CompressionType.DYNAMIC)
+        if _opt(self.deflateOptions, "lazy", 0):
+            raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
+        outs, res = deflate_many([self.input], ctype, _b200(self.deflateOptions).get("chunkBytes", 0), want_crc32=True,
+                                 prefixes=[hdr])
+        self.crc32 = int(res["crc32"][0])
+        trailer = struct.pack("<II", self.crc32, self.input.size & 0xFFFFFFFF)  # :180-185
+        self.output = np.concatenate([outs[0], _u8(trailer)])
+        return self.output
+
+
+class GUnzip:
+    def __init__(self, input):
+        self.input = _u8(input)
+        self.ip = 0
+        self.members = []
+        self.decompressed = False
+        self.crc32 = None
+
+    def getMembers(self):
+        if not self.decompressed:
+            self.decompress()
+        return list(self.members)
+
+    def decompress(self):
+        while self.ip < self.input.size:  # src/GUnzip.ts:56-58 (multi-member)
+            self.decodeMember()
+        self.decompressed = True
+        return np.concatenate([m["data"] for m in self.members]) if self.members else np.zeros(0, dtype=np.uint8)
+
+    def decodeMember(self):  # src/GUnzip.ts:66-183
+        inp, p = self.input, self.ip
+        m = {"id1": int(inp[p]), "id2": int(inp[p + 1])}
+        if m["id1"] != 0x1F or m["id2"] != 0x8B:
+            raise ZlibError("invalid file signature:%d,%d" % (m["id1"], m["id2"]))
+        m["cm"] = int(inp[p + 2])
+        if m["cm"] != 8:
+            raise ZlibError("unknown compression method: %d" % m["cm"])
+        flg = m["flg"] = int(inp[p + 3])
+        m["mtime"] = struct.unpack("<I", inp[p + 4:p + 8].tobytes())[0]
+        m["xfl"], m["os"] = int(inp[p + 8]), int(inp[p + 9])
+        p += 10
+        if flg & 0x04:
+            m["xlen"] = int(inp[p]) | (int(inp[p + 1]) << 8)
+            p += 2 + m["xlen"]
+        for bit, key in ((0x08, "name"), (0x10, "comment")):
+            if flg & bit:
+                e = p
+                while int(inp[e]) != 0:
+                    e += 1
+                m[key] = "".join(chr(c) for c in inp[p:e])
+                p = e + 1
+        if flg & 0x02:
+            m["crc16"] = CRC32.create(inp, 0, p) & 0xFFFF  # from offset 0, as the reference does (:128)
+            if m["crc16"] != (int(inp[p]) | (int(inp[p + 1]) << 8)):
+                raise ZlibError("invalid header crc16")
+            p += 2
+        isize = struct.unpack("<I", inp[-4:].tobytes())[0]  # size hint from the last 4 bytes of the buffer (:135-149)
+        hint = isize if inp.size - p - 8 < isize * 512 else None
+        outs, res = inflate_many([inp], [p], [hint], want_crc32=True)
+        data = outs[0]
+        m["data"] = data
+        p += int(res["in_used"][0])
+        crc32, isize2 = struct.unpack("<II", inp[p:p + 8].tobytes().ljust(8, b"\0"))
+        self.crc32 = int(res["crc32"][0])
+        if self.crc32 != crc32:
+            raise ZlibError("invalid CRC-32 checksum: 0x%x / 0x%x" % (self.crc32, crc32))
+        if (data.size & 0xFFFFFFFF) != isize2:
+            raise ZlibError("invalid input size: %d / %d" % (data.size & 0xFFFFFFFF, isize2))
+        m["crc32"], m["isize"] = crc32, isize2
+        self.members.append(m)
+        self.ip = p + 8
+
+
+# ------------------------------------------------------------------------------------------------------------
+# PKZIP container (src/Zip.ts, src/Unzip.ts)
+# ------------------------------------------------------------------------------------------------------------
+def _dos_time(date):  # src/Zip.ts:129-139
+    return bytes([((date.minute & 0x7) << 5) | (date.second >> 1), (date.hour << 3) | (date.minute >> 3),
+                  (((date.month) & 0x7) << 5) | date.day, (((date.year - 1980) & 0x7F) << 1) | (date.month >> 3)])
+
+
+class Zip:
+    """addFile() only queues; compress() deflates and checksums every queued entry in ONE GPU batch (the
+    reference compresses inside addFile, one file at a time, src/Zip.ts:92-96 -- same bytes, different schedule)."""
+
+    def __init__(self, comment=b""):
+        self.files = []
+        self.comment = _u8(comment)
+        self.password = None
+
+    def addFile(self, input, filename="", opts=None):
+        opts = dict(opts or {})
+        self.files.append({"filename": filename, "buffer": _u8(input), "option": opts, "size": _u8(input).size,
+                           "compressionMethod": _opt(opts, "compressionMethod", ZipCompressionMethod.DEFLATE),
+                           "compressed": False, "crc32": 0})
+
+    def setPassword(self, password):
+        self.password = password
+
+    def compress(self):
+        files = self.files
+        if self.password is not None or any(f["option"].get("password") is not None for f in files):
+            raise NotImplementedError("ZipCrypto is out of scope (SURVEY.md section 2)")
+        if len(files) > 0xFFFF:
+            raise ZlibError("too many entries for a ZIP32 end-of-central-directory record")
+        # one batch per compression type used by the entries (normally one)
+        todo = [i for i, f in enumerate(files) if not f["compressed"] and f["compressionMethod"] == ZipCompressionMethod.DEFLATE
+                and f["option"].get("compress") is not False]
+        by_type = {}
+        for i in todo:
+            do = files[i]["option"].get("deflateOptions") or {}
+            if _opt(do, "lazy", 0):
+                raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
+            by_type.setdefault((_opt(do, "compressionType", CompressionType.DYNAMIC), _b200(do).get("chunkBytes", 0)), []).append(i)
+        for (ctype, chunk), idxs in by_type.items():
+            outs, res = deflate_many([files[i]["buffer"] for i in idxs], ctype, chunk, want_crc32=True)
+            for i, o, r in zip(idxs, outs, res):
+                files[i]["crc32"], files[i]["buffer"], files[i]["compressed"] = int(r["crc32"]), o, True
+        rest = [i for i, f in enumerate(files) if not f["compressed"]]
+        if rest:  # stored entries: CRC-32 only (src/Zip.ts:144)
+            res = checksum_many([files[i]["buffer"] for i in rest], True, False)
+            for i, r in zip(rest, res):
+                files[i]["crc32"] = int(r["crc32"])
+        local, central = [], []
+        offset = 0
+        for f in files:
+            name = bytes(ord(c) & 0xFF for c in f["filename"])  # stringToByteArray
+            comment = bytes(ord(c) & 0xFF for c in (f["option"].get("comment") or ""))
+            date = f["option"].get("date") or datetime.datetime.now()
+            mt = _dos_time(date)
+            body = f["buffer"]
+            common = struct.pack("<HHH", 20, 0, f["compressionMethod"]) + mt + struct.pack(
+                "<IIIHH", f["crc32"], body.size, f["size"], len(name), 0)
+            local.append(b"PK\x03\x04" + common + name)
+            local.append(body)
+            central.append(b"PK\x01\x02" + bytes([20, _opt(f["option"], "os", 0)]) + common +
+                           struct.pack("<HHHII", len(comment), 0, 0, 0, offset) + name + comment)
+            offset += 30 + len(name) + body.size
+        cd = b"".join(central)
+        eocd = b"PK\x05\x06" + struct.pack("<HHHHIIH", 0, 0, len(files), len(files), len(cd), offset, self.comment.size)
+        parts = [(_u8(p) if not isinstance(p, np.ndarray) else p) for p in local] + [_u8(cd), _u8(eocd), self.comment]
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+
+
+class Unzip:
+    def __init__(self, input, opts=None):
+        self.input = _u8(input)
+        self.verify = _opt(opts, "verify", False)
+        self.password = (opts or {}).get("password")
+        self.EOCD = None
+        self.fileHeaderList = None
+        self.filenameToIndex = None
+
+    def setPassword(self, password):
+        self.password = password
+
+    def _search_eocd(self):  # src/Unzip.ts:150-161
+        inp = self.input
+        for ip in range(inp.size - 12, 0, -1):
+            if inp[ip] == 0x50 and inp[ip + 1] == 0x4B and inp[ip + 2] == 0x05 and inp[ip + 3] == 0x06:
+                return ip
+        raise ZlibError("End of Central Directory Record not found")
+
+    def parseFileHeader(self):  # src/Unzip.ts:220-246
+        if self.fileHeaderList is not None:
+            return
+        inp = self.input
+        p = self._search_eocd()
+        f = struct.unpack("<HHHHIIH", inp[p + 4:p + 22].tobytes())
+        eocd = dict(zip(["numberOfThisDisk", "startDisk", "totalEntriesThisDisk", "totalEntries", "centralDirectorySize",
+                         "centralDirectoryOffset", "commentLength"], f))
+        eocd["comment"] = inp[p + 22:p + 22 + eocd["commentLength"]]
+        lst, tab = [], {}
+        q = eocd["centralDirectoryOffset"]
+        for i in range(eocd["totalEntries"]):
+            if inp[q:q + 4].tobytes() != b"PK\x01\x02":
+                raise ZlibError("invalid file header signature")
+            v = struct.unpack("<BBHHHHHIIIHHHHHII", inp[q + 4:q + 46].tobytes())
+            fh = dict(zip(["version", "os", "needVersion", "flags", "compression", "time", "date", "crc32", "compressedSize",
+                           "plainSize", "fileNameLength", "extraFieldLength", "fileCommentLength", "diskNumberStart",
+                           "internalFileAttributes", "externalFileAttributes", "relativeOffset"], v))
+            q += 46
+            fh["filename"] = inp[q:q + fh["fileNameLength"]].tobytes().decode("utf-8", "replace")  # TextDecoder, readString
+            q += fh["fileNameLength"]
+            fh["extraField"] = inp[q:q + fh["extraFieldLength"]]
+            q += fh["extraFieldLength"]
+            fh["comment"] = inp[q:q + fh["fileCommentLength"]]
+            q += fh["fileCommentLength"]
+            lst.append(fh)
+            tab[fh["filename"]] = i
+        if eocd["centralDirectorySize"] < q - eocd["centralDirectoryOffset"]:
+            raise ZlibError("invalid file header size")
+        self.EOCD, self.fileHeaderList, self.filenameToIndex = eocd, lst, tab
+
+    def getFilenames(self):
+        self.parseFileHeader()
+        return [fh["filename"] for fh in self.fileHeaderList]
+
+    def _local(self, index):  # src/Unzip.ts:28-62
+        self.parseFileHeader()
+        if index is None or index < 0 or index >= len(self.fileHeaderList):
+            raise ZlibError("wrong index")
+        inp = self.input
+        off = self.fileHeaderList[index]["relativeOffset"]
+        if inp[off:off + 4].tobytes() != b"PK\x03\x04":
+            raise ZlibError("invalid local file header signature")
+        v = struct.unpack("<HHHHHIIIHH", inp[off + 4:off + 30].tobytes())
+        lh = dict(zip(["needVersion", "flags", "compression", "time", "date", "crc32", "compressedSize", "plainSize",
+                       "fileNameLength", "extraFieldLength"], v))
+        lh["dataOffset"] = off + 30 + lh["fileNameLength"] + lh["extraFieldLength"]
+        if lh["flags"] & 0x0001:
+            raise NotImplementedError("ZipCrypto is out of scope (SURVEY.md section 2)")
+        return lh
+
+    def getFileData(self, index, opts=None):  # src/Unzip.ts:248-307
+        return self.getFilesData([index])[0]
+
+    def getFilesData(self, indices):
+        """Batch form of getFileData: every deflated entry of `indices` is inflated (and CRC-checked when
+        verify is set) in one GPU batch."""
+        lhs = [self._local(i) for i in indices]
+        out = [None] * len(lhs)
+        defl = [k for k, lh in enumerate(lhs) if lh["compression"] == ZipCompressionMethod.DEFLATE]
+        if defl:
+            outs, res = inflate_blob(self.input, [lhs[k]["dataOffset"] for k in defl],
+                                     [lhs[k]["compressedSize"] for k in defl], [lhs[k]["plainSize"] for k in defl],
+                                     want_crc32=self.verify)
+            for k, o, r in zip(defl, outs, res):
+                out[k] = o
+                if self.verify and lhs[k]["crc32"] != int(r["crc32"]):
+                    raise ZlibError("Incorrect crc: file=0x%x, data=0x%x" % (lhs[k]["crc32"], int(r["crc32"])))
+        stored = [k for k, lh in enumerate(lhs) if lh["compression"] != ZipCompressionMethod.DEFLATE]
+        for k in stored:
+            out[k] = self.input[lhs[k]["dataOffset"]:lhs[k]["dataOffset"] + lhs[k]["compressedSize"]]
+        if self.verify and stored:
+            res = checksum_many([out[k] for k in stored], True, False)
+            for k, r in zip(stored, res):
+                if lhs[k]["crc32"] != int(r["crc32"]):
+                    raise ZlibError("Incorrect crc: file=0x%x, data=0x%x" % (lhs[k]["crc32"], int(r["crc32"])))
+        return out
+
+    def decompress(self, filename, opts=None):  # src/Unzip.ts:327-334
+        self.parseFileHeader()
+        index = self.filenameToIndex.get(filename)
+        if index is None:
+            raise ZlibError(filename + " not found")
+        return self.getFileData(index, opts)
+
+    def decompressAll(self):
+        """{filename: data} of every entry, one GPU batch (engine-side extension for the C4 workload)."""
+        names = self.getFilenames()
+        return dict(zip(names, self.getFilesData(list(range(len(names))))))
+
+
+Zlib = {"GZip": GZip, "GUnzip": GUnzip, "Zip": Zip, "Unzip": Unzip, "Deflate": Deflate, "Inflate": Inflate}  # src/index.ts:8-12
