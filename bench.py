@@ -223,11 +223,14 @@ def run_b200(args, rank, world, local_rank):
 
     res = {}
 
+    # every rank but the last leaves its stream open, so the ranks' outputs concatenate into one stream
+    dflags = z.DEFLATE_NOT_FINAL if rank < world - 1 else 0
+
     def step_device():
-        res["r"] = eng.deflate_batch(d_in, d_out, items)
+        res["r"] = eng.deflate_batch(d_in, d_out, items, flags=dflags)
 
     def step_host():
-        res["h"] = eng.deflate_batch_host(h_in, h_out, items)
+        res["h"] = eng.deflate_batch_host(h_in, h_out, items, flags=dflags)
 
     # ---- device-resident leg (value) ---------------------------------------------------------------
     for _ in range(args.warmup):

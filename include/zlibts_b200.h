@@ -71,7 +71,9 @@ enum { ZLB_MODE_COMPAT = 0 };
 /* flags for zlb_deflate_batch */
 enum {
     ZLB_DEFLATE_WANT_CRC32 = 1u << 0,   /* results[i].crc32   = CRC-32 of item input  */
-    ZLB_DEFLATE_WANT_ADLER32 = 1u << 1  /* results[i].adler32 = Adler-32 of item input */
+    ZLB_DEFLATE_WANT_ADLER32 = 1u << 1, /* results[i].adler32 = Adler-32 of item input */
+    ZLB_DEFLATE_NOT_FINAL = 1u << 2     /* the last chunk of every item is not final either (BFINAL = 0 + join
+                                           marker): the item is a shard whose successor follows, e.g. on the next GPU */
 };
 
 /* flags for zlb_inflate_batch */

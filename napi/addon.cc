@@ -1,0 +1,267 @@
+// addon.cc -- Node.js N-API binding of libzlibts_b200.so (include/zlibts_b200.h).
+//
+// NOT COMPILED IN THIS IMAGE: there is no Node binary and no node_api.h here or on the GPU boxes (SURVEY.md
+// section 0.6). It is the binding a maintainer adds to the reference: pure marshalling, no algorithm. The tested
+// equivalent of this layer is zlib.ts_b200/api.py over the same C ABI.
+//
+// Exports (all synchronous, like the reference's API):
+//   deflateBatch(inputs: Uint8Array[], compressionType, chunkBytes, flags) -> {outputs: Uint8Array[], crc32: number[], adler32: number[]}
+//   inflateBatch(input: Uint8Array, offsets: number[], lengths: number[], caps: number[], flags)
+//                                                          -> {outputs, status: number[], inUsed: number[], crc32, adler32}
+//   checksumBatch(inputs: Uint8Array[], kinds)             -> {crc32: number[], adler32: number[]}
+//   crc32Combine(a, b, lenB), adler32Combine(a, b, lenB)
+#include <node_api.h>
+
+#include <cstring>
+#include <vector>
+
+#include "../include/zlibts_b200.h"
+
+static zlb_ctx* g_ctx = nullptr;
+
+static bool ensure_ctx(napi_env env)
+{
+    if (g_ctx) return true;
+    if (zlb_create(0, nullptr, &g_ctx) != ZLB_OK) {
+        napi_throw_error(env, nullptr, "zlib.ts-b200: no usable B200 device (there is no CPU fallback)");
+        return false;
+    }
+    return true;
+}
+
+struct Bytes {
+    uint8_t* p;
+    size_t n;
+};
+
+static bool get_u8(napi_env env, napi_value v, Bytes* out)
+{
+    bool is_ta = false;
+    napi_is_typedarray(env, v, &is_ta);
+    if (!is_ta) return false;
+    napi_typedarray_type t;
+    size_t len, off;
+    void* data;
+    napi_value ab;
+    napi_get_typedarray_info(env, v, &t, &len, &data, &ab, &off);
+    if (t != napi_uint8_array) return false;
+    out->p = (uint8_t*)data;
+    out->n = len;
+    return true;
+}
+
+static napi_value make_u8(napi_env env, const uint8_t* src, size_t n)
+{
+    void* data;
+    napi_value ab, ta;
+    napi_create_arraybuffer(env, n, &data, &ab);
+    if (n) memcpy(data, src, n);
+    napi_create_typedarray(env, napi_uint8_array, n, ab, 0, &ta);
+    return ta;
+}
+
+static napi_value num_array(napi_env env, const std::vector<double>& v)
+{
+    napi_value a;
+    napi_create_array_with_length(env, v.size(), &a);
+    for (size_t i = 0; i < v.size(); ++i) {
+        napi_value x;
+        napi_create_double(env, v[i], &x);
+        napi_set_element(env, a, (uint32_t)i, x);
+    }
+    return a;
+}
+
+static std::vector<double> get_numbers(napi_env env, napi_value arr)
+{
+    uint32_t n = 0;
+    napi_get_array_length(env, arr, &n);
+    std::vector<double> v(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_value e;
+        napi_get_element(env, arr, i, &e);
+        napi_get_value_double(env, e, &v[i]);
+    }
+    return v;
+}
+
+// deflateBatch(inputs, compressionType, chunkBytes, flags)  <- new RawDeflate(input, opts).compress()
+static napi_value DeflateBatch(napi_env env, napi_callback_info info)
+{
+    size_t argc = 4;
+    napi_value argv[4];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    if (!ensure_ctx(env)) return nullptr;
+    uint32_t n = 0, ctype = 2, chunk = 0, flags = 0;
+    napi_get_array_length(env, argv[0], &n);
+    napi_get_value_uint32(env, argv[1], &ctype);
+    napi_get_value_uint32(env, argv[2], &chunk);
+    napi_get_value_uint32(env, argv[3], &flags);
+    std::vector<zlb_item> items(n);
+    std::vector<zlb_result> res(n);
+    std::vector<Bytes> in(n);
+    uint64_t in_total = 0, out_total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_value e;
+        napi_get_element(env, argv[0], i, &e);
+        if (!get_u8(env, e, &in[i])) {
+            napi_throw_type_error(env, nullptr, "inputs must be Uint8Array");
+            return nullptr;
+        }
+        items[i].in_off = in_total;
+        items[i].in_len = in[i].n;
+        items[i].out_off = out_total;
+        items[i].out_cap = zlb_deflate_bound(in[i].n, chunk, (int)ctype);
+        in_total += in[i].n;
+        out_total += items[i].out_cap;
+    }
+    std::vector<uint8_t> blob(in_total ? in_total : 1), out(out_total ? out_total : 1);
+    for (uint32_t i = 0; i < n; ++i)
+        if (in[i].n) memcpy(blob.data() + items[i].in_off, in[i].p, in[i].n);
+    int rc = zlb_deflate_batch_host(g_ctx, blob.data(), blob.size(), out.data(), out.size(), items.data(), res.data(), n,
+                                    ZLB_MODE_COMPAT, (int)ctype, chunk, flags);
+    if (rc != ZLB_OK) {
+        napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
+        return nullptr;
+    }
+    napi_value result, outs;
+    napi_create_object(env, &result);
+    napi_create_array_with_length(env, n, &outs);
+    std::vector<double> crc(n), adler(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_set_element(env, outs, i, make_u8(env, out.data() + items[i].out_off, (size_t)res[i].out_len));
+        crc[i] = res[i].crc32;
+        adler[i] = res[i].adler32;
+    }
+    napi_set_named_property(env, result, "outputs", outs);
+    napi_set_named_property(env, result, "crc32", num_array(env, crc));
+    napi_set_named_property(env, result, "adler32", num_array(env, adler));
+    return result;
+}
+
+// inflateBatch(input, offsets, lengths, caps, flags)  <- new RawInflate(input, {index}).decompress()
+static napi_value InflateBatch(napi_env env, napi_callback_info info)
+{
+    size_t argc = 5;
+    napi_value argv[5];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    if (!ensure_ctx(env)) return nullptr;
+    Bytes in;
+    if (!get_u8(env, argv[0], &in)) {
+        napi_throw_type_error(env, nullptr, "input must be Uint8Array");
+        return nullptr;
+    }
+    std::vector<double> offs = get_numbers(env, argv[1]), lens = get_numbers(env, argv[2]), caps = get_numbers(env, argv[3]);
+    uint32_t flags = 0;
+    napi_get_value_uint32(env, argv[4], &flags);
+    const size_t n = offs.size();
+    std::vector<zlb_item> items(n);
+    std::vector<zlb_result> res(n);
+    uint64_t out_total = 0;
+    for (size_t i = 0; i < n; ++i) {
+        items[i].in_off = (uint64_t)offs[i];
+        items[i].in_len = (uint64_t)lens[i];
+        items[i].out_off = out_total;
+        items[i].out_cap = (uint64_t)caps[i];
+        out_total += items[i].out_cap;
+    }
+    std::vector<uint8_t> out(out_total ? out_total : 1);
+    int rc = zlb_inflate_batch_host(g_ctx, in.p, in.n, out.data(), out.size(), items.data(), res.data(), n, flags);
+    if (rc != ZLB_OK) {
+        napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
+        return nullptr;
+    }
+    napi_value result, outs;
+    napi_create_object(env, &result);
+    napi_create_array_with_length(env, n, &outs);
+    std::vector<double> st(n), used(n), crc(n), adler(n);
+    for (size_t i = 0; i < n; ++i) {
+        napi_set_element(env, outs, (uint32_t)i, make_u8(env, out.data() + items[i].out_off, (size_t)res[i].out_len));
+        st[i] = res[i].status;
+        used[i] = (double)res[i].in_used;
+        crc[i] = res[i].crc32;
+        adler[i] = res[i].adler32;
+    }
+    napi_set_named_property(env, result, "outputs", outs);
+    napi_set_named_property(env, result, "status", num_array(env, st));
+    napi_set_named_property(env, result, "inUsed", num_array(env, used));
+    napi_set_named_property(env, result, "crc32", num_array(env, crc));
+    napi_set_named_property(env, result, "adler32", num_array(env, adler));
+    return result;
+}
+
+// checksumBatch(inputs, kinds)  <- CRC32.create / Adler32.create
+static napi_value ChecksumBatch(napi_env env, napi_callback_info info)
+{
+    size_t argc = 2;
+    napi_value argv[2];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    if (!ensure_ctx(env)) return nullptr;
+    uint32_t n = 0, kinds = 3;
+    napi_get_array_length(env, argv[0], &n);
+    napi_get_value_uint32(env, argv[1], &kinds);
+    std::vector<zlb_item> items(n);
+    std::vector<zlb_result> res(n);
+    std::vector<Bytes> in(n);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_value e;
+        napi_get_element(env, argv[0], i, &e);
+        if (!get_u8(env, e, &in[i])) {
+            napi_throw_type_error(env, nullptr, "inputs must be Uint8Array");
+            return nullptr;
+        }
+        items[i].in_off = total;
+        items[i].in_len = in[i].n;
+        total += in[i].n;
+    }
+    std::vector<uint8_t> blob(total ? total : 1);
+    for (uint32_t i = 0; i < n; ++i)
+        if (in[i].n) memcpy(blob.data() + items[i].in_off, in[i].p, in[i].n);
+    if (zlb_checksum_batch_host(g_ctx, blob.data(), blob.size(), items.data(), res.data(), n, kinds) != ZLB_OK) {
+        napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
+        return nullptr;
+    }
+    std::vector<double> crc(n), adler(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        crc[i] = res[i].crc32;
+        adler[i] = res[i].adler32;
+    }
+    napi_value result;
+    napi_create_object(env, &result);
+    napi_set_named_property(env, result, "crc32", num_array(env, crc));
+    napi_set_named_property(env, result, "adler32", num_array(env, adler));
+    return result;
+}
+
+static napi_value Combine(napi_env env, napi_callback_info info, bool crc)
+{
+    size_t argc = 3;
+    napi_value argv[3];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    double a, b, n;
+    napi_get_value_double(env, argv[0], &a);
+    napi_get_value_double(env, argv[1], &b);
+    napi_get_value_double(env, argv[2], &n);
+    uint32_t r = crc ? zlb_crc32_combine((uint32_t)a, (uint32_t)b, (uint64_t)n)
+                     : zlb_adler32_combine((uint32_t)a, (uint32_t)b, (uint64_t)n);
+    napi_value v;
+    napi_create_uint32(env, r, &v);
+    return v;
+}
+static napi_value Crc32Combine(napi_env env, napi_callback_info info) { return Combine(env, info, true); }
+static napi_value Adler32Combine(napi_env env, napi_callback_info info) { return Combine(env, info, false); }
+
+static napi_value Init(napi_env env, napi_value exports)
+{
+    napi_property_descriptor d[] = {
+        {"deflateBatch", nullptr, DeflateBatch, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"inflateBatch", nullptr, InflateBatch, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"checksumBatch", nullptr, ChecksumBatch, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"crc32Combine", nullptr, Crc32Combine, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"adler32Combine", nullptr, Adler32Combine, nullptr, nullptr, nullptr, napi_default, nullptr},
+    };
+    napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
+    return exports;
+}
+NAPI_MODULE(NODE_GYP_MODULE_NAME, Init)

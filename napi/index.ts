@@ -1,0 +1,115 @@
+// index.ts -- the reference's public object (src/index.ts:8-12) over the B200 addon.
+// NOT COMPILED IN THIS IMAGE (no Node / tsc). Signatures equal the reference's; bodies only marshal.
+// The tested equivalent is zlib.ts_b200/api.py (same C ABI, same glue).
+/* eslint-disable @typescript-eslint/no-var-requires */
+const native = require('./build/Release/zlibts_b200.node');
+
+export enum CompressionType { NONE = 0, FIXED = 1, DYNAMIC = 2, RESERVED = 3 }      // src/RawDeflate.ts:12-17
+export enum BufferType { BLOCK = 0, ADAPTIVE = 1 }                                   // src/RawInflate.ts:5-8
+export interface RawDeflateOptions { lazy?: number; compressionType?: CompressionType;
+    outputBuffer?: number[] | Uint8Array; outputIndex?: number; b200?: { chunkBytes?: number } }
+export interface RawInflateOptions { index?: number; bufferSize?: number; bufferType?: BufferType; resize?: boolean }
+
+const STATUS_TEXT: { [k: number]: string } = {                                       // include/zlibts_b200.h
+    1: 'input buffer is broken', 2: 'unknown BTYPE: 3', 3: 'invalid code length',
+    5: 'invalid uncompressed block header: LEN', 6: 'invalid deflate stream: undefined code or distance',
+    7: 'invalid deflate stream: over-subscribed code lengths' };
+const u8 = (x: number[] | Uint8Array) => x instanceof Uint8Array ? x : new Uint8Array(x);
+
+export class RawDeflate {                                                            // src/RawDeflate.ts:50-114
+    input: Uint8Array; output: Uint8Array; op: number; compressionType: CompressionType; lazy: number; chunk: number;
+    constructor(input: number[] | Uint8Array, opts: RawDeflateOptions = {}) {
+        this.input = u8(input);
+        this.lazy = opts.lazy ?? 0;
+        if (this.lazy) throw new Error('lazy matching is not supported: the reference corrupts data with lazy > 0');
+        this.compressionType = opts.compressionType ?? CompressionType.DYNAMIC;
+        this.output = opts.outputBuffer ? u8(opts.outputBuffer) : new Uint8Array(0);
+        this.op = opts.outputIndex ?? 0;
+        this.chunk = opts.b200?.chunkBytes ?? 0;
+    }
+    compress(): Uint8Array {
+        const r = native.deflateBatch([this.input], this.compressionType, this.chunk, 0);
+        const body: Uint8Array = r.outputs[0];
+        const out = new Uint8Array(this.op + body.length);
+        out.set(this.output.subarray(0, Math.min(this.op, this.output.length)));     // caller's prefix survives
+        out.set(body, this.op);
+        this.output = out; this.op = out.length;
+        return out;
+    }
+}
+
+export class RawInflate {                                                            // src/RawInflate.ts:70-140
+    input: Uint8Array; ip: number; bufferSize?: number; buffer: Uint8Array | null = null; op = 0;
+    constructor(input: Uint8Array, opts: RawInflateOptions = {}) {
+        this.input = u8(input); this.ip = opts.index ?? 0; this.bufferSize = opts.bufferSize;
+    }
+    decompress(flags = 0): Uint8Array {
+        let cap = this.bufferSize ?? Math.max(0x8000, 4 * (this.input.length - this.ip));
+        for (;;) {                                                                   // the reference grows its buffer
+            const r = native.inflateBatch(this.input, [this.ip], [this.input.length - this.ip], [cap], flags);
+            if (r.status[0] === 4) { cap *= 4; continue; }
+            if (r.status[0] !== 0) throw new Error(STATUS_TEXT[r.status[0]] ?? 'inflate failed');
+            this.ip += r.inUsed[0]; this.buffer = r.outputs[0]; this.op = r.outputs[0].length;
+            (this as any).crc32 = r.crc32[0]; (this as any).adler32 = r.adler32[0];
+            return r.outputs[0];
+        }
+    }
+}
+
+export const CRC32 = {                                                               // src/CRC32.ts
+    create(data: number[] | Uint8Array, pos?: number, length?: number): number { return CRC32.update(data, 0, pos, length); },
+    update(data: number[] | Uint8Array, crc: number, pos = 0, length?: number): number {
+        const piece = u8(data).subarray(pos, pos + (length ?? data.length));
+        const c = native.checksumBatch([piece], 1).crc32[0];
+        return crc ? native.crc32Combine(crc >>> 0, c, piece.length) : c;
+    } };
+export const Adler32 = {                                                             // src/Adler32.ts
+    create(array: string | number[] | Uint8Array): number {
+        if (typeof array === 'string') array = Array.from(array, ch => ch.charCodeAt(0) & 0xFF);
+        return Adler32.update(1, u8(array)); },
+    update(adler: number, array: Uint8Array, len?: number, pos = 0): number {
+        const piece = array.subarray(pos, pos + (len ?? array.length));
+        const c = native.checksumBatch([piece], 2).adler32[0];
+        return adler === 1 ? c : native.adler32Combine(adler >>> 0, c, piece.length);
+    } };
+
+export class Deflate {                                                               // src/Deflate.ts
+    adler32: number | null = null; output: Uint8Array | null = null;
+    constructor(public input: Uint8Array | number[], public opts: RawDeflateOptions = {}) {}
+    static compress(input: number[] | Uint8Array, opts: RawDeflateOptions) { return new Deflate(input, opts).compress(); }
+    compress(): Uint8Array {
+        const type = this.opts.compressionType ?? CompressionType.DYNAMIC;
+        const cmf = 120; let flg = type << 6; flg |= 31 - ((cmf << 8) + flg) % 31;     // :67-78
+        const r = native.deflateBatch([u8(this.input)], type, this.opts.b200?.chunkBytes ?? 0, 2 /* want adler */);
+        const body: Uint8Array = r.outputs[0]; const a = r.adler32[0]; this.adler32 = a;
+        const out = new Uint8Array(2 + body.length + 4);
+        out[0] = cmf; out[1] = flg; out.set(body, 2);
+        out.set([a >>> 24 & 255, a >>> 16 & 255, a >>> 8 & 255, a & 255], 2 + body.length);   // writeUintBE, :95
+        return this.output = out;
+    }
+}
+
+export class Inflate {                                                               // src/Inflate.ts
+    ip: number; verify: boolean; adler32: number | null = null; rawinflate: RawInflate;
+    constructor(public input: Uint8Array, opts: RawInflateOptions & { verify?: boolean } = {}) {
+        this.ip = opts.index ?? 0; this.verify = opts.verify ?? false;
+        const cmf = input[this.ip++], flg = input[this.ip++];
+        if ((cmf & 0x0f) !== 8) throw new Error('unsupported compression method');
+        if (((cmf << 8) + flg) % 31 !== 0) throw new Error('invalid fcheck flag:' + ((cmf << 8) + flg) % 31);
+        if (flg & 0x20) throw new Error('fdict flag is not supported');
+        this.rawinflate = new RawInflate(input, { index: this.ip, bufferSize: opts.bufferSize });
+    }
+    decompress(): Uint8Array {
+        const buffer = this.rawinflate.decompress(this.verify ? 2 : 0);
+        this.ip = this.rawinflate.ip;
+        if (this.verify) {
+            const i = this.input, p = this.ip;
+            this.adler32 = (this.rawinflate as any).adler32;
+            if (this.adler32 !== ((i[p] << 24 | i[p + 1] << 16 | i[p + 2] << 8 | i[p + 3]) >>> 0)) throw new Error('invalid adler-32 checksum');
+        }
+        return buffer;
+    }
+}
+// GZip / GUnzip / Zip / Unzip keep the reference's own source (src/GZip.ts, src/GUnzip.ts, src/Zip.ts, src/Unzip.ts)
+// unchanged: they only call RawDeflate, RawInflate and CRC32, which resolve to the classes above once the
+// reference's imports of "./RawDeflate", "./RawInflate", "./CRC32", "./Adler32" point at this file (INTEGRATION.md).

@@ -209,3 +209,23 @@ def test_gpu_roundtrip_large_property(engine):
     want = bytearray(oracle.raw_deflate(data[:65536]))
     want[0] &= 0xFE
     assert bytes(d_z[:len(want)].cpu().numpy()) == bytes(want)
+
+
+def test_not_final_shards_concatenate_into_one_stream(engine):
+    """Multi-GPU layout: every rank but the last deflates its shard with NOT_FINAL; the shards'
+    outputs, laid end to end at the scanned offsets, are ONE stream for zlib and for the reference's decoder."""
+    import zlibts_b200 as z
+    from zlibts_b200 import shard, synth
+    data = synth.mixed(9 * 65536 + 777, 41).tobytes()
+    ranges = shard.chunk_ranges(len(data), 65536, 3)
+    pieces, parts = [], []
+    for r, (lo, hi) in enumerate(ranges):
+        fl = z.DEFLATE_WANT_CRC32 | z.DEFLATE_WANT_ADLER32 | (0 if r == 2 else z.DEFLATE_NOT_FINAL)
+        outs, res = _deflate_items(engine, [data[lo:hi]], oracle.DYNAMIC, flags=fl)
+        pieces.append(outs[0])
+        parts.append((int(res["crc32"][0]), int(res["adler32"][0]), hi - lo))
+    whole = b"".join(pieces)
+    assert zlib.decompress(whole, -15) == data
+    ref, ip = oracle.raw_inflate(whole + b"\0\0\0\0", 0, out_cap=len(data))
+    assert ref == data and ip == len(whole)
+    assert shard.combine_checksums(parts, z.crc32_combine, z.adler32_combine) == (zlib.crc32(data), zlib.adler32(data), len(data))

@@ -20,7 +20,7 @@ assert ITEM_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32
 NONE, FIXED, DYNAMIC = 0, 1, 2
 MODE_COMPAT = 0
 
-DEFLATE_WANT_CRC32, DEFLATE_WANT_ADLER32 = 1, 2
+DEFLATE_WANT_CRC32, DEFLATE_WANT_ADLER32, DEFLATE_NOT_FINAL = 1, 2, 4
 INFLATE_WANT_CRC32, INFLATE_WANT_ADLER32, INFLATE_CHECK_NLEN = 1, 2, 4
 SUM_CRC32, SUM_ADLER32 = 1, 2
 

@@ -442,7 +442,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                 c.in_off = h_items[i].in_off + j * cb;
                 c.len = (uint32_t)(len - j * cb < cb ? len - j * cb : cb);
                 c.item = (uint32_t)i;
-                c.flags = (j + 1 == nc) ? CHUNK_LAST : 0u;
+                c.flags = (j + 1 == nc && !(flags & ZLB_DEFLATE_NOT_FINAL)) ? CHUNK_LAST : 0u;
                 c.pad0 = c.pad1 = 0;
                 // first chunk of this item inside the chunk's wave
                 const size_t wave_base = (k / wave) * wave;
