@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -339,7 +339,11 @@ def run_b200(args, rank, world, local_rank):
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
-            roofline["traffic"] = json.load(open(traffic_file)).get(top_name)
+            tj = json.load(open(traffic_file))
+            # the capture may be of a smaller launch than this run's: traffic scales with the chunks per launch
+            per_unit = tj.get(top_name, 0) / max(1, tj.get("_units_per_launch", 1))
+            roofline["traffic"] = per_unit * (n_chunks * args.steps / max(1, top_launches)) or None
+            roofline["traffic_source"] = tj.get("_note")
         except Exception:
             pass
     inf_top_ms = prof_i["inflate_warp_kernel"]["ms"] / max(1, prof_i["inflate_warp_kernel"]["launches"])

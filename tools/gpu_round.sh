@@ -8,7 +8,7 @@ nproc
 python -m pytest tests -x -q -m gpu 2>&1 | tail -15
 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench rc=$?"; cat gpurun_out/bench_$tag.json; tail -5 gpurun_out/bench_$tag.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>&1; cat gpurun_out/bench_ref_$tag.json
-SMALL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --bytes 67108864"
+SMALL="python bench.py --steps 1 --warmup 1 --no-cpu-baseline"
 $SMALL > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $SMALL > gpurun_out/ncu_launch_$tag.log 2>&1
 echo "ncu launches rc=$?"
