@@ -14,7 +14,7 @@
 
 size_t zts_lz77_smem_bytes();
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
-                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint16_t* d_sortT,
+                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint32_t* d_sortT,
                     uint32_t* d_counter, uint32_t grid);
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type);
@@ -464,7 +464,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_codes, wave * sizeof(ZtsChunkCodes) + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 2 + 64);
+    rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 64);
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_misc, n * 8 + wave * 8 + 256);
     if (rc) return rc;
@@ -537,7 +537,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             if (k + 1 < n_waves && (rc = wave_in_copy(k + 1))) return rc;
             ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 * k), 0));
         }
-        rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist, (uint16_t*)ctx->d_sortT.p,
+        rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist, (uint32_t*)ctx->d_sortT.p,
                              d_counter, g);
         if (rc) return rc;
         rc = zts_huffman_launch(ctx, d_chunks + w0, wn, d_hist, d_info, d_codes, block_type);
@@ -627,14 +627,14 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
     if ((rc = zts_reserve(ctx, &ctx->d_tokens, (size_t)LZ_TOK_PER_CHUNK * 4 + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_spec, (size_t)LZ_TOK_PER_CHUNK * 4 + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_hist, 316 * 4 + 64))) return rc;
-    if ((rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 2 + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_misc, 256))) return rc;
     ZtsChunk ch = {0, n, 0, 0, CHUNK_LAST, 0, 0};
     ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunks.p, &ch, sizeof ch, cudaMemcpyHostToDevice, ctx->stream));
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     rc = zts_lz77_launch(ctx, (const uint8_t*)d_in, (const ZtsChunk*)ctx->d_chunks.p, 1, (ZtsChunkInfo*)ctx->d_chunk_info.p,
                          (uint32_t*)ctx->d_spec.p, (uint32_t*)ctx->d_tokens.p, (uint32_t*)ctx->d_hist.p,
-                         (uint16_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1);
+                         (uint32_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1);
     if (rc) return rc;
     std::vector<uint32_t> spec(LZ_TOK_PER_CHUNK), fix(LZ_TOK_PER_CHUNK);
     ZtsChunkInfo ci;

@@ -7,7 +7,7 @@
 // per-key JS arrays newest-first; here the same function is evaluated as:
 //
 //   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
-//   2. all positions are radix-sorted (stable, 2 LSD passes, warp match.any ranking, no atomics)
+//   2. all positions are radix-sorted (stable, 2 LSD passes, ballot-based ranking inside a warp, no atomics)
 //      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
 //   3. the chunk is cut into 128 tiles of 512 positions which the 32 warps take from a shared counter
 //      (segments of different entropy cost very different time) and parse speculatively, each from
@@ -46,6 +46,7 @@ struct LzMisc {
     unsigned long long mbar;
     uint32_t chunk;
     uint32_t tile_next;              // next tile of the speculative parse
+    uint32_t tile_next2;             // next tile of the re-entry pass
     uint32_t warp_tot[32];
     uint32_t warp_min[32];
     uint32_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)
@@ -90,6 +91,23 @@ __device__ __forceinline__ void ld_u128(const LzS& V, uint32_t i, uint32_t (&o)[
 }
 
 __device__ __forceinline__ uint32_t hash13(uint32_t key3) { return (key3 * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
+
+// lanes holding the same NBITS-bit digit as this lane (invalid lanes only match each other). Same result as
+// __match_any_sync, built from NBITS + 1 ballots: MATCH.ANY issues far too slowly on sm_100 to sit in a loop that
+// runs once per 32 positions (ncu: the instruction behind it carried a fifth of the kernel's stall samples).
+template <int NBITS>
+__device__ __forceinline__ unsigned peers_of(uint32_t d, bool valid)
+{
+    unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
+    unsigned peers = valid ? m : ~m;
+#pragma unroll
+    for (int b = 0; b < NBITS; ++b) {
+        const bool bit = (d >> b) & 1u;
+        m = __ballot_sync(0xFFFFFFFFu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
 
 // exclusive block scan (sum) over 1024 threads
 __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* warp_tot, uint32_t* total)
@@ -151,47 +169,46 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
         cur = a + __popc(__ballot_sync(0xFFFFFFFFu, less));
     }
     const uint32_t maxlen = min(LZ_MAXLEN, n - p);
+    const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
     while (cur > lo) {
         const uint32_t cnt = min(32u, cur - lo);
         const bool act = lane < cnt;
         const uint32_t q = act ? sorted[cur - 1 - lane] : 0u;  // lane 0 = newest candidate
         const bool inwin = act && (p - q <= LZ_WINDOW);
+        const uint8_t ptail = S[p + best_len];
         uint32_t len = 0;
-        if (inwin) {
+        // only a strictly longer match can replace the best of the nearer blocks (:183): its byte at best_len
+        // must match, which is the cheapest test and rejects nearly everything once a match is known
+        if (inwin && (best_len < 3 || S[q + best_len] == ptail)) {
             const uint32_t x0 = ld_u32(S, q) ^ pw;
             if ((x0 & 0xFFFFFFu) == 0) {  // same table[] key (src/LZ77.ts:204-214)
-                // only a strictly longer match can replace the best of the nearer blocks (:183)
-                bool ok = true;
-                if (best_len >= 3) ok = S[q + best_len] == S[p + best_len];
-                if (ok) {
-                    uint32_t k = 3;
-                    if (x0 == 0) {
-                        k = 4;
-                        // most matches end within the next word; long ones continue 16 bytes per step
-                        const uint32_t x1 = ld_u32(S, q + 4) ^ ld_u32(S, p + 4);
-                        if (x1) {
-                            k += (uint32_t)(__ffs((int)x1) - 1) >> 3;
-                        } else {
-                            k = 8;
-                            while (k < maxlen) {
-                                uint32_t a4[4], b4[4];
-                                ld_u128(S, q + k, a4);
-                                ld_u128(S, p + k, b4);
-                                const uint32_t y0 = a4[0] ^ b4[0], y1 = a4[1] ^ b4[1], y2 = a4[2] ^ b4[2],
-                                               y3 = a4[3] ^ b4[3];
-                                if (y0 | y1 | y2 | y3) {
-                                    const uint32_t y = y0 ? y0 : y1 ? y1 : y2 ? y2 : y3;
-                                    const uint32_t wsel = y0 ? 0u : y1 ? 4u : y2 ? 8u : 12u;
-                                    k += wsel + ((uint32_t)(__ffs((int)y) - 1) >> 3);
-                                    break;
-                                }
-                                k += 16;
+                uint32_t k = 3;
+                if (x0 == 0) {
+                    k = 4;
+                    // most matches end within the next word; long ones continue 16 bytes per step
+                    const uint32_t x1 = ld_u32(S, q + 4) ^ pw1;
+                    if (x1) {
+                        k += (uint32_t)(__ffs((int)x1) - 1) >> 3;
+                    } else {
+                        k = 8;
+                        while (k < maxlen) {
+                            uint32_t a4[4], b4[4];
+                            ld_u128(S, q + k, a4);
+                            ld_u128(S, p + k, b4);
+                            const uint32_t y0 = a4[0] ^ b4[0], y1 = a4[1] ^ b4[1], y2 = a4[2] ^ b4[2],
+                                           y3 = a4[3] ^ b4[3];
+                            if (y0 | y1 | y2 | y3) {
+                                const uint32_t y = y0 ? y0 : y1 ? y1 : y2 ? y2 : y3;
+                                const uint32_t wsel = y0 ? 0u : y1 ? 4u : y2 ? 8u : 12u;
+                                k += wsel + ((uint32_t)(__ffs((int)y) - 1) >> 3);
+                                break;
                             }
+                            k += 16;
                         }
                     }
-                    len = min(k, maxlen);
                 }
+                len = min(k, maxlen);
             }
         }
         const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, (len << 16) | q);  // longest, then nearest
@@ -343,7 +360,7 @@ __device__ __forceinline__ void hist_token(uint32_t tok, uint32_t* hist)
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ chunks, uint32_t n_chunks,
                   ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ spec_tok, uint32_t* __restrict__ fix_tok,
-                  uint32_t* __restrict__ hist_out, uint16_t* __restrict__ sortT, uint32_t* __restrict__ work_counter)
+                  uint32_t* __restrict__ hist_out, uint32_t* __restrict__ sortT, uint32_t* __restrict__ work_counter)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint8_t* Sbuf = smem + LzSmem::S_OFF;
@@ -354,7 +371,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
     LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint16_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;  // per-CTA radix temp (L2 resident)
+    uint32_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;  // per-CTA radix temp (L2 resident): pos | hash << 16
     uint32_t phase = 0;
 
     if (tid == 0) {
@@ -409,76 +426,104 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
 
         const uint32_t m = n >= 3 ? n - 2 : 0;  // positions that own a 3-byte key
 
-        // ---- 2. stable LSD radix sort of positions by hash13(key): pass 1 (low 7 bits) -> T (global)
-        for (int pass = 0; pass < 2; ++pass) {
-            const uint32_t ndig = pass == 0 ? 128u : 64u;
-            for (uint32_t i = tid; i < 32u * 128u; i += LZ_THREADS) cnt16[i] = 0;
+        // ---- 2. stable LSD radix sort of positions by hash13(key), low 7 bits then high 6 bits, three sweeps:
+        //   A  count the low digits per (warp range, digit)            -- shared-memory atomics, order irrelevant
+        //   B  scatter by low digit into T (global, L2 resident) as pos | hash << 16, stable (ballot ranking),
+        //      and count the high digits per (destination range, digit) on the way
+        //   C  scatter by high digit from T into `sorted`, stable
+        // The u32 counters of A and B live in the `sorted` area, which is not written before sweep C.
+        {
+            uint32_t* cntA = reinterpret_cast<uint32_t*>(sorted);   // [32 ranges][128 digits]
+            uint32_t* cntB = cntA + 32 * 128;                       // [32 ranges][64 digits]
+            for (uint32_t i = tid; i < 32u * 128u + 32u * 64u; i += LZ_THREADS) cntA[i] = 0;
             __syncthreads();
             const uint32_t w_begin = warp * LZ_SORT_TILE;
-            uint16_t* wc = cnt16 + warp * ndig;
-            // count
+            // sweep A
             if (w_begin < m) {
                 for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
                     const uint32_t i = w_begin + it * 32 + lane;
-                    const bool v = i < m;
-                    uint32_t d = 0xFFFFFFFFu;
-                    if (v) {
-                        const uint32_t q = pass == 0 ? i : (uint32_t)__ldcg(&T[i]);
-                        const uint32_t hh = hash13(ld_u32(SV, q) & 0xFFFFFFu);
-                        d = pass == 0 ? (hh & 127u) : (hh >> 7);
-                    }
-                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
-                    if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
-                    __syncwarp();
+                    if (i < m) atomicAdd(&cntA[warp * 128u + (hash13(ld_u32(SV, i) & 0xFFFFFFu) & 127u)], 1u);
                 }
             }
             __syncthreads();
-            // exclusive scan in (digit major, warp minor) order: entry e = d * 32 + w
+            // exclusive scan in (digit major, range minor) order: entry e = d * 32 + w  ->  u16 running offsets
             {
-                const uint32_t per = (ndig * 32u) / LZ_THREADS;  // 4 or 2
                 uint32_t vals[4];
                 uint32_t sum = 0;
-                for (uint32_t k = 0; k < per; ++k) {
-                    const uint32_t e = tid * per + k;
-                    const uint32_t d = e >> 5, w = e & 31u;
-                    vals[k] = cnt16[w * ndig + d];
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const uint32_t e = tid * 4 + k;
+                    vals[k] = cntA[(e & 31u) * 128u + (e >> 5)];
                     sum += vals[k];
                 }
                 uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
-                for (uint32_t k = 0; k < per; ++k) {
-                    const uint32_t e = tid * per + k;
-                    const uint32_t d = e >> 5, w = e & 31u;
-                    cnt16[w * ndig + d] = (uint16_t)base;
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const uint32_t e = tid * 4 + k;
+                    cnt16[(e & 31u) * 128u + (e >> 5)] = (uint16_t)base;
                     base += vals[k];
                 }
             }
             __syncthreads();
-            // scatter
+            // sweep B
             if (w_begin < m) {
+                uint16_t* wc = cnt16 + warp * 128u;
                 for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
                     const uint32_t i = w_begin + it * 32 + lane;
                     const bool v = i < m;
-                    uint32_t d = 0xFFFFFFFFu, q = 0;
-                    if (v) {
-                        q = pass == 0 ? i : (uint32_t)__ldcg(&T[i]);
-                        const uint32_t hh = hash13(ld_u32(SV, q) & 0xFFFFFFu);
-                        d = pass == 0 ? (hh & 127u) : (hh >> 7);
-                    }
-                    const unsigned peers = __match_any_sync(0xFFFFFFFFu, d);
+                    uint32_t hh = 0x1FFFu;
+                    if (v) hh = hash13(ld_u32(SV, i) & 0xFFFFFFu);
+                    const uint32_t d = hh & 127u;
+                    const unsigned peers = peers_of<7>(d, v);
                     uint32_t dst = 0;
                     if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
                     __syncwarp();
                     if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
                     if (v) {
-                        if (pass == 0)
-                            __stcg(&T[dst], (uint16_t)q);
-                        else
-                            sorted[dst] = (uint16_t)q;
+                        __stcg(&T[dst], i | (hh << 16));
+                        atomicAdd(&cntB[(dst >> 11) * 64u + (hh >> 7)], 1u);
                     }
                     __syncwarp();
                 }
             }
             __threadfence_block();
+            __syncthreads();
+            {
+                uint32_t vals[2];
+                uint32_t sum = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k) {
+                    const uint32_t e = tid * 2 + k;
+                    vals[k] = cntB[(e & 31u) * 64u + (e >> 5)];
+                    sum += vals[k];
+                }
+                uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
+#pragma unroll
+                for (uint32_t k = 0; k < 2; ++k) {
+                    const uint32_t e = tid * 2 + k;
+                    cnt16[(e & 31u) * 64u + (e >> 5)] = (uint16_t)base;
+                    base += vals[k];
+                }
+            }
+            __syncthreads();
+            // sweep C (overwrites the counters, which are dead now)
+            if (w_begin < m) {
+                uint16_t* wc = cnt16 + warp * 64u;
+                for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
+                    const uint32_t i = w_begin + it * 32 + lane;
+                    const bool v = i < m;
+                    uint32_t e = 0xFFFFFFFFu;
+                    if (v) e = __ldcg(&T[i]);
+                    const uint32_t d = (e >> 23) & 63u;
+                    const unsigned peers = peers_of<6>(d, v);
+                    uint32_t dst = 0;
+                    if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
+                    __syncwarp();
+                    if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                    if (v) sorted[dst] = (uint16_t)e;
+                    __syncwarp();
+                }
+            }
             __syncthreads();
         }
 
@@ -525,7 +570,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
 
         // ---- 3. speculative parse: warps take tiles from a shared counter
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
-        if (tid == 0) M->tile_next = 0;
+        if (tid == 0) {
+            M->tile_next = 0;
+            M->tile_next2 = 1;  // tile 0 needs no re-entry
+        }
         __syncthreads();
         const uint32_t n_tiles = (n + LZ_TILE - 1) / LZ_TILE;
         uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
@@ -550,14 +598,22 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         //          the true parse wherever the predecessor did converge to its speculative parse
         ZtsChunkInfo* ci = info + c;
         if (tid < LZ_NTILES / 32) M->start_mask[tid] = 0;
-        for (uint32_t w = warp; w < n_tiles; w += LZ_WARPS) {
-            uint32_t nfix = 0, from = 0, ex = M->spec_exit[w], entry = 0;
-            if (w) {
-                const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
-                entry = M->spec_exit[w - 1];
-                ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE, visited,
-                                    M->spec_count[w], M->spec_exit[w], &nfix, &from);
-            }
+        if (tid == 0 && n_tiles) {
+            M->entry_used[0] = 0;
+            M->fix_exit[0] = M->spec_exit[0];
+            M->fix_count[0] = 0;
+            M->spec_from[0] = 0;
+        }
+        for (;;) {
+            uint32_t w = 0;
+            if (lane == 0) w = atomicAdd(&M->tile_next2, 1u);
+            w = __shfl_sync(0xFFFFFFFFu, w, 0);
+            if (w >= n_tiles) break;
+            const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+            const uint32_t entry = M->spec_exit[w - 1];
+            uint32_t nfix, from;
+            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE,
+                                               visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
             if (lane == 0) {
                 M->entry_used[w] = entry;
                 M->fix_exit[w] = ex;
@@ -652,7 +708,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
 size_t zts_lz77_smem_bytes() { return LzSmem::TOTAL; }
 
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
-                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint16_t* d_sortT,
+                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint32_t* d_sortT,
                     uint32_t* d_counter, uint32_t grid)
 {
     static_assert(sizeof(LzMisc) <= LzSmem::MISC_BYTES, "misc area too small");
