@@ -91,23 +91,74 @@ __global__ void deflate_finalize_kernel(const zlb_item* __restrict__ items, zlb_
 }
 
 // ---- bit packer: one CTA per chunk ------------------------------------------------------------------------
+// Every warp owns a contiguous range of the chunk's tokens. Pass 1 adds up the bits of each range, a 16-entry
+// scan gives every range its first bit, pass 2 re-derives the codes and ORs them into a shared-memory image of the
+// block with warp-level prefix sums only (no block barrier per batch of tokens). Launched twice per wave with two
+// image sizes: a CTA whose block fits the small image runs in the small launch (4 CTAs per SM), the others in
+// the large one; the CTA of the other class exits at once.
 struct PackSeg {
     uint32_t prefix;      // tokens before this segment
     uint32_t src;         // index into the fix (bit 31 clear) or spec (bit 31 set) token buffer
 };
 
+#define PACK_WARPS (PACK_THREADS / 32)
+#define PACK_SMALL_WORDS 13312u  // 52 KiB image: 4 CTAs per SM
+
+struct PackTok {
+    unsigned long long bits;
+    uint32_t nb;
+};
+
+// code bits of token g (g == n_tok is the end-of-block symbol); `seg` is the lane's segment hint
+__device__ __forceinline__ PackTok pack_token(uint32_t g, uint32_t n_tok, uint32_t& seg, const PackSeg* s_seg,
+                                              const uint32_t* __restrict__ sp, const uint32_t* __restrict__ fx,
+                                              const uint32_t* s_ll, const uint32_t* s_d)
+{
+    PackTok r = {0ull, 0u};
+    if (g < n_tok) {
+        while (s_seg[seg + 1].prefix <= g) ++seg;  // g only grows: the hint moves forward a slot or two per call
+        const uint32_t src = s_seg[seg].src;
+        const uint32_t idx = (src & 0x7FFFFFFFu) + (g - s_seg[seg].prefix);
+        const uint32_t tok = (src & 0x80000000u) ? __ldg(sp + idx) : __ldg(fx + idx);
+        if (tok & TOK_MATCH) {
+            uint32_t ls, lb, lv, ds, db, dv;
+            zts_len_code(((tok >> 16) & 0xFF) + 3, ls, lb, lv);
+            zts_dist_code((tok & 0xFFFF) + 1, ds, db, dv);
+            const uint32_t le = s_ll[257 + ls], de = s_d[ds];
+            // litlen code, length extra, distance code, distance extra (src/RawDeflate.ts:279-289)
+            r.bits = le & 0xFFFF;
+            r.nb = le >> 16;
+            r.bits |= (unsigned long long)lv << r.nb;
+            r.nb += lb;
+            r.bits |= (unsigned long long)(de & 0xFFFF) << r.nb;
+            r.nb += de >> 16;
+            r.bits |= (unsigned long long)dv << r.nb;
+            r.nb += db;
+        } else {
+            const uint32_t le = s_ll[tok & 0xFF];
+            r.bits = le & 0xFFFF;
+            r.nb = le >> 16;
+        }
+    } else if (g == n_tok) {
+        const uint32_t le = s_ll[256];
+        r.bits = le & 0xFFFF;
+        r.nb = le >> 16;
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(PACK_THREADS)
 bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restrict__ info,
                const ZtsChunkCodes* __restrict__ codes, const uint32_t* __restrict__ spec_tok,
-               const uint32_t* __restrict__ fix_tok, const zlb_item* __restrict__ items, uint8_t* __restrict__ out)
+               const uint32_t* __restrict__ fix_tok, const zlb_item* __restrict__ items, uint8_t* __restrict__ out,
+               uint32_t stage_words, uint32_t min_words)
 {
-    extern __shared__ __align__(16) uint32_t stage[];  // PACK_STAGE_WORDS
+    extern __shared__ __align__(16) uint32_t stage[];  // stage_words
     __shared__ uint32_t s_ll[286];
     __shared__ uint32_t s_d[30];
-    __shared__ PackSeg s_seg[2 * LZ_NTILES + 1];
-    __shared__ uint32_t s_nseg;
-    __shared__ uint32_t warp_tot[PACK_THREADS / 32];
-    __shared__ uint32_t tile_total;
+    __shared__ PackSeg s_seg[2 * LZ_NTILES + 2];
+    __shared__ uint32_t warp_tot[PACK_WARPS];
+    __shared__ unsigned long long range_bits[PACK_WARPS];
 
     const uint32_t c = blockIdx.x;
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -120,14 +171,15 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     uint8_t* dst = out + ci->out_off;
     const uint32_t shift = (uint32_t)((uintptr_t)dst & 3u);  // image word j <-> aligned global word j
     const uint32_t n_words = (shift + out_bytes + 3) >> 2;
-    if (n_words > PACK_STAGE_WORDS) return;  // cannot happen for <= 64 KiB chunks (optimal codes)
+    if (n_words > stage_words || n_words <= min_words) return;  // the other launch's size class
 
     for (uint32_t i = tid; i < n_words; i += PACK_THREADS) stage[i] = 0;
     for (uint32_t i = tid; i < 286; i += PACK_THREADS) s_ll[i] = codes[c].ll[i];
     if (tid < 30) s_d[tid] = codes[c].d[tid];
+    const uint32_t n_tok = ci->n_tokens;
     // token segments in stream order: per tile the re-parsed tokens, then the reused speculative ones.
-    // Slot 2w = fix tokens of tile w, slot 2w+1 = its speculative tail; empty slots share the prefix of
-    // their successor, so "last slot with prefix <= g" always lands on a non-empty one.
+    // Slot 2w = fix tokens of tile w, slot 2w+1 = its speculative tail; an empty slot shares the prefix of its
+    // successor, so "last slot with prefix <= g" always lands on a non-empty one.
     {
         uint32_t cnt = 0, src = 0;
         if (tid < 2 * LZ_NTILES) {
@@ -149,23 +201,22 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
         if (lane == 31) warp_tot[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            uint32_t w = lane < PACK_THREADS / 32 ? warp_tot[lane] : 0u, winc = w;
+            uint32_t w = lane < PACK_WARPS ? warp_tot[lane] : 0u, winc = w;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
                 if (lane >= (unsigned)d) winc += t;
             }
-            if (lane < PACK_THREADS / 32) warp_tot[lane] = winc - w;
+            if (lane < PACK_WARPS) warp_tot[lane] = winc - w;
         }
         __syncthreads();
         if (tid < 2 * LZ_NTILES) {
             s_seg[tid].prefix = warp_tot[warp] + inc - cnt;
             s_seg[tid].src = src;
         }
-        if (tid == 2 * LZ_NTILES) {
-            s_seg[tid].prefix = ci->n_tokens;
+        if (tid >= 2 * LZ_NTILES && tid < 2 * LZ_NTILES + 2) {  // two sentinels end the forward walk of the hint
+            s_seg[tid].prefix = 0xFFFFFFFFu;
             s_seg[tid].src = 0;
-            s_nseg = 2 * LZ_NTILES;
         }
     }
     __syncthreads();
@@ -177,89 +228,64 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
         const uint32_t bit = base_bit + i * 8;
         if (b) atomicOr(&stage[bit >> 5], b << (bit & 31));  // byte-aligned inside a word: never straddles
     }
-    const uint32_t n_tok = ci->n_tokens;
-    const uint32_t nseg = s_nseg;
     const uint32_t* sp = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
     const uint32_t* fx = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
-    unsigned long long bitpos = (unsigned long long)base_bit + hdr_bits;
 
-    // tokens 0 .. n_tok-1, then the end-of-block symbol
-    for (uint32_t base = 0; base <= n_tok; base += PACK_THREADS) {
-        const uint32_t g = base + tid;
-        unsigned long long bits = 0;
-        uint32_t nb = 0;
-        if (g < n_tok) {
-            // segment lookup: last segment with prefix <= g
-            uint32_t lo = 0, hi = nseg;
-            while (hi - lo > 1) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_seg[mid].prefix <= g)
-                    lo = mid;
-                else
-                    hi = mid;
-            }
-            const uint32_t src = s_seg[lo].src;
-            const uint32_t idx = (src & 0x7FFFFFFFu) + (g - s_seg[lo].prefix);
-            const uint32_t tok = (src & 0x80000000u) ? sp[idx] : fx[idx];
-            if (tok & TOK_MATCH) {
-                uint32_t ls, lb, lv, ds, db, dv;
-                zts_len_code(((tok >> 16) & 0xFF) + 3, ls, lb, lv);
-                zts_dist_code((tok & 0xFFFF) + 1, ds, db, dv);
-                const uint32_t le = s_ll[257 + ls], de = s_d[ds];
-                // litlen code, length extra, distance code, distance extra (src/RawDeflate.ts:279-289)
-                bits = le & 0xFFFF;
-                nb = le >> 16;
-                bits |= (unsigned long long)lv << nb;
-                nb += lb;
-                bits |= (unsigned long long)(de & 0xFFFF) << nb;
-                nb += de >> 16;
-                bits |= (unsigned long long)dv << nb;
-                nb += db;
-            } else {
-                const uint32_t le = s_ll[tok & 0xFF];
-                bits = le & 0xFFFF;
-                nb = le >> 16;
-            }
-        } else if (g == n_tok) {
-            const uint32_t le = s_ll[256];
-            bits = le & 0xFFFF;
-            nb = le >> 16;
+    // tokens 0 .. n_tok-1, then the end-of-block symbol: warp w owns [w * per, (w + 1) * per)
+    const uint32_t per = (((n_tok + 1 + PACK_WARPS - 1) / PACK_WARPS) + 31u) & ~31u;
+    const uint32_t g_begin = warp * per, g_end = min(n_tok + 1, g_begin + per);
+    uint32_t seg0 = 0;
+    if (g_begin < n_tok) {  // last slot with prefix <= g_begin
+        uint32_t lo = 0, hi = 2 * LZ_NTILES;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (s_seg[mid].prefix <= g_begin)
+                lo = mid;
+            else
+                hi = mid;
         }
-        // exclusive prefix sum of the bit counts of this batch
-        uint32_t inc = nb;
+        seg0 = lo;
+    }
+    {
+        unsigned long long tot = 0;
+        uint32_t seg = seg0;
+        for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            tot += pack_token(g < g_end ? g : 0xFFFFFFFFu, n_tok, seg, s_seg, sp, fx, s_ll, s_d).nb;
+        }
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= (unsigned)d) inc += t;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = lane < PACK_THREADS / 32 ? warp_tot[lane] : 0u, winc = w;
+        for (int d = 16; d; d >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, d);
+        if (lane == 0) range_bits[warp] = tot;
+    }
+    __syncthreads();
+    unsigned long long bitpos = (unsigned long long)base_bit + hdr_bits;
+    for (uint32_t w = 0; w < warp; ++w) bitpos += range_bits[w];
+    {
+        uint32_t seg = seg0;
+        for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
+            const uint32_t g = g0 + lane;
+            const PackTok t = pack_token(g < g_end ? g : 0xFFFFFFFFu, n_tok, seg, s_seg, sp, fx, s_ll, s_d);
+            uint32_t inc = t.nb;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
-                if (lane >= (unsigned)d) winc += t;
+                uint32_t u = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= (unsigned)d) inc += u;
             }
-            if (lane < PACK_THREADS / 32) warp_tot[lane] = winc - w;
-            if (lane == 31) tile_total = winc;
-        }
-        __syncthreads();
-        if (nb) {
-            const unsigned long long bp = bitpos + warp_tot[warp] + inc - nb;
-            const uint32_t w0 = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
-            // up to 48 + 31 bits -> three words
-            const unsigned long long lo64 = bits << sh;
-            atomicOr(&stage[w0], (uint32_t)lo64);
-            const uint32_t mid = (uint32_t)(lo64 >> 32);
-            if (mid) atomicOr(&stage[w0 + 1], mid);
-            if (sh && nb + sh > 64) {
-                const uint32_t hi32 = (uint32_t)(bits >> (64 - sh));
-                if (hi32) atomicOr(&stage[w0 + 2], hi32);
+            if (t.nb) {
+                const unsigned long long bp = bitpos + inc - t.nb;
+                const uint32_t w0 = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
+                // up to 48 + 31 bits -> three words
+                const unsigned long long lo64 = t.bits << sh;
+                atomicOr(&stage[w0], (uint32_t)lo64);
+                const uint32_t mid = (uint32_t)(lo64 >> 32);
+                if (mid) atomicOr(&stage[w0 + 1], mid);
+                if (sh && t.nb + sh > 64) {
+                    const uint32_t hi32 = (uint32_t)(t.bits >> (64 - sh));
+                    if (hi32) atomicOr(&stage[w0 + 2], hi32);
+                }
             }
+            bitpos += __shfl_sync(0xFFFFFFFFu, inc, 31);
         }
-        bitpos += tile_total;
-        __syncthreads();
     }
     // join marker: (byte align incl. the 3 header bits of an empty stored block) 00 00 FF FF
     if (tid == 0 && !(ch.flags & CHUNK_LAST)) {
@@ -545,8 +571,12 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         ZTS_LAUNCH(ctx, ZK_SCAN,
                    chunk_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_chunks + w0, d_info, wn, d_items, d_running, d_gpos));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
+                   bitpack_kernel<<<wn, PACK_THREADS, PACK_SMALL_WORDS * 4, ctx->stream>>>(
+                       d_chunks + w0, d_info, d_codes, d_spec, d_fix, d_items, d_out, PACK_SMALL_WORDS, 0u));
+        ZTS_LAUNCH(ctx, ZK_BITPACK,
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, ctx->stream>>>(
-                       d_chunks + w0, d_info, d_codes, d_spec, d_fix, d_items, d_out));
+                       d_chunks + w0, d_info, d_codes, d_spec, d_fix, d_items, d_out, PACK_STAGE_WORDS,
+                       PACK_SMALL_WORDS));
         if (delta_out) {
             ZTS_CUDA(ctx, cudaMemcpyAsync(h_run + k * n, d_running, n * sizeof(unsigned long long),
                                           cudaMemcpyDeviceToHost, ctx->stream));
