@@ -137,6 +137,40 @@ __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* warp_to
     return r;
 }
 
+// length of the match between candidate q and position p given that both share the 3-byte key test below;
+// 0 when q has another key. pw / pw1 = the 8 bytes at p.
+__device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint32_t p, uint32_t pw, uint32_t pw1,
+                                                 uint32_t maxlen)
+{
+    const uint32_t x0 = ld_u32(S, q) ^ pw;
+    if (x0 & 0xFFFFFFu) return 0;  // another table[] key (src/LZ77.ts:204-214)
+    uint32_t k = 3;
+    if (x0 == 0) {
+        k = 4;
+        // most matches end within the next word; long ones continue 16 bytes per step
+        const uint32_t x1 = ld_u32(S, q + 4) ^ pw1;
+        if (x1) {
+            k += (uint32_t)(__ffs((int)x1) - 1) >> 3;
+        } else {
+            k = 8;
+            while (k < maxlen) {
+                uint32_t a4[4], b4[4];
+                ld_u128(S, q + k, a4);
+                ld_u128(S, p + k, b4);
+                const uint32_t y0 = a4[0] ^ b4[0], y1 = a4[1] ^ b4[1], y2 = a4[2] ^ b4[2], y3 = a4[3] ^ b4[3];
+                if (y0 | y1 | y2 | y3) {
+                    const uint32_t y = y0 ? y0 : y1 ? y1 : y2 ? y2 : y3;
+                    const uint32_t wsel = y0 ? 0u : y1 ? 4u : y2 ? 8u : 12u;
+                    k += wsel + ((uint32_t)(__ffs((int)y) - 1) >> 3);
+                    break;
+                }
+                k += 16;
+            }
+        }
+    }
+    return min(k, maxlen);
+}
+
 // ---- warp-cooperative longest/nearest match search at position p (requires p + 3 < n) ----------
 // returns (len << 16) | dist, or 0 when no candidate exists (src/LZ77.ts:157-194 + :242)
 __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __restrict__ sorted,
@@ -144,6 +178,27 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
 {
     const unsigned lane = zts_lane();
     const uint32_t pw = ld_u32(S, p);
+    const uint32_t maxlen = min(LZ_MAXLEN, n - p);
+    // inside a run of one byte the distance-1 candidate reaches the maximum length: nothing is nearer and nothing
+    // is longer, so that is the reference's answer (it stops at the first candidate there, :189 / end of input)
+    {
+        const uint32_t b0 = pw & 0xFFu;
+        if (p > 0 && (pw & 0xFFFFFFu) == b0 * 0x010101u && S[p - 1] == b0) {
+            const uint32_t splat = b0 * 0x01010101u;
+            bool same = true;
+#pragma unroll
+            for (uint32_t w = 0; w < 3; ++w) {  // lane j checks bytes [12 j, 12 j + 12) of the 258 ahead
+                const uint32_t k0 = lane * 12u + w * 4u;
+                if (k0 < maxlen) {
+                    uint32_t x = ld_u32(S, p + k0) ^ splat;
+                    const uint32_t nbytes = maxlen - k0;
+                    if (nbytes < 4u) x &= (1u << (8u * nbytes)) - 1u;
+                    same = same && x == 0;
+                }
+            }
+            if (__all_sync(0xFFFFFFFFu, same)) return (maxlen << 16) | 1u;
+        }
+    }
     const uint32_t h = hash13(pw & 0xFFFFFFu);
     const uint32_t lo = bstart[h];
     uint32_t a = lo, b = bstart[h + 1];
@@ -168,7 +223,6 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
         const bool less = (s < b) && (sorted[s] < p);
         cur = a + __popc(__ballot_sync(0xFFFFFFFFu, less));
     }
-    const uint32_t maxlen = min(LZ_MAXLEN, n - p);
     const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
     while (cur > lo) {
@@ -177,41 +231,11 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
         const uint32_t q = act ? sorted[cur - 1 - lane] : 0u;  // lane 0 = newest candidate
         const bool inwin = act && (p - q <= LZ_WINDOW);
         const uint8_t ptail = S[p + best_len];
-        uint32_t len = 0;
         // only a strictly longer match can replace the best of the nearer blocks (:183): its byte at best_len
         // must match, which is the cheapest test and rejects nearly everything once a match is known
-        if (inwin && (best_len < 3 || S[q + best_len] == ptail)) {
-            const uint32_t x0 = ld_u32(S, q) ^ pw;
-            if ((x0 & 0xFFFFFFu) == 0) {  // same table[] key (src/LZ77.ts:204-214)
-                uint32_t k = 3;
-                if (x0 == 0) {
-                    k = 4;
-                    // most matches end within the next word; long ones continue 16 bytes per step
-                    const uint32_t x1 = ld_u32(S, q + 4) ^ pw1;
-                    if (x1) {
-                        k += (uint32_t)(__ffs((int)x1) - 1) >> 3;
-                    } else {
-                        k = 8;
-                        while (k < maxlen) {
-                            uint32_t a4[4], b4[4];
-                            ld_u128(S, q + k, a4);
-                            ld_u128(S, p + k, b4);
-                            const uint32_t y0 = a4[0] ^ b4[0], y1 = a4[1] ^ b4[1], y2 = a4[2] ^ b4[2],
-                                           y3 = a4[3] ^ b4[3];
-                            if (y0 | y1 | y2 | y3) {
-                                const uint32_t y = y0 ? y0 : y1 ? y1 : y2 ? y2 : y3;
-                                const uint32_t wsel = y0 ? 0u : y1 ? 4u : y2 ? 8u : 12u;
-                                k += wsel + ((uint32_t)(__ffs((int)y) - 1) >> 3);
-                                break;
-                            }
-                            k += 16;
-                        }
-                    }
-                }
-                len = min(k, maxlen);
-            }
-        }
-        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, (len << 16) | q);  // longest, then nearest
+        uint32_t key = 0;
+        if (inwin && (best_len < 3 || S[q + best_len] == ptail)) key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
+        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);  // longest, then nearest
         if ((m >> 16) > best_len) {
             best_len = m >> 16;
             best = m;
