@@ -181,6 +181,7 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     // Slot 2w = fix tokens of tile w, slot 2w+1 = its speculative tail; an empty slot shares the prefix of its
     // successor, so "last slot with prefix <= g" always lands on a non-empty one.
     {
+        static_assert(2 * LZ_NTILES <= PACK_THREADS, "one thread per token segment");
         uint32_t cnt = 0, src = 0;
         if (tid < 2 * LZ_NTILES) {
             const ZtsTile t = ci->tiles[tid >> 1];
@@ -214,9 +215,9 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
             s_seg[tid].prefix = warp_tot[warp] + inc - cnt;
             s_seg[tid].src = src;
         }
-        if (tid >= 2 * LZ_NTILES && tid < 2 * LZ_NTILES + 2) {  // two sentinels end the forward walk of the hint
-            s_seg[tid].prefix = 0xFFFFFFFFu;
-            s_seg[tid].src = 0;
+        if (tid < 2) {  // two sentinels end the forward walk of the hint
+            s_seg[2 * LZ_NTILES + tid].prefix = 0xFFFFFFFFu;
+            s_seg[2 * LZ_NTILES + tid].src = 0;
         }
     }
     __syncthreads();

@@ -38,7 +38,7 @@ struct LzSmem {
     static constexpr uint32_t AUX_OFF = BSTART_OFF + BSTART_BYTES;     // 8 KiB: radix counters | visited bits
     static constexpr uint32_t AUX_BYTES = 8192;
     static constexpr uint32_t MISC_OFF = AUX_OFF + AUX_BYTES;
-    static constexpr uint32_t MISC_BYTES = 6144;
+    static constexpr uint32_t MISC_BYTES = 8192;
     static constexpr uint32_t TOTAL = MISC_OFF + MISC_BYTES;
 };
 
