@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""The other BASELINE.json configs at full size on one GPU, with parity checks (not the contract bench: bench.py is).
+
+    python tools/bench_configs.py [c1] [c3] [c4]  -> one JSON object per config on stdout
+
+C1  Zlib.Deflate / Inflate round trip of 1 MiB synthetic text through the host API.
+C3  batched inflate of 65 536 independent 64 KiB zlib streams (stream i = reference-compatible encoder output of
+    text(65536, 1000+i) for even i, mixed(65536, 1000+i) for odd i; produced by the GPU compat encoder, whose bytes
+    are checked against the oracle on a sample), device resident, 4 GiB of output.
+C4  Zlib.Zip of 10 000 synthetic files (256 B .. 256 KiB, log-uniform) + Unzip round trip with per-entry CRC-32.
+"""
+import json
+import os
+import sys
+import time
+import zlib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+import zlibts_b200 as z
+from zlibts_b200 import synth
+
+
+def lcg_sizes(n, seed=4):
+    x, out = seed, []
+    for _ in range(n):
+        x = (x * 1664525 + 1013904223) & 0xFFFFFFFF
+        k = (x >> 16) % 81
+        out.append(int(256 * 2 ** (k / 8)))
+    return out
+
+
+def c1(eng):
+    d = synth.text(1 << 20, 1).tobytes()
+    z.api.set_engine(eng)
+    t0 = time.perf_counter()
+    c = z.Deflate(d).compress()
+    t1 = time.perf_counter()
+    out = z.Inflate(c, {"verify": True}).decompress()
+    t2 = time.perf_counter()
+    assert out.tobytes() == d and zlib.decompress(c.tobytes()) == d
+    return {"config": "C1", "bytes": len(d), "compressed": int(c.size), "ratio": c.size / len(d),
+            "deflate_ms_host_api": (t1 - t0) * 1e3, "inflate_ms_host_api": (t2 - t1) * 1e3, "roundtrip_ok": True}
+
+
+def c3(eng, n_streams=65536):
+    import oracle
+    stream = torch.cuda.Stream()
+    eng2 = z.Engine(0, stream.cuda_stream)
+    CH = 65536
+    slot = z.deflate_bound(CH) + 8
+    group = 4096  # generate + compress in groups, keep only the packed zlib streams
+    packed, lens = [], []
+    samples = {}
+    for g0 in range(0, n_streams, group):
+        g = min(group, n_streams - g0)
+        h = np.empty(g * CH, dtype=np.uint8)
+        for k in range(g):
+            i = g0 + k
+            if i % 2 == 0:
+                synth.text(CH, 1000 + i, out=h[k * CH:(k + 1) * CH])
+            else:
+                synth.mixed(CH, 1000 + i, 4096, out=h[k * CH:(k + 1) * CH])
+        items = z.make_items(g)
+        items["in_off"] = np.arange(g, dtype=np.uint64) * CH
+        items["in_len"] = CH
+        items["out_off"] = np.arange(g, dtype=np.uint64) * slot + 2   # room for the 2-byte zlib header
+        items["out_cap"] = slot - 8
+        with torch.cuda.stream(stream):
+            d_in = torch.from_numpy(h).cuda()
+            d_out = torch.zeros(g * slot, dtype=torch.uint8, device="cuda")
+            r = eng2.deflate_batch(d_in, d_out, items, flags=z.DEFLATE_WANT_ADLER32)
+            ho = d_out.cpu().numpy()
+        assert int(r["status"].max()) == 0
+        for k in range(g):
+            n = int(r["out_len"][k])
+            s = ho[k * slot:k * slot + 2 + n + 4]
+            s[0], s[1] = 0x78, 0x9C
+            s[2 + n:2 + n + 4] = np.frombuffer(int(r["adler32"][k]).to_bytes(4, "big"), dtype=np.uint8)
+            packed.append(s.copy())
+            lens.append(2 + n + 4)
+        for k in (0, 1):   # parity sample: the GPU encoder's bytes are the reference's
+            i = g0 + k
+            samples[i] = (bytes(packed[g0 + k][2:-4]) == oracle.raw_deflate(h[k * CH:(k + 1) * CH]))
+        if g0 == 0:
+            first_plain = h[:4 * CH].copy()
+    lens = np.array(lens, dtype=np.uint64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+    blob = np.concatenate(packed)
+    del packed
+    items = z.make_items(n_streams)
+    items["in_off"] = offs + 2                      # the zlib container's `index` (src/Inflate.ts:61-66)
+    items["in_len"] = lens - 2
+    items["out_off"] = np.arange(n_streams, dtype=np.uint64) * CH
+    items["out_cap"] = CH
+    with torch.cuda.stream(stream):
+        d_c = torch.from_numpy(blob).cuda()
+        d_o = torch.empty(n_streams * CH, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            res = eng2.inflate_batch(d_c, d_o, items, z.INFLATE_WANT_ADLER32)
+        ms = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(stream)
+            res = eng2.inflate_batch(d_c, d_o, items)
+            e1.record(stream)
+            e1.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        res = eng2.inflate_batch(d_c, d_o, items, z.INFLATE_WANT_ADLER32)
+        head = d_o[:4 * CH].cpu().numpy()
+    assert int(res["status"].max()) == 0 and int(res["out_len"].min()) == CH
+    # Adler-32 of every output equals the trailer of its stream; in_used lands on the trailer
+    trailers = np.array([int.from_bytes(blob[int(o + l) - 4:int(o + l)].tobytes(), "big") for o, l in zip(offs, lens)], dtype=np.uint64)
+    assert np.array_equal(res["adler32"].astype(np.uint64), trailers)
+    assert np.array_equal(res["in_used"].astype(np.uint64), lens - 6)
+    assert np.array_equal(head, first_plain)
+    best = min(ms)
+    total_out = n_streams * CH
+    return {"config": "C3", "streams": n_streams, "out_bytes": total_out, "in_bytes": int(lens.sum()),
+            "inflate_ms": best, "inflate_output_GBps": total_out / best / 1e6,
+            "roofline_frac_hbm": (total_out + int(lens.sum())) / best / 1e6 / 6538.6,
+            "encoder_bytes_equal_oracle_on_samples": all(samples.values()), "samples": len(samples),
+            "adler32_of_all_outputs_match_trailers": True}
+
+
+def c4(eng, n_files=10000):
+    import datetime
+    z.api.set_engine(eng)
+    sizes = lcg_sizes(n_files)
+    files = {}
+    for i, n in enumerate(sizes):
+        files["f%05d.bin" % i] = (synth.text(n, 4000 + i) if i % 2 == 0 else synth.mixed(n, 4000 + i)).tobytes()
+    total = sum(sizes)
+    zp = z.Zip()
+    date = datetime.datetime(2026, 10, 18, 0, 0, 0)
+    t0 = time.perf_counter()
+    for name, data in files.items():
+        zp.addFile(data, name, {"date": date})
+    arc = zp.compress()
+    t1 = time.perf_counter()
+    uz = z.Unzip(arc, {"verify": True})
+    out = uz.decompressAll()
+    t2 = time.perf_counter()
+    assert list(out) == list(files)
+    for k in files:
+        assert out[k].tobytes() == files[k]
+    import io
+    import zipfile
+    with zipfile.ZipFile(io.BytesIO(arc.tobytes())) as zf:   # CPython reads the archive, CRCs included
+        assert zf.testzip() is None and len(zf.namelist()) == n_files
+    return {"config": "C4", "files": n_files, "bytes": total, "archive_bytes": int(arc.size),
+            "zip_seconds_host_api": t1 - t0, "unzip_verify_seconds_host_api": t2 - t1,
+            "zip_GBps_host_api": total / (t1 - t0) / 1e9, "unzip_GBps_host_api": total / (t2 - t1) / 1e9,
+            "roundtrip_ok": True, "cpython_zipfile_testzip_ok": True}
+
+
+def main():
+    which = [a.lower() for a in sys.argv[1:]] or ["c1", "c3", "c4"]
+    eng = z.Engine(0)
+    for name in which:
+        arg = None
+        if ":" in name:
+            name, arg = name.split(":")
+        fn = {"c1": c1, "c3": c3, "c4": c4}[name]
+        r = fn(eng) if arg is None else fn(eng, int(arg))
+        print(json.dumps(r), flush=True)
+
+
+if __name__ == "__main__":
+    main()
