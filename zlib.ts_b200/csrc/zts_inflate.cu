@@ -409,8 +409,12 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             uint32_t mytok = 0, ntok = 0;
             uint32_t stop = 0;  // 1 = end of block, 2 = undefined code / symbol
             {
-                const uint32_t lit_s = (uint32_t)__cvta_generic_to_shared(S->lit_root);
-                const uint32_t dist_s = (uint32_t)__cvta_generic_to_shared(S->dist_root);
+                uint32_t lit_s = (uint32_t)__cvta_generic_to_shared(S->lit_root);
+                uint32_t dist_s = (uint32_t)__cvta_generic_to_shared(S->dist_root);
+                // the addresses are warp-uniform; routing them through a shuffle keeps them in registers (ptxas
+                // otherwise recomputes them from %tid and %cluster_ctaid in front of every look-up: 9 instructions)
+                lit_s = __shfl_sync(0xFFFFFFFFu, lit_s, 0);
+                dist_s = __shfl_sync(0xFFFFFFFFu, dist_s, 0);
                 unsigned long long buf = br.buf;
                 int cnt = br.cnt;
                 uint32_t wpos = br.win_pos, wtaken = 0;
