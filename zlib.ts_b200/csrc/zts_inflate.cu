@@ -415,6 +415,8 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                 // otherwise recomputes them from %tid and %cluster_ctaid in front of every look-up: 9 instructions)
                 lit_s = __shfl_sync(0xFFFFFFFFu, lit_s, 0);
                 dist_s = __shfl_sync(0xFFFFFFFFu, dist_s, 0);
+                // same for the end-of-input pointer of the bit reader (recomputed from the item table otherwise)
+                br.end = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)br.end, 0));
                 unsigned long long buf = br.buf;
                 int cnt = br.cnt;
                 uint32_t wpos = br.win_pos, wtaken = 0;
