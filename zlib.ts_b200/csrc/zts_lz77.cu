@@ -290,45 +290,44 @@ __device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* 
                                                   uint32_t* count_out)
 {
     const unsigned lane = zts_lane();
-    uint32_t p = t_begin, ntok = 0;
-    uint32_t wbase = 0, wmask = 0;
-    bool have = false;
+    uint32_t p = t_begin;
+    uint32_t* tp = tok_out;          // next token slot
+    uint32_t vis = 0;                // lane j keeps the visited bits of positions [t_begin + 32 j, + 32): 16 lanes
+    const uint32_t my_lo = lane * 32u;
+    uint32_t wbase = p - 32u, wmask = 0;  // forces a probe at the first step
     while (p < t_end) {
-        if (!have || p >= wbase + 32) {
+        if (p - wbase >= 32u) {
             // probe the next 32 positions, one per lane
             wbase = p;
             const uint32_t pl = p + lane;
             bool hc = false;
             if (pl < t_end && pl + 3 < n) hc = lz_probe(S, sorted, bstart, pl);
             wmask = __ballot_sync(0xFFFFFFFFu, hc);
-            have = true;
         }
         const uint32_t off = p - wbase;
         const uint32_t m = wmask >> off;  // bit 0 <-> position p
         const uint32_t avail = min(32u - off, t_end - p);
         const uint32_t k = m ? min((uint32_t)__ffs((int)m) - 1u, avail) : avail;
+        const uint32_t rel = p - t_begin;
         if (k) {
             // k positions without any candidate: k literals (src/LZ77.ts:267-272)
-            if (lane < k) tok_out[ntok + lane] = S[p + lane];
-            if (lane == 0) {
-                const unsigned long long bits = ((1ull << k) - 1ull) << (p & 31);
-                visited[p >> 5] |= (uint32_t)bits;
-                if (bits >> 32) visited[(p >> 5) + 1] |= (uint32_t)(bits >> 32);
-            }
-            ntok += k;
+            if (lane < k) tp[lane] = S[p + lane];
+            tp += k;
+            // bits [rel, rel + k) of the tile, cut to this lane's word
+            const uint32_t a = max(rel, my_lo), e = min(rel + k, my_lo + 32u);
+            if (a < e) vis |= (0xFFFFFFFFu >> (32u - (e - a))) << (a - my_lo);
             p += k;
             continue;
         }
         uint32_t tok;
         const uint32_t np = lz_step(S, sorted, bstart, p, n, &tok);
-        if (lane == 0) {
-            visited[p >> 5] |= 1u << (p & 31);
-            tok_out[ntok] = tok;
-        }
-        ntok++;
+        if (lane == 0) *tp = tok;
+        ++tp;
+        if (lane == (rel >> 5)) vis |= 1u << (rel & 31u);
         p = np;
     }
-    *count_out = ntok;
+    if (lane < LZ_TILE / 32u) visited[(t_begin >> 5) + lane] = vis;
+    *count_out = (uint32_t)(tp - tok_out);
     return p;
 }
 
