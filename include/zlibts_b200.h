@@ -80,8 +80,13 @@ enum {
 enum {
     ZLB_INFLATE_WANT_CRC32 = 1u << 0,   /* results[i].crc32   = CRC-32 of item output  */
     ZLB_INFLATE_WANT_ADLER32 = 1u << 1, /* results[i].adler32 = Adler-32 of item output */
-    ZLB_INFLATE_CHECK_NLEN = 1u << 2    /* verify NLEN == ~LEN in stored blocks (the reference
+    ZLB_INFLATE_CHECK_NLEN = 1u << 2,   /* verify NLEN == ~LEN in stored blocks (the reference
                                            never does: src/RawInflate.ts:277 is always false) */
+    ZLB_INFLATE_SPLIT = 1u << 3,        /* large items may be cut at sync-flush markers (empty stored blocks,
+                                           `00 00 FF FF`) and their pieces decoded side by side when the pieces
+                                           turn out to be independent (what zlb_deflate_batch emits); anything
+                                           else falls back to the one-warp decoder. Results are identical. */
+    ZLB_INFLATE_SEGMENT = 1u << 4       /* internal: an item may end at a block boundary without BFINAL */
 };
 
 /* flags for zlb_checksum_batch */

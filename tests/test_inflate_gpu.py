@@ -101,3 +101,43 @@ def test_checksums_of_output(engine):
     for d, o, r in zip(datas, outs, res):
         assert o == d and int(r["status"]) == 0
         assert int(r["crc32"]) == zlib.crc32(d) and int(r["adler32"]) == zlib.adler32(d)
+
+
+def test_marker_split_matches_serial_decoder(engine):
+    """ZLB_INFLATE_SPLIT: big streams are cut at `00 00 FF FF` and decoded piecewise when the pieces are independent;
+    everything else falls back. Output, out_len and in_used must equal the one-warp decoder's in every case."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    rng = np.random.default_rng(6)
+    base = synth.mixed(3 * 1024 * 1024 + 777, 9).tobytes()
+    cases = []
+    # (a) this engine's own multi-chunk stream (independent pieces): deflate on the GPU
+    items = z.make_items(1)
+    cap = z.deflate_bound(len(base))
+    items["in_len"], items["out_cap"] = len(base), cap
+    d_z = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    r = engine.deflate_batch(torch.from_numpy(np.frombuffer(base, dtype=np.uint8).copy()).cuda(), d_z, items)
+    cases.append(("own", base, bytes(d_z[:int(r["out_len"][0])].cpu().numpy())))
+    # (b) stock zlib with full flushes (independent pieces) and (c) sync flushes (history crosses: must fall back)
+    for name, mode in (("full", zlib.Z_FULL_FLUSH), ("sync", zlib.Z_SYNC_FLUSH)):
+        co = zlib.compressobj(6, zlib.DEFLATED, -15)
+        s = b"".join(co.compress(base[k:k + 100000]) + co.flush(mode) for k in range(0, len(base), 100000)) + co.flush()
+        cases.append((name, base, s))
+    # (d) no markers at all, (e) marker bytes inside stored payload (false markers)
+    cases.append(("plain", base, zlib_raw(base, 9)))
+    fake = (b"\x00\x00\xff\xff" * 50 + rand_bytes(rng, 3000).tobytes()) * 100
+    cases.append(("stored", fake, zlib_raw(fake, 0)))
+    for name, d, s in cases:
+        outs0, res0 = gpu_inflate_many(engine, [s], [len(d)], trailer=b"\0\0\0\0")
+        outs1, res1 = gpu_inflate_many(engine, [s], [len(d)], flags=z.INFLATE_SPLIT | z.INFLATE_WANT_CRC32, trailer=b"\0\0\0\0")
+        assert outs0[0] == d and outs1[0] == d, name
+        assert int(res1["status"][0]) == 0 and int(res1["out_len"][0]) == len(d), name
+        assert int(res1["in_used"][0]) == int(res0["in_used"][0]) == len(s), name
+        assert int(res1["crc32"][0]) == zlib.crc32(d), name
+    # a batch that mixes big (split) and small (batch path) items
+    smalls = [rand_bytes(rng, 2000, 4).tobytes() for _ in range(5)]
+    streams = [cases[0][2]] + [zlib_raw(x) for x in smalls] + [cases[1][2]]
+    datas = [base] + smalls + [base]
+    outs, res = gpu_inflate_many(engine, streams, [len(x) for x in datas], flags=z.INFLATE_SPLIT, trailer=b"\0\0")
+    assert outs == datas and int(res["status"].max()) == 0

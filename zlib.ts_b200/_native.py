@@ -21,7 +21,7 @@ NONE, FIXED, DYNAMIC = 0, 1, 2
 MODE_COMPAT = 0
 
 DEFLATE_WANT_CRC32, DEFLATE_WANT_ADLER32, DEFLATE_NOT_FINAL = 1, 2, 4
-INFLATE_WANT_CRC32, INFLATE_WANT_ADLER32, INFLATE_CHECK_NLEN = 1, 2, 4
+INFLATE_WANT_CRC32, INFLATE_WANT_ADLER32, INFLATE_CHECK_NLEN, INFLATE_SPLIT = 1, 2, 4, 8
 SUM_CRC32, SUM_ADLER32 = 1, 2
 
 ST_OK, ST_INPUT_BROKEN, ST_BTYPE, ST_CODE_LENGTH, ST_OUT_OVERFLOW, ST_STORED_LEN, ST_BAD_CODE, ST_BAD_LENGTHS = range(8)

@@ -130,7 +130,8 @@ def inflate_blob(blob, offs, lens, size_hints=None, want_crc32=False, want_adler
     for i in range(n):
         hint = None if size_hints is None else size_hints[i]
         caps[i] = int(hint) if hint is not None else max(0x8000, 4 * int(lens[i]))  # DefaultInflateBufferSize
-    flags = (N.INFLATE_WANT_CRC32 if want_crc32 else 0) | (N.INFLATE_WANT_ADLER32 if want_adler32 else 0)
+    # large streams written by this engine decode piecewise at their sync-flush markers (same result, see the header)
+    flags = (N.INFLATE_WANT_CRC32 if want_crc32 else 0) | (N.INFLATE_WANT_ADLER32 if want_adler32 else 0) | N.INFLATE_SPLIT
     if blob.size == 0:
         blob = np.zeros(1, dtype=np.uint8)
     outs = [None] * n

@@ -22,6 +22,8 @@
 // replaces the reference's 2^15-entry single-level table.
 //
 // Algorithmic bytes per stream: C (compressed, read once) + N (output, written once).
+#include <algorithm>
+
 #include "zts_common.cuh"
 
 #define INF_WARPS_PER_CTA 4
@@ -279,6 +281,8 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
     bool bfinal = false;
 
     while (!bfinal && status == ZLB_ST_OK) {
+        // segment mode: a piece of a larger stream ends cleanly where a block ends and its input is used up
+        if ((flags & ZLB_INFLATE_SEGMENT) && blocks > 0 && br_bits_used(br) == in_bits) break;
         br_refill(br);
         if (br_bits_used(br) + 3 > in_bits) {
             status = ZLB_ST_INPUT_BROKEN;
@@ -589,7 +593,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
     if (lane == 0) {
         zlb_result r = results[item];
         r.status = status;
-        r.blocks = blocks;
+        r.blocks = blocks | ((flags & ZLB_INFLATE_SEGMENT) && bfinal ? 0x80000000u : 0u);  // segment mode: saw BFINAL
         r.out_len = op;
         r.in_used = (br_bits_used(br) + 7) >> 3;  // whole unread bytes are given back (:511-514)
         results[item] = r;
@@ -605,6 +609,146 @@ static int inflate_launch(zlb_ctx* ctx, cudaStream_t st, const uint8_t* d_in, ui
     ZTS_LAUNCH(ctx, ZK_INFLATE,
                inflate_warp_kernel<<<grid, INF_WARPS_PER_CTA * 32, smem, st>>>(d_in, d_out, d_items, d_results,
                                                                               (uint32_t)n, flags));
+    return ZLB_OK;
+}
+
+// ---- marker split (ZLB_INFLATE_SPLIT) ------------------------------------------------------------------------
+// A stream written by zlb_deflate_batch is a sequence of independent pieces: every chunk was compressed on its own
+// (no match reaches into an earlier chunk) and ends with an empty stored block, `00 00 FF FF` after byte alignment.
+// One warp per piece decodes a 1 GiB stream in the time of a 64 KiB one. Nothing is assumed about the input: the
+// pieces are decoded into scratch slots in segment mode, and only if every piece (a) ends exactly where the next
+// one starts, (b) never reaches before its own first byte and (c) fits its slot is the result gathered; a false
+// marker or a foreign stream with history across blocks fails one of these and the item is decoded serially.
+#define SPLIT_MIN_BYTES (256u << 10)   // items at least this large are worth splitting
+#define SPLIT_SLOT (128u << 10)        // scratch bytes per piece (pieces of this engine's streams are <= 64 KiB)
+#define SPLIT_MAX_MARKS (1u << 22)
+
+__global__ void __launch_bounds__(256)
+marker_scan_kernel(const uint8_t* __restrict__ in, unsigned long long n, unsigned long long* __restrict__ marks,
+                   uint32_t* __restrict__ count, uint32_t cap)
+{
+    // thread t looks at 16 consecutive start offsets
+    const unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 16ull;
+    if (base + 4 > n) return;
+    uint8_t b[19];
+#pragma unroll
+    for (int k = 0; k < 19; ++k) b[k] = (base + k < n) ? in[base + k] : (uint8_t)0x55;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        if (b[k] == 0 && b[k + 1] == 0 && b[k + 2] == 0xFF && b[k + 3] == 0xFF && base + k + 4 <= n) {
+            const uint32_t slot = atomicAdd(count, 1u);
+            if (slot < cap) marks[slot] = base + k + 4;  // first byte after the marker
+        }
+    }
+}
+
+struct ZtsGather {
+    unsigned long long src, dst, len;
+};
+
+__global__ void __launch_bounds__(256)
+segment_gather_kernel(const uint8_t* __restrict__ scratch, uint8_t* __restrict__ out, const ZtsGather* __restrict__ g)
+{
+    const ZtsGather e = g[blockIdx.x];
+    const uint8_t* s = scratch + e.src;
+    uint8_t* d = out + e.dst;
+    // 16-byte copies where both sides allow it (slots are 16-byte aligned; the destination decides)
+    const uint32_t head = (uint32_t)min((unsigned long long)((16u - ((uintptr_t)d & 15u)) & 15u), e.len);
+    for (uint32_t i = threadIdx.x; i < head; i += 256) d[i] = s[i];
+    const unsigned long long body = (e.len - head) & ~15ull;
+    if ((((uintptr_t)(s + head)) & 15u) == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(s + head);
+        uint4* d4 = reinterpret_cast<uint4*>(d + head);
+        for (unsigned long long i = threadIdx.x; i < body / 16; i += 256) d4[i] = s4[i];
+    } else {
+        for (unsigned long long i = threadIdx.x; i < body; i += 256) d[head + i] = s[head + i];
+    }
+    for (unsigned long long i = head + body + threadIdx.x; i < e.len; i += 256) d[i] = s[i];
+}
+
+static int inflate_launch(zlb_ctx* ctx, cudaStream_t st, const uint8_t* d_in, uint8_t* d_out, const zlb_item* d_items,
+                          zlb_result* d_results, size_t n, uint32_t flags);
+
+// Tries to decode item `it` piecewise. Returns ZLB_OK with *done = true and *res filled when it worked, *done = false
+// when the item has to go through the serial decoder, < 0 on API errors.
+static int inflate_split_item(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item& it, uint32_t flags,
+                              zlb_result* res, bool* done)
+{
+    *done = false;
+    cudaStream_t st = ctx->stream;
+    int rc = zts_reserve(ctx, &ctx->d_misc, (size_t)SPLIT_MAX_MARKS * 8 + 256);
+    if (rc) return rc;
+    unsigned long long* d_marks = (unsigned long long*)((uint8_t*)ctx->d_misc.p + 256);
+    uint32_t* d_count = (uint32_t*)ctx->d_misc.p;
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_count, 0, 4, st));
+    const unsigned long long n = it.in_len;
+    const unsigned grid = (unsigned)((n / 16 + 255) / 256 + 1);
+    ZTS_LAUNCH(ctx, ZK_MARKER_SCAN,
+               marker_scan_kernel<<<grid, 256, 0, st>>>(d_in + it.in_off, n, d_marks, d_count, SPLIT_MAX_MARKS));
+    uint32_t count = 0;
+    ZTS_CUDA(ctx, cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, st));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(st));
+    if (count == 0 || count > SPLIT_MAX_MARKS) return ZLB_OK;
+    std::vector<unsigned long long> marks(count);
+    ZTS_CUDA(ctx, cudaMemcpyAsync(marks.data(), d_marks, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(st));
+    std::sort(marks.begin(), marks.end());
+    // piece starts: 0 and every marker end that leaves at least one byte
+    std::vector<unsigned long long> starts;
+    starts.push_back(0);
+    for (unsigned long long m : marks)
+        if (m < n && m != starts.back()) starts.push_back(m);
+    const size_t np = starts.size();
+    if (np < 2) return ZLB_OK;
+    // segment items + scratch
+    rc = zts_reserve(ctx, &ctx->d_split, np * (size_t)SPLIT_SLOT + np * (sizeof(zlb_item) + sizeof(zlb_result) + sizeof(ZtsGather)) + 1024);
+    if (rc) return rc;
+    uint8_t* d_scratch = (uint8_t*)ctx->d_split.p;
+    zlb_item* d_seg = (zlb_item*)(d_scratch + np * (size_t)SPLIT_SLOT);
+    zlb_result* d_segres = (zlb_result*)(d_seg + np);
+    ZtsGather* d_gather = (ZtsGather*)(d_segres + np);
+    std::vector<zlb_item> seg(np);
+    for (size_t k = 0; k < np; ++k) {
+        seg[k].in_off = it.in_off + starts[k];
+        seg[k].in_len = (k + 1 < np ? starts[k + 1] : n) - starts[k];
+        seg[k].out_off = k * (size_t)SPLIT_SLOT;
+        seg[k].out_cap = SPLIT_SLOT;
+    }
+    ZTS_CUDA(ctx, cudaMemcpyAsync(d_seg, seg.data(), np * sizeof(zlb_item), cudaMemcpyHostToDevice, st));
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_segres, 0, np * sizeof(zlb_result), st));
+    rc = inflate_launch(ctx, st, d_in, d_scratch, d_seg, d_segres, np,
+                        (flags & ZLB_INFLATE_CHECK_NLEN) | ZLB_INFLATE_SEGMENT);
+    if (rc) return rc;
+    std::vector<zlb_result> sres(np);
+    ZTS_CUDA(ctx, cudaMemcpyAsync(sres.data(), d_segres, np * sizeof(zlb_result), cudaMemcpyDeviceToHost, st));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(st));
+    // validate the chain
+    unsigned long long total = 0, blocks = 0;
+    std::vector<ZtsGather> gath(np);
+    for (size_t k = 0; k < np; ++k) {
+        const zlb_result& r = sres[k];
+        const bool last = k + 1 == np;
+        const bool fin = (r.blocks & 0x80000000u) != 0;
+        if (r.status != ZLB_ST_OK) return ZLB_OK;                 // incl. a distance before the piece's first byte
+        if (!last && (fin || r.in_used != seg[k].in_len)) return ZLB_OK;
+        if (last && !fin) return ZLB_OK;
+        gath[k].src = seg[k].out_off;
+        gath[k].dst = it.out_off + total;
+        gath[k].len = r.out_len;
+        total += r.out_len;
+        blocks += r.blocks & 0x7FFFFFFFu;
+    }
+    res->status = total > it.out_cap ? ZLB_ST_OUT_OVERFLOW : ZLB_ST_OK;
+    res->out_len = total > it.out_cap ? 0 : total;
+    res->in_used = starts[np - 1] + sres[np - 1].in_used;
+    res->blocks = (uint32_t)blocks;
+    res->crc32 = res->adler32 = 0;
+    if (total <= it.out_cap && total) {
+        ZTS_CUDA(ctx, cudaMemcpyAsync(d_gather, gath.data(), np * sizeof(ZtsGather), cudaMemcpyHostToDevice, st));
+        ZTS_LAUNCH(ctx, ZK_GATHER, segment_gather_kernel<<<(unsigned)np, 256, 0, st>>>(d_scratch, d_out, d_gather));
+        ZTS_CUDA(ctx, cudaStreamSynchronize(st));  // gath / seg vectors go out of scope
+    }
+    *done = true;
     return ZLB_OK;
 }
 
@@ -632,6 +776,61 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (flags & ZLB_INFLATE_WANT_CRC32) kinds |= ZLB_SUM_CRC32;
     if (flags & ZLB_INFLATE_WANT_ADLER32) kinds |= ZLB_SUM_ADLER32;
 
+    // large items that may be cut at sync-flush markers are decoded piecewise, one after the other (each is
+    // massively parallel by itself); whatever is left goes through the batch path below
+    if ((flags & ZLB_INFLATE_SPLIT) && !(flags & ZLB_INFLATE_SEGMENT)) {
+        std::vector<size_t> big;
+        for (size_t i = 0; i < n; ++i)
+            if (h_items[i].in_len >= SPLIT_MIN_BYTES) big.push_back(i);
+        if (!big.empty()) {
+            if (hio) ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            std::vector<zlb_item> rest_items;
+            std::vector<size_t> rest_idx;
+            std::vector<char> is_done(n, 0);
+            for (size_t i : big) {
+                bool done = false;
+                zlb_result r;
+                memset(&r, 0, sizeof r);
+                rc = inflate_split_item(ctx, d_in, d_out, h_items[i], flags, &r, &done);
+                if (rc) return rc;
+                if (done) {
+                    is_done[i] = 1;
+                    ZTS_CUDA(ctx, cudaMemcpyAsync(d_results + i, &r, sizeof r, cudaMemcpyHostToDevice, ctx->stream));
+                    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                }
+            }
+            for (size_t i = 0; i < n; ++i)
+                if (!is_done[i]) {
+                    rest_items.push_back(h_items[i]);
+                    rest_idx.push_back(i);
+                }
+            if (!rest_items.empty()) {
+                // the remaining items in one batch; their results are scattered back to their slots
+                const size_t m = rest_items.size();
+                rc = zts_reserve(ctx, &ctx->d_sums, m * (sizeof(zlb_item) + sizeof(zlb_result)) + 256);
+                if (rc) return rc;
+                zlb_item* d_ri = (zlb_item*)ctx->d_sums.p;
+                zlb_result* d_rr = (zlb_result*)(d_ri + m);
+                ZTS_CUDA(ctx, cudaMemcpyAsync(d_ri, rest_items.data(), m * sizeof(zlb_item), cudaMemcpyHostToDevice, ctx->stream));
+                ZTS_CUDA(ctx, cudaMemsetAsync(d_rr, 0, m * sizeof(zlb_result), ctx->stream));
+                rc = inflate_launch(ctx, ctx->stream, d_in, d_out, d_ri, d_rr, m, flags & ~(uint32_t)ZLB_INFLATE_SPLIT);
+                if (rc) return rc;
+                std::vector<zlb_result> rr(m);
+                ZTS_CUDA(ctx, cudaMemcpyAsync(rr.data(), d_rr, m * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+                ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                for (size_t k = 0; k < m; ++k)
+                    ZTS_CUDA(ctx, cudaMemcpyAsync(d_results + rest_idx[k], &rr[k], sizeof(zlb_result), cudaMemcpyHostToDevice, ctx->stream));
+                ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            }
+            if (kinds) {
+                rc = zts_checksum_device(ctx, d_out, d_items, d_results, h_items, n, kinds, 1);
+                if (rc) return rc;
+            }
+            if (hio) ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out, d_out, hio->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+            return ZLB_OK;
+        }
+    }
     // waves only pay when the items are laid out in order on both sides (then a wave is one contiguous copy each way)
     size_t n_waves = 1;
     if (hio && n >= 1024) {
