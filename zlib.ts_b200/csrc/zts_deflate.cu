@@ -187,10 +187,10 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
             const ZtsTile t = ci->tiles[tid >> 1];
             if (tid & 1) {
                 cnt = (uint32_t)t.spec_count - t.spec_from;
-                src = 0x80000000u | ((tid >> 1) * LZ_TOK_STRIDE + t.spec_from);
+                src = 0x80000000u | (lz_tok_off(tid >> 1) + t.spec_from);
             } else {
                 cnt = t.fix_count;
-                src = (tid >> 1) * LZ_TOK_STRIDE;
+                src = lz_tok_off(tid >> 1);
             }
         }
         uint32_t inc = cnt;
@@ -677,8 +677,8 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
     uint32_t k = 0;
     for (uint32_t w = 0; w < LZ_NTILES; ++w) {
         const ZtsTile t = ci.tiles[w];
-        for (uint32_t i = 0; i < t.fix_count && k <= n; ++i) h_tokens_out[k++] = fix[w * LZ_TOK_STRIDE + i];
-        for (uint32_t i = t.spec_from; i < t.spec_count && k <= n; ++i) h_tokens_out[k++] = spec[w * LZ_TOK_STRIDE + i];
+        for (uint32_t i = 0; i < t.fix_count && k <= n; ++i) h_tokens_out[k++] = fix[lz_tok_off(w) + i];
+        for (uint32_t i = t.spec_from; i < t.spec_count && k <= n; ++i) h_tokens_out[k++] = spec[lz_tok_off(w) + i];
     }
     *n_tokens = k;
     if (k != ci.n_tokens) return zts_fail(ctx, ZLB_E_CUDA, "token count mismatch %u vs %u", k, ci.n_tokens);

@@ -5,15 +5,17 @@
 #define LZ_THREADS 1024
 #define LZ_WARPS 32
 #define LZ_MAX_CHUNK 65536u
-#define LZ_TILE 512u                    // positions of one speculative parse tile (warps take tiles dynamically)
-#define LZ_NTILES (LZ_MAX_CHUNK / LZ_TILE)
+// Speculative parse tiles (warps take them from a counter in order). Sizes shrink towards the end of the chunk --
+// 96 x 512, 48 x 256, 32 x 128 positions -- so that the last tiles to finish are small ones and the warps reach
+// the barrier behind the speculative parse close together.
+#define LZ_TILE 512u                    // largest tile
+#define LZ_NTILES 176u
 #define LZ_SORT_TILE 2048u              // positions ranked by one warp in a radix pass
 #define LZ_HASH_BITS 13
 #define LZ_NB (1u << LZ_HASH_BITS)
 #define LZ_WINDOW 32768u                // WindowSize, src/LZ77.ts:8
 #define LZ_MAXLEN 258u                  // LZ77MaxLength, src/LZ77.ts:5
-#define LZ_TOK_STRIDE (LZ_TILE + 8)     // token slots per tile in the spec / fix buffers
-#define LZ_TOK_PER_CHUNK (LZ_NTILES * LZ_TOK_STRIDE)
+#define LZ_TOK_PER_CHUNK (LZ_MAX_CHUNK + 8u * LZ_NTILES + 8u)  // token slots per chunk in the spec / fix buffers
 
 #define TOK_MATCH 0x80000000u           // literal: byte ; match: TOK_MATCH | (len-3) << 16 | (dist-1)
 
@@ -29,6 +31,19 @@ struct ZtsChunk {      // host-built, one per chunk
     uint32_t flags;
     uint32_t pad0, pad1;
 };
+
+// first position of tile t (t == LZ_NTILES gives the chunk size)
+__host__ __device__ __forceinline__ uint32_t lz_tile_begin(uint32_t t)
+{
+    return t < 96u ? t * 512u : t < 144u ? 49152u + (t - 96u) * 256u : 61440u + (t - 144u) * 128u;
+}
+// tiles that a chunk of n bytes has
+__host__ __device__ __forceinline__ uint32_t lz_tile_count(uint32_t n)
+{
+    return n <= 49152u ? (n + 511u) / 512u : n <= 61440u ? 96u + (n - 49152u + 255u) / 256u : 144u + (n - 61440u + 127u) / 128u;
+}
+// first token slot of tile t: a tile never holds more tokens than positions
+__host__ __device__ __forceinline__ uint32_t lz_tok_off(uint32_t t) { return lz_tile_begin(t) + 8u * t; }
 
 struct ZtsTile {
     uint16_t fix_count;   // tokens re-parsed from the true entry point until it met the speculative parse

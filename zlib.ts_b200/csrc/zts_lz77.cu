@@ -9,7 +9,7 @@
 //   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
 //   2. all positions are radix-sorted (stable, 2 LSD passes, ballot-based ranking inside a warp, no atomics)
 //      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
-//   3. the chunk is cut into 128 tiles of 512 positions which the 32 warps take from a shared counter
+//   3. the chunk is cut into 176 tiles (512, then 256, then 128 positions) which the 32 warps take from a counter
 //      (segments of different entropy cost very different time) and parse speculatively, each from
 //      its tile start. A parse step first probes 32 positions at once, one per lane, for "has any
 //      earlier position with the same 3 bytes": runs of positions without one are literals and are
@@ -52,7 +52,7 @@ struct LzMisc {
     uint32_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)
     uint32_t fix_exit[LZ_NTILES];    // exit of the tile for the entry it was last parsed from
     uint32_t entry_used[LZ_NTILES];  // that entry
-    uint32_t start_mask[LZ_NTILES / 32];  // tiles that start a chain of wrongly entered tiles
+    uint32_t start_mask[(LZ_NTILES + 31) / 32];  // tiles that start a chain of wrongly entered tiles
     uint16_t spec_count[LZ_NTILES];
     uint16_t fix_count[LZ_NTILES];
     uint16_t spec_from[LZ_NTILES];
@@ -326,7 +326,7 @@ __device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* 
         if (lane == (rel >> 5)) vis |= 1u << (rel & 31u);
         p = np;
     }
-    if (lane < LZ_TILE / 32u) visited[(t_begin >> 5) + lane] = vis;
+    if (lane < ((t_end - t_begin + 31u) >> 5)) visited[(t_begin >> 5) + lane] = vis;
     *count_out = (uint32_t)(tp - tok_out);
     return p;
 }
@@ -598,7 +598,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             M->tile_next2 = 1;  // tile 0 needs no re-entry
         }
         __syncthreads();
-        const uint32_t n_tiles = (n + LZ_TILE - 1) / LZ_TILE;
+        const uint32_t n_tiles = lz_tile_count(n);
         uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         uint32_t* fix_c = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         for (;;) {
@@ -606,9 +606,9 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (lane == 0) t = atomicAdd(&M->tile_next, 1u);
             t = __shfl_sync(0xFFFFFFFFu, t, 0);
             if (t >= n_tiles) break;
-            const uint32_t t_begin = t * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+            const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
             uint32_t cnt;
-            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, n, spec_c + t * LZ_TOK_STRIDE,
+            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, n, spec_c + lz_tok_off(t),
                                               visited, &cnt);
             if (lane == 0) {
                 M->spec_exit[t] = ex;
@@ -620,7 +620,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel); this is already
         //          the true parse wherever the predecessor did converge to its speculative parse
         ZtsChunkInfo* ci = info + c;
-        if (tid < LZ_NTILES / 32) M->start_mask[tid] = 0;
+        if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
         if (tid == 0 && n_tiles) {
             M->entry_used[0] = 0;
             M->fix_exit[0] = M->spec_exit[0];
@@ -632,10 +632,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (lane == 0) w = atomicAdd(&M->tile_next2, 1u);
             w = __shfl_sync(0xFFFFFFFFu, w, 0);
             if (w >= n_tiles) break;
-            const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+            const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
             const uint32_t entry = M->spec_exit[w - 1];
             uint32_t nfix, from;
-            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE,
+            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + lz_tok_off(w),
                                                visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
             if (lane == 0) {
                 M->entry_used[w] = entry;
@@ -660,10 +660,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             uint32_t entry = M->fix_exit[w - 1];
             for (uint32_t t = w; t < end; ++t) {
                 if (entry == M->entry_used[t]) break;
-                const uint32_t t_begin = t * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+                const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
                 uint32_t nfix, from;
                 const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n,
-                                                   fix_c + t * LZ_TOK_STRIDE, visited, M->spec_count[t],
+                                                   fix_c + lz_tok_off(t), visited, M->spec_count[t],
                                                    M->spec_exit[t], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[t] = entry;
@@ -685,10 +685,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                     true_exit = M->fix_exit[w];
                     continue;
                 }
-                const uint32_t t_begin = w * LZ_TILE, t_end = min(n, t_begin + LZ_TILE);
+                const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
                 uint32_t nfix, from;
                 const uint32_t entry = true_exit;
-                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + w * LZ_TOK_STRIDE,
+                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + lz_tok_off(w),
                                            visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[w] = entry;
@@ -715,8 +715,8 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 ci->tiles[w] = t;
                 atomicAdd(&M->n_tokens, (uint32_t)t.fix_count + (t.spec_count - t.spec_from));
             }
-            const uint32_t* fx = fix_c + w * LZ_TOK_STRIDE;
-            const uint32_t* sp = spec_c + w * LZ_TOK_STRIDE;
+            const uint32_t* fx = fix_c + lz_tok_off(w);
+            const uint32_t* sp = spec_c + lz_tok_off(w);
             for (uint32_t k = lane; k < t.fix_count; k += 32) hist_token(fx[k], M->hist);
             for (uint32_t k = t.spec_from + lane; k < t.spec_count; k += 32) hist_token(sp[k], M->hist);
         }
