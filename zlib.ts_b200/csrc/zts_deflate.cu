@@ -10,6 +10,8 @@
 //                        block, image copied out with aligned word stores (byte stores at the edges)
 // Chunks of one item are joined by an empty stored block that byte-aligns; the
 // reference's RawInflate accepts this (src/RawInflate.ts:128-130,261-262,311).
+#include <stdlib.h>
+
 #include "zts_deflate.cuh"
 
 size_t zts_lz77_smem_bytes();

@@ -225,7 +225,23 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
     }
     const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
+    uint32_t misses = 0;  // consecutive 32-wide steps in which the tail-byte filter rejected every candidate
     while (cur > lo) {
+        // long candidate lists behind a known match (ends of runs, low-entropy records): 128 candidates per step
+        // through the tail-byte filter alone, four independent look-ups per lane in flight; the first group in
+        // which anything survives (or leaves the window) is handed to the exact 32-wide step below
+        if (misses >= 2u && cur - lo >= 128u) {  // misses > 0 implies a known match (best_len >= 3)
+            const uint8_t pt = S[p + best_len];
+            do {
+                const uint32_t c0 = sorted[cur - 1 - lane], c1 = sorted[cur - 33 - lane], c2 = sorted[cur - 65 - lane],
+                               c3 = sorted[cur - 97 - lane];
+                const bool hit = S[c0 + best_len] == pt || S[c1 + best_len] == pt || S[c2 + best_len] == pt ||
+                                 S[c3 + best_len] == pt || p - c3 > LZ_WINDOW;  // c3 is the oldest of the lane's four
+                if (__any_sync(0xFFFFFFFFu, hit)) break;
+                cur -= 128u;
+            } while (cur - lo >= 128u);
+            if (cur <= lo) break;
+        }
         const uint32_t cnt = min(32u, cur - lo);
         const bool act = lane < cnt;
         const uint32_t q = act ? sorted[cur - 1 - lane] : 0u;  // lane 0 = newest candidate
@@ -236,6 +252,7 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
         uint32_t key = 0;
         if (inwin && (best_len < 3 || S[q + best_len] == ptail)) key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
         const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);  // longest, then nearest
+        misses = m ? 0u : misses + 1u;
         if ((m >> 16) > best_len) {
             best_len = m >> 16;
             best = m;
