@@ -66,7 +66,13 @@ enum { ZLB_NONE = 0, ZLB_FIXED = 1, ZLB_DYNAMIC = 2 };
 /* deflate mode. COMPAT: every chunk's bytes equal the reference's RawDeflate run on that chunk
  * (lazy = 0, src/LZ77.ts:196-283 exhaustive longest/nearest match, src/RawDeflate.ts:484-571 code
  * lengths). */
-enum { ZLB_MODE_COMPAT = 0 };
+enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1 };
+/* FAST: same pipeline and the same exact Huffman construction, but the match search looks only at the newest
+ * `depth` candidates of a position (default ZLB_FAST_DEFAULT_DEPTH) instead of all of them: still a valid stream for
+ * the reference's Inflate, no longer byte-identical; the ratio stays within a few per cent of the reference's
+ * (bench.py reports it). A depth is passed as ZLB_MODE_FAST_DEPTH(d). */
+#define ZLB_FAST_DEFAULT_DEPTH 64
+#define ZLB_MODE_FAST_DEPTH(d) (ZLB_MODE_FAST | ((int)(d) << 8))
 
 /* flags for zlb_deflate_batch */
 enum {

@@ -229,3 +229,32 @@ def test_not_final_shards_concatenate_into_one_stream(engine):
     ref, ip = oracle.raw_inflate(whole + b"\0\0\0\0", 0, out_cap=len(data))
     assert ref == data and ip == len(whole)
     assert shard.combine_checksums(parts, z.crc32_combine, z.adler32_combine) == (zlib.crc32(data), zlib.adler32(data), len(data))
+
+
+def test_fast_mode_valid_streams_and_ratio_within_tolerance(engine):
+    """ZLB_MODE_FAST (bounded candidate depth): still a valid stream for zlib and for the reference's decoder, ratio
+    within 3 % of the reference-compatible mode per chunk set (north_star tolerance); depth 0xFFFFFF equals compat."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    for data in (synth.mixed(40 * 65536 + 99, 51).tobytes(), synth.text(24 * 65536, 52).tobytes(),
+                 (b"0123456789abcdefghijklmnopqrstuvwxyz" * 40000)[:20 * 65536]):
+        n = len(data)
+        d_in = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
+        cap = z.deflate_bound(n)
+        it = z.make_items(1)
+        it["in_len"], it["out_cap"] = n, cap
+        sizes = {}
+        for name, mode in (("compat", z.MODE_COMPAT), ("fast", z.MODE_FAST), ("fast32", z.mode_fast(32)),
+                           ("fast_all", z.mode_fast(0xFFFFFF))):
+            d_z = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+            r = engine.deflate_batch(d_in, d_z, it, mode=mode)
+            assert int(r["status"][0]) == 0
+            out = d_z[:int(r["out_len"][0])].cpu().numpy().tobytes()
+            assert zlib.decompress(out, -15) == data, name
+            ref, ip = oracle.raw_inflate(out + b"\0\0\0\0", 0, out_cap=n)
+            assert ref == data and ip == len(out), name
+            sizes[name] = (len(out), out)
+        assert sizes["fast_all"][1] == sizes["compat"][1]
+        for name in ("fast", "fast32"):
+            assert sizes[name][0] <= sizes["compat"][0] * 1.03, (name, sizes[name][0], sizes["compat"][0])

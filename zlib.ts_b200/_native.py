@@ -18,7 +18,12 @@ assert ITEM_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32
 
 # CompressionType (src/RawDeflate.ts:12-17)
 NONE, FIXED, DYNAMIC = 0, 1, 2
-MODE_COMPAT = 0
+MODE_COMPAT, MODE_FAST = 0, 1
+
+
+def mode_fast(depth=0):
+    """ZLB_MODE_FAST_DEPTH(depth); 0 = the library default (64 candidates)."""
+    return MODE_FAST | (int(depth) << 8)
 
 DEFLATE_WANT_CRC32, DEFLATE_WANT_ADLER32, DEFLATE_NOT_FINAL = 1, 2, 4
 INFLATE_WANT_CRC32, INFLATE_WANT_ADLER32, INFLATE_CHECK_NLEN, INFLATE_SPLIT = 1, 2, 4, 8

@@ -17,7 +17,7 @@
 size_t zts_lz77_smem_bytes();
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
                     ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint32_t* d_sortT,
-                    uint32_t* d_counter, uint32_t grid);
+                    uint32_t* d_counter, uint32_t grid, uint32_t depth);
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type);
 int zts_huffman_lengths_debug(zlb_ctx* ctx, const uint32_t* d_freqs, int nsym, int limit, uint8_t* d_lengths);
@@ -401,7 +401,13 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                           zlb_result* h_results, size_t n, int mode, int block_type, uint32_t chunk_bytes,
                           uint32_t flags, HostIO* hio)
 {
-    if (mode != ZLB_MODE_COMPAT) return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
+    if ((mode & 0xFF) != ZLB_MODE_COMPAT && (mode & 0xFF) != ZLB_MODE_FAST)
+        return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
+    uint32_t depth = 0xFFFFFFFFu;  // compat: every candidate, like the reference
+    if ((mode & 0xFF) == ZLB_MODE_FAST) {
+        depth = ((uint32_t)mode >> 8) ? ((uint32_t)mode >> 8) : ZLB_FAST_DEFAULT_DEPTH;
+        depth = (depth + 31u) & ~31u;
+    }
     if (block_type != ZLB_NONE && block_type != ZLB_FIXED && block_type != ZLB_DYNAMIC)
         return zts_fail(ctx, ZLB_E_ARG, "invalid compression type");  // src/RawDeflate.ts:110
     const uint32_t cb = (chunk_bytes == 0 || chunk_bytes > LZ_MAX_CHUNK) ? LZ_MAX_CHUNK : chunk_bytes;
@@ -567,7 +573,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 * k), 0));
         }
         rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist, (uint32_t*)ctx->d_sortT.p,
-                             d_counter, g);
+                             d_counter, g, depth);
         if (rc) return rc;
         rc = zts_huffman_launch(ctx, d_chunks + w0, wn, d_hist, d_info, d_codes, block_type);
         if (rc) return rc;
@@ -667,7 +673,7 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     rc = zts_lz77_launch(ctx, (const uint8_t*)d_in, (const ZtsChunk*)ctx->d_chunks.p, 1, (ZtsChunkInfo*)ctx->d_chunk_info.p,
                          (uint32_t*)ctx->d_spec.p, (uint32_t*)ctx->d_tokens.p, (uint32_t*)ctx->d_hist.p,
-                         (uint32_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1);
+                         (uint32_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1, 0xFFFFFFFFu);
     if (rc) return rc;
     std::vector<uint32_t> spec(LZ_TOK_PER_CHUNK), fix(LZ_TOK_PER_CHUNK);
     ZtsChunkInfo ci;

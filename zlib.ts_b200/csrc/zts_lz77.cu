@@ -173,8 +173,10 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
 
 // ---- warp-cooperative longest/nearest match search at position p (requires p + 3 < n) ----------
 // returns (len << 16) | dist, or 0 when no candidate exists (src/LZ77.ts:157-194 + :242)
+// `depth` = how many candidates (newest first) are looked at: 0xFFFFFFFF in the reference-compatible mode (all of
+// them, like the reference), a small multiple of 32 in the fast mode.
 __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __restrict__ sorted,
-                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n)
+                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n, uint32_t depth)
 {
     const unsigned lane = zts_lane();
     const uint32_t pw = ld_u32(S, p);
@@ -260,6 +262,8 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
         if (best_len >= maxlen) break;                          // :189 (258) or capped by the input end
         if (__any_sync(0xFFFFFFFFu, act && !inwin)) break;      // older ones are outside the window (:223)
         cur -= cnt;
+        if (depth <= 32u) break;                                // fast mode: candidate budget spent
+        depth -= 32u;
     }
     if (best_len < 3) return 0;
     return (best_len << 16) | (p - (best & 0xFFFFu));
@@ -267,10 +271,10 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
 
 // one greedy step at parse position p: emits the token, returns the next parse position
 __device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                            uint32_t p, uint32_t n, uint32_t* tok_out)
+                                            uint32_t p, uint32_t n, uint32_t depth, uint32_t* tok_out)
 {
     uint32_t r = 0;
-    if (p + 3 < n) r = lz_search(S, sorted, bstart, p, n);  // src/LZ77.ts:228: no search in the last 3 bytes
+    if (p + 3 < n) r = lz_search(S, sorted, bstart, p, n, depth);  // src/LZ77.ts:228: no search in the last 3 bytes
     if (r) {
         const uint32_t len = r >> 16, dist = r & 0xFFFFu;
         *tok_out = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
@@ -302,7 +306,7 @@ __device__ __forceinline__ bool lz_probe(const LzS& S, const uint16_t* __restric
 // Speculative parse of tile [t_begin, t_end): tokens to tok_out, visited bit per parsed position.
 // Returns the exit position (>= t_end); *count_out = tokens written.
 __device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                                  uint32_t t_begin, uint32_t t_end, uint32_t n,
+                                                  uint32_t t_begin, uint32_t t_end, uint32_t n, uint32_t depth,
                                                   uint32_t* __restrict__ tok_out, uint32_t* visited,
                                                   uint32_t* count_out)
 {
@@ -337,7 +341,7 @@ __device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* 
             continue;
         }
         uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, bstart, p, n, &tok);
+        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
         if (lane == 0) *tp = tok;
         ++tp;
         if (lane == (rel >> 5)) vis |= 1u << (rel & 31u);
@@ -353,7 +357,7 @@ __device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* 
 // Writes fix tokens, returns the exit; *nfix_out / *from_out describe the splice.
 __device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
                                                    uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
-                                                   uint32_t* __restrict__ fix_out, const uint32_t* visited,
+                                                   uint32_t depth, uint32_t* __restrict__ fix_out, const uint32_t* visited,
                                                    uint32_t spec_count, uint32_t spec_exit, uint32_t* nfix_out,
                                                    uint32_t* from_out)
 {
@@ -374,7 +378,7 @@ __device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t*
             break;
         }
         uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, bstart, p, n, &tok);
+        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
         if (lane == 0) fix_out[nfix] = tok;
         nfix++;
         p = np;
@@ -400,7 +404,8 @@ __device__ __forceinline__ void hist_token(uint32_t tok, uint32_t* hist)
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ chunks, uint32_t n_chunks,
                   ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ spec_tok, uint32_t* __restrict__ fix_tok,
-                  uint32_t* __restrict__ hist_out, uint32_t* __restrict__ sortT, uint32_t* __restrict__ work_counter)
+                  uint32_t* __restrict__ hist_out, uint32_t* __restrict__ sortT, uint32_t* __restrict__ work_counter,
+                  uint32_t depth)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint8_t* Sbuf = smem + LzSmem::S_OFF;
@@ -625,7 +630,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (t >= n_tiles) break;
             const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
             uint32_t cnt;
-            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, n, spec_c + lz_tok_off(t),
+            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, n, depth, spec_c + lz_tok_off(t),
                                               visited, &cnt);
             if (lane == 0) {
                 M->spec_exit[t] = ex;
@@ -652,7 +657,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
             const uint32_t entry = M->spec_exit[w - 1];
             uint32_t nfix, from;
-            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + lz_tok_off(w),
+            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
                                                visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
             if (lane == 0) {
                 M->entry_used[w] = entry;
@@ -679,7 +684,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 if (entry == M->entry_used[t]) break;
                 const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
                 uint32_t nfix, from;
-                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n,
+                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth,
                                                    fix_c + lz_tok_off(t), visited, M->spec_count[t],
                                                    M->spec_exit[t], &nfix, &from);
                 if (lane == 0) {
@@ -705,7 +710,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
                 uint32_t nfix, from;
                 const uint32_t entry = true_exit;
-                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, fix_c + lz_tok_off(w),
+                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
                                            visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[w] = entry;
@@ -749,7 +754,7 @@ size_t zts_lz77_smem_bytes() { return LzSmem::TOTAL; }
 
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
                     ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint32_t* d_sortT,
-                    uint32_t* d_counter, uint32_t grid)
+                    uint32_t* d_counter, uint32_t grid, uint32_t depth)
 {
     static_assert(sizeof(LzMisc) <= LzSmem::MISC_BYTES, "misc area too small");
     static_assert(LzSmem::TOTAL <= 232448, "exceeds 227 KiB of dynamic shared memory");
@@ -758,6 +763,6 @@ int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks,
     ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->stream));
     ZTS_LAUNCH(ctx, ZK_LZ77,
                lz77_chunk_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->stream>>>(
-                   d_in, d_chunks, n_chunks, d_info, d_spec, d_fix, d_hist, d_sortT, d_counter));
+                   d_in, d_chunks, n_chunks, d_info, d_spec, d_fix, d_hist, d_sortT, d_counter, depth));
     return ZLB_OK;
 }
