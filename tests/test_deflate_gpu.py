@@ -258,3 +258,42 @@ def test_fast_mode_valid_streams_and_ratio_within_tolerance(engine):
         assert sizes["fast_all"][1] == sizes["compat"][1]
         for name in ("fast", "fast32"):
             assert sizes[name][0] <= sizes["compat"][0] * 1.03, (name, sizes[name][0], sizes["compat"][0])
+
+
+def test_differential_fuzz_against_oracle(engine):
+    """2000 structured random inputs in one batch: every output must equal the oracle's RawDeflate bytes (this is where
+    LZ77 tie-breaks, heap order and run-length-coding corner cases show up), for DYNAMIC and FIXED."""
+    rng = np.random.default_rng(2026)
+    datas = []
+    for i in range(2000):
+        kind = i % 8
+        n = int(rng.integers(1, 6000)) if i % 50 else int(rng.integers(60000, 65537))
+        if kind == 0:
+            d = rand_bytes(rng, n, int(rng.choice([1, 2, 3, 4, 8]))).tobytes()
+        elif kind == 1:
+            d = rand_bytes(rng, n, 256).tobytes()
+        elif kind == 2:  # repeated blocks with mutations: many equal-length candidates
+            blk = rand_bytes(rng, int(rng.integers(3, 300)), int(rng.choice([2, 16, 256]))).tobytes()
+            b = bytearray((blk * (n // len(blk) + 1))[:n])
+            for _ in range(int(rng.integers(0, 6))):
+                b[int(rng.integers(0, n))] ^= 1
+            d = bytes(b)
+        elif kind == 3:  # runs of varying length
+            d = b"".join(bytes([int(rng.integers(0, 4))]) * int(rng.integers(1, 700)) for _ in range(40))[:n] or b"z"
+        elif kind == 4:  # words
+            words = [rand_bytes(rng, int(rng.integers(2, 9)), 26).tobytes() for _ in range(int(rng.integers(2, 60)))]
+            d = b" ".join(words[int(k)] for k in rng.integers(0, len(words), n // 4 + 1))[:n]
+        elif kind == 5:  # skewed literals: long code lengths, limit may bind
+            p = 0.5 ** np.arange(1, 30)
+            p = np.concatenate([p, np.full(256 - p.size, p[-1] / 400)])
+            d = rng.choice(256, size=n, p=p / p.sum()).astype(np.uint8).tobytes()
+        elif kind == 6:  # records
+            d = b"".join(int(7 * k).to_bytes(4, "little") + bytes([int(rng.integers(0, 16)), 0, 0, 0]) for k in range(n // 8 + 1))[:n]
+        else:  # tails: lengths around the 3-byte search cut-off and 258
+            d = (b"ab" * 200)[:int(rng.integers(1, 8))] if i % 3 else b"q" * int(rng.integers(255, 265))
+        datas.append(d)
+    for btype in (oracle.DYNAMIC, oracle.FIXED):
+        outs, res = _deflate_items(engine, datas, btype)
+        assert int(res["status"].max()) == 0
+        bad = [i for i, (d, o) in enumerate(zip(datas, outs)) if o != oracle.raw_deflate(d, btype)]
+        assert not bad, (btype, bad[:5], [len(datas[i]) for i in bad[:5]])
