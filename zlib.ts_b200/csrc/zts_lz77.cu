@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
     // is longer, so that is the reference's answer (it stops at the first candidate there, :189 / end of input)
     {
         const uint32_t b0 = pw & 0xFFu;
-        if (p > 0 && (pw & 0xFFFFFFu) == b0 * 0x010101u && S[p - 1] == b0) {
+        if (((pw ^ (pw >> 8)) & 0xFFFFu) == 0 && p > 0 && S[p - 1] == b0) {  // bytes 0..2 equal, and the one before
             const uint32_t splat = b0 * 0x01010101u;
             bool same = true;
 #pragma unroll
@@ -204,6 +204,19 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
     const uint32_t h = hash13(pw & 0xFFFFFFu);
     const uint32_t lo = bstart[h];
     uint32_t a = lo, b = bstart[h + 1];
+    if (b - lo <= 32u) {
+        // the whole bucket fits one step (the common case): lane j takes entry j, whatever its position; entries at
+        // or behind p and outside the window drop out, REDUX.MAX over len << 16 | q picks longest, then nearest
+        const uint32_t pw1s = ld_u32(S, p + 4);
+        uint32_t key = 0;
+        if (lo + lane < b) {
+            const uint32_t q = sorted[lo + lane];
+            if (q < p && p - q <= LZ_WINDOW) key = (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q;
+        }
+        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
+        if ((m >> 16) < 3u) return 0;
+        return (m & 0xFFFF0000u) | (p - (m & 0xFFFFu));
+    }
     // slot of p inside its bucket (positions ascending): 32-way search
     while (b - a > 32) {
         const uint32_t step = (b - a + 31) >> 5;
