@@ -414,6 +414,208 @@ __device__ __forceinline__ void hist_token(uint32_t tok, uint32_t* hist)
     }
 }
 
+// ---- stages 1 and 2 of both kernels: the chunk into shared memory, the position index over it ----------------
+// On return S holds the chunk (+ zeroed slack), `sorted` the positions grouped by hash13 of their 3-byte key
+// (ascending inside a bucket), `bstart` the first slot of every bucket (empty buckets point at the next one).
+// With `startbits` (64 Ki bits, may alias cnt16) bit i is set where slot i starts a bucket.
+struct LzIndexed {
+    LzS SV;
+    uint32_t m;  // positions that own a 3-byte key
+};
+
+__device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restrict__ src, uint32_t n, uint8_t* Sbuf,
+                                                        uint16_t* sorted, uint16_t* bstart, uint16_t* cnt16, LzMisc* M,
+                                                        uint32_t* T, uint32_t& phase, uint32_t* startbits)
+{
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- 1. stage the chunk: 16-byte aligned body by TMA bulk copy, ragged ends by plain loads
+    const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)src & 15u)) & 15u));
+    const uint32_t body = (n - head) & ~15u;
+    const uint32_t tail = n - head - body;
+    uint8_t* S = Sbuf + ((16u - head) & 15u);  // S + head is 16-byte aligned
+    const LzS SV = {S, (16u - head) & 15u};
+    if (tid == 0 && body) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&M->mbar)), "r"(body)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(S + head)),
+            "l"(src + head), "r"(body), "r"(smem_u32(&M->mbar))
+            : "memory");
+    }
+    if (tid < head) S[tid] = src[tid];
+    if (tid < tail) S[head + body + tid] = src[head + body + tid];
+    if (tid < 32) S[n + tid] = 0;  // slack read by the word-wise compares
+    if (body) {
+        uint32_t done = 0, spins = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(smem_u32(&M->mbar)), "r"(phase)
+                : "memory");
+            if (!done && ++spins > (1u << 26)) __trap();  // never hang the device
+        }
+        phase ^= 1;
+    }
+    __syncthreads();
+
+    const uint32_t m = n >= 3 ? n - 2 : 0;  // positions that own a 3-byte key
+
+    // ---- 2. stable LSD radix sort of positions by hash13(key), low 7 bits then high 6 bits, three sweeps:
+    //   A  count the low digits per (warp range, digit)            -- shared-memory atomics, order irrelevant
+    //   B  scatter by low digit into T (global, L2 resident) as pos | hash << 16, stable (ballot ranking),
+    //      and count the high digits per (destination range, digit) on the way
+    //   C  scatter by high digit from T into `sorted`, stable
+    // The u32 counters of A and B live in the `sorted` area, which is not written before sweep C.
+    {
+        uint32_t* cntA = reinterpret_cast<uint32_t*>(sorted);   // [32 ranges][128 digits]
+        uint32_t* cntB = cntA + 32 * 128;                       // [32 ranges][64 digits]
+        for (uint32_t i = tid; i < 32u * 128u + 32u * 64u; i += LZ_THREADS) cntA[i] = 0;
+        __syncthreads();
+        const uint32_t w_begin = warp * LZ_SORT_TILE;
+        // sweep A
+        if (w_begin < m) {
+            for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
+                const uint32_t i = w_begin + it * 32 + lane;
+                if (i < m) atomicAdd(&cntA[warp * 128u + (hash13(ld_u32(SV, i) & 0xFFFFFFu) & 127u)], 1u);
+            }
+        }
+        __syncthreads();
+        // exclusive scan in (digit major, range minor) order: entry e = d * 32 + w  ->  u16 running offsets
+        {
+            uint32_t vals[4];
+            uint32_t sum = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t e = tid * 4 + k;
+                vals[k] = cntA[(e & 31u) * 128u + (e >> 5)];
+                sum += vals[k];
+            }
+            uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t e = tid * 4 + k;
+                cnt16[(e & 31u) * 128u + (e >> 5)] = (uint16_t)base;
+                base += vals[k];
+            }
+        }
+        __syncthreads();
+        // sweep B
+        if (w_begin < m) {
+            uint16_t* wc = cnt16 + warp * 128u;
+            for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
+                const uint32_t i = w_begin + it * 32 + lane;
+                const bool v = i < m;
+                uint32_t hh = 0x1FFFu;
+                if (v) hh = hash13(ld_u32(SV, i) & 0xFFFFFFu);
+                const uint32_t d = hh & 127u;
+                const unsigned peers = peers_of<7>(d, v);
+                uint32_t dst = 0;
+                if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
+                __syncwarp();
+                if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                if (v) {
+                    __stcg(&T[dst], i | (hh << 16));
+                    atomicAdd(&cntB[(dst >> 11) * 64u + (hh >> 7)], 1u);
+                }
+                __syncwarp();
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        {
+            uint32_t vals[2];
+            uint32_t sum = 0;
+#pragma unroll
+            for (uint32_t k = 0; k < 2; ++k) {
+                const uint32_t e = tid * 2 + k;
+                vals[k] = cntB[(e & 31u) * 64u + (e >> 5)];
+                sum += vals[k];
+            }
+            uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
+#pragma unroll
+            for (uint32_t k = 0; k < 2; ++k) {
+                const uint32_t e = tid * 2 + k;
+                cnt16[(e & 31u) * 64u + (e >> 5)] = (uint16_t)base;
+                base += vals[k];
+            }
+        }
+        __syncthreads();
+        // sweep C (overwrites the counters, which are dead now)
+        if (w_begin < m) {
+            uint16_t* wc = cnt16 + warp * 64u;
+            for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
+                const uint32_t i = w_begin + it * 32 + lane;
+                const bool v = i < m;
+                uint32_t e = 0xFFFFFFFFu;
+                if (v) e = __ldcg(&T[i]);
+                const uint32_t d = (e >> 23) & 63u;
+                const unsigned peers = peers_of<6>(d, v);
+                uint32_t dst = 0;
+                if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
+                __syncwarp();
+                if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                if (v) sorted[dst] = (uint16_t)e;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- bucket starts: first slot of every hash, empty buckets point at the next one
+    for (uint32_t i = tid; i < LZ_NB + 1; i += LZ_THREADS) bstart[i] = 0xFFFF;
+    if (startbits)
+        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) startbits[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < m; i += LZ_THREADS) {
+        const uint32_t hcur = hash13(ld_u32(SV, sorted[i]) & 0xFFFFFFu);
+        const uint32_t hprev = i ? hash13(ld_u32(SV, sorted[i - 1]) & 0xFFFFFFu) : 0xFFFFFFFFu;
+        if (hcur != hprev) {
+            bstart[hcur] = (uint16_t)i;
+            if (startbits) atomicOr(&startbits[i >> 5], 1u << (i & 31));
+        }
+    }
+    if (tid == 0) bstart[LZ_NB] = (uint16_t)m;
+    __syncthreads();
+    {
+        // suffix-min over bstart[0 .. LZ_NB]: thread t owns 8 consecutive entries
+        uint32_t v[8];
+        uint32_t mn = 0xFFFFu;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            v[k] = bstart[tid * 8 + k];
+            mn = min(mn, v[k]);
+        }
+        // suffix-min across threads (exclusive: the minimum of everything to the right)
+        uint32_t inc = mn;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t t = __shfl_down_sync(0xFFFFFFFFu, inc, d);
+            if (lane + d < 32) inc = min(inc, t);
+        }
+        if (lane == 0) M->warp_min[warp] = inc;
+        __syncthreads();
+        uint32_t right = m;  // bstart[LZ_NB]
+        for (uint32_t w = warp + 1; w < 32; ++w) right = min(right, M->warp_min[w]);
+        uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, inc, 1);
+        if (lane < 31) right = min(right, nxt);
+        uint32_t run = right;
+#pragma unroll
+        for (int k = 7; k >= 0; --k) {
+            run = min(run, v[k]);
+            bstart[tid * 8 + k] = (uint16_t)run;
+        }
+    }
+    __syncthreads();
+
+    LzIndexed r = {SV, m};
+    return r;
+}
+
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ chunks, uint32_t n_chunks,
                   ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ spec_tok, uint32_t* __restrict__ fix_tok,
@@ -447,184 +649,11 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         const uint32_t n = ch.len;
         const uint8_t* src = in + ch.in_off;
 
-        // ---- 1. stage the chunk: 16-byte aligned body by TMA bulk copy, ragged ends by plain loads
-        const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)src & 15u)) & 15u));
-        const uint32_t body = (n - head) & ~15u;
-        const uint32_t tail = n - head - body;
-        uint8_t* S = Sbuf + ((16u - head) & 15u);  // S + head is 16-byte aligned
-        const LzS SV = {S, (16u - head) & 15u};
-        if (tid == 0 && body) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&M->mbar)), "r"(body)
-                         : "memory");
-            asm volatile(
-                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                    smem_u32(S + head)),
-                "l"(src + head), "r"(body), "r"(smem_u32(&M->mbar))
-                : "memory");
-        }
-        if (tid < head) S[tid] = src[tid];
-        if (tid < tail) S[head + body + tid] = src[head + body + tid];
-        if (tid < 32) S[n + tid] = 0;  // slack read by the word-wise compares
-        if (body) {
-            uint32_t done = 0, spins = 0;
-            while (!done) {
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(done)
-                    : "r"(smem_u32(&M->mbar)), "r"(phase)
-                    : "memory");
-                if (!done && ++spins > (1u << 26)) __trap();  // never hang the device
-            }
-            phase ^= 1;
-        }
-        __syncthreads();
-
-        const uint32_t m = n >= 3 ? n - 2 : 0;  // positions that own a 3-byte key
-
-        // ---- 2. stable LSD radix sort of positions by hash13(key), low 7 bits then high 6 bits, three sweeps:
-        //   A  count the low digits per (warp range, digit)            -- shared-memory atomics, order irrelevant
-        //   B  scatter by low digit into T (global, L2 resident) as pos | hash << 16, stable (ballot ranking),
-        //      and count the high digits per (destination range, digit) on the way
-        //   C  scatter by high digit from T into `sorted`, stable
-        // The u32 counters of A and B live in the `sorted` area, which is not written before sweep C.
-        {
-            uint32_t* cntA = reinterpret_cast<uint32_t*>(sorted);   // [32 ranges][128 digits]
-            uint32_t* cntB = cntA + 32 * 128;                       // [32 ranges][64 digits]
-            for (uint32_t i = tid; i < 32u * 128u + 32u * 64u; i += LZ_THREADS) cntA[i] = 0;
-            __syncthreads();
-            const uint32_t w_begin = warp * LZ_SORT_TILE;
-            // sweep A
-            if (w_begin < m) {
-                for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
-                    const uint32_t i = w_begin + it * 32 + lane;
-                    if (i < m) atomicAdd(&cntA[warp * 128u + (hash13(ld_u32(SV, i) & 0xFFFFFFu) & 127u)], 1u);
-                }
-            }
-            __syncthreads();
-            // exclusive scan in (digit major, range minor) order: entry e = d * 32 + w  ->  u16 running offsets
-            {
-                uint32_t vals[4];
-                uint32_t sum = 0;
-#pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) {
-                    const uint32_t e = tid * 4 + k;
-                    vals[k] = cntA[(e & 31u) * 128u + (e >> 5)];
-                    sum += vals[k];
-                }
-                uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
-#pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) {
-                    const uint32_t e = tid * 4 + k;
-                    cnt16[(e & 31u) * 128u + (e >> 5)] = (uint16_t)base;
-                    base += vals[k];
-                }
-            }
-            __syncthreads();
-            // sweep B
-            if (w_begin < m) {
-                uint16_t* wc = cnt16 + warp * 128u;
-                for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
-                    const uint32_t i = w_begin + it * 32 + lane;
-                    const bool v = i < m;
-                    uint32_t hh = 0x1FFFu;
-                    if (v) hh = hash13(ld_u32(SV, i) & 0xFFFFFFu);
-                    const uint32_t d = hh & 127u;
-                    const unsigned peers = peers_of<7>(d, v);
-                    uint32_t dst = 0;
-                    if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
-                    __syncwarp();
-                    if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
-                    if (v) {
-                        __stcg(&T[dst], i | (hh << 16));
-                        atomicAdd(&cntB[(dst >> 11) * 64u + (hh >> 7)], 1u);
-                    }
-                    __syncwarp();
-                }
-            }
-            __threadfence_block();
-            __syncthreads();
-            {
-                uint32_t vals[2];
-                uint32_t sum = 0;
-#pragma unroll
-                for (uint32_t k = 0; k < 2; ++k) {
-                    const uint32_t e = tid * 2 + k;
-                    vals[k] = cntB[(e & 31u) * 64u + (e >> 5)];
-                    sum += vals[k];
-                }
-                uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
-#pragma unroll
-                for (uint32_t k = 0; k < 2; ++k) {
-                    const uint32_t e = tid * 2 + k;
-                    cnt16[(e & 31u) * 64u + (e >> 5)] = (uint16_t)base;
-                    base += vals[k];
-                }
-            }
-            __syncthreads();
-            // sweep C (overwrites the counters, which are dead now)
-            if (w_begin < m) {
-                uint16_t* wc = cnt16 + warp * 64u;
-                for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
-                    const uint32_t i = w_begin + it * 32 + lane;
-                    const bool v = i < m;
-                    uint32_t e = 0xFFFFFFFFu;
-                    if (v) e = __ldcg(&T[i]);
-                    const uint32_t d = (e >> 23) & 63u;
-                    const unsigned peers = peers_of<6>(d, v);
-                    uint32_t dst = 0;
-                    if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
-                    __syncwarp();
-                    if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
-                    if (v) sorted[dst] = (uint16_t)e;
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- bucket starts: first slot of every hash, empty buckets point at the next one
-        for (uint32_t i = tid; i < LZ_NB + 1; i += LZ_THREADS) bstart[i] = 0xFFFF;
-        __syncthreads();
-        for (uint32_t i = tid; i < m; i += LZ_THREADS) {
-            const uint32_t hcur = hash13(ld_u32(SV, sorted[i]) & 0xFFFFFFu);
-            const uint32_t hprev = i ? hash13(ld_u32(SV, sorted[i - 1]) & 0xFFFFFFu) : 0xFFFFFFFFu;
-            if (hcur != hprev) bstart[hcur] = (uint16_t)i;
-        }
-        if (tid == 0) bstart[LZ_NB] = (uint16_t)m;
-        __syncthreads();
-        {
-            // suffix-min over bstart[0 .. LZ_NB]: thread t owns 8 consecutive entries
-            uint32_t v[8];
-            uint32_t mn = 0xFFFFu;
-#pragma unroll
-            for (int k = 7; k >= 0; --k) {
-                v[k] = bstart[tid * 8 + k];
-                mn = min(mn, v[k]);
-            }
-            // suffix-min across threads (exclusive: the minimum of everything to the right)
-            uint32_t inc = mn;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t t = __shfl_down_sync(0xFFFFFFFFu, inc, d);
-                if (lane + d < 32) inc = min(inc, t);
-            }
-            if (lane == 0) M->warp_min[warp] = inc;
-            __syncthreads();
-            uint32_t right = m;  // bstart[LZ_NB]
-            for (uint32_t w = warp + 1; w < 32; ++w) right = min(right, M->warp_min[w]);
-            uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, inc, 1);
-            if (lane < 31) right = min(right, nxt);
-            uint32_t run = right;
-#pragma unroll
-            for (int k = 7; k >= 0; --k) {
-                run = min(run, v[k]);
-                bstart[tid * 8 + k] = (uint16_t)run;
-            }
-        }
-        __syncthreads();
+        // ---- 1 + 2. stage the chunk (TMA bulk copy) and index its positions (radix sort by key hash)
+        const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, bstart, cnt16, M, T, phase, nullptr);
+        const LzS SV = ix.SV;
+        const uint32_t m = ix.m;
+        (void)m;
 
         // ---- 3. speculative parse: warps take tiles from a shared counter
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
