@@ -67,11 +67,12 @@ enum { ZLB_NONE = 0, ZLB_FIXED = 1, ZLB_DYNAMIC = 2 };
  * (lazy = 0, src/LZ77.ts:196-283 exhaustive longest/nearest match, src/RawDeflate.ts:484-571 code
  * lengths). */
 enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1 };
-/* FAST: same pipeline and the same exact Huffman construction, but the match search looks only at the newest
- * `depth` candidates of a position (default ZLB_FAST_DEFAULT_DEPTH) instead of all of them: still a valid stream for
- * the reference's Inflate, no longer byte-identical; the ratio stays within a few per cent of the reference's
+/* FAST: same pipeline and the same exact Huffman construction, but the match search follows only the nearest
+ * `depth` links of a position's hash chain (default ZLB_FAST_DEFAULT_DEPTH), runs one position per lane, and
+ * matches are cut at tile boundaries (at most ~127 bytes): still a valid stream for the reference's Inflate, no
+ * longer byte-identical; the size stays within 3 % of the reference-compatible mode on the benchmark data
  * (bench.py reports it). A depth is passed as ZLB_MODE_FAST_DEPTH(d). */
-#define ZLB_FAST_DEFAULT_DEPTH 64
+#define ZLB_FAST_DEFAULT_DEPTH 16
 #define ZLB_MODE_FAST_DEPTH(d) (ZLB_MODE_FAST | ((int)(d) << 8))
 
 /* flags for zlb_deflate_batch */

@@ -12,7 +12,7 @@ for kind, n in (("mixed", 256 << 20), ("text", 64 << 20)):
         d_z = torch.empty(cap, dtype=torch.uint8, device="cuda"); d_o = torch.empty(n, dtype=torch.uint8, device="cuda")
         it = z.make_items(1); it["in_len"], it["out_cap"] = n, cap
         base = None
-        for mode, name in [(z.MODE_COMPAT, "compat")] + [(z.mode_fast(d), "fast%d" % d) for d in (32, 64, 128, 256)]:
+        for mode, name in [(z.MODE_COMPAT, "compat")] + [(z.mode_fast(d), "fast%d" % d) for d in (4, 8, 16, 32, 64)]:
             best = 1e9
             for _ in range(3):
                 e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)

@@ -18,6 +18,10 @@ size_t zts_lz77_smem_bytes();
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
                     ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint32_t* d_sortT,
                     uint32_t* d_counter, uint32_t grid, uint32_t depth);
+size_t zts_lz77_fast_scratch_bytes(int sm_count);
+int zts_lz77_fast_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
+                         ZtsChunkInfo* d_info, uint32_t* d_tok, uint32_t* d_tile_tok, uint32_t* d_hist,
+                         uint32_t* d_sortT, uint32_t* d_counter, uint32_t grid, uint32_t depth);
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type);
 int zts_huffman_lengths_debug(zlb_ctx* ctx, const uint32_t* d_freqs, int nsym, int limit, uint8_t* d_lengths);
@@ -185,7 +189,10 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     {
         static_assert(2 * LZ_NTILES <= PACK_THREADS, "one thread per token segment");
         uint32_t cnt = 0, src = 0;
-        if (tid < 2 * LZ_NTILES) {
+        if (ci->pad) {  // fast mode: one contiguous token list (kept in the "speculative" buffer)
+            if (tid == 1) cnt = n_tok;
+            src = 0x80000000u;
+        } else if (tid < 2 * LZ_NTILES) {
             const ZtsTile t = ci->tiles[tid >> 1];
             if (tid & 1) {
                 cnt = (uint32_t)t.spec_count - t.spec_from;
@@ -404,10 +411,8 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if ((mode & 0xFF) != ZLB_MODE_COMPAT && (mode & 0xFF) != ZLB_MODE_FAST)
         return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
     uint32_t depth = 0xFFFFFFFFu;  // compat: every candidate, like the reference
-    if ((mode & 0xFF) == ZLB_MODE_FAST) {
-        depth = ((uint32_t)mode >> 8) ? ((uint32_t)mode >> 8) : ZLB_FAST_DEFAULT_DEPTH;
-        depth = (depth + 31u) & ~31u;
-    }
+    const bool fast = (mode & 0xFF) == ZLB_MODE_FAST;
+    if (fast) depth = ((uint32_t)mode >> 8) ? ((uint32_t)mode >> 8) : ZLB_FAST_DEFAULT_DEPTH;
     if (block_type != ZLB_NONE && block_type != ZLB_FIXED && block_type != ZLB_DYNAMIC)
         return zts_fail(ctx, ZLB_E_ARG, "invalid compression type");  // src/RawDeflate.ts:110
     const uint32_t cb = (chunk_bytes == 0 || chunk_bytes > LZ_MAX_CHUNK) ? LZ_MAX_CHUNK : chunk_bytes;
@@ -503,6 +508,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_misc, n * 8 + wave * 8 + 256);
     if (rc) return rc;
+    if (fast && (rc = zts_reserve(ctx, &ctx->d_fast, zts_lz77_fast_scratch_bytes(ctx->sm_count) + 64))) return rc;
     ZtsChunk* d_chunks = (ZtsChunk*)ctx->d_chunks.p;
     uint32_t* d_blocks = (uint32_t*)(d_chunks + n_chunks);
     ZtsChunkInfo* d_info = (ZtsChunkInfo*)ctx->d_chunk_info.p;
@@ -572,8 +578,12 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             if (k + 1 < n_waves && (rc = wave_in_copy(k + 1))) return rc;
             ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 * k), 0));
         }
-        rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist, (uint32_t*)ctx->d_sortT.p,
-                             d_counter, g, depth);
+        if (fast)
+            rc = zts_lz77_fast_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, (uint32_t*)ctx->d_fast.p, d_hist,
+                                      (uint32_t*)ctx->d_sortT.p, d_counter, g, depth);
+        else
+            rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist,
+                                 (uint32_t*)ctx->d_sortT.p, d_counter, g, depth);
         if (rc) return rc;
         rc = zts_huffman_launch(ctx, d_chunks + w0, wn, d_hist, d_info, d_codes, block_type);
         if (rc) return rc;
