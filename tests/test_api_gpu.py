@@ -185,3 +185,14 @@ def test_config_c1_text_1mib_roundtrip(Z):
     # the reference's own decoder (oracle restatement) accepts the joined stream
     o2, ip = oracle.raw_inflate(c, 2, out_cap=len(d))
     assert o2 == d and ip == len(c) - 4
+
+
+def test_fast_mode_option_through_the_api(Z):
+    from zlibts_b200 import synth
+    d = synth.text(300000, 77).tobytes()
+    slow = Z.Deflate(d).compress().tobytes()
+    fast = Z.Deflate(d, {"b200": {"mode": "fast"}}).compress().tobytes()
+    assert zlib.decompress(fast) == d and fast != slow and len(fast) <= 1.03 * len(slow)
+    assert Z.Inflate(fast, {"verify": True}).decompress().tobytes() == d
+    g = Z.GZip(d, {"deflateOptions": {"b200": {"mode": "fast", "depth": 8}}}).compress().tobytes()
+    assert gzip.decompress(g) == d

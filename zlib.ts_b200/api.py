@@ -13,6 +13,8 @@ Deviations from the reference, all deliberate:
   * Deflate.compress does not raise the reference's RangeError for outputs > 32 KiB (B-1): it returns header +
     body + Adler-32 as evidently intended.
   * `lazy` > 0 is refused: the reference corrupts data with it (B-2).
+  * `b200: {mode: "fast"}` selects the engine's fast mode (valid streams, not the reference's bytes; default is
+    the reference-compatible mode).
   * corrupt streams that make the reference loop or emit zeros (B-8) raise ZlibError instead.
   * ZipCrypto (password) is out of scope (serial byte cipher, broken upstream).
 """
@@ -85,8 +87,16 @@ def _b200(opts):
 # ------------------------------------------------------------------------------------------------------------
 # batch entry points (what the N-API addon exposes below the classes)
 # ------------------------------------------------------------------------------------------------------------
+def _mode_of(opts):
+    """engine-only knob `b200: {mode: 'compat' | 'fast', depth: N}` (default: reference-compatible bytes)."""
+    b = _b200(opts)
+    if b.get("mode", "compat") == "fast":
+        return N.mode_fast(int(b.get("depth", 0)))
+    return N.MODE_COMPAT
+
+
 def deflate_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0, want_crc32=False,
-                 want_adler32=False, prefixes=None):
+                 want_adler32=False, prefixes=None, mode=N.MODE_COMPAT):
     """Raw-deflates every input in one GPU batch. Returns (list of uint8 arrays, results table). With `prefixes`
     each output starts with its prefix bytes (RawDeflate's outputBuffer / outputIndex contract)."""
     arrs = [_u8(x) for x in inputs]
@@ -104,7 +114,7 @@ def deflate_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0
     items = N.make_items(n)
     items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = in_off, lens, out_off, caps
     flags = (N.DEFLATE_WANT_CRC32 if want_crc32 else 0) | (N.DEFLATE_WANT_ADLER32 if want_adler32 else 0)
-    res = engine().deflate_batch_host(blob, out, items, compression_type, chunk_bytes, flags)
+    res = engine().deflate_batch_host(blob, out, items, compression_type, chunk_bytes, flags, mode)
     outs = []
     for i in range(n):
         if int(res["status"][i]) != N.ST_OK:
@@ -235,6 +245,7 @@ class RawDeflate:
         self.output = _u8(ob) if ob is not None else np.zeros(0, dtype=np.uint8)
         self.op = _opt(opts, "outputIndex", 0)
         self.chunkBytes = _b200(opts).get("chunkBytes", 0)
+        self.mode = _mode_of(opts)
         if self.lazy:
             raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
 
@@ -242,7 +253,7 @@ class RawDeflate:
         prefix = self.output[:self.op]
         if prefix.size < self.op:  # outputIndex beyond the given buffer: the reference doubles it, zero filled
             prefix = np.concatenate([prefix, np.zeros(self.op - prefix.size, dtype=np.uint8)])
-        outs, _ = deflate_many([self.input], self.compressionType, self.chunkBytes, prefixes=[prefix])
+        outs, _ = deflate_many([self.input], self.compressionType, self.chunkBytes, prefixes=[prefix], mode=self.mode)
         self.output = outs[0]
         self.op = int(self.output.size)
         return self.output
@@ -293,7 +304,7 @@ class Deflate:
     def compress(self):
         hdr = _zlib_header(self.compressionType)
         outs, res = deflate_many([self.input], self.compressionType, _b200(self.opts).get("chunkBytes", 0),
-                                 want_adler32=True, prefixes=[hdr])
+                                 want_adler32=True, prefixes=[hdr], mode=_mode_of(self.opts))
         self.adler32 = int(res["adler32"][0])
         self.output = np.concatenate([outs[0], _u8(struct.pack(">I", self.adler32))])  # writeUintBE, :95
         return self.output
@@ -371,7 +382,7 @@ class GZip:
         if _opt(self.deflateOptions, "lazy", 0):
             raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
         outs, res = deflate_many([self.input], ctype, _b200(self.deflateOptions).get("chunkBytes", 0), want_crc32=True,
-                                 prefixes=[hdr])
+                                 prefixes=[hdr], mode=_mode_of(self.deflateOptions))
         self.crc32 = int(res["crc32"][0])
         trailer = struct.pack("<II", self.crc32, self.input.size & 0xFFFFFFFF)  # :180-185
         self.output = np.concatenate([outs[0], _u8(trailer)])
@@ -481,9 +492,10 @@ class Zip:
             do = files[i]["option"].get("deflateOptions") or {}
             if _opt(do, "lazy", 0):
                 raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
-            by_type.setdefault((_opt(do, "compressionType", CompressionType.DYNAMIC), _b200(do).get("chunkBytes", 0)), []).append(i)
-        for (ctype, chunk), idxs in by_type.items():
-            outs, res = deflate_many([files[i]["buffer"] for i in idxs], ctype, chunk, want_crc32=True)
+            by_type.setdefault((_opt(do, "compressionType", CompressionType.DYNAMIC), _b200(do).get("chunkBytes", 0),
+                                _mode_of(do)), []).append(i)
+        for (ctype, chunk, mode), idxs in by_type.items():
+            outs, res = deflate_many([files[i]["buffer"] for i in idxs], ctype, chunk, want_crc32=True, mode=mode)
             for i, o, r in zip(idxs, outs, res):
                 files[i]["crc32"], files[i]["buffer"], files[i]["compressed"] = int(r["crc32"]), o, True
         rest = [i for i, f in enumerate(files) if not f["compressed"]]

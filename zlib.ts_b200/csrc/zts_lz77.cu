@@ -98,6 +98,9 @@ __device__ __forceinline__ uint32_t hash13(uint32_t key3) { return (key3 * 0x9E3
 template <int NBITS>
 __device__ __forceinline__ unsigned peers_of(uint32_t d, bool valid)
 {
+#ifdef ZTS_USE_MATCH
+    return __match_any_sync(0xFFFFFFFFu, valid ? d : 0xFFFFFFFFu);
+#else
     unsigned m = __ballot_sync(0xFFFFFFFFu, valid);
     unsigned peers = valid ? m : ~m;
 #pragma unroll
@@ -107,6 +110,7 @@ __device__ __forceinline__ unsigned peers_of(uint32_t d, bool valid)
         peers &= bit ? m : ~m;
     }
     return peers;
+#endif
 }
 
 // exclusive block scan (sum) over 1024 threads
