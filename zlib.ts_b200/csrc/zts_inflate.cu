@@ -110,7 +110,6 @@ __device__ bool build_table(int which, const uint8_t* lens, int n, int root_bits
     __syncwarp();
     // first codes / first indices, Kraft check (every lane computes the same values)
     uint32_t code = 0, idx = 0, kraft = 0;
-    uint32_t my_first_idx = 0;
 #pragma unroll
     for (uint32_t L = 1; L <= 15; ++L) {
         uint32_t c = tab->count[L];
@@ -118,12 +117,10 @@ __device__ bool build_table(int which, const uint8_t* lens, int n, int root_bits
             tab->first_code[L] = (uint16_t)code;
             tab->first_idx[L] = (uint16_t)idx;
         }
-        if (lane == L) my_first_idx = idx;
         code = (code + c) << 1;
         idx += c;
         kraft += c << (15 - L);
     }
-    (void)my_first_idx;
     if (kraft > (1u << 15)) return false;
     // root table: 0 = "not resolved here" (long code or unused pattern)
     for (int i = (int)lane; i < (1 << root_bits); i += 32) root[i] = 0;

@@ -994,9 +994,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
             sc = TL->spec_count[t];
             mine = nfix + (sc - from);
         }
-        uint32_t total = 0;
         const uint32_t base = block_excl_sum(mine, M->warp_tot, &M->n_tokens);
-        (void)total;
         uint32_t* out = tok_out + (size_t)c * LZ_TOK_PER_CHUNK;
         {
             // the 32 tiles of a warp are copied one after the other by the whole warp: coalesced, no dependent loads
