@@ -890,7 +890,6 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
 
     const unsigned tid = threadIdx.x;
     uint32_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;
-    uint16_t* T16 = reinterpret_cast<uint16_t*>(T);
     uint32_t* my_spec = tile_tok + (size_t)blockIdx.x * (LZF_NTILES * (LZF_SPEC_STRIDE + LZF_FIX_STRIDE));
     uint32_t* my_fix = my_spec + LZF_NTILES * LZF_SPEC_STRIDE;
     uint32_t phase = 0;
