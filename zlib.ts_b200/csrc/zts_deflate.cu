@@ -26,7 +26,7 @@ int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type);
 int zts_huffman_lengths_debug(zlb_ctx* ctx, const uint32_t* d_freqs, int nsym, int limit, uint8_t* d_lengths);
 
-#define WAVE_CHUNKS 2048u
+#define WAVE_CHUNKS 8192u
 #define PACK_THREADS 512
 #define PACK_STAGE_WORDS 31744u  // 124 KiB image: 64 Ki literals * 15 bits + header + join marker
 
