@@ -70,42 +70,63 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        # nvidia-smi needs a moment before its first line: wait for it so that the timed region is covered
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 3.0 and os.path.getsize(self.f.name) == 0:
+            time.sleep(0.02)
+
+    def mark(self):
+        """call at the start of the timed region: only samples written after this point are reported"""
+        self.f.flush()
+        self.mark_offset = os.path.getsize(self.f.name)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.flush()
+
+        def parse(text):
+            sm, mx, reasons = [], [], set()
+            for line in text.splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        text = self.f.read()
+        off = getattr(self, "mark_offset", 0)
+        sm, mx, reasons = parse(text[off:])
+        window = "timed region"
+        if len(sm) < 2:  # region shorter than two sampling periods: report the whole run under load, say so
+            sm, mx, reasons = parse(text)
+            window = "warm-up + timed region"
         try:
             os.unlink(self.f.name)
         except OSError:
             pass
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       window=window)
         return out
 
 
@@ -233,12 +254,13 @@ def run_b200(args, rank, world, local_rank):
         res["h"] = eng.deflate_batch_host(h_in, h_out, items, flags=dflags)
 
     # ---- device-resident leg (value) ---------------------------------------------------------------
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     for _ in range(args.warmup):
         step_device()
     eng.profile_enable(True)
     eng.profile_reset()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     l0 = eng.launch_count
     ms = timed(step_device, args.steps)
     launches = eng.launch_count - l0
@@ -392,7 +414,7 @@ def run_b200(args, rank, world, local_rank):
                     "ms_per_step": ms_h / e2e_steps, "api": "zlb_deflate_batch_host (pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
-                       "samples": clk["samples"]},
+                       "samples": clk["samples"], "window": clk.get("window")},
             "roofline": roofline,
             "cpu_baseline": cpu,
             "inflate": {"metric": "inflate_output_GBps", "value": inf_value, "unit": UNIT, "streams_per_gpu": n_chunks,

@@ -13,9 +13,13 @@ $SMALL > gpurun_out/plain_$tag.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$tag.csv $SMALL > gpurun_out/ncu_launch_$tag.log 2>&1
 echo "ncu launches rc=$?"
 $SMALL > gpurun_out/plain2_$tag.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:"lz77_chunk|huffman_build|bitpack" -s 3 -c 3 -f -o gpurun_out/prof_deflate_$tag $SMALL > gpurun_out/ncu_full_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"lz77_chunk|huffman_build|bitpack" -s 4 -c 3 -f -o gpurun_out/prof_deflate_$tag $SMALL > gpurun_out/ncu_full_$tag.log 2>&1
 echo "ncu deflate rc=$?"
+$SMALL > gpurun_out/plain4_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"lz77_fast" -s 1 -c 1 -f -o gpurun_out/prof_fast_$tag $SMALL > gpurun_out/ncu_full_fast_$tag.log 2>&1
+echo "ncu fast rc=$?"
 $SMALL > gpurun_out/plain3_$tag.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"inflate_warp" -s 1 -c 1 -f -o gpurun_out/prof_inflate_$tag $SMALL > gpurun_out/ncu_full_inf_$tag.log 2>&1
 echo "ncu inflate rc=$?"
+python tools/bench_configs.py c1 c3 c4 c5 > gpurun_out/configs_$tag.jsonl 2> gpurun_out/configs_$tag.err; echo "configs rc=$?"; cat gpurun_out/configs_$tag.jsonl
 ls -la gpurun_out

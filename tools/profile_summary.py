@@ -33,7 +33,7 @@ def main():
     units_per_launch = int(sys.argv[2]) if len(sys.argv) > 2 else 2048  # chunks (streams) one captured launch processed
     out = {}
     traffic = {}
-    for leg in ("deflate", "inflate"):
+    for leg in ("deflate", "fast", "inflate"):
         rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (leg, tag))
         if not os.path.exists(rep):
             continue
@@ -61,7 +61,8 @@ def main():
                "_units_per_launch": units_per_launch, **traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     with open(os.path.join(ROOT, "profiles", "%s_source_hotspots.txt" % tag), "w") as f:
         for leg, pat, stem in (("deflate", "lz77_chunk", "zts_lz77"), ("deflate", "huffman_build", "zts_huffman"),
-                               ("deflate", "bitpack", "zts_deflate"), ("inflate", "inflate_warp", "zts_inflate")):
+                               ("deflate", "bitpack", "zts_deflate"), ("fast", "lz77_fast", "zts_lz77"),
+                               ("inflate", "inflate_warp", "zts_inflate")):
             rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (leg, tag))
             if os.path.exists(rep):
                 f.write("==== %s ====\n" % pat)
