@@ -60,6 +60,32 @@ struct LzMisc {
     uint32_t n_tokens;
 };
 
+// The radix scratch T is the one global buffer a CTA keeps re-using (256 KiB per chunk, written and read twice):
+// it is marked evict_last in L2 so that the streaming traffic next to it (input, tokens) does not push it out to
+// DRAM, and the streaming token stores are marked evict_first.
+__device__ __forceinline__ unsigned long long l2_policy_keep()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_stream()
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_u32_hint(uint32_t* p, uint32_t v, unsigned long long pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_u32_hint(const uint32_t* p, unsigned long long pol)
+{
+    uint32_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 // 4 bytes at byte offset i of S. S = (128-byte aligned shared buffer) + shift, so the misalignment of
@@ -432,6 +458,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                                                         uint32_t* T, uint32_t& phase, uint32_t* startbits)
 {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned long long keep = l2_policy_keep();
     // ---- 1. stage the chunk: 16-byte aligned body by TMA bulk copy, ragged ends by plain loads
     const uint32_t head = min(n, (uint32_t)((16u - ((uintptr_t)src & 15u)) & 15u));
     const uint32_t body = (n - head) & ~15u;
@@ -523,7 +550,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                 __syncwarp();
                 if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
                 if (v) {
-                    __stcg(&T[dst], i | (hh << 16));
+                    st_u32_hint(&T[dst], i | (hh << 16), keep);
                     atomicAdd(&cntB[(dst >> 11) * 64u + (hh >> 7)], 1u);
                 }
                 __syncwarp();
@@ -556,7 +583,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                 const uint32_t i = w_begin + it * 32 + lane;
                 const bool v = i < m;
                 uint32_t e = 0xFFFFFFFFu;
-                if (v) e = __ldcg(&T[i]);
+                if (v) e = ld_u32_hint(&T[i], keep);
                 const uint32_t d = (e >> 23) & 63u;
                 const unsigned peers = peers_of<6>(d, v);
                 uint32_t dst = 0;
@@ -889,6 +916,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
     LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
 
     const unsigned tid = threadIdx.x;
+    const unsigned long long keep = l2_policy_keep(), stream = l2_policy_stream();
     uint32_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;
     uint32_t* my_spec = tile_tok + (size_t)blockIdx.x * (LZF_NTILES * (LZF_SPEC_STRIDE + LZF_FIX_STRIDE));
     uint32_t* my_fix = my_spec + LZF_NTILES * LZF_SPEC_STRIDE;
@@ -919,12 +947,12 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
         for (uint32_t i = tid; i < m; i += LZ_THREADS) {
             const bool first = (bits[i >> 5] >> (i & 31)) & 1u;
             const uint32_t pos = sorted[i];
-            __stcg(&T[i], (pos << 16) | (first ? (uint32_t)LZF_NONE : (uint32_t)sorted[i - 1]));
+            st_u32_hint(&T[i], (pos << 16) | (first ? (uint32_t)LZF_NONE : (uint32_t)sorted[i - 1]), keep);
         }
         __threadfence_block();
         __syncthreads();
         for (uint32_t i = tid; i < m; i += LZ_THREADS) {
-            const uint32_t e = __ldcg(&T[i]);
+            const uint32_t e = ld_u32_hint(&T[i], keep);
             prev[e >> 16] = (uint16_t)e;
         }
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) bits[i] = 0;  // now: visited bits
@@ -943,7 +971,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
             while (p < t_end) {
                 uint32_t tok;
                 const uint32_t np = lzf_step(SV, prev, p, n, limit, depth, &tok);
-                sp[cnt++] = tok;
+                st_u32_hint(&sp[cnt++], tok, keep);
                 const uint32_t rel = p - t_begin;
                 if (rel < 32u)
                     v0 |= 1u << rel;
@@ -978,7 +1006,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
                 }
                 uint32_t tok;
                 p = lzf_step(SV, prev, p, n, target, depth, &tok);  // never past the speculative exit
-                fx[nfix++] = tok;
+                st_u32_hint(&fx[nfix++], tok, keep);
             }
             TL->spec_from[t] = (uint8_t)from;
             TL->fix_count[t] = (uint8_t)nfix;
@@ -1006,8 +1034,8 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
                 const uint32_t* sp = my_spec + jt * LZF_SPEC_STRIDE + jf;
                 const uint32_t ns = js - jf;
                 for (uint32_t k = lane; k < jn + ns; k += 32) {
-                    const uint32_t tok = k < jn ? fx[k] : sp[k - jn];
-                    out[jb + k] = tok;
+                    const uint32_t tok = ld_u32_hint(k < jn ? &fx[k] : &sp[k - jn], keep);
+                    st_u32_hint(&out[jb + k], tok, stream);
                     hist_token(tok, M->hist);
                 }
             }
