@@ -46,6 +46,7 @@ struct ZtsProfRec {
 struct zlb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t work = nullptr;  // the stream kernels are launched on right now (== stream unless waves overlap)
     bool own_stream = false;
     int sm_count = 148;
     char err[512] = {0};

@@ -102,7 +102,7 @@ void zts_prof_begin(zlb_ctx* ctx, int slot)
     r.slot = slot;
     r.a = prof_event(ctx);
     r.b = prof_event(ctx);
-    cudaEventRecord(r.a, ctx->stream);
+    cudaEventRecord(r.a, ctx->work);
     ctx->pending.push_back(r);
 }
 
@@ -110,7 +110,7 @@ void zts_prof_end(zlb_ctx* ctx, int slot)
 {
     (void)slot;
     if (!ctx->prof) return;
-    cudaEventRecord(ctx->pending.back().b, ctx->stream);
+    cudaEventRecord(ctx->pending.back().b, ctx->work);
 }
 
 static void prof_resolve(zlb_ctx* ctx)
@@ -154,6 +154,7 @@ int zlb_create(int device, void* stream, zlb_ctx** out)
         }
         ctx->own_stream = true;
     }
+    ctx->work = ctx->stream;
     *out = ctx;
     return ZLB_OK;
 }

@@ -417,6 +417,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         return zts_fail(ctx, ZLB_E_ARG, "invalid compression type");  // src/RawDeflate.ts:110
     const uint32_t cb = (chunk_bytes == 0 || chunk_bytes > LZ_MAX_CHUNK) ? LZ_MAX_CHUNK : chunk_bytes;
     if (n > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many items");
+    ctx->work = ctx->stream;
 
     int rc = zts_reserve(ctx, &ctx->d_items, n * sizeof(zlb_item) + 64);
     if (rc) return rc;
@@ -460,12 +461,13 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (n_chunks > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many chunks");
     size_t wave = n_chunks < WAVE_CHUNKS ? n_chunks : WAVE_CHUNKS;
     if (hio && n_chunks > 4u * (size_t)ctx->sm_count) {
-        // host path: about four waves so that the copies overlap the kernels, but never so small that the
-        // tail of the persistent LZ77 kernel (one chunk time per wave) starts to matter
-        size_t w4 = (n_chunks + 3) / 4;
-        const size_t lo = 4u * (size_t)ctx->sm_count;
-        if (w4 < lo) w4 = lo;
-        if (w4 < wave) wave = w4;
+        // host path: about eight waves so that the copies overlap the kernels (the first wave's input and the last
+        // wave's output are the only transfers left in the open); consecutive waves overlap on two streams, so a
+        // wave only needs to be large enough to keep every SM busy for a couple of chunks
+        size_t w8 = (n_chunks + 7) / 8;
+        const size_t lo = 2u * (size_t)ctx->sm_count;
+        if (w8 < lo) w8 = lo;
+        if (w8 < wave) wave = w8;
     }
     rc = zts_reserve_pinned(ctx, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t));
     if (rc) return rc;
@@ -492,41 +494,67 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         }
     }
     const uint32_t grid = (uint32_t)(wave < (size_t)ctx->sm_count ? wave : (size_t)ctx->sm_count);
+    const size_t n_waves = (n_chunks + wave - 1) / wave;
+    // Host path with several waves: consecutive waves run on two streams with a scratch set each, so that the next
+    // wave's LZ77 CTAs take over the SMs as the previous wave's drain (no idle tail per wave) and its small kernels
+    // overlap too; only the offset scan is chained from wave to wave.
+    const int n_sets = (hio && n_waves > 1) ? 2 : 1;
     rc = zts_reserve(ctx, &ctx->d_chunks, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t) + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_chunk_info, wave * sizeof(ZtsChunkInfo) + 64);
+    const size_t info_b = (wave * sizeof(ZtsChunkInfo) + 255) & ~(size_t)255;
+    const size_t tok_b = (wave * (size_t)LZ_TOK_PER_CHUNK * 4 + 255) & ~(size_t)255;
+    const size_t hist_b = (wave * 316 * 4 + 255) & ~(size_t)255;
+    const size_t codes_b = (wave * sizeof(ZtsChunkCodes) + 255) & ~(size_t)255;
+    const size_t sort_b = ((size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 255) & ~(size_t)255;
+    const size_t fast_b = (zts_lz77_fast_scratch_bytes(ctx->sm_count) + 255) & ~(size_t)255;
+    const size_t gpos_b = (wave * 8 + 256 + 255) & ~(size_t)255;  // chunk offsets of the wave + the work counter
+    rc = zts_reserve(ctx, &ctx->d_chunk_info, n_sets * info_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_tokens, wave * (size_t)LZ_TOK_PER_CHUNK * 4 + 64);
+    rc = zts_reserve(ctx, &ctx->d_tokens, n_sets * tok_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_spec, wave * (size_t)LZ_TOK_PER_CHUNK * 4 + 64);
+    rc = zts_reserve(ctx, &ctx->d_spec, n_sets * tok_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_hist, wave * 316 * 4 + 64);
+    rc = zts_reserve(ctx, &ctx->d_hist, n_sets * hist_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_codes, wave * sizeof(ZtsChunkCodes) + 64);
+    rc = zts_reserve(ctx, &ctx->d_codes, n_sets * codes_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 64);
+    rc = zts_reserve(ctx, &ctx->d_sortT, n_sets * sort_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_misc, n * 8 + wave * 8 + 256);
+    rc = zts_reserve(ctx, &ctx->d_misc, n * 8 + n_sets * gpos_b + 256);
     if (rc) return rc;
-    if (fast && (rc = zts_reserve(ctx, &ctx->d_fast, zts_lz77_fast_scratch_bytes(ctx->sm_count) + 64))) return rc;
+    if (fast && (rc = zts_reserve(ctx, &ctx->d_fast, n_sets * fast_b + 64))) return rc;
     ZtsChunk* d_chunks = (ZtsChunk*)ctx->d_chunks.p;
     uint32_t* d_blocks = (uint32_t*)(d_chunks + n_chunks);
-    ZtsChunkInfo* d_info = (ZtsChunkInfo*)ctx->d_chunk_info.p;
-    uint32_t* d_fix = (uint32_t*)ctx->d_tokens.p;
-    uint32_t* d_spec = (uint32_t*)ctx->d_spec.p;
-    uint32_t* d_hist = (uint32_t*)ctx->d_hist.p;
-    ZtsChunkCodes* d_codes = (ZtsChunkCodes*)ctx->d_codes.p;
     unsigned long long* d_running = (unsigned long long*)ctx->d_misc.p;
-    unsigned long long* d_gpos = d_running + n;
-    uint32_t* d_counter = (uint32_t*)(d_gpos + wave);
+    struct Set {
+        ZtsChunkInfo* info;
+        uint32_t *fix, *spec, *hist, *sortT, *fastT, *counter;
+        ZtsChunkCodes* codes;
+        unsigned long long* gpos;
+    } sets[2];
+    for (int b = 0; b < n_sets; ++b) {
+        sets[b].info = (ZtsChunkInfo*)((uint8_t*)ctx->d_chunk_info.p + b * info_b);
+        sets[b].fix = (uint32_t*)((uint8_t*)ctx->d_tokens.p + b * tok_b);
+        sets[b].spec = (uint32_t*)((uint8_t*)ctx->d_spec.p + b * tok_b);
+        sets[b].hist = (uint32_t*)((uint8_t*)ctx->d_hist.p + b * hist_b);
+        sets[b].codes = (ZtsChunkCodes*)((uint8_t*)ctx->d_codes.p + b * codes_b);
+        sets[b].sortT = (uint32_t*)((uint8_t*)ctx->d_sortT.p + b * sort_b);
+        sets[b].fastT = fast ? (uint32_t*)((uint8_t*)ctx->d_fast.p + b * fast_b) : nullptr;
+        sets[b].gpos = (unsigned long long*)((uint8_t*)(d_running + n) + b * gpos_b);
+        sets[b].counter = (uint32_t*)(sets[b].gpos + wave);
+    }
     ZTS_CUDA(ctx, cudaMemcpyAsync(d_chunks, h_chunks, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t),
                                   cudaMemcpyHostToDevice, ctx->stream));
     ZTS_CUDA(ctx, cudaMemsetAsync(d_running, 0, n * 8, ctx->stream));
+    if (n_sets == 2) {
+        rc = zts_host_streams(ctx);
+        if (rc) return rc;
+        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 4 * n_waves), ctx->stream));
+    }
     ZTS_CUDA(ctx, cudaFuncSetAttribute(bitpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(PACK_STAGE_WORDS * 4)));
 
     // ---- host path: copy plan
-    const size_t n_waves = (n_chunks + wave - 1) / wave;
     bool pipe_in = false, delta_out = false;
     unsigned long long* h_run = nullptr;      // [n_waves][n] running totals read back after each wave
     std::vector<unsigned long long> copied;   // bytes of every item already copied to the host
@@ -571,37 +599,51 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     };
     if (pipe_in && (rc = wave_in_copy(0))) return rc;
 
+    // events: 2k = input of wave k arrived, 2k+1 = wave k done; 2 n_waves + k = offset scan of wave k done
     for (size_t w0 = 0, k = 0; w0 < n_chunks; w0 += wave, ++k) {
         const uint32_t wn = (uint32_t)(n_chunks - w0 < wave ? n_chunks - w0 : wave);
         const uint32_t g = wn < grid ? wn : grid;
+        const Set& S = sets[n_sets == 2 ? (k & 1) : 0];
+        cudaStream_t st = (n_sets == 2 && (k & 1)) ? ctx->s_aux[0] : ctx->stream;
+        ctx->work = st;
+        if (n_sets == 2 && k == 1)  // the tables uploaded on ctx->stream must be there before the second stream starts
+            ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 4 * n_waves), 0));
         if (pipe_in) {
             if (k + 1 < n_waves && (rc = wave_in_copy(k + 1))) return rc;
-            ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 * k), 0));
+            ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * k), 0));
         }
         if (fast)
-            rc = zts_lz77_fast_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, (uint32_t*)ctx->d_fast.p, d_hist,
-                                      (uint32_t*)ctx->d_sortT.p, d_counter, g, depth);
+            rc = zts_lz77_fast_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.spec, S.fastT, S.hist, S.sortT, S.counter, g,
+                                      depth);
         else
-            rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, d_info, d_spec, d_fix, d_hist,
-                                 (uint32_t*)ctx->d_sortT.p, d_counter, g, depth);
+            rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.spec, S.fix, S.hist, S.sortT, S.counter, g, depth);
         if (rc) return rc;
-        rc = zts_huffman_launch(ctx, d_chunks + w0, wn, d_hist, d_info, d_codes, block_type);
+        rc = zts_huffman_launch(ctx, d_chunks + w0, wn, S.hist, S.info, S.codes, block_type);
         if (rc) return rc;
+        if (n_sets == 2 && k > 0)  // item_running is handed from wave to wave
+            ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * n_waves + k - 1), 0));
         ZTS_LAUNCH(ctx, ZK_SCAN,
-                   chunk_scan_kernel<<<1, 1024, 0, ctx->stream>>>(d_chunks + w0, d_info, wn, d_items, d_running, d_gpos));
+                   chunk_scan_kernel<<<1, 1024, 0, st>>>(d_chunks + w0, S.info, wn, d_items, d_running, S.gpos));
+        if (delta_out)  // snapshot of the running totals before the next wave's scan moves them on
+            ZTS_CUDA(ctx, cudaMemcpyAsync(h_run + k * n, d_running, n * sizeof(unsigned long long),
+                                          cudaMemcpyDeviceToHost, st));
+        if (n_sets == 2) ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * n_waves + k), st));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
-                   bitpack_kernel<<<wn, PACK_THREADS, PACK_SMALL_WORDS * 4, ctx->stream>>>(
-                       d_chunks + w0, d_info, d_codes, d_spec, d_fix, d_items, d_out, PACK_SMALL_WORDS, 0u));
+                   bitpack_kernel<<<wn, PACK_THREADS, PACK_SMALL_WORDS * 4, st>>>(
+                       d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_SMALL_WORDS, 0u));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
-                   bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, ctx->stream>>>(
-                       d_chunks + w0, d_info, d_codes, d_spec, d_fix, d_items, d_out, PACK_STAGE_WORDS,
+                   bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, st>>>(
+                       d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_STAGE_WORDS,
                        PACK_SMALL_WORDS));
         if (delta_out) {
-            ZTS_CUDA(ctx, cudaMemcpyAsync(h_run + k * n, d_running, n * sizeof(unsigned long long),
-                                          cudaMemcpyDeviceToHost, ctx->stream));
-            ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * k + 1), ctx->stream));
+            ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * k + 1), st));
             if (k > 0 && (rc = wave_out_copy(k - 1))) return rc;  // wave k is queued: now wait for wave k-1
         }
+    }
+    ctx->work = ctx->stream;
+    if (n_sets == 2) {  // everything that follows on ctx->stream comes after the second stream's last wave
+        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 4 * n_waves + 1), ctx->s_aux[0]));
+        ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 4 * n_waves + 1), 0));
     }
     if (delta_out) {
         if ((rc = wave_out_copy(n_waves - 1))) return rc;

@@ -486,7 +486,7 @@ int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type)
 {
     ZTS_LAUNCH(ctx, ZK_HUFFMAN,
-               huffman_build_kernel<<<n_chunks, 32, 0, ctx->stream>>>(d_chunks, n_chunks, d_hist, d_info, d_codes,
+               huffman_build_kernel<<<n_chunks, 32, 0, ctx->work>>>(d_chunks, n_chunks, d_hist, d_info, d_codes,
                                                                        block_type));
     return ZLB_OK;
 }

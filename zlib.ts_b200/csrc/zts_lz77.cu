@@ -1061,9 +1061,9 @@ int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks,
     static_assert(LzSmem::TOTAL <= 232448, "exceeds 227 KiB of dynamic shared memory");
     ZTS_CUDA(ctx, cudaFuncSetAttribute(lz77_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)LzSmem::TOTAL));
-    ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->stream));
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->work));
     ZTS_LAUNCH(ctx, ZK_LZ77,
-               lz77_chunk_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->stream>>>(
+               lz77_chunk_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->work>>>(
                    d_in, d_chunks, n_chunks, d_info, d_spec, d_fix, d_hist, d_sortT, d_counter, depth));
     return ZLB_OK;
 }
@@ -1079,9 +1079,9 @@ int zts_lz77_fast_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_ch
 {
     ZTS_CUDA(ctx, cudaFuncSetAttribute(lz77_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)LzSmem::TOTAL));
-    ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->stream));
+    ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->work));
     ZTS_LAUNCH(ctx, ZK_LZ77_FAST,
-               lz77_fast_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->stream>>>(
+               lz77_fast_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->work>>>(
                    d_in, d_chunks, n_chunks, d_info, d_tok, d_tile_tok, d_hist, d_sortT, d_counter, depth));
     return ZLB_OK;
 }
