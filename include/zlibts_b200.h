@@ -157,6 +157,50 @@ int zlb_checksum_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_bytes, con
 uint32_t zlb_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
 uint32_t zlb_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b);
 
+/* ---- container assembly on the device ---------------------------------------
+ * Replaces the byte shuffling around the codec in Deflate.compress (src/Deflate.ts:60-99: 2-byte header, raw
+ * stream, Adler-32 big endian), GZip.compress (src/GZip.ts:96-194: member header, raw stream, CRC-32 and ISIZE
+ * little endian) and Zip.compress (src/Zip.ts:117-372: local header + data per entry, central directory, end
+ * record): every entry is checksummed and deflated in ONE batch, then framed and packed back to back by kernels,
+ * so the archive leaves the GPU as one contiguous buffer and the host never touches an entry's bytes.
+ *
+ * The caller supplies the parts that do not depend on the data as byte templates in a `meta` blob:
+ *   ZLB_FRAME_ZLIB  head = CMF, FLG (src/Deflate.ts:67-78)
+ *   ZLB_FRAME_GZIP  head = the member header incl. name / comment / header CRC (src/GZip.ts:108-156)
+ *   ZLB_FRAME_ZIP   head = local file header, 30 bytes + name (src/Zip.ts:228-312); cdir = the entry's central
+ *                   directory header, 46 bytes + name + comment (src/Zip.ts:234-326); tail = end record,
+ *                   22 bytes + comment (src/Zip.ts:340-369). The engine fills in what only it knows: CRC-32 and
+ *                   compressed size (local +14, +18; central +16, +20), the local header offset (central +42),
+ *                   directory size and offset (end record +12, +16).
+ * Archive layout: entries in order, each head | body | trailer; for ZIP the central directory and the end record
+ * follow the last entry. results[i]: status, crc32 / adler32, out_len = bytes of the framed entry,
+ * in_used = offset of its first header byte in the archive.                                               */
+enum { ZLB_FRAME_ZLIB = 1, ZLB_FRAME_GZIP = 2, ZLB_FRAME_ZIP = 3 };
+
+typedef struct {
+    uint64_t in_off;    /* the entry's plain bytes in the input blob                          */
+    uint64_t in_len;
+    uint64_t head_off;  /* header template in the meta blob                                   */
+    uint32_t head_len;
+    uint32_t method;    /* ZIP: 0 = stored, 8 = deflate (src/Zip.ts:7-10); otherwise ignored  */
+    uint64_t cdir_off;  /* ZIP: central directory header template in the meta blob            */
+    uint32_t cdir_len;
+    uint32_t reserved;
+} zlb_entry;
+
+/* archive bytes that always suffice for these entries */
+uint64_t zlb_archive_bound(int kind, const zlb_entry* entries, size_t n_entries, uint64_t tail_len,
+                           uint32_t chunk_bytes, int block_type);
+/* device buffers: d_in (plain bytes), d_meta (templates), d_out (archive, out_cap bytes). *out_len = archive size;
+ * when out_cap is too small nothing is written, *out_len is the size needed and ZLB_E_ARG is returned. */
+int zlb_archive(zlb_ctx* ctx, int kind, const void* d_in, const void* d_meta, const zlb_entry* entries,
+                size_t n_entries, uint64_t tail_off, uint64_t tail_len, void* d_out, uint64_t out_cap,
+                uint64_t* out_len, zlb_result* results, int mode, int block_type, uint32_t chunk_bytes);
+int zlb_archive_host(zlb_ctx* ctx, int kind, const void* h_in, size_t in_bytes, const void* h_meta,
+                     size_t meta_bytes, const zlb_entry* entries, size_t n_entries, uint64_t tail_off,
+                     uint64_t tail_len, void* h_out, uint64_t out_cap, uint64_t* out_len, zlb_result* results,
+                     int mode, int block_type, uint32_t chunk_bytes);
+
 /* ---- instrumentation ----------------------------------------------------------------------- */
 /* When enabled every kernel launch is bracketed by CUDA events on the ctx stream.            */
 int zlb_profile_enable(zlb_ctx* ctx, int on);

@@ -249,3 +249,36 @@ def _decode_one_block_bits(block):
     r = js.RawInflate(block + b"\0\0\0\0\0\0\0\0")
     r.parse_block()
     return bytes(r.out), r.ip * 8 - r.bitsbuflen
+
+
+def test_container_restatement_is_read_by_cpython():
+    """oracle/containers.py (Deflate / GZip / Zip framing) against independent readers: zlib, gzip, zipfile."""
+    import datetime
+    import gzip
+    import io
+    import zipfile
+    from oracle import containers as oc
+    rng = np.random.default_rng(12)
+    date = datetime.datetime(2026, 10, 18, 12, 34, 56)
+    datas = [b"", b"a", rand_bytes(rng, 3000, 4).tobytes(), rand_bytes(rng, 9000, 256).tobytes()]
+    for d in datas:
+        for ctype in (oracle.DYNAMIC, oracle.FIXED, oracle.NONE):
+            if ctype != oracle.DYNAMIC and not d:
+                # upstream quirk: NONE of nothing writes no block at all (src/RawDeflate.ts:122-153) and FIXED of
+                # nothing loses its end-of-block symbol (LZ77 output array of length 0, src/LZ77.ts:122,278)
+                assert oc.zlib_stream(d, ctype).hex() == ("780100000001" if ctype == oracle.NONE else "785e0300000001")
+                continue
+            assert zlib.decompress(oc.zlib_stream(d, ctype)) == d
+        g = oc.gzip_member(d, "name.bin", "note", True, 1234567890)
+        assert gzip.decompress(g) == d and g[4:8] == (1234567890).to_bytes(4, "little")
+    assert oc.zlib_stream(b"a").hex() == "789c05c081080000000020d6fd254e00620062"  # SURVEY Appendix C
+    assert gzip.decompress(b"".join(oc.gzip_member(d) for d in datas)) == b"".join(datas)
+    files = [{"name": "f%d" % i, "data": d, "date": date, "method": 8 if i % 2 == 0 else 0, "comment": "c%d" % i}
+             for i, d in enumerate(datas)]
+    arc = oc.zip_archive(files, b"zc")
+    with zipfile.ZipFile(io.BytesIO(arc)) as zf:
+        assert zf.testzip() is None and zf.comment == b"zc"
+        for f in files:
+            assert zf.read(f["name"]) == f["data"]
+            assert zf.getinfo(f["name"]).date_time == (2026, 10, 18, 12, 34, 56)
+            assert zf.getinfo(f["name"]).comment == f["comment"].encode()

@@ -14,7 +14,9 @@ LIB_PATH = os.path.join(_HERE, "libzlibts_b200.so")
 ITEM_DTYPE = np.dtype([("in_off", "<u8"), ("in_len", "<u8"), ("out_off", "<u8"), ("out_cap", "<u8")])
 RESULT_DTYPE = np.dtype([("status", "<u4"), ("crc32", "<u4"), ("adler32", "<u4"), ("blocks", "<u4"),
                          ("out_len", "<u8"), ("in_used", "<u8")])
-assert ITEM_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32
+ENTRY_DTYPE = np.dtype([("in_off", "<u8"), ("in_len", "<u8"), ("head_off", "<u8"), ("head_len", "<u4"),
+                        ("method", "<u4"), ("cdir_off", "<u8"), ("cdir_len", "<u4"), ("reserved", "<u4")])
+assert ITEM_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32 and ENTRY_DTYPE.itemsize == 48
 
 # CompressionType (src/RawDeflate.ts:12-17)
 NONE, FIXED, DYNAMIC = 0, 1, 2
@@ -28,6 +30,7 @@ def mode_fast(depth=0):
 DEFLATE_WANT_CRC32, DEFLATE_WANT_ADLER32, DEFLATE_NOT_FINAL = 1, 2, 4
 INFLATE_WANT_CRC32, INFLATE_WANT_ADLER32, INFLATE_CHECK_NLEN, INFLATE_SPLIT = 1, 2, 4, 8
 SUM_CRC32, SUM_ADLER32 = 1, 2
+FRAME_ZLIB, FRAME_GZIP, FRAME_ZIP = 1, 2, 3
 
 ST_OK, ST_INPUT_BROKEN, ST_BTYPE, ST_CODE_LENGTH, ST_OUT_OVERFLOW, ST_STORED_LEN, ST_BAD_CODE, ST_BAD_LENGTHS = range(8)
 
@@ -36,6 +39,7 @@ EXPORTS = [
     "zlb_deflate_batch", "zlb_deflate_batch_host", "zlb_deflate_bound",
     "zlb_inflate_batch", "zlb_inflate_batch_host",
     "zlb_checksum_batch", "zlb_checksum_batch_host", "zlb_crc32_combine", "zlb_adler32_combine",
+    "zlb_archive", "zlb_archive_host", "zlb_archive_bound",
     "zlb_profile_enable", "zlb_profile_read", "zlb_profile_reset", "zlb_launch_count",
     "zlb_debug_lz77", "zlb_debug_code_lengths",
 ]
@@ -81,6 +85,13 @@ def load_library():
     lib.zlb_crc32_combine.restype = u32
     lib.zlb_adler32_combine.argtypes = [u32, u32, u64]
     lib.zlb_adler32_combine.restype = u32
+    lib.zlb_archive_bound.argtypes = [i32, vp, sz, u64, u32, i32]
+    lib.zlb_archive_bound.restype = u64
+    lib.zlb_archive.argtypes = [vp, i32, vp, vp, vp, sz, u64, u64, vp, u64, ctypes.POINTER(u64), vp, i32, i32, u32]
+    lib.zlb_archive.restype = i32
+    lib.zlb_archive_host.argtypes = [vp, i32, vp, sz, vp, sz, vp, sz, u64, u64, vp, u64, ctypes.POINTER(u64), vp,
+                                     i32, i32, u32]
+    lib.zlb_archive_host.restype = i32
     lib.zlb_profile_enable.argtypes = [vp, i32]
     lib.zlb_profile_enable.restype = i32
     lib.zlb_profile_read.argtypes = [vp, ctypes.POINTER(i32), vp, vp, vp]
@@ -111,6 +122,16 @@ def deflate_bound(in_len, chunk_bytes=0, block_type=DYNAMIC):
 
 def make_items(n):
     return np.zeros(n, dtype=ITEM_DTYPE)
+
+
+def make_entries(n):
+    return np.zeros(n, dtype=ENTRY_DTYPE)
+
+
+def archive_bound(kind, entries, tail_len=0, chunk_bytes=0, block_type=DYNAMIC):
+    entries = np.ascontiguousarray(entries, dtype=ENTRY_DTYPE)
+    return int(load_library().zlb_archive_bound(kind, entries.ctypes.data, len(entries), tail_len, chunk_bytes,
+                                                block_type))
 
 
 class EngineError(RuntimeError):
@@ -231,6 +252,36 @@ class Engine:
         rc = self.lib.zlb_checksum_batch_host(self.h, pi, ni, items.ctypes.data, results.ctypes.data, len(items), kinds)
         self._check(rc, "zlb_checksum_batch_host")
         return results
+
+    # ---- container assembly -------------------------------------------------------------------
+    def archive(self, kind, d_in, d_meta, entries, d_out, tail=(0, 0), block_type=DYNAMIC, chunk_bytes=0,
+                mode=MODE_COMPAT):
+        """zlb_archive on device tensors; returns (archive bytes written, results)."""
+        entries = np.ascontiguousarray(entries, dtype=ENTRY_DTYPE)
+        results = np.zeros(len(entries), dtype=RESULT_DTYPE)
+        total = ctypes.c_uint64(0)
+        rc = self.lib.zlb_archive(self.h, kind, d_in.data_ptr(), d_meta.data_ptr(), entries.ctypes.data, len(entries),
+                                  tail[0], tail[1], d_out.data_ptr(), d_out.numel(), ctypes.byref(total),
+                                  results.ctypes.data, mode, block_type, chunk_bytes)
+        self._check(rc, "zlb_archive")
+        return int(total.value), results
+
+    def archive_host(self, kind, h_in, h_meta, entries, tail=(0, 0), block_type=DYNAMIC, chunk_bytes=0,
+                     mode=MODE_COMPAT, h_out=None):
+        """zlb_archive_host; returns (archive as a uint8 array, results)."""
+        entries = np.ascontiguousarray(entries, dtype=ENTRY_DTYPE)
+        results = np.zeros(len(entries), dtype=RESULT_DTYPE)
+        pi, ni, ki = self._host_ptr(h_in)
+        pm, nm, km = self._host_ptr(h_meta)
+        if h_out is None:
+            h_out = np.empty(max(1, archive_bound(kind, entries, tail[1], chunk_bytes, block_type)), dtype=np.uint8)
+        po, no, ko = self._host_ptr(h_out)
+        total = ctypes.c_uint64(0)
+        rc = self.lib.zlb_archive_host(self.h, kind, pi, ni, pm, nm, entries.ctypes.data, len(entries), tail[0],
+                                       tail[1], po, no, ctypes.byref(total), results.ctypes.data, mode, block_type,
+                                       chunk_bytes)
+        self._check(rc, "zlb_archive_host")
+        return h_out[:int(total.value)], results
 
     # ---- test hooks ---------------------------------------------------------------------------
     def debug_lz77(self, d_in, n):

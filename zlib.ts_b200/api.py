@@ -15,6 +15,8 @@ Deviations from the reference, all deliberate:
   * `lazy` > 0 is refused: the reference corrupts data with it (B-2).
   * `b200: {mode: "fast"}` selects the engine's fast mode (valid streams, not the reference's bytes; default is
     the reference-compatible mode).
+  * an empty input with compressionType FIXED gets its end-of-block symbol ("03 00"); upstream drops it ("03",
+    which no inflater accepts) because LZ77's output array has length 0 there (src/LZ77.ts:122,278).
   * corrupt streams that make the reference loop or emit zeros (B-8) raise ZlibError instead.
   * ZipCrypto (password) is out of scope (serial byte cipher, broken upstream).
 """
@@ -199,6 +201,49 @@ def checksum_many(buffers, crc32=True, adler32=True):
     return engine().checksum_batch_host(blob, items, (N.SUM_CRC32 if crc32 else 0) | (N.SUM_ADLER32 if adler32 else 0))
 
 
+def archive_many(kind, inputs, heads, compression_type=CompressionType.DYNAMIC, chunk_bytes=0, mode=N.MODE_COMPAT,
+                 methods=None, cdirs=None, tail=b""):
+    """Checksums, deflates and frames every input on the device (zlb_archive_host): entry i becomes
+    heads[i] | body | trailer, packed back to back; for FRAME_ZIP the central directory (cdirs) and the end
+    record (tail) follow. Returns (archive as one uint8 array, results table: crc32 / adler32, out_len = framed
+    bytes of the entry, in_used = its offset in the archive)."""
+    arrs = [_u8(x) for x in inputs]
+    n = len(arrs)
+    if compression_type not in (0, 1, 2):
+        raise ZlibError("invalid compression type")  # src/RawDeflate.ts:110
+    lens = np.array([a.size for a in arrs], dtype=np.uint64)
+    blob = np.concatenate(arrs) if n and int(lens.sum()) else np.zeros(1, dtype=np.uint8)
+    parts = [bytes(h) for h in heads] + [bytes(c) for c in (cdirs or [])] + [bytes(tail)]
+    plens = np.array([len(p) for p in parts], dtype=np.uint64)
+    poffs = np.concatenate([[0], np.cumsum(plens)[:-1]]).astype(np.uint64)
+    meta = np.frombuffer(b"".join(parts) or b"\0", dtype=np.uint8)
+    ent = N.make_entries(n)
+    if n:
+        ent["in_off"] = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
+        ent["in_len"] = lens
+        ent["head_off"], ent["head_len"] = poffs[:n], plens[:n]
+        ent["method"] = 8 if methods is None else np.asarray(methods, dtype=np.uint32)
+        if cdirs:
+            ent["cdir_off"], ent["cdir_len"] = poffs[n:2 * n], plens[n:2 * n]
+    out, res = engine().archive_host(kind, blob, meta, ent, (int(poffs[-1]), int(plens[-1])), compression_type,
+                                     chunk_bytes, mode)
+    return out, res
+
+
+def zlib_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0, mode=N.MODE_COMPAT):
+    """Every input as a zlib stream (what Deflate.compress returns), back to back in one buffer; stream i is
+    archive[res['in_used'][i] : + res['out_len'][i]]."""
+    return archive_many(N.FRAME_ZLIB, inputs, [_zlib_header(compression_type)] * len(inputs), compression_type,
+                        chunk_bytes, mode)
+
+
+def gzip_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0, mode=N.MODE_COMPAT, mtime=0):
+    """Every input as one gzip member; the members back to back are one multi-member gzip file that
+    GUnzip.decompress (src/GUnzip.ts:56-58) and gzip(1) read as the concatenation of the inputs."""
+    hdr = b"\x1f\x8b\x08\x00" + struct.pack("<I", int(mtime) & 0xFFFFFFFF) + b"\x00\x03"
+    return archive_many(N.FRAME_GZIP, inputs, [hdr] * len(inputs), compression_type, chunk_bytes, mode)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # CRC32 / Adler32 (src/CRC32.ts, src/Adler32.ts)
 # ------------------------------------------------------------------------------------------------------------
@@ -302,11 +347,10 @@ class Deflate:
         return Deflate(input, opts).compress()
 
     def compress(self):
-        hdr = _zlib_header(self.compressionType)
-        outs, res = deflate_many([self.input], self.compressionType, _b200(self.opts).get("chunkBytes", 0),
-                                 want_adler32=True, prefixes=[hdr], mode=_mode_of(self.opts))
+        # header (:67-78), raw stream (:84-85) and Adler-32 big endian (:95) are put together on the device
+        self.output, res = archive_many(N.FRAME_ZLIB, [self.input], [_zlib_header(self.compressionType)],
+                                        self.compressionType, _b200(self.opts).get("chunkBytes", 0), _mode_of(self.opts))
         self.adler32 = int(res["adler32"][0])
-        self.output = np.concatenate([outs[0], _u8(struct.pack(">I", self.adler32))])  # writeUintBE, :95
         return self.output
 
 
@@ -381,11 +425,10 @@ class GZip:
         ctype = _opt(self.deflateOptions, "compressionType", CompressionType.DYNAMIC)
         if _opt(self.deflateOptions, "lazy", 0):
             raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
-        outs, res = deflate_many([self.input], ctype, _b200(self.deflateOptions).get("chunkBytes", 0), want_crc32=True,
-                                 prefixes=[hdr], mode=_mode_of(self.deflateOptions))
+        # member header, raw stream (:159-166), CRC-32 and ISIZE (:180-185) are put together on the device
+        self.output, res = archive_many(N.FRAME_GZIP, [self.input], [hdr], ctype,
+                                        _b200(self.deflateOptions).get("chunkBytes", 0), _mode_of(self.deflateOptions))
         self.crc32 = int(res["crc32"][0])
-        trailer = struct.pack("<II", self.crc32, self.input.size & 0xFFFFFFFF)  # :180-185
-        self.output = np.concatenate([outs[0], _u8(trailer)])
         return self.output
 
 
@@ -485,8 +528,8 @@ class Zip:
         if len(files) > 0xFFFF:
             raise ZlibError("too many entries for a ZIP32 end-of-central-directory record")
         # one batch per compression type used by the entries (normally one)
-        todo = [i for i, f in enumerate(files) if not f["compressed"] and f["compressionMethod"] == ZipCompressionMethod.DEFLATE
-                and f["option"].get("compress") is not False]
+        # (`compress: false` only defers the work from addFile to here in the reference, src/Zip.ts:92,142-149)
+        todo = [i for i, f in enumerate(files) if not f["compressed"] and f["compressionMethod"] == ZipCompressionMethod.DEFLATE]
         by_type = {}
         for i in todo:
             do = files[i]["option"].get("deflateOptions") or {}
@@ -494,6 +537,8 @@ class Zip:
                 raise ZlibError("lazy matching is not supported: the reference corrupts data with lazy > 0")
             by_type.setdefault((_opt(do, "compressionType", CompressionType.DYNAMIC), _b200(do).get("chunkBytes", 0),
                                 _mode_of(do)), []).append(i)
+        if len(by_type) <= 1 and not any(f["compressed"] for f in files):
+            return self._compress_on_device(next(iter(by_type), (CompressionType.DYNAMIC, 0, N.MODE_COMPAT)))
         for (ctype, chunk, mode), idxs in by_type.items():
             outs, res = deflate_many([files[i]["buffer"] for i in idxs], ctype, chunk, want_crc32=True, mode=mode)
             for i, o, r in zip(idxs, outs, res):
@@ -522,6 +567,36 @@ class Zip:
         eocd = b"PK\x05\x06" + struct.pack("<HHHHIIH", 0, 0, len(files), len(files), len(cd), offset, self.comment.size)
         parts = [(_u8(p) if not isinstance(p, np.ndarray) else p) for p in local] + [_u8(cd), _u8(eocd), self.comment]
         return np.concatenate(parts) if parts else np.zeros(0, dtype=np.uint8)
+
+
+    def _compress_on_device(self, settings):
+        """All entries share one deflate setting and none is compressed yet (the usual case): header templates
+        go to the device with the data, and local headers, bodies, central directory and end record are laid
+        out there (zlb_archive_host) -- the same bytes as the loop below produces."""
+        ctype, chunk, mode = settings
+        files = self.files
+        heads, cdirs, methods = [], [], []
+        for f in files:
+            name = bytes(ord(c) & 0xFF for c in f["filename"])  # stringToByteArray
+            comment = bytes(ord(c) & 0xFF for c in (f["option"].get("comment") or ""))
+            mt = _dos_time(f["option"].get("date") or datetime.datetime.now())
+            deflated = f["compressionMethod"] == ZipCompressionMethod.DEFLATE
+            # CRC-32 and compressed size (0 here) are filled in by the engine
+            common = struct.pack("<HHH", 20, 0, f["compressionMethod"]) + mt + struct.pack(
+                "<IIIHH", 0, 0, f["size"], len(name), 0)
+            heads.append(b"PK\x03\x04" + common + name)
+            cdirs.append(b"PK\x01\x02" + bytes([20, _opt(f["option"], "os", 0)]) + common +
+                         struct.pack("<HHHII", len(comment), 0, 0, 0, 0) + name + comment)
+            methods.append(8 if deflated else 0)
+        eocd = b"PK\x05\x06" + struct.pack("<HHHHIIH", 0, 0, len(files), len(files), 0, 0, self.comment.size)
+        out, res = archive_many(N.FRAME_ZIP, [f["buffer"] for f in files], heads, ctype, chunk, mode, methods, cdirs,
+                                eocd + self.comment.tobytes())
+        for f, h, r in zip(files, heads, res):  # what the reference leaves in its file table (src/Zip.ts:144-149)
+            f["crc32"] = int(r["crc32"])
+            if f["compressionMethod"] == ZipCompressionMethod.DEFLATE:
+                a = int(r["in_used"]) + len(h)
+                f["buffer"], f["compressed"] = out[a:int(r["in_used"]) + int(r["out_len"])], True
+        return out
 
 
 class Unzip:
