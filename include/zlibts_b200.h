@@ -66,12 +66,21 @@ enum { ZLB_NONE = 0, ZLB_FIXED = 1, ZLB_DYNAMIC = 2 };
 /* deflate mode. COMPAT: every chunk's bytes equal the reference's RawDeflate run on that chunk
  * (lazy = 0, src/LZ77.ts:196-283 exhaustive longest/nearest match, src/RawDeflate.ts:484-571 code
  * lengths). */
-enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1 };
+enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1, ZLB_MODE_PRIMED = 2 };
 /* FAST: same pipeline and the same exact Huffman construction, but the match search follows only the nearest
  * `depth` links of a position's hash chain (default ZLB_FAST_DEFAULT_DEPTH), runs one position per lane, and
  * matches are cut at tile boundaries (at most ~127 bytes): still a valid stream for the reference's Inflate, no
  * longer byte-identical; the size stays within 3 % of the reference-compatible mode on the benchmark data
  * (bench.py reports it). A depth is passed as ZLB_MODE_FAST_DEPTH(d). */
+/* PRIMED (pigz-style dictionary priming; may be or-ed with FAST): the match search of a chunk also
+ * reaches into the 32 KiB of the same item in front of it, which recovers the ratio independent chunks lose. History
+ * and chunk share the 64 KiB a CTA indexes, so chunks are at most ZLB_PRIMED_CHUNK bytes (chunk_bytes 0 = that; pass
+ * the same value to zlb_deflate_bound). Blocks are still one per chunk with their own codes, joined by the
+ * byte-aligning empty stored block, so the item remains one RFC-1951 stream for the reference's RawInflate; what is
+ * given up is per-chunk byte identity with RawDeflate(chunk) and chunk-parallel decoding (ZLB_INFLATE_SPLIT detects
+ * the back references and takes the one-warp route). Without FAST the search is the reference's exhaustive one, and
+ * every block equals the reference's block construction run with that history (oracle: zo_raw_deflate_dict). */
+#define ZLB_PRIMED_CHUNK 32768u
 #define ZLB_FAST_DEFAULT_DEPTH 16
 #define ZLB_MODE_FAST_DEPTH(d) (ZLB_MODE_FAST | ((int)(d) << 8))
 

@@ -41,6 +41,8 @@ def lib():
         L.zo_get_lengths.restype = i32
         L.zo_raw_deflate.argtypes = [vp, sz, i32, i32, vp, sz, sz, ctypes.POINTER(sz)]
         L.zo_raw_deflate.restype = i32
+        L.zo_raw_deflate_dict.argtypes = [vp, sz, sz, i32, i32, vp, sz, ctypes.POINTER(sz)]
+        L.zo_raw_deflate_dict.restype = i32
         L.zo_raw_deflate_bound.argtypes = [sz]
         L.zo_raw_deflate_bound.restype = sz
         L.zo_raw_inflate.argtypes = [vp, sz, sz, vp, sz, ctypes.POINTER(sz), ctypes.POINTER(sz), i32]
@@ -88,6 +90,34 @@ def raw_deflate(data, compression_type=DYNAMIC, lazy=0, prefix=b""):
     if rc:
         raise OracleError(rc)
     return out[:n.value].tobytes()
+
+
+def raw_deflate_dict(data, dict_len, bfinal=True, compression_type=DYNAMIC):
+    """One block over data[dict_len:] with data[:dict_len] as LZ77 history (zo_raw_deflate_dict)."""
+    a = _u8(data)
+    cap = int(lib().zo_raw_deflate_bound(a.size))
+    out = np.zeros(cap, dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    rc = lib().zo_raw_deflate_dict(a.ctypes.data, a.size, dict_len, 1 if bfinal else 0, compression_type,
+                                   out.ctypes.data, cap, ctypes.byref(n))
+    if rc:
+        raise OracleError(rc)
+    return out[:n.value].tobytes()
+
+
+def primed_blocks(data, chunk=32768, compression_type=DYNAMIC):
+    """The blocks the engine's dictionary-primed mode writes for one item, in order: one per chunk, each searching
+    the 32 KiB before it as well; all but the last with BFINAL = 0 (the engine joins them with the byte-aligning
+    empty stored block of SURVEY App. A.7)."""
+    a = _u8(data)
+    n = a.size
+    n_chunks = max(1, -(-n // chunk))
+    blocks = []
+    for k in range(n_chunks):
+        lo, hi = k * chunk, min(n, (k + 1) * chunk)
+        d = min(lo, 32768)
+        blocks.append(raw_deflate_dict(a[lo - d:hi], d, k + 1 == n_chunks, compression_type))
+    return blocks
 
 
 def raw_inflate(data, index=0, out_cap=None, mirror_readbits_quirk=False):

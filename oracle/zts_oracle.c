@@ -197,11 +197,16 @@ static lz_match lz_search(lz_state* s, size_t position)
     return r;
 }
 
-int zo_lz77_encode(const uint8_t* in, size_t n, int lazy, uint16_t* tokens, size_t* ntok,
-                   uint32_t fl[286], uint32_t fd[30])
+/* LZ77.encode over in[0, n) whose first dict_len bytes are history only: they enter the match table exactly as
+ * positions inside a match do (:217-220, the skipLength path) and produce no output -- the state the reference's
+ * loop is in at position dict_len after a parse that happened to end there. dict_len = 0 is LZ77.encode itself. */
+int zo_lz77_encode_dict(const uint8_t* in, size_t n, size_t dict_len, int lazy, uint16_t* tokens, size_t* ntok,
+                        uint32_t fl[286], uint32_t fd[30])
 {
     lz_state s;
     memset(&s, 0, sizeof s);
+    if (dict_len > n || dict_len > 0x7FFFFFFF) return ZO_E_INPUT_BROKEN;
+    s.skip = (long)dict_len;
     s.in = in;
     s.n = n;
     s.out = tokens;
@@ -263,6 +268,12 @@ int zo_lz77_encode(const uint8_t* in, size_t n, int lazy, uint16_t* tokens, size
     free(s.head);
     free(s.link);
     return ZO_OK;
+}
+
+int zo_lz77_encode(const uint8_t* in, size_t n, int lazy, uint16_t* tokens, size_t* ntok,
+                   uint32_t fl[286], uint32_t fd[30])
+{
+    return zo_lz77_encode_dict(in, n, 0, lazy, tokens, ntok, fl, fd);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -651,17 +662,23 @@ static void emit_tokens(zo_bits* s, const uint16_t* tok, size_t ntok, int fixed,
     }
 }
 
-int zo_raw_deflate(const uint8_t* in, size_t n, int type, int lazy, uint8_t* out, size_t out_cap,
-                   size_t out_index, size_t* out_len)
+/* RawDeflate.compress of in[dict_len, n) with in[0, dict_len) as match history and a chosen BFINAL bit.
+ * dict_len = 0, bfinal = 1 is the reference's function; the other settings restate the same block construction
+ * for the chunk-joined / dictionary-primed streams the engine writes. */
+static int raw_deflate_core(const uint8_t* in, size_t n, size_t dict_len, int bfinal, int type, int lazy, uint8_t* out,
+                            size_t out_cap, size_t out_index, size_t* out_len)
 {
     if (out_index > out_cap) return ZO_E_OUT_OVERFLOW;
+    if (dict_len > n) return ZO_E_INPUT_BROKEN;
     if (type == ZO_NONE) { /* :93-100 + makeNocompressBlock :122-153 */
         size_t op = out_index;
+        in += dict_len;
+        n -= dict_len;
         for (size_t position = 0; position < n;) {
             size_t blen = n - position < 0xFFFF ? n - position : 0xFFFF;
             position += blen;
             if (op + 5 + blen > out_cap) return ZO_E_OUT_OVERFLOW;
-            out[op++] = (uint8_t)((position == n ? 1 : 0) | (ZO_NONE << 1));
+            out[op++] = (uint8_t)((position == n && bfinal ? 1 : 0) | (ZO_NONE << 1));
             uint32_t len = (uint32_t)blen, nlen = len ^ 0xFFFFu;
             out[op++] = len & 0xFF;
             out[op++] = (len >> 8) & 0xFF;
@@ -679,13 +696,13 @@ int zo_raw_deflate(const uint8_t* in, size_t n, int type, int lazy, uint8_t* out
     if (!tok) return ZO_E_NOMEM;
     uint32_t fl[286], fd[30];
     size_t ntok = 0;
-    int rc = zo_lz77_encode(in, n, lazy, tok, &ntok, fl, fd);
+    int rc = zo_lz77_encode_dict(in, n, dict_len, lazy, tok, &ntok, fl, fd);
     if (rc != ZO_OK) {
         free(tok);
         return rc;
     }
     zo_bits s = {out, out_cap, out_index, 0, 0};
-    bits_write(&s, 1, 1, 1);                  /* bfinal :165/:185 */
+    bits_write(&s, bfinal ? 1 : 0, 1, 1);     /* bfinal :165/:185 */
     bits_write(&s, (uint32_t)type, 2, 1);     /* btype  :166/:186 */
 
     if (type == ZO_FIXED) { /* :161-173 */
@@ -737,6 +754,18 @@ int zo_raw_deflate(const uint8_t* in, size_t n, int type, int lazy, uint8_t* out
     free(tok);
     *out_len = bits_finish(&s);
     return s.overflow ? ZO_E_OUT_OVERFLOW : ZO_OK;
+}
+
+int zo_raw_deflate(const uint8_t* in, size_t n, int type, int lazy, uint8_t* out, size_t out_cap,
+                   size_t out_index, size_t* out_len)
+{
+    return raw_deflate_core(in, n, 0, 1, type, lazy, out, out_cap, out_index, out_len);
+}
+
+int zo_raw_deflate_dict(const uint8_t* in, size_t n, size_t dict_len, int bfinal, int type, uint8_t* out,
+                        size_t out_cap, size_t* out_len)
+{
+    return raw_deflate_core(in, n, dict_len, bfinal, type, 0, out, out_cap, 0, out_len);
 }
 
 /* ------------------------------------------------------------------------------------------

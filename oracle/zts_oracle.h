@@ -73,6 +73,15 @@ uint64_t zo_diag_rpm_freq_oob(void);
 int zo_raw_deflate(const uint8_t* in, size_t n, int compression_type, int lazy,
                    uint8_t* out, size_t out_cap, size_t out_index, size_t* out_len);
 
+/* The same block construction over in[dict_len, n) with in[0, dict_len) as LZ77 history (its positions enter the
+ * match table like positions inside a match, src/LZ77.ts:217-220, and emit nothing) and a chosen BFINAL bit:
+ * the restatement the dictionary-primed mode of the engine is checked against.
+ * dict_len = 0, bfinal = 1 is zo_raw_deflate. */
+int zo_raw_deflate_dict(const uint8_t* in, size_t n, size_t dict_len, int bfinal, int compression_type,
+                        uint8_t* out, size_t out_cap, size_t* out_len);
+int zo_lz77_encode_dict(const uint8_t* in, size_t n, size_t dict_len, int lazy, uint16_t* tokens, size_t* ntok,
+                        uint32_t fl[286], uint32_t fd[30]);
+
 /* upper bound on zo_raw_deflate output size for n input bytes (excluding out_index) */
 size_t zo_raw_deflate_bound(size_t n);
 

@@ -316,3 +316,77 @@ def test_differential_fuzz_against_oracle(engine):
         assert int(res["status"].max()) == 0
         bad = [i for i, (d, o) in enumerate(zip(datas, outs)) if o != oracle.raw_deflate(d, btype)]
         assert not bad, (btype, bad[:5], [len(datas[i]) for i in bad[:5]])
+
+
+def test_primed_mode_blocks_equal_the_oracle_with_history(engine):
+    """every chunk also searches the 32 KiB in front of it. Block k must equal the oracle's block
+    construction run with that history (zo_raw_deflate_dict), the blocks are joined as in the compat mode, and the
+    item is one stream for zlib and for the reference's decoder."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    rng = np.random.default_rng(23)
+    datas = [synth.mixed(300000, 21).tobytes(), synth.text(200001, 22).tobytes(), rand_bytes(rng, 70000, 3).tobytes(),
+             b"z" * 131072, rand_bytes(rng, 98305, 256).tobytes(), b"", b"q", synth.text(32768, 5).tobytes(),
+             synth.text(32769, 6).tobytes()]
+    for chunk in (0, 4096, 1000, 20000):
+        cb = chunk or 32768
+        blob, offs, lens = pack(datas)
+        caps = [z.deflate_bound(len(d), chunk, oracle.DYNAMIC, z.MODE_PRIMED) for d in datas]
+        ooffs = np.concatenate([[0], np.cumsum(caps)]).astype(np.uint64)
+        items = z.make_items(len(datas))
+        items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = offs, lens, ooffs[:-1], caps
+        d_out = torch.zeros(int(ooffs[-1]), dtype=torch.uint8, device="cuda")
+        res = engine.deflate_batch(torch.from_numpy(blob).cuda(), d_out, items, oracle.DYNAMIC, chunk, 0, z.MODE_PRIMED)
+        h = d_out.cpu().numpy()
+        for d, o0, r in zip(datas, ooffs[:-1], res):
+            o = h[int(o0):int(o0) + int(r["out_len"])].tobytes()
+            assert int(r["status"]) == 0
+            assert zlib.decompress(o, -15) == d
+            ref, ip = oracle.raw_inflate(o + b"\0\0\0\0", 0, out_cap=len(d) + 8)
+            assert ref == d and ip == len(o)
+            if not d:
+                continue
+            blocks = oracle.primed_blocks(d, cb)
+            assert int(r["blocks"]) == len(blocks)
+            pos = 0
+            for k, want in enumerate(blocks):
+                assert o[pos:pos + len(want)] == want, (chunk, len(d), k)
+                pos += len(want)
+                if k + 1 < len(blocks):  # join marker: [00] 00 00 FF FF
+                    if o[pos:pos + 4] == b"\x00\x00\xff\xff":
+                        pos += 4
+                    else:
+                        assert o[pos:pos + 5] == b"\x00\x00\x00\xff\xff", (chunk, k)
+                        pos += 5
+            assert pos == len(o)
+
+
+def test_primed_mode_ratio_fast_variant_and_split_inflate(engine):
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    d = synth.text(4 << 20, 31)
+    d_in = torch.from_numpy(d).cuda()
+    sizes = {}
+    for name, mode in (("compat", z.MODE_COMPAT), ("primed", z.MODE_PRIMED), ("fast", z.mode_fast()),
+                       ("fast-primed", z.mode_fast() | z.MODE_PRIMED)):
+        cap = z.deflate_bound(d.size, 0, oracle.DYNAMIC, mode)
+        items = z.make_items(1)
+        items["in_len"], items["out_cap"] = d.size, cap
+        d_z = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+        r = engine.deflate_batch(d_in, d_z, items, mode=mode)
+        assert int(r["status"][0]) == 0
+        n = int(r["out_len"][0])
+        sizes[name] = n
+        comp = d_z[:n].cpu().numpy().tobytes()
+        assert zlib.decompress(comp, -15) == d.tobytes()
+        # our own inflate, with the chunk-parallel route requested: primed streams must take the serial route
+        it2 = z.make_items(1)
+        it2["in_len"], it2["out_cap"] = n, d.size
+        d_o = torch.zeros(d.size, dtype=torch.uint8, device="cuda")
+        r2 = engine.inflate_batch(d_z, d_o, it2, z.INFLATE_SPLIT | z.INFLATE_WANT_CRC32)
+        assert int(r2["status"][0]) == 0 and int(r2["out_len"][0]) == d.size and int(r2["in_used"][0]) == n
+        assert torch.equal(d_o, d_in) and int(r2["crc32"][0]) == zlib.crc32(d.tobytes())
+    assert sizes["primed"] < 0.97 * sizes["compat"]          # text: history across chunk boundaries pays
+    assert sizes["fast-primed"] < sizes["fast"]

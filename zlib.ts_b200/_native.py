@@ -20,7 +20,8 @@ assert ITEM_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32 and ENTRY_DTYPE
 
 # CompressionType (src/RawDeflate.ts:12-17)
 NONE, FIXED, DYNAMIC = 0, 1, 2
-MODE_COMPAT, MODE_FAST = 0, 1
+MODE_COMPAT, MODE_FAST, MODE_PRIMED = 0, 1, 2   # PRIMED may be or-ed with FAST
+PRIMED_CHUNK = 32768
 
 
 def mode_fast(depth=0):
@@ -116,8 +117,15 @@ def adler32_combine(adler_a, adler_b, len_b):
     return load_library().zlb_adler32_combine(adler_a, adler_b, len_b)
 
 
-def deflate_bound(in_len, chunk_bytes=0, block_type=DYNAMIC):
-    return int(load_library().zlb_deflate_bound(in_len, chunk_bytes, block_type))
+def deflate_bound(in_len, chunk_bytes=0, block_type=DYNAMIC, mode=MODE_COMPAT):
+    return int(load_library().zlb_deflate_bound(in_len, mode_chunk(mode, chunk_bytes), block_type))
+
+
+def mode_chunk(mode, chunk_bytes=0):
+    """The chunk size a deflate call with this mode really uses (primed modes: at most 32 KiB)."""
+    if mode & MODE_PRIMED and (chunk_bytes == 0 or chunk_bytes > PRIMED_CHUNK):
+        return PRIMED_CHUNK
+    return chunk_bytes
 
 
 def make_items(n):
@@ -274,7 +282,8 @@ class Engine:
         pi, ni, ki = self._host_ptr(h_in)
         pm, nm, km = self._host_ptr(h_meta)
         if h_out is None:
-            h_out = np.empty(max(1, archive_bound(kind, entries, tail[1], chunk_bytes, block_type)), dtype=np.uint8)
+            h_out = np.empty(max(1, archive_bound(kind, entries, tail[1], mode_chunk(mode, chunk_bytes), block_type)),
+                             dtype=np.uint8)
         po, no, ko = self._host_ptr(h_out)
         total = ctypes.c_uint64(0)
         rc = self.lib.zlb_archive_host(self.h, kind, pi, ni, pm, nm, entries.ctypes.data, len(entries), tail[0],

@@ -13,8 +13,8 @@ Deviations from the reference, all deliberate:
   * Deflate.compress does not raise the reference's RangeError for outputs > 32 KiB (B-1): it returns header +
     body + Adler-32 as evidently intended.
   * `lazy` > 0 is refused: the reference corrupts data with it (B-2).
-  * `b200: {mode: "fast"}` selects the engine's fast mode (valid streams, not the reference's bytes; default is
-    the reference-compatible mode).
+  * `b200: {mode: "fast" | "primed" | "fast-primed"}` selects the engine's other modes (valid streams, not the
+    reference's bytes; default is the reference-compatible mode).
   * an empty input with compressionType FIXED gets its end-of-block symbol ("03 00"); upstream drops it ("03",
     which no inflater accepts) because LZ77's output array has length 0 there (src/LZ77.ts:122,278).
   * corrupt streams that make the reference loop or emit zeros (B-8) raise ZlibError instead.
@@ -90,11 +90,15 @@ def _b200(opts):
 # batch entry points (what the N-API addon exposes below the classes)
 # ------------------------------------------------------------------------------------------------------------
 def _mode_of(opts):
-    """engine-only knob `b200: {mode: 'compat' | 'fast', depth: N}` (default: reference-compatible bytes)."""
+    """engine-only knob `b200: {mode: 'compat' | 'fast' | 'primed' | 'fast-primed', depth: N}` (default:
+    reference-compatible bytes). 'primed' = every chunk also searches the 32 KiB in front of it (better ratio,
+    still one stream the reference inflates, no longer RawDeflate(chunk) per chunk)."""
     b = _b200(opts)
-    if b.get("mode", "compat") == "fast":
-        return N.mode_fast(int(b.get("depth", 0)))
-    return N.MODE_COMPAT
+    name = b.get("mode", "compat")
+    if name not in ("compat", "fast", "primed", "fast-primed"):
+        raise ZlibError("unknown b200 mode: %s" % name)
+    mode = N.mode_fast(int(b.get("depth", 0))) if name.startswith("fast") else N.MODE_COMPAT
+    return mode | (N.MODE_PRIMED if name.endswith("primed") else 0)
 
 
 def deflate_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0, want_crc32=False,
@@ -110,7 +114,7 @@ def deflate_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0
     lens = np.array([a.size for a in arrs], dtype=np.uint64)
     in_off = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.uint64)
     blob = np.concatenate(arrs) if int(lens.sum()) else np.zeros(1, dtype=np.uint8)
-    caps = np.array([N.deflate_bound(int(l), chunk_bytes, compression_type) for l in lens], dtype=np.uint64)
+    caps = np.array([N.deflate_bound(int(l), chunk_bytes, compression_type, mode) for l in lens], dtype=np.uint64)
     out_off = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.uint64)
     out = np.zeros(int(caps.sum()), dtype=np.uint8)
     items = N.make_items(n)

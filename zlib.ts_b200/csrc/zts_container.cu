@@ -152,6 +152,7 @@ static int archive_compress(zlb_ctx* ctx, int kind, const uint8_t* d_in, const z
     if (kind != ZLB_FRAME_ZLIB && kind != ZLB_FRAME_GZIP && kind != ZLB_FRAME_ZIP)
         return zts_fail(ctx, ZLB_E_ARG, "unknown container kind %d", kind);
     if (n > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many entries");
+    if ((mode & ZLB_MODE_PRIMED) && (chunk_bytes == 0 || chunk_bytes > ZLB_PRIMED_CHUNK)) chunk_bytes = ZLB_PRIMED_CHUNK;
     std::vector<zlb_item> items;
     std::vector<uint32_t> defl, stor;
     uint64_t slot = 0;

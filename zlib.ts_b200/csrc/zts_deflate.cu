@@ -408,14 +408,17 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                           zlb_result* h_results, size_t n, int mode, int block_type, uint32_t chunk_bytes,
                           uint32_t flags, HostIO* hio)
 {
-    if ((mode & 0xFF) != ZLB_MODE_COMPAT && (mode & 0xFF) != ZLB_MODE_FAST)
+    if ((mode & 0xFF) & ~(ZLB_MODE_FAST | ZLB_MODE_PRIMED))
         return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
     uint32_t depth = 0xFFFFFFFFu;  // compat: every candidate, like the reference
-    const bool fast = (mode & 0xFF) == ZLB_MODE_FAST;
+    const bool fast = (mode & ZLB_MODE_FAST) != 0;
+    const bool primed = (mode & ZLB_MODE_PRIMED) != 0 && block_type != ZLB_NONE;
     if (fast) depth = ((uint32_t)mode >> 8) ? ((uint32_t)mode >> 8) : ZLB_FAST_DEFAULT_DEPTH;
     if (block_type != ZLB_NONE && block_type != ZLB_FIXED && block_type != ZLB_DYNAMIC)
         return zts_fail(ctx, ZLB_E_ARG, "invalid compression type");  // src/RawDeflate.ts:110
-    const uint32_t cb = (chunk_bytes == 0 || chunk_bytes > LZ_MAX_CHUNK) ? LZ_MAX_CHUNK : chunk_bytes;
+    // primed: history + chunk share the 64 KiB a CTA stages and indexes, so a chunk is at most 32 KiB
+    const uint32_t cb_max = primed ? ZLB_PRIMED_CHUNK : LZ_MAX_CHUNK;
+    const uint32_t cb = (chunk_bytes == 0 || chunk_bytes > cb_max) ? cb_max : chunk_bytes;
     if (n > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many items");
     ctx->work = ctx->stream;
 
@@ -485,7 +488,8 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                 c.len = (uint32_t)(len - j * cb < cb ? len - j * cb : cb);
                 c.item = (uint32_t)i;
                 c.flags = (j + 1 == nc && !(flags & ZLB_DEFLATE_NOT_FINAL)) ? CHUNK_LAST : 0u;
-                c.pad0 = c.pad1 = 0;
+                c.dict_len = primed ? (uint32_t)(j * cb < LZ_WINDOW ? j * cb : LZ_WINDOW) : 0u;
+                c.pad1 = 0;
                 // first chunk of this item inside the chunk's wave
                 const size_t wave_base = (k / wave) * wave;
                 const size_t item_first = k - j;
@@ -720,7 +724,7 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
     if ((rc = zts_reserve(ctx, &ctx->d_hist, 316 * 4 + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_misc, 256))) return rc;
-    ZtsChunk ch = {0, n, 0, 0, CHUNK_LAST, 0, 0};
+    ZtsChunk ch = {0, n, 0, 0, CHUNK_LAST, 0, 0};  // no history
     ZTS_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunks.p, &ch, sizeof ch, cudaMemcpyHostToDevice, ctx->stream));
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     rc = zts_lz77_launch(ctx, (const uint8_t*)d_in, (const ZtsChunk*)ctx->d_chunks.p, 1, (ZtsChunkInfo*)ctx->d_chunk_info.p,

@@ -29,7 +29,8 @@ struct ZtsChunk {      // host-built, one per chunk
     uint32_t item;
     uint32_t seg_first;  // index (within the wave) of the first chunk of the same item
     uint32_t flags;
-    uint32_t pad0, pad1;
+    uint32_t dict_len;   // primed mode: bytes in front of the chunk (same item, <= 32768) the match search may reach into
+    uint32_t pad1;
 };
 
 // first position of tile t (t == LZ_NTILES gives the chunk size)
@@ -41,6 +42,11 @@ __host__ __device__ __forceinline__ uint32_t lz_tile_begin(uint32_t t)
 __host__ __device__ __forceinline__ uint32_t lz_tile_count(uint32_t n)
 {
     return n <= 49152u ? (n + 511u) / 512u : n <= 61440u ? 96u + (n - 49152u + 255u) / 256u : 144u + (n - 61440u + 127u) / 128u;
+}
+// tile that holds position pos
+__host__ __device__ __forceinline__ uint32_t lz_tile_of(uint32_t pos)
+{
+    return pos < 49152u ? pos / 512u : pos < 61440u ? 96u + (pos - 49152u) / 256u : 144u + (pos - 61440u) / 128u;
 }
 // first token slot of tile t: a tile never holds more tokens than positions
 __host__ __device__ __forceinline__ uint32_t lz_tok_off(uint32_t t) { return lz_tile_begin(t) + 8u * t; }

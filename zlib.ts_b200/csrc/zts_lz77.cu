@@ -346,15 +346,15 @@ __device__ __forceinline__ bool lz_probe(const LzS& S, const uint16_t* __restric
     return false;
 }
 
-// Speculative parse of tile [t_begin, t_end): tokens to tok_out, visited bit per parsed position.
+// Speculative parse of tile [t_begin, t_end) from p0 >= t_begin: tokens to tok_out, visited bit per parsed position.
 // Returns the exit position (>= t_end); *count_out = tokens written.
 __device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                                  uint32_t t_begin, uint32_t t_end, uint32_t n, uint32_t depth,
-                                                  uint32_t* __restrict__ tok_out, uint32_t* visited,
+                                                  uint32_t t_begin, uint32_t t_end, uint32_t p0, uint32_t n,
+                                                  uint32_t depth, uint32_t* __restrict__ tok_out, uint32_t* visited,
                                                   uint32_t* count_out)
 {
     const unsigned lane = zts_lane();
-    uint32_t p = t_begin;
+    uint32_t p = p0;                 // t_begin, or the first position behind the history inside the first tile
     uint32_t* tp = tok_out;          // next token slot
     uint32_t vis = 0;                // lane j keeps the visited bits of positions [t_begin + 32 j, + 32): 16 lanes
     const uint32_t my_lo = lane * 32u;
@@ -677,20 +677,24 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         const uint32_t c = M->chunk;
         if (c >= n_chunks) break;
         const ZtsChunk ch = chunks[c];
-        const uint32_t n = ch.len;
-        const uint8_t* src = in + ch.in_off;
+        // primed mode: `base` bytes of history are staged and indexed in front of the chunk; positions below base
+        // are candidates only (the state of src/LZ77.ts:202-275 after it has walked them), parsing starts at base
+        const uint32_t base = ch.dict_len;
+        const uint32_t n = base + ch.len;
+        const uint8_t* src = in + ch.in_off - base;
 
         // ---- 1 + 2. stage the chunk (TMA bulk copy) and index its positions (radix sort by key hash)
         const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, bstart, cnt16, M, T, phase, nullptr);
         const LzS SV = ix.SV;
         const uint32_t m = ix.m;
         (void)m;
+        const uint32_t t0 = base ? lz_tile_of(base) : 0u;  // first tile with anything to parse
 
         // ---- 3. speculative parse: warps take tiles from a shared counter
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
         if (tid == 0) {
-            M->tile_next = 0;
-            M->tile_next2 = 1;  // tile 0 needs no re-entry
+            M->tile_next = t0;
+            M->tile_next2 = t0 + 1;  // the first tile needs no re-entry
         }
         __syncthreads();
         const uint32_t n_tiles = lz_tile_count(n);
@@ -703,8 +707,8 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (t >= n_tiles) break;
             const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
             uint32_t cnt;
-            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, n, depth, spec_c + lz_tok_off(t),
-                                              visited, &cnt);
+            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, max(t_begin, base), n, depth,
+                                              spec_c + lz_tok_off(t), visited, &cnt);
             if (lane == 0) {
                 M->spec_exit[t] = ex;
                 M->spec_count[t] = (uint16_t)cnt;
@@ -716,11 +720,11 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         //          the true parse wherever the predecessor did converge to its speculative parse
         ZtsChunkInfo* ci = info + c;
         if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
-        if (tid == 0 && n_tiles) {
-            M->entry_used[0] = 0;
-            M->fix_exit[0] = M->spec_exit[0];
-            M->fix_count[0] = 0;
-            M->spec_from[0] = 0;
+        if (tid == 0 && t0 < n_tiles) {
+            M->entry_used[t0] = base;
+            M->fix_exit[t0] = M->spec_exit[t0];
+            M->fix_count[t0] = 0;
+            M->spec_from[t0] = 0;
         }
         for (;;) {
             uint32_t w = 0;
@@ -742,13 +746,13 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         __syncthreads();
         // ---- 4b. tiles entered at the wrong place form chains (consecutive tiles inside one long run of
         //          matches that never meets the speculative parse); chains are independent, one warp each
-        for (uint32_t w = tid + 1; w < n_tiles; w += LZ_THREADS) {
+        for (uint32_t w = t0 + 1 + tid; w < n_tiles; w += LZ_THREADS) {
             const bool bad = M->fix_exit[w - 1] != M->entry_used[w];
-            const bool bad_prev = w >= 2 && M->fix_exit[w - 2] != M->entry_used[w - 1];
+            const bool bad_prev = w >= t0 + 2 && M->fix_exit[w - 2] != M->entry_used[w - 1];
             if (bad && !bad_prev) atomicOr(&M->start_mask[w >> 5], 1u << (w & 31));
         }
         __syncthreads();
-        for (uint32_t w = warp + 1; w < n_tiles; w += LZ_WARPS) {
+        for (uint32_t w = t0 + 1 + warp; w < n_tiles; w += LZ_WARPS) {
             if (!((M->start_mask[w >> 5] >> (w & 31)) & 1u)) continue;
             uint32_t end = w + 1;  // next chain start (or the end of the chunk)
             while (end < n_tiles && !((M->start_mask[end >> 5] >> (end & 31)) & 1u)) ++end;
@@ -773,9 +777,9 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         __syncthreads();
         // ---- 4c. walk the chain of true exits once; anything still entered at the wrong place is redone here
         //          (normally nothing: this pass is what makes 4a/4b safe to run optimistically)
-        if (warp == 0 && n_tiles) {
-            uint32_t true_exit = M->fix_exit[0];
-            for (uint32_t w = 1; w < n_tiles; ++w) {
+        if (warp == 0 && t0 < n_tiles) {
+            uint32_t true_exit = M->fix_exit[t0];
+            for (uint32_t w = t0 + 1; w < n_tiles; ++w) {
                 if (true_exit == M->entry_used[w]) {
                     true_exit = M->fix_exit[w];
                     continue;
@@ -801,7 +805,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         // ---- 5. tile table + histograms over the surviving tokens (src/LZ77.ts:126-128,141-142,236,251,271,279)
         for (uint32_t w = warp; w < LZ_NTILES; w += LZ_WARPS) {
             ZtsTile t = {0, 0, 0, 0};
-            if (w < n_tiles) {
+            if (w >= t0 && w < n_tiles) {
                 t.fix_count = M->fix_count[w];
                 t.spec_from = M->spec_from[w];
                 t.spec_count = M->spec_count[w];
@@ -934,8 +938,9 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
         const uint32_t c = M->chunk;
         if (c >= n_chunks) break;
         const ZtsChunk ch = chunks[c];
-        const uint32_t n = ch.len;
-        const uint8_t* src = in + ch.in_off;
+        const uint32_t base = ch.dict_len;  // primed mode: history in front of the chunk, see lz77_chunk_kernel
+        const uint32_t n = base + ch.len;
+        const uint8_t* src = in + ch.in_off - base;
 
         const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, bstart, cnt16, M, T, phase, bits);
         const LzS SV = ix.SV;
@@ -961,12 +966,13 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
 
         // ---- speculative parse: thread t parses tile t from its first position
         const uint32_t n_tiles = (n + LZF_TILE - 1) / LZF_TILE;
+        const uint32_t t0 = base / LZF_TILE;  // first tile with anything to parse
         const uint32_t t = tid;
         const uint32_t t_begin = t * LZF_TILE, t_end = min(n, t_begin + LZF_TILE);
         // a match of this tile may reach into the next one, but not to its last position
         const uint32_t limit = (t + 1 < n_tiles) ? min(n, t_begin + 2 * LZF_TILE) - 1u : n;
-        if (t < n_tiles) {
-            uint32_t p = t_begin, cnt = 0, v0 = 0, v1 = 0;
+        if (t >= t0 && t < n_tiles) {
+            uint32_t p = max(t_begin, base), cnt = 0, v0 = 0, v1 = 0;
             uint32_t* sp = my_spec + t * LZF_SPEC_STRIDE;
             while (p < t_end) {
                 uint32_t tok;
@@ -989,7 +995,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
         __syncthreads();
 
         // ---- re-entry: tile t starts where tile t-1 ended and must end where its own speculative parse ended
-        if (t >= 1 && t < n_tiles) {
+        if (t > t0 && t < n_tiles) {
             const uint32_t target = TL->exit_a[t];
             const uint32_t v0 = bits[2 * t], v1 = bits[2 * t + 1];
             uint32_t p = TL->exit_a[t - 1], nfix = 0, from = TL->spec_count[t];
@@ -1015,20 +1021,20 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
 
         // ---- compaction into one contiguous token list + histograms
         uint32_t mine = 0, nfix = 0, from = 0, sc = 0;
-        if (t < n_tiles) {
+        if (t >= t0 && t < n_tiles) {
             nfix = TL->fix_count[t];
             from = TL->spec_from[t];
             sc = TL->spec_count[t];
             mine = nfix + (sc - from);
         }
-        const uint32_t base = block_excl_sum(mine, M->warp_tot, &M->n_tokens);
+        const uint32_t tbase = block_excl_sum(mine, M->warp_tot, &M->n_tokens);
         uint32_t* out = tok_out + (size_t)c * LZ_TOK_PER_CHUNK;
         {
             // the 32 tiles of a warp are copied one after the other by the whole warp: coalesced, no dependent loads
             const unsigned lane = tid & 31;
             for (int j = 0; j < 32; ++j) {
                 const uint32_t jn = __shfl_sync(0xFFFFFFFFu, nfix, j), jf = __shfl_sync(0xFFFFFFFFu, from, j),
-                               js = __shfl_sync(0xFFFFFFFFu, sc, j), jb = __shfl_sync(0xFFFFFFFFu, base, j);
+                               js = __shfl_sync(0xFFFFFFFFu, sc, j), jb = __shfl_sync(0xFFFFFFFFu, tbase, j);
                 const uint32_t jt = (tid & ~31u) + (uint32_t)j;
                 const uint32_t* fx = my_fix + jt * LZF_FIX_STRIDE;
                 const uint32_t* sp = my_spec + jt * LZF_SPEC_STRIDE + jf;
