@@ -196,3 +196,22 @@ def test_fast_mode_option_through_the_api(Z):
     assert Z.Inflate(fast, {"verify": True}).decompress().tobytes() == d
     g = Z.GZip(d, {"deflateOptions": {"b200": {"mode": "fast", "depth": 8}}}).compress().tobytes()
     assert gzip.decompress(g) == d
+
+
+def test_primed_mode_option_through_the_api(Z):
+    from zlibts_b200 import synth
+    d = synth.text(400000, 78).tobytes()
+    plain = Z.Deflate(d).compress().tobytes()
+    for name in ("primed", "fast-primed"):
+        c = Z.Deflate(d, {"b200": {"mode": name}}).compress().tobytes()
+        assert zlib.decompress(c) == d and Z.Inflate(c, {"verify": True}).decompress().tobytes() == d
+        if name == "primed":
+            assert len(c) < 0.97 * len(plain)
+    g = Z.GZip(d, {"deflateOptions": {"b200": {"mode": "primed"}}}).compress().tobytes()
+    assert gzip.decompress(g) == d and Z.GUnzip(g).decompress().tobytes() == d
+    zp = Z.Zip()
+    zp.addFile(d, "t.txt", {"deflateOptions": {"b200": {"mode": "primed"}}})
+    with zipfile.ZipFile(io.BytesIO(zp.compress().tobytes())) as zf:
+        assert zf.read("t.txt") == d
+    with pytest.raises(Z.ZlibError, match="unknown b200 mode"):
+        Z.Deflate(d, {"b200": {"mode": "turbo"}}).compress()
