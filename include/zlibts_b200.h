@@ -66,7 +66,7 @@ enum { ZLB_NONE = 0, ZLB_FIXED = 1, ZLB_DYNAMIC = 2 };
 /* deflate mode. COMPAT: every chunk's bytes equal the reference's RawDeflate run on that chunk
  * (lazy = 0, src/LZ77.ts:196-283 exhaustive longest/nearest match, src/RawDeflate.ts:484-571 code
  * lengths). */
-enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1, ZLB_MODE_PRIMED = 2 };
+enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1, ZLB_MODE_PRIMED = 2, ZLB_MODE_SMALLEST = 4 };
 /* FAST: same pipeline and the same exact Huffman construction, but the match search follows only the nearest
  * `depth` links of a position's hash chain (default ZLB_FAST_DEFAULT_DEPTH), runs one position per lane, and
  * matches are cut at tile boundaries (at most ~127 bytes): still a valid stream for the reference's Inflate, no
@@ -80,6 +80,11 @@ enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1, ZLB_MODE_PRIMED = 2 };
  * given up is per-chunk byte identity with RawDeflate(chunk) and chunk-parallel decoding (ZLB_INFLATE_SPLIT detects
  * the back references and takes the one-warp route). Without FAST the search is the reference's exhaustive one, and
  * every block equals the reference's block construction run with that history (oracle: zo_raw_deflate_dict). */
+/* SMALLEST (a flag for block_type DYNAMIC, may be or-ed with the others): each chunk is written as the
+ * shortest of the reference's three block constructions over the chunk's tokens -- dynamic, fixed, or stored
+ * (stored only if strictly shorter than both, fixed only if strictly shorter than dynamic; sizes compared in whole
+ * bytes of the block alone). The reference never falls back (src/RawDeflate.ts:105-108), so incompressible data grows
+ * by a code table per chunk there; here it grows by 5 bytes per 65535. results[i].blocks counts chunks. */
 #define ZLB_PRIMED_CHUNK 32768u
 #define ZLB_FAST_DEFAULT_DEPTH 16
 #define ZLB_MODE_FAST_DEPTH(d) (ZLB_MODE_FAST | ((int)(d) << 8))

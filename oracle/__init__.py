@@ -179,3 +179,17 @@ def inflate_streams_mt(comp, offs, lens, out_stride, threads=1):
     if rc:
         raise OracleError(rc)
     return out, int(total.value)
+
+
+def smallest_block(data, dict_len=0, bfinal=True):
+    """The block ZLB_MODE_SMALLEST writes for data[dict_len:]: the shortest of the reference's dynamic, fixed and
+    stored constructions over the same tokens (stored only if strictly shorter than both, fixed only if strictly
+    shorter than dynamic). Returns (bytes, 'dynamic' | 'fixed' | 'stored')."""
+    dyn = raw_deflate_dict(data, dict_len, bfinal, DYNAMIC)
+    fix = raw_deflate_dict(data, dict_len, bfinal, FIXED)
+    sto = raw_deflate_dict(data, dict_len, bfinal, NONE)
+    if len(_u8(data)) - dict_len > 0 and len(sto) < min(len(dyn), len(fix)):
+        return sto, "stored"
+    if len(fix) < len(dyn):
+        return fix, "fixed"
+    return dyn, "dynamic"

@@ -390,3 +390,68 @@ def test_primed_mode_ratio_fast_variant_and_split_inflate(engine):
         assert torch.equal(d_o, d_in) and int(r2["crc32"][0]) == zlib.crc32(d.tobytes())
     assert sizes["primed"] < 0.97 * sizes["compat"]          # text: history across chunk boundaries pays
     assert sizes["fast-primed"] < sizes["fast"]
+
+
+def test_smallest_mode_picks_the_shortest_block_per_chunk(engine):
+    """per chunk the shortest of dynamic / fixed / stored, each equal to the oracle's construction."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    rng = np.random.default_rng(24)
+    # chunks of every kind: incompressible (stored wins), tiny (fixed wins), ordinary (dynamic wins)
+    big = rand_bytes(rng, 65536, 256).tobytes() + synth.text(65536, 40).tobytes() + rand_bytes(rng, 65536, 256).tobytes() \
+        + b"ab" * 20 + rand_bytes(rng, 30000, 256).tobytes()
+    datas = [big, b"hello hello", rand_bytes(rng, 65535, 256).tobytes(), rand_bytes(rng, 65536, 256).tobytes(),
+             synth.mixed(200000, 41).tobytes(), b"", b"x", rand_bytes(rng, 100, 256).tobytes()]
+    for mode, cb in ((z.MODE_SMALLEST, 65536), (z.MODE_SMALLEST | z.MODE_PRIMED, 32768)):
+        blob, offs, lens = pack(datas)
+        caps = [z.deflate_bound(len(d), 0, oracle.DYNAMIC, mode) for d in datas]
+        ooffs = np.concatenate([[0], np.cumsum(caps)]).astype(np.uint64)
+        items = z.make_items(len(datas))
+        items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = offs, lens, ooffs[:-1], caps
+        d_out = torch.zeros(int(ooffs[-1]), dtype=torch.uint8, device="cuda")
+        res = engine.deflate_batch(torch.from_numpy(blob).cuda(), d_out, items, oracle.DYNAMIC, 0, 0, mode)
+        h = d_out.cpu().numpy()
+        kinds = set()
+        for d, o0, r in zip(datas, ooffs[:-1], res):
+            o = h[int(o0):int(o0) + int(r["out_len"])].tobytes()
+            assert int(r["status"]) == 0 and zlib.decompress(o, -15) == d
+            ref, ip = oracle.raw_inflate(o + b"\0\0\0\0", 0, out_cap=len(d) + 8)
+            assert ref == d and ip == len(o)
+            if not d:   # fixed wins; upstream drops the end-of-block symbol of an empty fixed block, the engine keeps it
+                assert o == b"\x03\x00"
+                continue
+            n_chunks = max(1, -(-len(d) // cb))
+            pos = 0
+            for k in range(n_chunks):
+                lo, hi = k * cb, min(len(d), (k + 1) * cb)
+                dl = min(lo, 32768) if mode & z.MODE_PRIMED else 0
+                want, kind = oracle.smallest_block(d[lo - dl:hi], dl, k + 1 == n_chunks)
+                kinds.add(kind)
+                assert o[pos:pos + len(want)] == want, (mode, len(d), k, kind)
+                pos += len(want)
+                if k + 1 < n_chunks:
+                    if kind == "stored":
+                        assert o[pos:pos + 5] == b"\x00\x00\x00\xff\xff"
+                        pos += 5
+                    elif o[pos:pos + 4] == b"\x00\x00\xff\xff":
+                        pos += 4
+                    else:
+                        assert o[pos:pos + 5] == b"\x00\x00\x00\xff\xff", (mode, k)
+                        pos += 5
+            assert pos == len(o)
+            assert len(o) <= len(d) + 5 * (len(d) // 65535 + 1) + 5 * n_chunks + 16   # never much larger than the input
+        assert kinds == {"dynamic", "fixed", "stored"}
+    # our own inflate reads it, chunk-parallel route requested (stored bytes may mimic a marker: must still be right)
+    d = np.frombuffer(big, dtype=np.uint8)
+    cap = z.deflate_bound(d.size)
+    items = z.make_items(1)
+    items["in_len"], items["out_cap"] = d.size, cap
+    d_in = torch.from_numpy(d.copy()).cuda()
+    d_z = torch.zeros(cap, dtype=torch.uint8, device="cuda")
+    r = engine.deflate_batch(d_in, d_z, items, mode=z.MODE_SMALLEST)
+    it2 = z.make_items(1)
+    it2["in_len"], it2["out_cap"] = int(r["out_len"][0]), d.size
+    d_o = torch.zeros(d.size, dtype=torch.uint8, device="cuda")
+    r2 = engine.inflate_batch(d_z, d_o, it2, z.INFLATE_SPLIT)
+    assert int(r2["status"][0]) == 0 and torch.equal(d_o, d_in)

@@ -20,7 +20,7 @@ assert ITEM_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32 and ENTRY_DTYPE
 
 # CompressionType (src/RawDeflate.ts:12-17)
 NONE, FIXED, DYNAMIC = 0, 1, 2
-MODE_COMPAT, MODE_FAST, MODE_PRIMED = 0, 1, 2   # PRIMED may be or-ed with FAST
+MODE_COMPAT, MODE_FAST, MODE_PRIMED, MODE_SMALLEST = 0, 1, 2, 4   # PRIMED / SMALLEST are flags (or-ed in)
 PRIMED_CHUNK = 32768
 
 

@@ -98,7 +98,8 @@ def _mode_of(opts):
     if name not in ("compat", "fast", "primed", "fast-primed"):
         raise ZlibError("unknown b200 mode: %s" % name)
     mode = N.mode_fast(int(b.get("depth", 0))) if name.startswith("fast") else N.MODE_COMPAT
-    return mode | (N.MODE_PRIMED if name.endswith("primed") else 0)
+    # `smallest: true` lets every chunk fall back to a fixed or stored block when that is shorter
+    return mode | (N.MODE_PRIMED if name.endswith("primed") else 0) | (N.MODE_SMALLEST if b.get("smallest") else 0)
 
 
 def deflate_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0, want_crc32=False,

@@ -112,6 +112,26 @@ int zts_checksum_device(zlb_ctx* ctx, const uint8_t* d_in, const zlb_item* d_ite
 // ---- small device helpers ----------------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned zts_lane() { return threadIdx.x & 31u; }
+// block-wide copy of len bytes, any alignment on either side: aligned 4-byte stores, the source read as aligned
+// words and shifted into place (all threads of the block call it)
+__device__ __forceinline__ void zts_block_copy(uint8_t* dst, const uint8_t* src, uint32_t len, uint32_t tid, uint32_t nthr)
+{
+    const uint32_t head = min(len, (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u));
+    if (tid < head) dst[tid] = src[tid];
+    const uint32_t words = (len - head) >> 2;
+    const uint8_t* s0 = src + head;
+    const uint32_t mis = (uint32_t)((uintptr_t)s0 & 3u);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - mis);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    if (mis == 0) {
+        for (uint32_t i = tid; i < words; i += nthr) dw[i] = sw[i];
+    } else {
+        // sw[i + 1] holds the upper bytes of word i, so it lies inside the source whenever it is read
+        for (uint32_t i = tid; i < words; i += nthr) dw[i] = __funnelshift_r(sw[i], sw[i + 1], mis * 8);
+    }
+    const uint32_t done = head + (words << 2);
+    if (tid < len - done) dst[done + tid] = src[done + tid];
+}
 __device__ __forceinline__ unsigned zts_lanemask_lt()
 {
     unsigned m;

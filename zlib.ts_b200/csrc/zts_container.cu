@@ -80,7 +80,7 @@ frame_header_kernel(const uint8_t* __restrict__ meta, const ZtsFrame* __restrict
     }
 }
 
-// one 64 KiB piece of one body per CTA: aligned 4-byte stores, the source read as aligned words and shifted
+// one 64 KiB piece of one body per CTA
 __global__ void __launch_bounds__(256)
 frame_body_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ body,
                   const ZtsFrame* __restrict__ frames, uint32_t n, uint8_t* __restrict__ out)
@@ -105,21 +105,7 @@ frame_body_kernel(const uint8_t* __restrict__ in, const uint8_t* __restrict__ bo
     const uint32_t len = (uint32_t)min((uint64_t)FRAME_PIECE, f.body_len - begin);
     const uint8_t* src = (f.stored ? in : body) + f.body_src + begin;
     uint8_t* dst = out + f.dst_off + f.head_len + begin;
-    const uint32_t head = min(len, (uint32_t)((4u - ((uintptr_t)dst & 3u)) & 3u));
-    if (tid < head) dst[tid] = src[tid];
-    const uint32_t words = (len - head) >> 2;
-    const uint8_t* s0 = src + head;
-    const uint32_t mis = (uint32_t)((uintptr_t)s0 & 3u);
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - mis);
-    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-    if (mis == 0) {
-        for (uint32_t i = tid; i < words; i += 256) dw[i] = sw[i];
-    } else {
-        // sw[i + 1] exists whenever word i is misaligned: its upper bytes are part of the body
-        for (uint32_t i = tid; i < words; i += 256) dw[i] = __funnelshift_r(sw[i], sw[i + 1], mis * 8);
-    }
-    const uint32_t done = head + (words << 2);
-    if (tid < len - done) dst[done + tid] = src[done + tid];
+    zts_block_copy(dst, src, len, tid, 256);
 }
 
 static uint32_t trailer_bytes(int kind) { return kind == ZLB_FRAME_ZLIB ? 4u : kind == ZLB_FRAME_GZIP ? 8u : 0u; }

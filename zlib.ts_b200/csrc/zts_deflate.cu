@@ -23,7 +23,7 @@ int zts_lz77_fast_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_ch
                          ZtsChunkInfo* d_info, uint32_t* d_tok, uint32_t* d_tile_tok, uint32_t* d_hist,
                          uint32_t* d_sortT, uint32_t* d_counter, uint32_t grid, uint32_t depth);
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
-                       ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type);
+                       ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type, int smallest);
 int zts_huffman_lengths_debug(zlb_ctx* ctx, const uint32_t* d_freqs, int nsym, int limit, uint8_t* d_lengths);
 
 #define WAVE_CHUNKS 8192u
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(PACK_THREADS)
 bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restrict__ info,
                const ZtsChunkCodes* __restrict__ codes, const uint32_t* __restrict__ spec_tok,
                const uint32_t* __restrict__ fix_tok, const zlb_item* __restrict__ items, uint8_t* __restrict__ out,
-               uint32_t stage_words, uint32_t min_words)
+               uint32_t stage_words, uint32_t min_words, const uint8_t* __restrict__ in)
 {
     extern __shared__ __align__(16) uint32_t stage[];  // stage_words
     __shared__ uint32_t s_ll[286];
@@ -178,6 +178,31 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     const uint32_t shift = (uint32_t)((uintptr_t)dst & 3u);  // image word j <-> aligned global word j
     const uint32_t n_words = (shift + out_bytes + 3) >> 2;
     if (n_words > stage_words || n_words <= min_words) return;  // the other launch's size class
+
+    if (ci->hdr_bits == ZTS_HDR_STORED) {
+        // ZLB_MODE_SMALLEST chose stored blocks for this chunk (makeNocompressBlock, src/RawDeflate.ts:122-153):
+        // pieces of at most 65535 bytes, each header byte | LEN | NLEN | bytes; the chunk starts byte-aligned
+        const uint8_t* src = in + ch.in_off;
+        uint32_t o = 0;
+        for (uint32_t pos = 0; pos < ch.len;) {
+            const uint32_t len = min(0xFFFFu, ch.len - pos);
+            if (tid == 0) {
+                dst[o] = ((ch.flags & CHUNK_LAST) && pos + len == ch.len) ? 1 : 0;  // bfinal | btype(0) << 1
+                dst[o + 1] = len & 0xFF;
+                dst[o + 2] = len >> 8;
+                dst[o + 3] = (len ^ 0xFFFFu) & 0xFF;
+                dst[o + 4] = (len ^ 0xFFFFu) >> 8;
+            }
+            zts_block_copy(dst + o + 5, src + pos, len, tid, PACK_THREADS);
+            o += 5 + len;
+            pos += len;
+        }
+        if (tid == 0 && !(ch.flags & CHUNK_LAST)) {  // join marker behind a byte-aligned block: 00 | 00 00 FF FF
+            dst[o] = dst[o + 1] = dst[o + 2] = 0;
+            dst[o + 3] = dst[o + 4] = 0xFF;
+        }
+        return;
+    }
 
     for (uint32_t i = tid; i < n_words; i += PACK_THREADS) stage[i] = 0;
     for (uint32_t i = tid; i < 286; i += PACK_THREADS) s_ll[i] = codes[c].ll[i];
@@ -408,11 +433,12 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                           zlb_result* h_results, size_t n, int mode, int block_type, uint32_t chunk_bytes,
                           uint32_t flags, HostIO* hio)
 {
-    if ((mode & 0xFF) & ~(ZLB_MODE_FAST | ZLB_MODE_PRIMED))
+    if ((mode & 0xFF) & ~(ZLB_MODE_FAST | ZLB_MODE_PRIMED | ZLB_MODE_SMALLEST))
         return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
     uint32_t depth = 0xFFFFFFFFu;  // compat: every candidate, like the reference
     const bool fast = (mode & ZLB_MODE_FAST) != 0;
     const bool primed = (mode & ZLB_MODE_PRIMED) != 0 && block_type != ZLB_NONE;
+    const bool smallest = (mode & ZLB_MODE_SMALLEST) != 0 && block_type == ZLB_DYNAMIC;
     if (fast) depth = ((uint32_t)mode >> 8) ? ((uint32_t)mode >> 8) : ZLB_FAST_DEFAULT_DEPTH;
     if (block_type != ZLB_NONE && block_type != ZLB_FIXED && block_type != ZLB_DYNAMIC)
         return zts_fail(ctx, ZLB_E_ARG, "invalid compression type");  // src/RawDeflate.ts:110
@@ -622,7 +648,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         else
             rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.spec, S.fix, S.hist, S.sortT, S.counter, g, depth);
         if (rc) return rc;
-        rc = zts_huffman_launch(ctx, d_chunks + w0, wn, S.hist, S.info, S.codes, block_type);
+        rc = zts_huffman_launch(ctx, d_chunks + w0, wn, S.hist, S.info, S.codes, block_type, smallest ? 1 : 0);
         if (rc) return rc;
         if (n_sets == 2 && k > 0)  // item_running is handed from wave to wave
             ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * n_waves + k - 1), 0));
@@ -634,11 +660,11 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         if (n_sets == 2) ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * n_waves + k), st));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_SMALL_WORDS * 4, st>>>(
-                       d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_SMALL_WORDS, 0u));
+                       d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_SMALL_WORDS, 0u, d_in));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, st>>>(
                        d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_STAGE_WORDS,
-                       PACK_SMALL_WORDS));
+                       PACK_SMALL_WORDS, d_in));
         if (delta_out) {
             ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * k + 1), st));
             if (k > 0 && (rc = wave_out_copy(k - 1))) return rc;  // wave k is queued: now wait for wave k-1

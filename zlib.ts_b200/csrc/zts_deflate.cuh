@@ -21,6 +21,8 @@
 
 #define ZTS_HDR_BYTES 576               // 3 + 14 + 19*3 + 316*14 bits = 4498 bits = 563 bytes
 
+#define ZTS_HDR_STORED 0xFFFFFFFFu       // ZtsChunkInfo.hdr_bits of a chunk written as stored block(s)
+
 #define CHUNK_LAST 1u                   // last chunk of its item: BFINAL = 1, no join marker
 
 struct ZtsChunk {      // host-built, one per chunk

@@ -365,8 +365,10 @@ __constant__ uint8_t c_huff_order_enc[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 1
 __constant__ uint8_t c_lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
 __constant__ uint8_t c_dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
-__device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, int block_type, ZtsChunkInfo* ci,
-                            ZtsChunkCodes* cc, HufWork* W)
+// `smallest` (ZLB_MODE_SMALLEST, DYNAMIC only): the block is written as whichever of the reference's three block
+// constructions is shortest for this chunk's tokens -- dynamic (:181-251), fixed (:161-173) or stored (:122-153).
+__device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, uint32_t chunk_len, int block_type,
+                            bool smallest, ZtsChunkInfo* ci, ZtsChunkCodes* cc, HufWork* W)
 {
     const unsigned lane = zts_lane();
     for (int i = (int)lane; i < ZTS_HDR_BYTES; i += 32) W->hdr[i] = 0;
@@ -427,8 +429,49 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, int bl
         }
     }
     __syncwarp();
+    bool use_fixed = false, use_stored = false;
+    uint32_t stored_bytes = 0;
+    if (smallest && block_type == ZLB_DYNAMIC) {
+        // byte sizes of the three encodings of this block alone (before any join marker)
+        unsigned long long dyn = 0, fix = 0;
+        for (int i = (int)lane; i < 286; i += 32) {
+            uint32_t f = hist_g[i];
+            if (i == 256) f = 1;
+            const uint32_t ex = i > 256 ? c_lext[i - 257] : 0;
+            dyn += (unsigned long long)f * (W->ll_len[i] + ex);
+            fix += (unsigned long long)f * ((i <= 143 ? 8u : i <= 255 ? 9u : i <= 279 ? 7u : 8u) + ex);
+        }
+        if (lane < 30) {
+            const unsigned long long f = hist_g[286 + lane];
+            dyn += f * (W->d_len[lane] + c_dext[lane]);
+            fix += f * (5u + c_dext[lane]);
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            dyn += __shfl_xor_sync(0xFFFFFFFFu, dyn, d);
+            fix += __shfl_xor_sync(0xFFFFFFFFu, fix, d);
+        }
+        const unsigned long long dyn_bytes = (dyn + W->hdr_bits + 7) >> 3, fix_bytes = (fix + 3 + 7) >> 3;
+        stored_bytes = chunk_len + 5u * ((chunk_len + 0xFFFEu) / 0xFFFFu);
+        use_stored = chunk_len > 0 && stored_bytes < min(dyn_bytes, fix_bytes);
+        use_fixed = !use_stored && fix_bytes < dyn_bytes;
+        __syncwarp();
+        if (use_fixed) {
+            for (int i = (int)lane; i < ZTS_HDR_BYTES; i += 32) W->hdr[i] = 0;
+            for (int i = (int)lane; i < 288; i += 32) W->ll_len[i] = i <= 143 ? 8 : i <= 255 ? 9 : i <= 279 ? 7 : 8;
+            if (lane < 30) W->d_len[lane] = 5;
+            __syncwarp();
+            if (lane == 0) {
+                HdrBits hf = {W->hdr, 0ull, 0u, 0u};
+                hf.put((chunk_flags & CHUNK_LAST) ? 1u : 0u, 1);
+                hf.put((uint32_t)ZLB_FIXED, 2);
+                W->hdr_bits = hf.finish();
+            }
+            __syncwarp();
+        }
+    }
     // code tables for the packer + exact body size
-    codes_from_lengths(W->ll_len, block_type == ZLB_FIXED ? 288 : 286, W->code_tmp);
+    codes_from_lengths(W->ll_len, (block_type == ZLB_FIXED || use_fixed) ? 288 : 286, W->code_tmp);
     unsigned long long bits = 0;
     for (int i = (int)lane; i < 286; i += 32) {
         const uint32_t l = W->ll_len[i];
@@ -460,17 +503,22 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, int bl
             nbytes += (pad >= 3 ? 0 : 1) + 4;
         }
         ci->out_bytes = (uint32_t)nbytes;
+        if (use_stored) {  // the packer copies the chunk's bytes instead; a join marker behind it is 5 whole bytes
+            ci->hdr_bits = ZTS_HDR_STORED;
+            ci->body_bits = 0;
+            ci->out_bytes = stored_bytes + ((chunk_flags & CHUNK_LAST) ? 0u : 5u);
+        }
     }
 }
 
 __global__ void __launch_bounds__(32)
 huffman_build_kernel(const ZtsChunk* __restrict__ chunks, uint32_t n_chunks, const uint32_t* __restrict__ hist,
-                     ZtsChunkInfo* __restrict__ info, ZtsChunkCodes* __restrict__ codes, int block_type)
+                     ZtsChunkInfo* __restrict__ info, ZtsChunkCodes* __restrict__ codes, int block_type, int smallest)
 {
     __shared__ HufWork W;
     const uint32_t c = blockIdx.x;
     if (c >= n_chunks) return;
-    build_chunk(hist + (size_t)c * 316, chunks[c].flags, block_type, info + c, codes + c, &W);
+    build_chunk(hist + (size_t)c * 316, chunks[c].flags, chunks[c].len, block_type, smallest != 0, info + c, codes + c, &W);
 }
 
 // test hook: code lengths of one histogram
@@ -483,11 +531,11 @@ huffman_lengths_kernel(const uint32_t* __restrict__ freqs, int nsym, int limit, 
 }
 
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
-                       ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type)
+                       ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type, int smallest)
 {
     ZTS_LAUNCH(ctx, ZK_HUFFMAN,
                huffman_build_kernel<<<n_chunks, 32, 0, ctx->work>>>(d_chunks, n_chunks, d_hist, d_info, d_codes,
-                                                                       block_type));
+                                                                       block_type, smallest));
     return ZLB_OK;
 }
 
