@@ -57,7 +57,7 @@ def main():
         if not r or r[0] in ("Kernel Name", "Address"):
             break
         body.append(r)
-    sass = sass_lines(stem, kpat)
+    sass = sass_lines(stem, os.environ.get("NCU_CUBIN_PAT", kpat))  # mangled-name pattern when kpat is ambiguous there
     if len(sass) != len(body):
         print("warning: %d SASS instructions in the cubin vs %d in the report (rebuilt since the capture?)" %
               (len(sass), len(body)), file=sys.stderr)
