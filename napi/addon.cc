@@ -5,11 +5,15 @@
 // equivalent of this layer is zlib.ts_b200/api.py over the same C ABI.
 //
 // Exports (all synchronous, like the reference's API):
-//   deflateBatch(inputs: Uint8Array[], compressionType, chunkBytes, flags) -> {outputs: Uint8Array[], crc32: number[], adler32: number[]}
+//   deflateBatch(inputs: Uint8Array[], compressionType, chunkBytes, flags, mode?) -> {outputs: Uint8Array[], crc32: number[], adler32: number[]}
 //   inflateBatch(input: Uint8Array, offsets: number[], lengths: number[], caps: number[], flags)
 //                                                          -> {outputs, status: number[], inUsed: number[], crc32, adler32}
 //   checksumBatch(inputs: Uint8Array[], kinds)             -> {crc32: number[], adler32: number[]}
 //   crc32Combine(a, b, lenB), adler32Combine(a, b, lenB)
+//   archive(kind, inputs: Uint8Array[], heads: Uint8Array[], cdirs: Uint8Array[] | null, methods: number[] | null,
+//           tail: Uint8Array, compressionType, chunkBytes, mode)
+//                                   -> {output: Uint8Array, crc32, adler32, offsets: number[], lengths: number[]}
+//     the whole container (zlib streams / gzip members / zip archive) framed and packed on the device
 #include <node_api.h>
 
 #include <cstring>
@@ -85,18 +89,20 @@ static std::vector<double> get_numbers(napi_env env, napi_value arr)
     return v;
 }
 
-// deflateBatch(inputs, compressionType, chunkBytes, flags)  <- new RawDeflate(input, opts).compress()
+// deflateBatch(inputs, compressionType, chunkBytes, flags, mode = 0)  <- new RawDeflate(input, opts).compress()
 static napi_value DeflateBatch(napi_env env, napi_callback_info info)
 {
-    size_t argc = 4;
-    napi_value argv[4];
+    size_t argc = 5;
+    napi_value argv[5];
     napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
     if (!ensure_ctx(env)) return nullptr;
-    uint32_t n = 0, ctype = 2, chunk = 0, flags = 0;
+    uint32_t n = 0, ctype = 2, chunk = 0, flags = 0, mode = ZLB_MODE_COMPAT;
     napi_get_array_length(env, argv[0], &n);
     napi_get_value_uint32(env, argv[1], &ctype);
     napi_get_value_uint32(env, argv[2], &chunk);
     napi_get_value_uint32(env, argv[3], &flags);
+    if (argc > 4) napi_get_value_uint32(env, argv[4], &mode);   // ZLB_MODE_FAST | ZLB_MODE_PRIMED | ZLB_MODE_SMALLEST
+    if ((mode & ZLB_MODE_PRIMED) && (chunk == 0 || chunk > ZLB_PRIMED_CHUNK)) chunk = ZLB_PRIMED_CHUNK;
     std::vector<zlb_item> items(n);
     std::vector<zlb_result> res(n);
     std::vector<Bytes> in(n);
@@ -119,7 +125,7 @@ static napi_value DeflateBatch(napi_env env, napi_callback_info info)
     for (uint32_t i = 0; i < n; ++i)
         if (in[i].n) memcpy(blob.data() + items[i].in_off, in[i].p, in[i].n);
     int rc = zlb_deflate_batch_host(g_ctx, blob.data(), blob.size(), out.data(), out.size(), items.data(), res.data(), n,
-                                    ZLB_MODE_COMPAT, (int)ctype, chunk, flags);
+                                    (int)mode, (int)ctype, chunk, flags);
     if (rc != ZLB_OK) {
         napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
         return nullptr;
@@ -234,6 +240,93 @@ static napi_value ChecksumBatch(napi_env env, napi_callback_info info)
     return result;
 }
 
+// archive(kind, inputs, heads, cdirs, methods, tail, compressionType, chunkBytes, mode)
+//   <- Deflate.compress (src/Deflate.ts:60-99), GZip.compress (src/GZip.ts:96-194), Zip.compress (src/Zip.ts:117-372)
+static napi_value Archive(napi_env env, napi_callback_info info)
+{
+    size_t argc = 9;
+    napi_value argv[9];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    if (!ensure_ctx(env)) return nullptr;
+    uint32_t kind = 0, n = 0, ctype = 2, chunk = 0, mode = 0;
+    napi_get_value_uint32(env, argv[0], &kind);
+    napi_get_array_length(env, argv[1], &n);
+    napi_get_value_uint32(env, argv[6], &ctype);
+    napi_get_value_uint32(env, argv[7], &chunk);
+    napi_get_value_uint32(env, argv[8], &mode);
+    napi_valuetype cd_t, me_t;
+    napi_typeof(env, argv[3], &cd_t);
+    napi_typeof(env, argv[4], &me_t);
+    const bool has_cdir = cd_t == napi_object, has_methods = me_t == napi_object;
+    std::vector<double> methods = has_methods ? get_numbers(env, argv[4]) : std::vector<double>();
+    std::vector<zlb_entry> ent(n);
+    std::vector<zlb_result> res(n);
+    std::vector<Bytes> in(n), head(n), cdir(n);
+    Bytes tail = {nullptr, 0};
+    get_u8(env, argv[5], &tail);
+    uint64_t in_total = 0, meta_total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        napi_value e;
+        napi_get_element(env, argv[1], i, &e);
+        bool ok = get_u8(env, e, &in[i]);
+        napi_get_element(env, argv[2], i, &e);
+        ok = ok && get_u8(env, e, &head[i]);
+        if (has_cdir) {
+            napi_get_element(env, argv[3], i, &e);
+            ok = ok && get_u8(env, e, &cdir[i]);
+        } else {
+            cdir[i] = {nullptr, 0};
+        }
+        if (!ok) {
+            napi_throw_type_error(env, nullptr, "inputs, heads and cdirs must be Uint8Array");
+            return nullptr;
+        }
+        memset(&ent[i], 0, sizeof ent[i]);
+        ent[i].in_off = in_total;
+        ent[i].in_len = in[i].n;
+        ent[i].head_off = meta_total;
+        ent[i].head_len = (uint32_t)head[i].n;
+        ent[i].cdir_off = meta_total + head[i].n;
+        ent[i].cdir_len = (uint32_t)cdir[i].n;
+        ent[i].method = has_methods ? (uint32_t)methods[i] : 8u;
+        in_total += in[i].n;
+        meta_total += head[i].n + cdir[i].n;
+    }
+    const uint64_t tail_off = meta_total;
+    meta_total += tail.n;
+    std::vector<uint8_t> blob(in_total ? in_total : 1), meta(meta_total ? meta_total : 1);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (in[i].n) memcpy(blob.data() + ent[i].in_off, in[i].p, in[i].n);
+        if (head[i].n) memcpy(meta.data() + ent[i].head_off, head[i].p, head[i].n);
+        if (cdir[i].n) memcpy(meta.data() + ent[i].cdir_off, cdir[i].p, cdir[i].n);
+    }
+    if (tail.n) memcpy(meta.data() + tail_off, tail.p, tail.n);
+    const uint32_t cb = (mode & ZLB_MODE_PRIMED) && (chunk == 0 || chunk > ZLB_PRIMED_CHUNK) ? ZLB_PRIMED_CHUNK : chunk;
+    std::vector<uint8_t> out(zlb_archive_bound((int)kind, ent.data(), n, tail.n, cb, (int)ctype) + 1);
+    uint64_t total = 0;
+    int rc = zlb_archive_host(g_ctx, (int)kind, blob.data(), in_total, meta.data(), meta_total, ent.data(), n, tail_off,
+                              tail.n, out.data(), out.size(), &total, res.data(), (int)mode, (int)ctype, chunk);
+    if (rc != ZLB_OK) {
+        napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
+        return nullptr;
+    }
+    std::vector<double> crc(n), adler(n), offs(n), lens(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        crc[i] = res[i].crc32;
+        adler[i] = res[i].adler32;
+        offs[i] = (double)res[i].in_used;
+        lens[i] = (double)res[i].out_len;
+    }
+    napi_value result;
+    napi_create_object(env, &result);
+    napi_set_named_property(env, result, "output", make_u8(env, out.data(), (size_t)total));
+    napi_set_named_property(env, result, "crc32", num_array(env, crc));
+    napi_set_named_property(env, result, "adler32", num_array(env, adler));
+    napi_set_named_property(env, result, "offsets", num_array(env, offs));
+    napi_set_named_property(env, result, "lengths", num_array(env, lens));
+    return result;
+}
+
 static napi_value Combine(napi_env env, napi_callback_info info, bool crc)
 {
     size_t argc = 3;
@@ -258,6 +351,7 @@ static napi_value Init(napi_env env, napi_value exports)
         {"deflateBatch", nullptr, DeflateBatch, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"inflateBatch", nullptr, InflateBatch, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"checksumBatch", nullptr, ChecksumBatch, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"archive", nullptr, Archive, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"crc32Combine", nullptr, Crc32Combine, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"adler32Combine", nullptr, Adler32Combine, nullptr, nullptr, nullptr, napi_default, nullptr},
     };

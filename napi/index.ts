@@ -7,7 +7,11 @@ const native = require('./build/Release/zlibts_b200.node');
 export enum CompressionType { NONE = 0, FIXED = 1, DYNAMIC = 2, RESERVED = 3 }      // src/RawDeflate.ts:12-17
 export enum BufferType { BLOCK = 0, ADAPTIVE = 1 }                                   // src/RawInflate.ts:5-8
 export interface RawDeflateOptions { lazy?: number; compressionType?: CompressionType;
-    outputBuffer?: number[] | Uint8Array; outputIndex?: number; b200?: { chunkBytes?: number } }
+    outputBuffer?: number[] | Uint8Array; outputIndex?: number;
+    b200?: { chunkBytes?: number; mode?: 'compat' | 'fast' | 'primed' | 'fast-primed'; depth?: number; smallest?: boolean } }
+// engine-only knob -> ZLB_MODE_* (include/zlibts_b200.h); the default is the reference-compatible mode
+const modeOf = (o: RawDeflateOptions = {}) => { const b = o.b200 ?? {}; const m = b.mode ?? 'compat';
+    return (m.startsWith('fast') ? 1 | ((b.depth ?? 0) << 8) : 0) | (m.endsWith('primed') ? 2 : 0) | (b.smallest ? 4 : 0); };
 export interface RawInflateOptions { index?: number; bufferSize?: number; bufferType?: BufferType; resize?: boolean }
 
 const STATUS_TEXT: { [k: number]: string } = {                                       // include/zlibts_b200.h
@@ -18,6 +22,7 @@ const u8 = (x: number[] | Uint8Array) => x instanceof Uint8Array ? x : new Uint8
 
 export class RawDeflate {                                                            // src/RawDeflate.ts:50-114
     input: Uint8Array; output: Uint8Array; op: number; compressionType: CompressionType; lazy: number; chunk: number;
+    mode: number;
     constructor(input: number[] | Uint8Array, opts: RawDeflateOptions = {}) {
         this.input = u8(input);
         this.lazy = opts.lazy ?? 0;
@@ -26,9 +31,10 @@ export class RawDeflate {                                                       
         this.output = opts.outputBuffer ? u8(opts.outputBuffer) : new Uint8Array(0);
         this.op = opts.outputIndex ?? 0;
         this.chunk = opts.b200?.chunkBytes ?? 0;
+        this.mode = modeOf(opts);
     }
     compress(): Uint8Array {
-        const r = native.deflateBatch([this.input], this.compressionType, this.chunk, 0);
+        const r = native.deflateBatch([this.input], this.compressionType, this.chunk, 0, this.mode);
         const body: Uint8Array = r.outputs[0];
         const out = new Uint8Array(this.op + body.length);
         out.set(this.output.subarray(0, Math.min(this.op, this.output.length)));     // caller's prefix survives
@@ -80,12 +86,11 @@ export class Deflate {                                                          
     compress(): Uint8Array {
         const type = this.opts.compressionType ?? CompressionType.DYNAMIC;
         const cmf = 120; let flg = type << 6; flg |= 31 - ((cmf << 8) + flg) % 31;     // :67-78
-        const r = native.deflateBatch([u8(this.input)], type, this.opts.b200?.chunkBytes ?? 0, 2 /* want adler */);
-        const body: Uint8Array = r.outputs[0]; const a = r.adler32[0]; this.adler32 = a;
-        const out = new Uint8Array(2 + body.length + 4);
-        out[0] = cmf; out[1] = flg; out.set(body, 2);
-        out.set([a >>> 24 & 255, a >>> 16 & 255, a >>> 8 & 255, a & 255], 2 + body.length);   // writeUintBE, :95
-        return this.output = out;
+        // header, raw stream and big-endian Adler-32 (:95) are put together on the device (zlb_archive_host, kind 1)
+        const r = native.archive(1, [u8(this.input)], [new Uint8Array([cmf, flg])], null, null, new Uint8Array(0),
+                                 type, this.opts.b200?.chunkBytes ?? 0, modeOf(this.opts));
+        this.adler32 = r.adler32[0];
+        return this.output = r.output;
     }
 }
 
@@ -110,6 +115,15 @@ export class Inflate {                                                          
         return buffer;
     }
 }
+// Whole containers in one call (what GZip.compress / Zip.compress do entry by entry, src/GZip.ts:96-194,
+// src/Zip.ts:117-372): every entry checksummed + deflated in one batch, headers / trailers / central directory / end
+// record written and packed on the device. heads / cdirs / tail are the byte templates described in the header.
+export const archive = (kind: 1 | 2 | 3, inputs: Uint8Array[], heads: Uint8Array[], cdirs: Uint8Array[] | null,
+                        methods: number[] | null, tail: Uint8Array, opts: RawDeflateOptions = {}) =>
+    native.archive(kind, inputs, heads, cdirs, methods, tail, opts.compressionType ?? CompressionType.DYNAMIC,
+                   opts.b200?.chunkBytes ?? 0, modeOf(opts)) as
+    { output: Uint8Array; crc32: number[]; adler32: number[]; offsets: number[]; lengths: number[] };
+
 // GZip / GUnzip / Zip / Unzip keep the reference's own source (src/GZip.ts, src/GUnzip.ts, src/Zip.ts, src/Unzip.ts)
 // unchanged: they only call RawDeflate, RawInflate and CRC32, which resolve to the classes above once the
 // reference's imports of "./RawDeflate", "./RawInflate", "./CRC32", "./Adler32" point at this file (INTEGRATION.md).
