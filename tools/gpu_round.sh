@@ -21,5 +21,10 @@ echo "ncu fast rc=$?"
 $SMALL > gpurun_out/plain3_$tag.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:"inflate_warp" -s 1 -c 1 -f -o gpurun_out/prof_inflate_$tag $SMALL > gpurun_out/ncu_full_inf_$tag.log 2>&1
 echo "ncu inflate rc=$?"
+python tools/bench_configs.py c4:2000 > gpurun_out/plain5_$tag.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:"frame_" -c 2 -f -o gpurun_out/prof_frame_$tag python tools/bench_configs.py c4:2000 > gpurun_out/ncu_full_frame_$tag.log 2>&1
+echo "ncu frame rc=$?"
+python tools/probe_kinds.py 64 > gpurun_out/kinds_$tag.log 2>&1; cat gpurun_out/kinds_$tag.log
+python __graft_entry__.py --smoke 2>&1 | tail -2
 python tools/bench_configs.py c1 c3 c4 c5 > gpurun_out/configs_$tag.jsonl 2> gpurun_out/configs_$tag.err; echo "configs rc=$?"; cat gpurun_out/configs_$tag.jsonl
 ls -la gpurun_out

@@ -33,7 +33,7 @@ def main():
     units_per_launch = int(sys.argv[2]) if len(sys.argv) > 2 else 2048  # chunks (streams) one captured launch processed
     out = {}
     traffic = {}
-    for leg in ("deflate", "fast", "inflate"):
+    for leg in ("deflate", "fast", "inflate", "frame"):
         rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (leg, tag))
         if not os.path.exists(rep):
             continue
@@ -51,6 +51,8 @@ def main():
                     u = units[i]
                     d[k] = {"value": v, "unit": u}
             out.setdefault(name, []).append(d)
+            if leg == "frame":   # captured on another workload (C4 sample): not part of the bench step's traffic table
+                continue
             try:
                 rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
                 traffic[name] = rd["value"] * UNIT_SCALE.get(rd["unit"], 1) + wr["value"] * UNIT_SCALE.get(wr["unit"], 1)

@@ -12,6 +12,7 @@
 // reference's RawInflate accepts this (src/RawInflate.ts:128-130,261-262,311).
 #include <stdlib.h>
 
+#include <stdlib.h>
 #include "zts_deflate.cuh"
 
 size_t zts_lz77_smem_bytes();
@@ -493,8 +494,10 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         // host path: about eight waves so that the copies overlap the kernels (the first wave's input and the last
         // wave's output are the only transfers left in the open); consecutive waves overlap on two streams, so a
         // wave only needs to be large enough to keep every SM busy for a couple of chunks
-        size_t w8 = (n_chunks + 7) / 8;
-        const size_t lo = 2u * (size_t)ctx->sm_count;
+        const char* wenv = getenv("ZTS_HOST_WAVES");  // EXPERIMENT
+        const size_t nw = wenv ? (size_t)atoi(wenv) : 8;
+        size_t w8 = (n_chunks + nw - 1) / nw;
+        const size_t lo = (wenv ? 1u : 2u) * (size_t)ctx->sm_count;
         if (w8 < lo) w8 = lo;
         if (w8 < wave) wave = w8;
     }
