@@ -70,7 +70,7 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "20"],
+                                       "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_CLOCK_MS", "20")],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None

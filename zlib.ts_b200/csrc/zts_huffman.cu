@@ -18,67 +18,81 @@
 
 struct HufWork {
     // val[0] doubles as the histogram being coded (read only while the heap is filled) and val[1] as
-    // the heap (dead once everything is popped): both are free again when the level lists are built
+    // the heap (dead once everything is popped): both are free again when the level lists are built.
+    // Three more tenants live in val[] while the level lists do not need the space (a code-length alphabet of
+    // 19 symbols uses 38 entries of each list): see huf_clen / huf_tree_sym / huf_code_tmp below.
     uint32_t val[2][HUF_LVL];        // value[j+1], value[j] of reversePackageMerge
     uint32_t pkbits[15][HUF_PKW];    // per level: bit t set <=> item t is a package (type[j][t] === symbols)
-    uint32_t nval[HUF_MAXSYM];       // frequencies in heap pop order (descending)
+    uint16_t nval[HUF_MAXSYM];       // frequencies in heap pop order (descending); Uint16 like the heap's values
     uint16_t nidx[HUF_MAXSYM];       // their symbols
-    uint8_t clen[HUF_MAXSYM];
-    uint8_t tree_sym[2 * (286 + 30)];
-    uint16_t code_tmp[HUF_MAXSYM];
     uint8_t ll_len[HUF_MAXSYM];
     uint8_t d_len[32];
     uint8_t t_len[20];
-    uint8_t hdr[ZTS_HDR_BYTES];
     uint32_t hdr_bits;
 };
+// 7.0 KiB: 28 chunks per SM (227 KiB less 1 KiB per CTA), so the 4096 chunks of a 256 MiB wave are all resident at
+// once on 148 SMs -- the kernel is latency-bound and its duration is that of the slowest round of chunks.
+static_assert(sizeof(HufWork) <= 7296, "HufWork must let 28 CTAs share an SM");
+
+// code lengths in pop order, written by reversePackageMerge when its level lists are dead
+__device__ __forceinline__ uint8_t* huf_clen(HufWork* W) { return reinterpret_cast<uint8_t*>(W->val[0]); }
+// getTreeSymbols result (<= 632 bytes): outlives the code-length alphabet's getLengths, which touches val[0][0..38)
+__device__ __forceinline__ uint8_t* huf_tree_sym(HufWork* W) { return reinterpret_cast<uint8_t*>(W->val[0] + 256); }
+// scratch of getCodesFromLengths (288 codes) and the staged code-length-symbol counts: val[1][64..208)
+__device__ __forceinline__ uint16_t* huf_code_tmp(HufWork* W) { return reinterpret_cast<uint16_t*>(W->val[1] + 64); }
 
 // ---- Heap (src/Heap.ts:49-132): (value,index) pairs in one Uint16Array --------------------------
+// A pair occupies heap[2k] (value) and heap[2k+1] (index): one aligned 32-bit word, value in the low half. The
+// reference swaps the moving pair with its parent / larger child level by level; carrying it in a register and
+// storing it once where it comes to rest leaves exactly the same array (every swap writes the other pair one level
+// along the path, which is what the hole does), with one load and one store per level instead of four of each.
 __device__ void heap_push(uint16_t* heap, int& length, uint16_t index, uint16_t value)
 {
-    int current = length;
-    heap[length++] = value;
-    heap[length++] = index;
+    uint32_t* h = reinterpret_cast<uint32_t*>(heap);
+    const uint32_t x = (uint32_t)value | ((uint32_t)index << 16);
+    int current = length;  // in Uint16 slots, as in the reference
+    length += 2;
     while (current > 0) {
-        int parent = ((current - 2) >> 2) << 1;
-        if (heap[current] > heap[parent]) {
-            uint16_t t = heap[current];
-            heap[current] = heap[parent];
-            heap[parent] = t;
-            t = heap[current + 1];
-            heap[current + 1] = heap[parent + 1];
-            heap[parent + 1] = t;
+        const int parent = ((current - 2) >> 2) << 1;  // src/Heap.ts:31
+        const uint32_t pp = h[parent >> 1];
+        if ((x & 0xFFFFu) > (pp & 0xFFFFu)) {          // src/Heap.ts:62
+            h[current >> 1] = pp;
             current = parent;
         } else {
             break;
         }
     }
+    h[current >> 1] = x;
 }
 
 __device__ void heap_pop(uint16_t* heap, int& length, uint16_t& index, uint16_t& value)
 {
-    value = heap[0];
-    index = heap[1];
+    uint32_t* h = reinterpret_cast<uint32_t*>(heap);
+    const uint32_t top = h[0];
+    value = (uint16_t)top;
+    index = (uint16_t)(top >> 16);
     length -= 2;
-    heap[0] = heap[length];
-    heap[1] = heap[length + 1];
+    const uint32_t x = h[length >> 1];  // the last pair moves to the root (src/Heap.ts:98-99) and sinks
     int parent = 0;
     for (;;) {
-        int current = 2 * parent + 2;
+        int current = 2 * parent + 2;   // src/Heap.ts:38
         if (current >= length) break;
-        if (current + 2 < length && heap[current + 2] > heap[current]) current += 2;
-        if (heap[current] > heap[parent]) {
-            uint16_t t = heap[parent];
-            heap[parent] = heap[current];
-            heap[current] = t;
-            t = heap[parent + 1];
-            heap[parent + 1] = heap[current + 1];
-            heap[current + 1] = t;
+        uint32_t c = h[current >> 1];
+        if (current + 2 < length) {     // the larger child; the left one on equal values (src/Heap.ts:108)
+            const uint32_t c2 = h[(current + 2) >> 1];
+            if ((c2 & 0xFFFFu) > (c & 0xFFFFu)) {
+                c = c2;
+                current += 2;
+            }
+        }
+        if ((c & 0xFFFFu) > (x & 0xFFFFu)) {  // src/Heap.ts:113
+            h[parent >> 1] = c;
         } else {
             break;
         }
         parent = current;
     }
+    if (length > 0) h[parent >> 1] = x;
 }
 
 // ---- reversePackageMerge (src/RawDeflate.ts:484-571), warp-cooperative ---------------------------------
@@ -96,7 +110,7 @@ __device__ void heap_pop(uint16_t* heap, int& length, uint16_t& index, uint16_t&
 // JS `undefined` (App. B-6): a sum with an out-of-range value[][] is NaN and compares false, i.e. "no
 // package left"; once the symbols are exhausted too the reference stores undefined items, which can
 // never be decremented -- modelled by HUF_UNDEF tail entries and the `defined` count.
-__device__ void rpm_warp(const uint32_t* freqs, int symbols, int limit, uint8_t* code_length, HufWork* W)
+__device__ void rpm_warp(const uint16_t* freqs, int symbols, int limit, uint8_t* code_length, HufWork* W)
 {
     const int lane = (int)zts_lane();
     int flag[16], size[16];
@@ -244,8 +258,8 @@ __device__ void get_lengths(const uint32_t* freqs_in, int nsym, int limit, uint8
     nodes = __shfl_sync(0xFFFFFFFFu, nodes, 0);
     __syncwarp();
     if (nodes < 2) return;
-    rpm_warp(W->nval, nodes, limit, W->clen, W);
-    for (int i = lane; i < nodes; i += 32) lengths[W->nidx[i]] = W->clen[i];
+    rpm_warp(W->nval, nodes, limit, huf_clen(W), W);
+    for (int i = lane; i < nodes; i += 32) lengths[W->nidx[i]] = huf_clen(W)[i];
     __syncwarp();
 }
 
@@ -371,13 +385,14 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, uint32
                             bool smallest, ZtsChunkInfo* ci, ZtsChunkCodes* cc, HufWork* W)
 {
     const unsigned lane = zts_lane();
-    for (int i = (int)lane; i < ZTS_HDR_BYTES; i += 32) W->hdr[i] = 0;
     for (int i = (int)lane; i < HUF_MAXSYM; i += 32) {
         W->ll_len[i] = 0;
         if (i < 32) W->d_len[i] = 0;
     }
     __syncwarp();
-    HdrBits hb = {W->hdr, 0ull, 0u, 0u};
+    // the header bit string goes straight to the chunk's record in global memory (bytes past its last bit are
+    // never read: the packer takes ceil(hdr_bits / 8) bytes, and the last one is zero above the last bit)
+    HdrBits hb = {cc->hdr, 0ull, 0u, 0u};
     hb.put((chunk_flags & CHUNK_LAST) ? 1u : 0u, 1);  // BFINAL
     hb.put((uint32_t)block_type, 2);                  // BTYPE
     if (block_type == ZLB_FIXED) {
@@ -397,16 +412,16 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, uint32
         int nsyms = 0;
         // the 19 code-length-symbol counts are staged in code_tmp (free until the codes are assigned);
         // get_lengths copies its input before it touches anything else
-        uint32_t* tf = reinterpret_cast<uint32_t*>(W->code_tmp);
+        uint32_t* tf = reinterpret_cast<uint32_t*>(huf_code_tmp(W));
         if (lane == 0) {
             uint8_t tf8[19];  // Uint8Array histogram (:346)
-            nsyms = tree_symbols(hlit, W->ll_len, hdist, W->d_len, W->tree_sym, tf8);  // :203
+            nsyms = tree_symbols(hlit, W->ll_len, hdist, W->d_len, huf_tree_sym(W), tf8);  // :203
             for (int i = 0; i < 19; ++i) tf[i] = tf8[i];
         }
         nsyms = __shfl_sync(0xFFFFFFFFu, nsyms, 0);
         __syncwarp();
         get_lengths(tf, 19, 7, W->t_len, W);               // :204
-        codes_from_lengths(W->t_len, 19, W->code_tmp);
+        codes_from_lengths(W->t_len, 19, huf_code_tmp(W));
         if (lane == 0) {
             uint8_t trans[19];
             for (int i = 0; i < 19; ++i) trans[i] = W->t_len[c_huff_order_enc[i]];
@@ -417,12 +432,12 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, uint32
             hb.put((uint32_t)(hclen - 4), 4);
             for (int i = 0; i < hclen; ++i) hb.put(trans[i], 3);
             for (int i = 0; i < nsyms; ++i) {  // :222-241
-                const uint32_t code = W->tree_sym[i];
-                hb.put(W->code_tmp[code], W->t_len[code]);
+                const uint32_t code = huf_tree_sym(W)[i];
+                hb.put(huf_code_tmp(W)[code], W->t_len[code]);
                 if (code >= 16) {
                     const uint32_t bl = code == 16 ? 2 : code == 17 ? 3 : 7;
                     i++;
-                    hb.put(W->tree_sym[i], bl);
+                    hb.put(huf_tree_sym(W)[i], bl);
                 }
             }
             W->hdr_bits = hb.finish();
@@ -457,12 +472,11 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, uint32
         use_fixed = !use_stored && fix_bytes < dyn_bytes;
         __syncwarp();
         if (use_fixed) {
-            for (int i = (int)lane; i < ZTS_HDR_BYTES; i += 32) W->hdr[i] = 0;
             for (int i = (int)lane; i < 288; i += 32) W->ll_len[i] = i <= 143 ? 8 : i <= 255 ? 9 : i <= 279 ? 7 : 8;
             if (lane < 30) W->d_len[lane] = 5;
             __syncwarp();
             if (lane == 0) {
-                HdrBits hf = {W->hdr, 0ull, 0u, 0u};
+                HdrBits hf = {cc->hdr, 0ull, 0u, 0u};
                 hf.put((chunk_flags & CHUNK_LAST) ? 1u : 0u, 1);
                 hf.put((uint32_t)ZLB_FIXED, 2);
                 W->hdr_bits = hf.finish();
@@ -471,26 +485,25 @@ __device__ void build_chunk(const uint32_t* hist_g, uint32_t chunk_flags, uint32
         }
     }
     // code tables for the packer + exact body size
-    codes_from_lengths(W->ll_len, (block_type == ZLB_FIXED || use_fixed) ? 288 : 286, W->code_tmp);
+    codes_from_lengths(W->ll_len, (block_type == ZLB_FIXED || use_fixed) ? 288 : 286, huf_code_tmp(W));
     unsigned long long bits = 0;
     for (int i = (int)lane; i < 286; i += 32) {
         const uint32_t l = W->ll_len[i];
-        cc->ll[i] = (uint32_t)W->code_tmp[i] | (l << 16);
+        cc->ll[i] = (uint32_t)huf_code_tmp(W)[i] | (l << 16);
         uint32_t f = hist_g[i];
         if (i == 256) f = 1;  // counted twice in the histogram, emitted once (src/LZ77.ts:127,279)
         const uint32_t ex = i > 256 ? c_lext[i - 257] : 0;
         bits += (unsigned long long)f * (l + ex);
     }
     __syncwarp();
-    codes_from_lengths(W->d_len, 30, W->code_tmp);
+    codes_from_lengths(W->d_len, 30, huf_code_tmp(W));
     if (lane < 30) {
         const uint32_t l = W->d_len[lane];
-        cc->d[lane] = (uint32_t)W->code_tmp[lane] | (l << 16);
+        cc->d[lane] = (uint32_t)huf_code_tmp(W)[lane] | (l << 16);
         bits += (unsigned long long)hist_g[286 + lane] * (l + c_dext[lane]);
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) bits += __shfl_xor_sync(0xFFFFFFFFu, bits, d);
-    for (int i = (int)lane; i < ZTS_HDR_BYTES; i += 32) cc->hdr[i] = W->hdr[i];
     if (lane == 0) {
         const uint32_t hbits = W->hdr_bits;
         ci->hdr_bits = hbits;
