@@ -116,38 +116,42 @@ struct PackTok {
     uint32_t nb;
 };
 
-// code bits of token g (g == n_tok is the end-of-block symbol); `seg` is the lane's segment hint
-__device__ __forceinline__ PackTok pack_token(uint32_t g, uint32_t n_tok, uint32_t& seg, const PackSeg* s_seg,
-                                              const uint32_t* __restrict__ sp, const uint32_t* __restrict__ fx,
-                                              const uint32_t* s_ll, const uint32_t* s_d)
+// Token g of the chunk (g == n_tok is the end-of-block symbol, g >= g_end nothing); `seg` is the lane's segment
+// hint. Loads are issued two batches ahead of their use (the loop bodies are short next to a trip to L2 / DRAM).
+#define PACK_TOK_EOB 0x7F000000u   // bits 24..30 are zero in every real token
+#define PACK_TOK_NONE 0x7E000000u
+__device__ __forceinline__ uint32_t fetch_token(uint32_t g, uint32_t g_end, uint32_t n_tok, uint32_t& seg,
+                                                const PackSeg* s_seg, const uint32_t* __restrict__ sp,
+                                                const uint32_t* __restrict__ fx)
+{
+    if (g >= g_end) return PACK_TOK_NONE;
+    if (g >= n_tok) return PACK_TOK_EOB;
+    while (s_seg[seg + 1].prefix <= g) ++seg;  // g only grows: the hint moves forward a slot or two per call
+    const uint32_t src = s_seg[seg].src;
+    const uint32_t idx = (src & 0x7FFFFFFFu) + (g - s_seg[seg].prefix);
+    return (src & 0x80000000u) ? __ldg(sp + idx) : __ldg(fx + idx);
+}
+
+// code bits of a token
+__device__ __forceinline__ PackTok encode_token(uint32_t tok, const uint32_t* s_ll, const uint32_t* s_d)
 {
     PackTok r = {0ull, 0u};
-    if (g < n_tok) {
-        while (s_seg[seg + 1].prefix <= g) ++seg;  // g only grows: the hint moves forward a slot or two per call
-        const uint32_t src = s_seg[seg].src;
-        const uint32_t idx = (src & 0x7FFFFFFFu) + (g - s_seg[seg].prefix);
-        const uint32_t tok = (src & 0x80000000u) ? __ldg(sp + idx) : __ldg(fx + idx);
-        if (tok & TOK_MATCH) {
-            uint32_t ls, lb, lv, ds, db, dv;
-            zts_len_code(((tok >> 16) & 0xFF) + 3, ls, lb, lv);
-            zts_dist_code((tok & 0xFFFF) + 1, ds, db, dv);
-            const uint32_t le = s_ll[257 + ls], de = s_d[ds];
-            // litlen code, length extra, distance code, distance extra (src/RawDeflate.ts:279-289)
-            r.bits = le & 0xFFFF;
-            r.nb = le >> 16;
-            r.bits |= (unsigned long long)lv << r.nb;
-            r.nb += lb;
-            r.bits |= (unsigned long long)(de & 0xFFFF) << r.nb;
-            r.nb += de >> 16;
-            r.bits |= (unsigned long long)dv << r.nb;
-            r.nb += db;
-        } else {
-            const uint32_t le = s_ll[tok & 0xFF];
-            r.bits = le & 0xFFFF;
-            r.nb = le >> 16;
-        }
-    } else if (g == n_tok) {
-        const uint32_t le = s_ll[256];
+    if (tok & TOK_MATCH) {
+        uint32_t ls, lb, lv, ds, db, dv;
+        zts_len_code(((tok >> 16) & 0xFF) + 3, ls, lb, lv);
+        zts_dist_code((tok & 0xFFFF) + 1, ds, db, dv);
+        const uint32_t le = s_ll[257 + ls], de = s_d[ds];
+        // litlen code, length extra, distance code, distance extra (src/RawDeflate.ts:279-289)
+        r.bits = le & 0xFFFF;
+        r.nb = le >> 16;
+        r.bits |= (unsigned long long)lv << r.nb;
+        r.nb += lb;
+        r.bits |= (unsigned long long)(de & 0xFFFF) << r.nb;
+        r.nb += de >> 16;
+        r.bits |= (unsigned long long)dv << r.nb;
+        r.nb += db;
+    } else if (tok != PACK_TOK_NONE) {
+        const uint32_t le = s_ll[tok == PACK_TOK_EOB ? 256u : (tok & 0xFFu)];
         r.bits = le & 0xFFFF;
         r.nb = le >> 16;
     }
@@ -285,9 +289,13 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     {
         unsigned long long tot = 0;
         uint32_t seg = seg0;
+        uint32_t t0 = fetch_token(g_begin + lane, g_end, n_tok, seg, s_seg, sp, fx);
+        uint32_t t1 = fetch_token(g_begin + 32 + lane, g_end, n_tok, seg, s_seg, sp, fx);
         for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
-            const uint32_t g = g0 + lane;
-            tot += pack_token(g < g_end ? g : 0xFFFFFFFFu, n_tok, seg, s_seg, sp, fx, s_ll, s_d).nb;
+            const uint32_t t2 = fetch_token(g0 + 64 + lane, g_end, n_tok, seg, s_seg, sp, fx);
+            tot += encode_token(t0, s_ll, s_d).nb;
+            t0 = t1;
+            t1 = t2;
         }
 #pragma unroll
         for (int d = 16; d; d >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, d);
@@ -298,9 +306,13 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     for (uint32_t w = 0; w < warp; ++w) bitpos += range_bits[w];
     {
         uint32_t seg = seg0;
+        uint32_t t0 = fetch_token(g_begin + lane, g_end, n_tok, seg, s_seg, sp, fx);
+        uint32_t t1 = fetch_token(g_begin + 32 + lane, g_end, n_tok, seg, s_seg, sp, fx);
         for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
-            const uint32_t g = g0 + lane;
-            const PackTok t = pack_token(g < g_end ? g : 0xFFFFFFFFu, n_tok, seg, s_seg, sp, fx, s_ll, s_d);
+            const uint32_t t2 = fetch_token(g0 + 64 + lane, g_end, n_tok, seg, s_seg, sp, fx);
+            const PackTok t = encode_token(t0, s_ll, s_d);
+            t0 = t1;
+            t1 = t2;
             uint32_t inc = t.nb;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
