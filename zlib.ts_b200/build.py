@@ -17,7 +17,7 @@ CU_SOURCES = ["zts_ctx.cu", "zts_checksum.cu", "zts_inflate.cu", "zts_lz77.cu", 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-] + (["-DZTS_USE_MATCH"] if os.environ.get("ZTS_USE_MATCH") else []) + [
+] + (["-DZTS_USE_MATCH"] if os.environ.get("ZTS_USE_MATCH") else []) + os.environ.get("ZTS_NVCC_EXTRA", "").split() + [
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
