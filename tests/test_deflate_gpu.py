@@ -455,3 +455,33 @@ def test_smallest_mode_picks_the_shortest_block_per_chunk(engine):
     d_o = torch.zeros(d.size, dtype=torch.uint8, device="cuda")
     r2 = engine.inflate_batch(d_z, d_o, it2, z.INFLATE_SPLIT)
     assert int(r2["status"][0]) == 0 and torch.equal(d_o, d_in)
+
+
+def test_host_path_wave_plans_equal_the_device_path(engine):
+    """The host entry point cuts large jobs into waves (equal waves for medium jobs; ramp-up, cruise, small last wave
+    for large ones) whose copies overlap the kernels. Whatever the plan, the bytes are those of the one-wave device
+    path, also for items that straddle wave boundaries."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    for sizes in ([48 << 20], [(50 << 20) + 12345, (61 << 20) + 1, 50 << 20, 777]):
+        total = sum(sizes)
+        data = synth.mixed(total, 91)
+        offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.uint64)
+        caps = [z.deflate_bound(n) for n in sizes]
+        ooffs = np.concatenate([[0], np.cumsum(caps)]).astype(np.uint64)
+        items = z.make_items(len(sizes))
+        items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = offs, sizes, ooffs[:-1], caps
+        flags = z.DEFLATE_WANT_CRC32
+        d_out = torch.zeros(int(ooffs[-1]), dtype=torch.uint8, device="cuda")
+        rd = engine.deflate_batch(torch.from_numpy(data).cuda(), d_out, items, flags=flags)
+        h_out = np.zeros(int(ooffs[-1]), dtype=np.uint8)
+        rh = engine.deflate_batch_host(data, h_out, items, flags=flags)
+        assert int(rd["status"].max()) == 0 and int(rh["status"].max()) == 0
+        assert np.array_equal(rd["out_len"], rh["out_len"]) and np.array_equal(rd["crc32"], rh["crc32"])
+        dev = d_out.cpu().numpy()
+        for o, n in zip(ooffs[:-1], rd["out_len"]):
+            assert np.array_equal(dev[int(o):int(o) + int(n)], h_out[int(o):int(o) + int(n)])
+        # spot check: the first item decodes
+        n0 = int(rh["out_len"][0])
+        assert zlib.decompress(h_out[:n0].tobytes(), -15) == data[:sizes[0]].tobytes()

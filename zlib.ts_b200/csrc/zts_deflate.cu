@@ -501,24 +501,45 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     size_t n_chunks = 0;
     for (size_t i = 0; i < n; ++i) n_chunks += h_items[i].in_len ? (h_items[i].in_len + cb - 1) / cb : 1;
     if (n_chunks > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "too many chunks");
-    size_t wave = n_chunks < WAVE_CHUNKS ? n_chunks : WAVE_CHUNKS;
-    if (hio && n_chunks > 4u * (size_t)ctx->sm_count) {
-        // host path: about eight waves so that the copies overlap the kernels (the first wave's input and the last
-        // wave's output are the only transfers left in the open); consecutive waves overlap on two streams, so a
-        // wave only needs to be large enough to keep every SM busy for a couple of chunks
-        const char* wenv = getenv("ZTS_HOST_WAVES");  // EXPERIMENT
-        const size_t nw = wenv ? (size_t)atoi(wenv) : 8;
-        size_t w8 = (n_chunks + nw - 1) / nw;
-        const size_t lo = (wenv ? 1u : 2u) * (size_t)ctx->sm_count;
-        if (w8 < lo) w8 = lo;
-        if (w8 < wave) wave = w8;
+    // ---- wave plan: wstart[k] = first chunk of wave k, wstart[n_waves] = n_chunks
+    std::vector<size_t> wstart;
+    {
+        const size_t sm = (size_t)ctx->sm_count;
+        if (hio && n_chunks >= 16u * sm) {
+            // host path, large job: the first wave's input and the last wave's small kernels + output are the
+            // transfers nothing hides, so the waves ramp up (one, then two chunks per SM), cruise in about four
+            // large waves (every wave costs ~0.15 ms of launches and tails) and end with a small one; consecutive
+            // waves overlap on two streams, so even a small wave keeps every SM busy
+            wstart.push_back(0);
+            wstart.push_back(sm);
+            wstart.push_back(3u * sm);
+            const size_t rest = n_chunks - 5u * sm;  // minus the ramp (3 sm) and the last wave (2 sm)
+            size_t cruise = (rest + 3) / 4;
+            if (cruise > WAVE_CHUNKS) cruise = WAVE_CHUNKS;
+            for (size_t at = 3u * sm; at + cruise < n_chunks - 2u * sm; at += cruise) wstart.push_back(at + cruise);
+            if (wstart.back() < n_chunks - 2u * sm) wstart.push_back(n_chunks - 2u * sm);
+            wstart.push_back(n_chunks);
+        } else {
+            size_t wave = n_chunks < WAVE_CHUNKS ? n_chunks : WAVE_CHUNKS;
+            if (hio && n_chunks > 4u * sm) {  // host path, medium job: about eight equal waves of at least two chunks per SM
+                size_t w8 = (n_chunks + 7) / 8;
+                if (w8 < 2u * sm) w8 = 2u * sm;
+                if (w8 < wave) wave = w8;
+            }
+            for (size_t at = 0; at < n_chunks; at += wave) wstart.push_back(at);
+            wstart.push_back(n_chunks);
+        }
     }
+    const size_t n_waves = wstart.size() - 1;
+    size_t wave = 0;  // the largest wave sizes the scratch sets
+    for (size_t k = 0; k < n_waves; ++k)
+        if (wstart[k + 1] - wstart[k] > wave) wave = wstart[k + 1] - wstart[k];
     rc = zts_reserve_pinned(ctx, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t));
     if (rc) return rc;
     ZtsChunk* h_chunks = (ZtsChunk*)ctx->h_pin;
     uint32_t* h_blocks = (uint32_t*)(h_chunks + n_chunks);
     {
-        size_t k = 0;
+        size_t k = 0, wk = 0;
         for (size_t i = 0; i < n; ++i) {
             const uint64_t len = h_items[i].in_len;
             const uint64_t nc = len ? (len + cb - 1) / cb : 1;
@@ -532,14 +553,14 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                 c.dict_len = primed ? (uint32_t)(j * cb < LZ_WINDOW ? j * cb : LZ_WINDOW) : 0u;
                 c.pad1 = 0;
                 // first chunk of this item inside the chunk's wave
-                const size_t wave_base = (k / wave) * wave;
+                while (k >= wstart[wk + 1]) ++wk;
+                const size_t wave_base = wstart[wk];
                 const size_t item_first = k - j;
                 c.seg_first = (uint32_t)((item_first > wave_base ? item_first : wave_base) - wave_base);
             }
         }
     }
     const uint32_t grid = (uint32_t)(wave < (size_t)ctx->sm_count ? wave : (size_t)ctx->sm_count);
-    const size_t n_waves = (n_chunks + wave - 1) / wave;
     // Host path with several waves: consecutive waves run on two streams with a scratch set each, so that the next
     // wave's LZ77 CTAs take over the SMs as the previous wave's drain (no idle tail per wave) and its small kernels
     // overlap too; only the offset scan is chained from wave to wave.
@@ -620,7 +641,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
     auto wave_in_copy = [&](size_t k) -> int {  // input bytes of wave k: one contiguous hull (chunks are in order)
-        const size_t a = k * wave, b = (a + wave < n_chunks ? a + wave : n_chunks) - 1;
+        const size_t a = wstart[k], b = wstart[k + 1] - 1;
         const uint64_t lo = h_chunks[a].in_off, hi = h_chunks[b].in_off + h_chunks[b].len;
         if (hi > lo)
             ZTS_CUDA(ctx, cudaMemcpyAsync((void*)(d_in + lo), hio->h_in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_in));
@@ -629,7 +650,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     };
     auto wave_out_copy = [&](size_t k) -> int {  // what wave k appended to the items it touched
         ZTS_CUDA(ctx, cudaEventSynchronize(zts_sync_event(ctx, 2 * k + 1)));
-        const size_t a = k * wave, b = (a + wave < n_chunks ? a + wave : n_chunks) - 1;
+        const size_t a = wstart[k], b = wstart[k + 1] - 1;
         for (uint32_t i = h_chunks[a].item; i <= h_chunks[b].item; ++i) {
             unsigned long long now = h_run[k * n + i];
             if (now > h_items[i].out_cap) now = copied[i];  // overflowed item: nothing more was written
@@ -645,8 +666,9 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (pipe_in && (rc = wave_in_copy(0))) return rc;
 
     // events: 2k = input of wave k arrived, 2k+1 = wave k done; 2 n_waves + k = offset scan of wave k done
-    for (size_t w0 = 0, k = 0; w0 < n_chunks; w0 += wave, ++k) {
-        const uint32_t wn = (uint32_t)(n_chunks - w0 < wave ? n_chunks - w0 : wave);
+    for (size_t k = 0; k < n_waves; ++k) {
+        const size_t w0 = wstart[k];
+        const uint32_t wn = (uint32_t)(wstart[k + 1] - w0);
         const uint32_t g = wn < grid ? wn : grid;
         const Set& S = sets[n_sets == 2 ? (k & 1) : 0];
         cudaStream_t st = (n_sets == 2 && (k & 1)) ? ctx->s_aux[0] : ctx->stream;
