@@ -187,7 +187,7 @@ uint32_t zlb_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b)
  *                   compressed size (local +14, +18; central +16, +20), the local header offset (central +42),
  *                   directory size and offset (end record +12, +16).
  * Archive layout: entries in order, each head | body | trailer; for ZIP the central directory and the end record
- * follow the last entry. results[i]: status, crc32 / adler32, out_len = bytes of the framed entry,
+ * follow the last entry (ZIP32 only, like the reference: more than 65 535 entries or 4 GiB are refused). results[i]: status, crc32 / adler32, out_len = bytes of the framed entry,
  * in_used = offset of its first header byte in the archive.                                               */
 enum { ZLB_FRAME_ZLIB = 1, ZLB_FRAME_GZIP = 2, ZLB_FRAME_ZIP = 3 };
 

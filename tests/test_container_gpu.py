@@ -176,3 +176,18 @@ def test_fast_mode_archives_are_valid(Z):
     arc, res = Z.gzip_many(data, mode=Z.mode_fast())
     assert gzip.decompress(arc.tobytes()) == b"".join(data)
     assert [int(c) for c in res["crc32"]] == [zlib.crc32(d) for d in data]
+
+
+def test_zip32_limits_are_refused_not_wrapped(Z, engine):
+    import torch
+    n = 65536   # one more than the 16-bit entry count of the end record holds (src/Zip.ts:351-354)
+    ent = Z.make_entries(n)
+    ent["head_len"], ent["cdir_len"], ent["method"] = 30, 46, 0
+    ent["cdir_off"] = 30
+    meta = torch.zeros(30 + 46 + 22, dtype=torch.uint8, device="cuda")
+    d_in = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    d_out = torch.zeros(Z.archive_bound(Z.FRAME_ZIP, ent, 22), dtype=torch.uint8, device="cuda")
+    with pytest.raises(Z.EngineError, match="does not fit ZIP32"):
+        engine.archive(Z.FRAME_ZIP, d_in, meta, ent, d_out, tail=(76, 22))
+    total, _ = engine.archive(Z.FRAME_ZIP, d_in, meta, ent[:65535], d_out, tail=(76, 22))
+    assert total == 65535 * 76 + 22

@@ -214,6 +214,15 @@ static int archive_compress(zlb_ctx* ctx, int kind, const uint8_t* d_in, const z
     plan.total = off + tail_len;
     plan.n_pieces = (size_t)pieces;
     if (plan.n_pieces > 0x7FFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "archive too large");
+    if (kind == ZLB_FRAME_ZIP) {
+        // the reference writes 32-bit sizes / offsets and a 16-bit entry count (src/Zip.ts:265-304,351-360) and has no
+        // ZIP64 records: refuse what would not fit instead of wrapping around
+        if (plan.tail_dst > 0xFFFFFFFFull || n > 0xFFFFull)
+            return zts_fail(ctx, ZLB_E_ARG, "archive does not fit ZIP32 (%zu entries, %llu bytes before the end record)", n,
+                            (unsigned long long)plan.tail_dst);
+        for (size_t i = 0; i < n; ++i)
+            if (entries[i].in_len > 0xFFFFFFFFull) return zts_fail(ctx, ZLB_E_ARG, "entry %zu does not fit ZIP32", i);
+    }
     return ZLB_OK;
 }
 
