@@ -279,14 +279,11 @@ def test_fast_mode_valid_streams_and_ratio_within_tolerance(engine):
         assert zlib.decompress(h[int(o):int(o) + int(r["out_len"])].tobytes(), -15) == d
 
 
-def test_differential_fuzz_against_oracle(engine):
-    """2000 structured random inputs in one batch: every output must equal the oracle's RawDeflate bytes (this is where
-    LZ77 tie-breaks, heap order and run-length-coding corner cases show up), for DYNAMIC and FIXED."""
-    rng = np.random.default_rng(2026)
+def _fuzz_inputs(rng, count, big_every=50, small_max=6000):
     datas = []
-    for i in range(2000):
+    for i in range(count):
         kind = i % 8
-        n = int(rng.integers(1, 6000)) if i % 50 else int(rng.integers(60000, 65537))
+        n = int(rng.integers(1, small_max)) if i % big_every else int(rng.integers(60000, 65537))
         if kind == 0:
             d = rand_bytes(rng, n, int(rng.choice([1, 2, 3, 4, 8]))).tobytes()
         elif kind == 1:
@@ -311,6 +308,30 @@ def test_differential_fuzz_against_oracle(engine):
         else:  # tails: lengths around the 3-byte search cut-off and 258
             d = (b"ab" * 200)[:int(rng.integers(1, 8))] if i % 3 else b"q" * int(rng.integers(255, 265))
         datas.append(d)
+    return datas
+
+
+def _walk_joined_blocks(o, blocks, stored):
+    """`o` must be the blocks in order, each followed (except the last) by the byte-aligning empty stored block:
+    00 00 FF FF when the block left at least 3 free bits in its last byte, otherwise 00 00 00 FF FF -- always the
+    latter behind a block that is stored itself."""
+    pos = 0
+    for k, want in enumerate(blocks):
+        assert o[pos:pos + len(want)] == want, ("block", k)
+        pos += len(want)
+        if k + 1 < len(blocks):
+            if not stored[k] and o[pos:pos + 4] == b"\x00\x00\xff\xff":
+                pos += 4
+            else:
+                assert o[pos:pos + 5] == b"\x00\x00\x00\xff\xff", ("join", k)
+                pos += 5
+    assert pos == len(o)
+
+
+def test_differential_fuzz_against_oracle(engine):
+    """2000 structured random inputs in one batch: every output must equal the oracle's RawDeflate bytes (this is where
+    LZ77 tie-breaks, heap order and run-length-coding corner cases show up), for DYNAMIC and FIXED."""
+    datas = _fuzz_inputs(np.random.default_rng(2026), 2000)
     for btype in (oracle.DYNAMIC, oracle.FIXED):
         outs, res = _deflate_items(engine, datas, btype)
         assert int(res["status"].max()) == 0
@@ -485,3 +506,42 @@ def test_host_path_wave_plans_equal_the_device_path(engine):
         # spot check: the first item decodes
         n0 = int(rh["out_len"][0])
         assert zlib.decompress(h_out[:n0].tobytes(), -15) == data[:sizes[0]].tobytes()
+
+
+def test_differential_fuzz_primed_and_smallest(engine):
+    """Structured random inputs cut into small chunks, so that most blocks have history in front of them: every block
+    of the primed mode must equal the oracle's construction with that history, and with SMALLEST the shortest of the
+    oracle's three constructions."""
+    import torch
+    import zlibts_b200 as z
+    datas = _fuzz_inputs(np.random.default_rng(2027), 480, big_every=60, small_max=12000)
+    for mode, chunk in ((z.MODE_PRIMED, 1500), (z.MODE_PRIMED, 4096), (z.MODE_PRIMED | z.MODE_SMALLEST, 2048),
+                        (z.MODE_SMALLEST, 3000)):
+        blob, offs, lens = pack(datas)
+        caps = [z.deflate_bound(len(d), chunk, oracle.DYNAMIC, mode) for d in datas]
+        ooffs = np.concatenate([[0], np.cumsum(caps)]).astype(np.uint64)
+        items = z.make_items(len(datas))
+        items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = offs, lens, ooffs[:-1], caps
+        d_out = torch.zeros(int(ooffs[-1]), dtype=torch.uint8, device="cuda")
+        res = engine.deflate_batch(torch.from_numpy(blob).cuda(), d_out, items, oracle.DYNAMIC, chunk, 0, mode)
+        h = d_out.cpu().numpy()
+        assert int(res["status"].max()) == 0
+        for i, (d, o0, r) in enumerate(zip(datas, ooffs[:-1], res)):
+            o = h[int(o0):int(o0) + int(r["out_len"])].tobytes()
+            n_chunks = max(1, -(-len(d) // chunk))
+            blocks, stored = [], []
+            for k in range(n_chunks):
+                lo, hi = k * chunk, min(len(d), (k + 1) * chunk)
+                dl = min(lo, 32768) if mode & z.MODE_PRIMED else 0
+                if mode & z.MODE_SMALLEST:
+                    blk, kind = oracle.smallest_block(d[lo - dl:hi], dl, k + 1 == n_chunks)
+                else:
+                    blk, kind = oracle.raw_deflate_dict(d[lo - dl:hi], dl, k + 1 == n_chunks), "dynamic"
+                blocks.append(blk)
+                stored.append(kind == "stored")
+            try:
+                _walk_joined_blocks(o, blocks, stored)
+            except AssertionError as e:
+                raise AssertionError((mode, chunk, i, len(d), e.args))
+            if i % 16 == 0:
+                assert zlib.decompress(o, -15) == d
