@@ -596,11 +596,22 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
         // sweep C (overwrites the counters, which are dead now)
         if (w_begin < m) {
             uint16_t* wc = cnt16 + warp * 64u;
+            // the entries come back from L2: the loads run four batches ahead of the ranking that consumes them
+            uint32_t pre[4];
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                const uint32_t i = w_begin + k * 32 + lane;
+                pre[k] = i < m ? ld_u32_hint(&T[i], keep) : 0xFFFFFFFFu;
+            }
+#pragma unroll 4
             for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
                 const uint32_t i = w_begin + it * 32 + lane;
                 const bool v = i < m;
-                uint32_t e = 0xFFFFFFFFu;
-                if (v) e = ld_u32_hint(&T[i], keep);
+                const uint32_t e = pre[it & 3u];
+                {
+                    const uint32_t i4 = i + 4u * 32u;
+                    pre[it & 3u] = (it + 4u < LZ_SORT_TILE / 32 && i4 < m) ? ld_u32_hint(&T[i4], keep) : 0xFFFFFFFFu;
+                }
                 const uint32_t d = (e >> 23) & 63u;
                 const unsigned peers = peers_of<6>(d, v);
                 uint32_t dst = 0;
