@@ -622,7 +622,7 @@ static int inflate_launch(zlb_ctx* ctx, cudaStream_t st, const uint8_t* d_in, ui
 
 __global__ void __launch_bounds__(256)
 marker_scan_kernel(const uint8_t* __restrict__ in, unsigned long long n, unsigned long long* __restrict__ marks,
-                   uint32_t* __restrict__ count, uint32_t cap)
+                   uint32_t* __restrict__ count, uint32_t cap, unsigned long long tag)
 {
     // thread t looks at 16 consecutive start offsets
     const unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 16ull;
@@ -634,7 +634,7 @@ marker_scan_kernel(const uint8_t* __restrict__ in, unsigned long long n, unsigne
     for (int k = 0; k < 16; ++k) {
         if (b[k] == 0 && b[k + 1] == 0 && b[k + 2] == 0xFF && b[k + 3] == 0xFF && base + k + 4 <= n) {
             const uint32_t slot = atomicAdd(count, 1u);
-            if (slot < cap) marks[slot] = base + k + 4;  // first byte after the marker
+            if (slot < cap) marks[slot] = tag | (base + k + 4);  // first byte after the marker (+ the item's tag)
         }
     }
 }
@@ -666,22 +666,33 @@ segment_gather_kernel(const uint8_t* __restrict__ scratch, uint8_t* __restrict__
 static int inflate_launch(zlb_ctx* ctx, cudaStream_t st, const uint8_t* d_in, uint8_t* d_out, const zlb_item* d_items,
                           zlb_result* d_results, size_t n, uint32_t flags);
 
-// Tries to decode item `it` piecewise. Returns ZLB_OK with *done = true and *res filled when it worked, *done = false
-// when the item has to go through the serial decoder, < 0 on API errors.
-static int inflate_split_item(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item& it, uint32_t flags,
-                              zlb_result* res, bool* done)
+// Tries to decode the items h_items[big[*]] piecewise, all of them in one pass: one marker scan per item (queued back
+// to back, one read-back for all), one segment-mode launch over the pieces of every item, one gather. done[k] tells
+// whether big[k] worked (then res[k] is filled); the others have to go through the serial decoder. < 0 on API errors.
+#define SPLIT_TAG_SHIFT 40  // marks carry the item's index above the byte offset (offsets < 1 TiB, < 16 M large items)
+static int inflate_split_batch(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item* h_items,
+                               const std::vector<size_t>& big, uint32_t flags, std::vector<zlb_result>& res,
+                               std::vector<char>& done)
 {
-    *done = false;
+    const size_t nb = big.size();
+    res.assign(nb, zlb_result());
+    done.assign(nb, 0);
+    for (size_t k = 0; k < nb; ++k) memset(&res[k], 0, sizeof(zlb_result));
+    if (nb >= (1ull << 24)) return ZLB_OK;
     cudaStream_t st = ctx->stream;
     int rc = zts_reserve(ctx, &ctx->d_misc, (size_t)SPLIT_MAX_MARKS * 8 + 256);
     if (rc) return rc;
     unsigned long long* d_marks = (unsigned long long*)((uint8_t*)ctx->d_misc.p + 256);
     uint32_t* d_count = (uint32_t*)ctx->d_misc.p;
     ZTS_CUDA(ctx, cudaMemsetAsync(d_count, 0, 4, st));
-    const unsigned long long n = it.in_len;
-    const unsigned grid = (unsigned)((n / 16 + 255) / 256 + 1);
-    ZTS_LAUNCH(ctx, ZK_MARKER_SCAN,
-               marker_scan_kernel<<<grid, 256, 0, st>>>(d_in + it.in_off, n, d_marks, d_count, SPLIT_MAX_MARKS));
+    for (size_t k = 0; k < nb; ++k) {
+        const zlb_item& it = h_items[big[k]];
+        if (it.in_len >= (1ull << SPLIT_TAG_SHIFT)) continue;
+        const unsigned grid = (unsigned)((it.in_len / 16 + 255) / 256 + 1);
+        ZTS_LAUNCH(ctx, ZK_MARKER_SCAN,
+                   marker_scan_kernel<<<grid, 256, 0, st>>>(d_in + it.in_off, it.in_len, d_marks, d_count, SPLIT_MAX_MARKS,
+                                                           (unsigned long long)k << SPLIT_TAG_SHIFT));
+    }
     uint32_t count = 0;
     ZTS_CUDA(ctx, cudaMemcpyAsync(&count, d_count, 4, cudaMemcpyDeviceToHost, st));
     ZTS_CUDA(ctx, cudaStreamSynchronize(st));
@@ -689,15 +700,30 @@ static int inflate_split_item(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
     std::vector<unsigned long long> marks(count);
     ZTS_CUDA(ctx, cudaMemcpyAsync(marks.data(), d_marks, (size_t)count * 8, cudaMemcpyDeviceToHost, st));
     ZTS_CUDA(ctx, cudaStreamSynchronize(st));
-    std::sort(marks.begin(), marks.end());
-    // piece starts: 0 and every marker end that leaves at least one byte
-    std::vector<unsigned long long> starts;
-    starts.push_back(0);
-    for (unsigned long long m : marks)
-        if (m < n && m != starts.back()) starts.push_back(m);
-    const size_t np = starts.size();
-    if (np < 2) return ZLB_OK;
-    // segment items + scratch
+    std::sort(marks.begin(), marks.end());  // by item, then by offset
+    // pieces of every item: it starts at 0 and behind every marker that leaves at least one byte
+    struct Piece {
+        uint32_t item;  // index into big
+        unsigned long long start;
+    };
+    std::vector<Piece> pieces;
+    std::vector<size_t> first(nb + 1, 0);  // pieces of item k: [first[k], first[k + 1])
+    {
+        size_t mi = 0;
+        for (size_t k = 0; k < nb; ++k) {
+            first[k] = pieces.size();
+            const unsigned long long n = h_items[big[k]].in_len;
+            pieces.push_back({(uint32_t)k, 0ull});
+            for (; mi < marks.size() && (marks[mi] >> SPLIT_TAG_SHIFT) == k; ++mi) {
+                const unsigned long long m = marks[mi] & ((1ull << SPLIT_TAG_SHIFT) - 1);
+                if (m < n && m != pieces.back().start) pieces.push_back({(uint32_t)k, m});
+            }
+            if (pieces.size() - first[k] < 2) pieces.resize(first[k]);  // no marker inside: nothing to gain
+        }
+        first[nb] = pieces.size();
+    }
+    const size_t np = pieces.size();
+    if (np == 0) return ZLB_OK;
     rc = zts_reserve(ctx, &ctx->d_split, np * (size_t)SPLIT_SLOT + np * (sizeof(zlb_item) + sizeof(zlb_result) + sizeof(ZtsGather)) + 1024);
     if (rc) return rc;
     uint8_t* d_scratch = (uint8_t*)ctx->d_split.p;
@@ -705,11 +731,14 @@ static int inflate_split_item(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
     zlb_result* d_segres = (zlb_result*)(d_seg + np);
     ZtsGather* d_gather = (ZtsGather*)(d_segres + np);
     std::vector<zlb_item> seg(np);
-    for (size_t k = 0; k < np; ++k) {
-        seg[k].in_off = it.in_off + starts[k];
-        seg[k].in_len = (k + 1 < np ? starts[k + 1] : n) - starts[k];
-        seg[k].out_off = k * (size_t)SPLIT_SLOT;
-        seg[k].out_cap = SPLIT_SLOT;
+    for (size_t k = 0; k < nb; ++k) {
+        const zlb_item& it = h_items[big[k]];
+        for (size_t j = first[k]; j < first[k + 1]; ++j) {
+            seg[j].in_off = it.in_off + pieces[j].start;
+            seg[j].in_len = (j + 1 < first[k + 1] ? pieces[j + 1].start : it.in_len) - pieces[j].start;
+            seg[j].out_off = j * (size_t)SPLIT_SLOT;
+            seg[j].out_cap = SPLIT_SLOT;
+        }
     }
     ZTS_CUDA(ctx, cudaMemcpyAsync(d_seg, seg.data(), np * sizeof(zlb_item), cudaMemcpyHostToDevice, st));
     ZTS_CUDA(ctx, cudaMemsetAsync(d_segres, 0, np * sizeof(zlb_result), st));
@@ -719,33 +748,44 @@ static int inflate_split_item(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out,
     std::vector<zlb_result> sres(np);
     ZTS_CUDA(ctx, cudaMemcpyAsync(sres.data(), d_segres, np * sizeof(zlb_result), cudaMemcpyDeviceToHost, st));
     ZTS_CUDA(ctx, cudaStreamSynchronize(st));
-    // validate the chain
-    unsigned long long total = 0, blocks = 0;
-    std::vector<ZtsGather> gath(np);
-    for (size_t k = 0; k < np; ++k) {
-        const zlb_result& r = sres[k];
-        const bool last = k + 1 == np;
-        const bool fin = (r.blocks & 0x80000000u) != 0;
-        if (r.status != ZLB_ST_OK) return ZLB_OK;                 // incl. a distance before the piece's first byte
-        if (!last && (fin || r.in_used != seg[k].in_len)) return ZLB_OK;
-        if (last && !fin) return ZLB_OK;
-        gath[k].src = seg[k].out_off;
-        gath[k].dst = it.out_off + total;
-        gath[k].len = r.out_len;
-        total += r.out_len;
-        blocks += r.blocks & 0x7FFFFFFFu;
+    // validate every item's chain of pieces; the valid ones are gathered in one launch
+    std::vector<ZtsGather> gath;
+    for (size_t k = 0; k < nb; ++k) {
+        const zlb_item& it = h_items[big[k]];
+        const size_t a = first[k], b = first[k + 1];
+        if (b - a < 2) continue;
+        unsigned long long total = 0, blocks = 0;
+        bool ok = true;
+        for (size_t j = a; j < b && ok; ++j) {
+            const zlb_result& r = sres[j];
+            const bool last = j + 1 == b;
+            const bool fin = (r.blocks & 0x80000000u) != 0;
+            if (r.status != ZLB_ST_OK) ok = false;                 // incl. a distance before the piece's first byte
+            else if (!last && (fin || r.in_used != seg[j].in_len)) ok = false;
+            else if (last && !fin) ok = false;
+            total += r.out_len;
+            blocks += r.blocks & 0x7FFFFFFFu;
+        }
+        if (!ok) continue;
+        zlb_result& o = res[k];
+        o.status = total > it.out_cap ? ZLB_ST_OUT_OVERFLOW : ZLB_ST_OK;
+        o.out_len = total > it.out_cap ? 0 : total;
+        o.in_used = pieces[b - 1].start + sres[b - 1].in_used;
+        o.blocks = (uint32_t)blocks;
+        done[k] = 1;
+        if (total <= it.out_cap && total) {
+            unsigned long long at = 0;
+            for (size_t j = a; j < b; ++j) {
+                if (sres[j].out_len) gath.push_back({seg[j].out_off, it.out_off + at, sres[j].out_len});
+                at += sres[j].out_len;
+            }
+        }
     }
-    res->status = total > it.out_cap ? ZLB_ST_OUT_OVERFLOW : ZLB_ST_OK;
-    res->out_len = total > it.out_cap ? 0 : total;
-    res->in_used = starts[np - 1] + sres[np - 1].in_used;
-    res->blocks = (uint32_t)blocks;
-    res->crc32 = res->adler32 = 0;
-    if (total <= it.out_cap && total) {
-        ZTS_CUDA(ctx, cudaMemcpyAsync(d_gather, gath.data(), np * sizeof(ZtsGather), cudaMemcpyHostToDevice, st));
-        ZTS_LAUNCH(ctx, ZK_GATHER, segment_gather_kernel<<<(unsigned)np, 256, 0, st>>>(d_scratch, d_out, d_gather));
-        ZTS_CUDA(ctx, cudaStreamSynchronize(st));  // gath / seg vectors go out of scope
+    if (!gath.empty()) {
+        ZTS_CUDA(ctx, cudaMemcpyAsync(d_gather, gath.data(), gath.size() * sizeof(ZtsGather), cudaMemcpyHostToDevice, st));  // <= np entries
+        ZTS_LAUNCH(ctx, ZK_GATHER, segment_gather_kernel<<<(unsigned)gath.size(), 256, 0, st>>>(d_scratch, d_out, d_gather));
+        ZTS_CUDA(ctx, cudaStreamSynchronize(st));  // gath goes out of scope
     }
-    *done = true;
     return ZLB_OK;
 }
 
@@ -784,17 +824,20 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             std::vector<zlb_item> rest_items;
             std::vector<size_t> rest_idx;
             std::vector<char> is_done(n, 0);
-            for (size_t i : big) {
-                bool done = false;
-                zlb_result r;
-                memset(&r, 0, sizeof r);
-                rc = inflate_split_item(ctx, d_in, d_out, h_items[i], flags, &r, &done);
+            {
+                std::vector<zlb_result> bres;
+                std::vector<char> bdone;
+                rc = inflate_split_batch(ctx, d_in, d_out, h_items, big, flags, bres, bdone);
                 if (rc) return rc;
-                if (done) {
-                    is_done[i] = 1;
-                    ZTS_CUDA(ctx, cudaMemcpyAsync(d_results + i, &r, sizeof r, cudaMemcpyHostToDevice, ctx->stream));
-                    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                }
+                bool any = false;
+                for (size_t k = 0; k < big.size(); ++k)
+                    if (bdone[k]) {
+                        is_done[big[k]] = 1;
+                        any = true;
+                        ZTS_CUDA(ctx, cudaMemcpyAsync(d_results + big[k], &bres[k], sizeof(zlb_result), cudaMemcpyHostToDevice,
+                                                      ctx->stream));
+                    }
+                if (any) ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // bres goes out of scope
             }
             for (size_t i = 0; i < n; ++i)
                 if (!is_done[i]) {
