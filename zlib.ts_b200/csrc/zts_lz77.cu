@@ -58,6 +58,7 @@ struct LzMisc {
     uint16_t spec_from[LZ_NTILES];
     uint32_t hist[316];
     uint32_t n_tokens;
+    uint8_t spec_done[LZ_NTILES];    // set (release) when a tile's speculative parse and its tables are complete
 };
 
 // The radix scratch T is the one global buffer a CTA keeps re-using (256 KiB per chunk, written and read twice):
@@ -720,14 +721,17 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
 
         // ---- 3. speculative parse: warps take tiles from a shared counter
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
+        if (tid < LZ_NTILES) M->spec_done[tid] = 0;
+        if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
         if (tid == 0) {
             M->tile_next = t0;
-            M->tile_next2 = t0 + 1;  // the first tile needs no re-entry
+            M->tile_next2 = t0;
         }
         __syncthreads();
         const uint32_t n_tiles = lz_tile_count(n);
         uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         uint32_t* fix_c = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
+        ZtsChunkInfo* ci = info + c;
         for (;;) {
             uint32_t t = 0;
             if (lane == 0) t = atomicAdd(&M->tile_next, 1u);
@@ -741,24 +745,38 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 M->spec_exit[t] = ex;
                 M->spec_count[t] = (uint16_t)cnt;
             }
+            // publish the tile: its visited bits and tables before the flag (no block barrier behind this loop)
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) *(volatile uint8_t*)&M->spec_done[t] = 1;
         }
-        __syncthreads();
 
         // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel); this is already
-        //          the true parse wherever the predecessor did converge to its speculative parse
-        ZtsChunkInfo* ci = info + c;
-        if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
-        if (tid == 0 && t0 < n_tiles) {
-            M->entry_used[t0] = base;
-            M->fix_exit[t0] = M->spec_exit[t0];
-            M->fix_count[t0] = 0;
-            M->spec_from[t0] = 0;
-        }
+        //          the true parse wherever the predecessor did converge to its speculative parse. A warp that runs
+        //          out of speculative tiles starts here at once: a tile only needs itself and its predecessor parsed
+        //          (all tiles have been taken by then, so the ones it waits for are being worked on).
         for (;;) {
             uint32_t w = 0;
             if (lane == 0) w = atomicAdd(&M->tile_next2, 1u);
             w = __shfl_sync(0xFFFFFFFFu, w, 0);
             if (w >= n_tiles) break;
+            {
+                uint32_t spins = 0;
+                while (*(volatile uint8_t*)&M->spec_done[w] == 0 || (w > t0 && *(volatile uint8_t*)&M->spec_done[w - 1] == 0)) {
+                    __nanosleep(40);
+                    if (++spins > (1u << 26)) __trap();  // never hang the device
+                }
+                __threadfence_block();
+            }
+            if (w == t0) {  // the first tile needs no re-entry
+                if (lane == 0) {
+                    M->entry_used[t0] = base;
+                    M->fix_exit[t0] = M->spec_exit[t0];
+                    M->fix_count[t0] = 0;
+                    M->spec_from[t0] = 0;
+                }
+                continue;
+            }
             const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
             const uint32_t entry = M->spec_exit[w - 1];
             uint32_t nfix, from;
