@@ -364,6 +364,63 @@ __device__ __forceinline__ bool lz_probe(const LzS& S, const uint16_t* __restric
     return false;
 }
 
+// Where should the speculative parse of a tile that begins inside a run of one byte start? Inside such a run every
+// match is a maximum-length distance-1 match (lz_search's first branch), so the true parse visits run_start + 1 +
+// 258 k when it entered the run with a literal at its first byte -- the usual case. Starting the tile's speculative
+// parse at the first such position >= t_begin makes the predecessor's exit land on it, and no chain of wrongly
+// entered tiles forms across the run. Purely a heuristic choice of the start: any start >= t_begin is a valid
+// speculative parse, the re-entry / chain / verification passes do not care where it came from.
+// Returns t_begin when the tile does not begin inside a run, the run's first byte is out of reach (LZ_RUN_LOOKBACK),
+// or the run ends before the aligned position.
+#define LZ_RUN_LOOKBACK 8192u
+__device__ __forceinline__ uint32_t lz_run_aligned_start(const LzS& S, uint32_t t_begin, uint32_t t_end, uint32_t n)
+{
+    const unsigned lane = zts_lane();
+    if (t_begin < 4u || t_begin + LZ_MAXLEN + 4u > n) return t_begin;
+    const uint32_t w = ld_u32(S, t_begin - 1u);  // bytes t_begin - 1 .. t_begin + 2
+    const uint32_t splat = (w & 0xFFu) * 0x01010101u;
+    if (w != splat) return t_begin;
+    // first byte of the run: look back 128 bytes per step (lane l: the word at pos - 4 (l + 1))
+    uint32_t pos = t_begin - 1u;  // S[pos] is in the run
+    const uint32_t lo = t_begin > LZ_RUN_LOOKBACK ? t_begin - LZ_RUN_LOOKBACK : 0u;
+    uint32_t r0 = 0xFFFFFFFFu;
+    while (pos > lo) {
+        const uint32_t at = pos - 4u * (lane + 1u);  // wraps below zero for lanes past the start of the buffer
+        const bool in = pos >= 4u * (lane + 1u) && at >= lo;
+        const uint32_t x = in ? (ld_u32(S, at) ^ splat) : 0xFFFFFFFFu;  // out of reach counts as a mismatch
+        const unsigned mm = __ballot_sync(0xFFFFFFFFu, x != 0u);
+        if (mm) {
+            const int src = __ffs((int)mm) - 1;  // nearest word with a mismatch
+            const uint32_t xs = __shfl_sync(0xFFFFFFFFu, x, src);
+            const bool ins = __shfl_sync(0xFFFFFFFFu, (int)in, src) != 0;
+            if (!ins) break;                     // the run reaches past what we may look at: unknown start
+            const uint32_t hb = (31u - (uint32_t)__clz((int)xs)) >> 3;  // highest mismatching byte of that word
+            r0 = pos - 4u * ((uint32_t)src + 1u) + hb + 1u;
+            break;
+        }
+        pos -= 128u;
+    }
+    if (r0 == 0xFFFFFFFFu) return t_begin;
+    const uint32_t phase = (t_begin - (r0 + 1u)) % LZ_MAXLEN;
+    if (phase == 0u) return t_begin;
+    const uint32_t p0 = t_begin + (LZ_MAXLEN - phase);
+    // the run has to reach the aligned position (and the 3 bytes behind it, or the match there would not be a run match)
+    bool same = true;
+#pragma unroll
+    for (uint32_t k = 0; k < 3u; ++k) {
+        const uint32_t o = 4u * (lane + 32u * k);
+        if (t_begin + o < p0 + 3u) {
+            uint32_t x = ld_u32(S, t_begin + o) ^ splat;
+            const uint32_t nb = p0 + 3u - (t_begin + o);
+            if (nb < 4u) x &= (1u << (8u * nb)) - 1u;
+            same = same && x == 0u;
+        }
+    }
+    if (!__all_sync(0xFFFFFFFFu, same)) return t_begin;
+    (void)t_end;
+    return p0;
+}
+
 // Speculative parse of tile [t_begin, t_end) from p0 >= t_begin: tokens to tok_out, visited bit per parsed position.
 // Returns the exit position (>= t_end); *count_out = tokens written.
 __device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
@@ -739,8 +796,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (t >= n_tiles) break;
             const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
             uint32_t cnt;
-            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, max(t_begin, base), n, depth,
-                                              spec_c + lz_tok_off(t), visited, &cnt);
+            uint32_t p0 = max(t_begin, base);
+            if (t != t0) p0 = lz_run_aligned_start(SV, t_begin, t_end, n);  // the first tile starts where the parse starts
+            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, p0, n, depth, spec_c + lz_tok_off(t),
+                                              visited, &cnt);
             if (lane == 0) {
                 M->spec_exit[t] = ex;
                 M->spec_count[t] = (uint16_t)cnt;
