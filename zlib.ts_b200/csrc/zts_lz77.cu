@@ -807,7 +807,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             // publish the tile: its visited bits and tables before the flag (no block barrier behind this loop)
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) *(volatile uint8_t*)&M->spec_done[t] = 1;
+            if (lane == 0) {
+                __threadfence_block();  // release: the other lanes' writes, ordered before this point by the warp barrier
+                *(volatile uint8_t*)&M->spec_done[t] = 1;
+            }
         }
 
         // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel); this is already
