@@ -89,28 +89,32 @@ __device__ __forceinline__ uint32_t ld_u32_hint(const uint32_t* p, unsigned long
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// 4 bytes at byte offset i of S. S = (128-byte aligned shared buffer) + shift, so the misalignment of
-// S + i is (shift + i) & 3; pointer arithmetic stays on S so the loads compile to LDS, not generic LD.
+// 4 bytes at byte offset i of S. The loads go through the 32-bit shared-memory address of S: the two aligned
+// words around S + i and a funnel shift whose amount is the address itself times 8 (SHF takes it mod 32, i.e.
+// the misalignment in bits) -- six instructions, none of which depends on where the chunk sits in the buffer.
 // >= 8 readable bytes follow any i <= n.
 struct LzS {
     const uint8_t* S;
-    uint32_t shift;
+    uint32_t sa;  // shared-space address of S
     __device__ __forceinline__ uint8_t operator[](uint32_t i) const { return S[i]; }
 };
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;  // volatile: keeps its place relative to the barriers that separate staging from reading
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ uint32_t ld_u32(const LzS& V, uint32_t i)
 {
-    const uint32_t mis = (V.shift + i) & 3u;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(V.S + i - mis);
-    return __funnelshift_r(w[0], w[1], mis * 8);
+    const uint32_t a = V.sa + i, w = a & ~3u;
+    return __funnelshift_r(lds_u32(w), lds_u32(w + 4u), a << 3);
 }
 
 // 16 bytes at byte offset i of S as four little-endian words (>= 24 readable bytes follow any i <= n)
 __device__ __forceinline__ void ld_u128(const LzS& V, uint32_t i, uint32_t (&o)[4])
 {
-    const uint32_t mis = (V.shift + i) & 3u;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(V.S + i - mis);
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-    const uint32_t sh = mis * 8;
+    const uint32_t a = V.sa + i, w = a & ~3u, sh = a << 3;
+    const uint32_t w0 = lds_u32(w), w1 = lds_u32(w + 4u), w2 = lds_u32(w + 8u), w3 = lds_u32(w + 12u), w4 = lds_u32(w + 16u);
     o[0] = __funnelshift_r(w0, w1, sh);
     o[1] = __funnelshift_r(w1, w2, sh);
     o[2] = __funnelshift_r(w2, w3, sh);
@@ -539,7 +543,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
     const uint32_t body = (n - head) & ~15u;
     const uint32_t tail = n - head - body;
     uint8_t* S = Sbuf + ((16u - head) & 15u);  // S + head is 16-byte aligned
-    const LzS SV = {S, (16u - head) & 15u};
+    const LzS SV = {S, smem_u32(S)};
     if (tid == 0 && body) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&M->mbar)), "r"(body)
