@@ -141,3 +141,44 @@ def test_marker_split_matches_serial_decoder(engine):
     datas = [base] + smalls + [base]
     outs, res = gpu_inflate_many(engine, streams, [len(x) for x in datas], flags=z.INFLATE_SPLIT, trailer=b"\0\0")
     assert outs == datas and int(res["status"].max()) == 0
+
+
+def test_marker_split_batch_of_many_large_items(engine):
+    """All large items of a call are split in ONE pass (one read-back of markers, one segment-mode launch, one gather):
+    a batch that mixes streams that split, streams that must fall back (history across markers, no markers, false
+    markers), small items and an undersized output slot has to give every item its own correct result."""
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    rng = np.random.default_rng(16)
+    datas, streams = [], []
+    for k in range(24):
+        d = synth.mixed(300000 + 70001 * (k % 5), 400 + k).tobytes()
+        kind = k % 6
+        if kind in (0, 1, 2):      # pieces independent: full flushes
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            s = b"".join(co.compress(d[j:j + 65536]) + co.flush(zlib.Z_FULL_FLUSH) for j in range(0, len(d), 65536)) + co.flush()
+        elif kind == 3:            # history crosses the markers: must fall back
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            s = b"".join(co.compress(d[j:j + 50000]) + co.flush(zlib.Z_SYNC_FLUSH) for j in range(0, len(d), 50000)) + co.flush()
+        elif kind == 4:            # no markers
+            s = zlib_raw(d, 6)
+        else:                      # stored blocks whose payload is full of marker bytes
+            d = (b"\x00\x00\xff\xff" * 40 + rand_bytes(rng, 2000).tobytes()) * 150
+            s = zlib_raw(d, 0)
+        datas.append(d)
+        streams.append(s)
+    datas += [b"tiny", rand_bytes(rng, 5000, 3).tobytes()]
+    streams += [zlib_raw(x) for x in datas[-2:]]
+    outs, res = gpu_inflate_many(engine, streams, [len(x) for x in datas], flags=z.INFLATE_SPLIT | z.INFLATE_WANT_CRC32,
+                                 trailer=b"\0\0\0")
+    ref_outs, ref_res = gpu_inflate_many(engine, streams, [len(x) for x in datas], trailer=b"\0\0\0")
+    for k, (d, s, o, r, r0) in enumerate(zip(datas, streams, outs, res, ref_res)):
+        assert int(r["status"]) == 0 and o == d, k
+        assert int(r["out_len"]) == len(d) and int(r["in_used"]) == int(r0["in_used"]) == len(s), k
+        assert int(r["crc32"]) == zlib.crc32(d), k
+    # one slot too small among them: that item alone reports the overflow
+    sizes = [len(x) for x in datas]
+    sizes[1] -= 1
+    outs, res = gpu_inflate_many(engine, streams, sizes, flags=z.INFLATE_SPLIT, trailer=b"\0\0\0")
+    assert int(res["status"][1]) == z.ST_OUT_OVERFLOW
+    assert all(int(res["status"][k]) == 0 and outs[k] == datas[k] for k in range(len(datas)) if k != 1)
