@@ -177,13 +177,15 @@ __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* warp_to
 __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint32_t p, uint32_t pw, uint32_t pw1,
                                                  uint32_t maxlen)
 {
-    const uint32_t x0 = ld_u32(S, q) ^ pw;
+    const uint32_t a = S.sa + q, w = a & ~3u, sh = a << 3;  // ld_u32(S, q) and ld_u32(S, q + 4) share a word
+    const uint32_t w1 = lds_u32(w + 4u);
+    const uint32_t x0 = __funnelshift_r(lds_u32(w), w1, sh) ^ pw;
     if (x0 & 0xFFFFFFu) return 0;  // another table[] key (src/LZ77.ts:204-214)
     uint32_t k = 3;
     if (x0 == 0) {
         k = 4;
         // most matches end within the next word; long ones continue 16 bytes per step
-        const uint32_t x1 = ld_u32(S, q + 4) ^ pw1;
+        const uint32_t x1 = __funnelshift_r(w1, lds_u32(w + 8u), sh) ^ pw1;
         if (x1) {
             k += (uint32_t)(__ffs((int)x1) - 1) >> 3;
         } else {
@@ -929,7 +931,16 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             const uint32_t* fx = fix_c + lz_tok_off(w);
             const uint32_t* sp = spec_c + lz_tok_off(w);
             for (uint32_t k = lane; k < t.fix_count; k += 32) hist_token(fx[k], M->hist);
-            for (uint32_t k = t.spec_from + lane; k < t.spec_count; k += 32) hist_token(sp[k], M->hist);
+            // the surviving speculative tokens come back from L2: four loads in flight before they are counted
+            uint32_t k = t.spec_from + lane;
+            for (; k + 96u < t.spec_count; k += 128u) {
+                const uint32_t a0 = sp[k], a1 = sp[k + 32u], a2 = sp[k + 64u], a3 = sp[k + 96u];
+                hist_token(a0, M->hist);
+                hist_token(a1, M->hist);
+                hist_token(a2, M->hist);
+                hist_token(a3, M->hist);
+            }
+            for (; k < t.spec_count; k += 32u) hist_token(sp[k], M->hist);
         }
         __syncthreads();
         for (uint32_t i = tid; i < 316; i += LZ_THREADS)
