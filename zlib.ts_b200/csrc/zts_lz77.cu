@@ -694,10 +694,13 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
     if (startbits)
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) startbits[i] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < m; i += LZ_THREADS) {
-        const uint32_t hcur = hash13(ld_u32(SV, sorted[i]) & 0xFFFFFFu);
-        const uint32_t hprev = i ? hash13(ld_u32(SV, sorted[i - 1]) & 0xFFFFFFu) : 0xFFFFFFFFu;
-        if (hcur != hprev) {
+    for (uint32_t i0 = 0; i0 < m; i0 += LZ_THREADS) {  // whole warps stay in the loop: the shuffle below needs them
+        const uint32_t i = i0 + tid;
+        const uint32_t hcur = i < m ? hash13(ld_u32(SV, sorted[i]) & 0xFFFFFFu) : 0xFFFFFFFFu;
+        // the predecessor's hash is the neighbouring lane's; only lane 0 has to compute it
+        uint32_t hprev = __shfl_up_sync(0xFFFFFFFFu, hcur, 1);
+        if (lane == 0) hprev = (i && i < m) ? hash13(ld_u32(SV, sorted[i - 1]) & 0xFFFFFFu) : 0xFFFFFFFFu;
+        if (i < m && hcur != hprev) {
             bstart[hcur] = (uint16_t)i;
             if (startbits) atomicOr(&startbits[i >> 5], 1u << (i & 31));
         }
