@@ -9,7 +9,14 @@
 // 96 x 512, 48 x 256, 32 x 128 positions -- so that the last tiles to finish are small ones and the warps reach
 // the barrier behind the speculative parse close together.
 #define LZ_TILE 512u                    // largest tile
-#define LZ_NTILES 176u
+// measured on the C2 data (lz77 ms per 64 MiB mixed): 96/48/32 3.03, 80/64/64 3.04, 112/16/32 3.08, 120/8/16 3.11
+#ifndef LZ_TA
+#define LZ_TA 96u                       // tiles of 512 positions
+#define LZ_TB 48u                       // then tiles of 256
+#define LZ_TC 32u                       // then tiles of 128
+#endif
+#define LZ_NTILES (LZ_TA + LZ_TB + LZ_TC)
+static_assert(LZ_TA * 512u + LZ_TB * 256u + LZ_TC * 128u == 65536u, "the tiles must cover a 64 KiB chunk");
 #define LZ_SORT_TILE 2048u              // positions ranked by one warp in a radix pass
 #define LZ_HASH_BITS 13
 #define LZ_NB (1u << LZ_HASH_BITS)
@@ -38,17 +45,22 @@ struct ZtsChunk {      // host-built, one per chunk
 // first position of tile t (t == LZ_NTILES gives the chunk size)
 __host__ __device__ __forceinline__ uint32_t lz_tile_begin(uint32_t t)
 {
-    return t < 96u ? t * 512u : t < 144u ? 49152u + (t - 96u) * 256u : 61440u + (t - 144u) * 128u;
+    return t < LZ_TA ? t * 512u : t < LZ_TA + LZ_TB ? LZ_TA * 512u + (t - LZ_TA) * 256u
+                                                    : LZ_TA * 512u + LZ_TB * 256u + (t - LZ_TA - LZ_TB) * 128u;
 }
 // tiles that a chunk of n bytes has
 __host__ __device__ __forceinline__ uint32_t lz_tile_count(uint32_t n)
 {
-    return n <= 49152u ? (n + 511u) / 512u : n <= 61440u ? 96u + (n - 49152u + 255u) / 256u : 144u + (n - 61440u + 127u) / 128u;
+    return n <= LZ_TA * 512u ? (n + 511u) / 512u
+         : n <= LZ_TA * 512u + LZ_TB * 256u ? LZ_TA + (n - LZ_TA * 512u + 255u) / 256u
+                                            : LZ_TA + LZ_TB + (n - LZ_TA * 512u - LZ_TB * 256u + 127u) / 128u;
 }
 // tile that holds position pos
 __host__ __device__ __forceinline__ uint32_t lz_tile_of(uint32_t pos)
 {
-    return pos < 49152u ? pos / 512u : pos < 61440u ? 96u + (pos - 49152u) / 256u : 144u + (pos - 61440u) / 128u;
+    return pos < LZ_TA * 512u ? pos / 512u
+         : pos < LZ_TA * 512u + LZ_TB * 256u ? LZ_TA + (pos - LZ_TA * 512u) / 256u
+                                             : LZ_TA + LZ_TB + (pos - LZ_TA * 512u - LZ_TB * 256u) / 128u;
 }
 // first token slot of tile t: a tile never holds more tokens than positions
 __host__ __device__ __forceinline__ uint32_t lz_tok_off(uint32_t t) { return lz_tile_begin(t) + 8u * t; }
