@@ -508,6 +508,38 @@ def test_host_path_wave_plans_equal_the_device_path(engine):
         assert zlib.decompress(h_out[:n0].tobytes(), -15) == data[:sizes[0]].tobytes()
 
 
+def test_host_path_items_out_of_order_with_pinned_input(engine):
+    """Items that are NOT laid out in ascending order switch the host path from wave-by-wave input copies to one
+    whole-input copy; the second compute stream must wait for that copy too (it used to wait only for the tables:
+    with a pinned input its first wave could start before the bytes had arrived). Several waves, two streams."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    sizes = [(24 << 20) + 333, 31 << 20, (17 << 20) + 5]   # > 4 * sm_count chunks in total: several waves
+    total = sum(sizes)
+    data_t = torch.from_numpy(synth.mixed(total, 92)).pin_memory()
+    data = data_t.numpy()
+    # reversed placement: item 0 reads the last bytes of the input, item 2 the first
+    ends = np.cumsum(sizes[::-1])[::-1]
+    offs = np.array([total - int(e) for e in ends], dtype=np.uint64)
+    offs = np.array([int(sum(sizes[i + 1:])) for i in range(len(sizes))], dtype=np.uint64)
+    caps = [z.deflate_bound(n) for n in sizes]
+    ooffs = np.concatenate([[0], np.cumsum(caps)]).astype(np.uint64)
+    items = z.make_items(len(sizes))
+    items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = offs, sizes, ooffs[:-1], caps
+    out_t = torch.zeros(int(ooffs[-1]), dtype=torch.uint8).pin_memory()
+    h_out = out_t.numpy()
+    for rep in range(3):
+        h_out[:] = 0
+        rh = engine.deflate_batch_host(data, h_out, items, flags=z.DEFLATE_WANT_CRC32)
+        assert int(rh["status"].max()) == 0
+        for i, n in enumerate(sizes):
+            o, m = int(ooffs[i]), int(rh["out_len"][i])
+            want = data[int(offs[i]):int(offs[i]) + n].tobytes()
+            assert int(rh["crc32"][i]) == zlib.crc32(want)
+            assert zlib.decompress(h_out[o:o + m].tobytes(), -15) == want, (rep, i)
+
+
 def test_differential_fuzz_primed_and_smallest(engine):
     """Structured random inputs cut into small chunks, so that most blocks have history in front of them: every block
     of the primed mode must equal the oracle's construction with that history, and with SMALLEST the shortest of the

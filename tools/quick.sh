@@ -1,6 +1,6 @@
 #!/bin/bash
-# quick GPU check: deflate parity tests + per-kernel timings (mixed 256 MiB, text 64 MiB)
+# quick GPU check: deflate parity tests + LZ77 time per kind of data
 mkdir -p gpurun_out
-python -m pytest tests/test_deflate_gpu.py -x -q -m gpu 2>&1 | tail -5
-python tools/probe.py 256 mixed > gpurun_out/p1.log 2>&1; grep -A5 "^deflate" gpurun_out/p1.log | tail -6; grep "^inflate" gpurun_out/p1.log | tail -1
-python tools/probe.py 64 text > gpurun_out/p2.log 2>&1; grep -A5 "^deflate" gpurun_out/p2.log | tail -6; grep "^inflate" gpurun_out/p2.log | tail -1
+python -m pytest tests/test_deflate_gpu.py -x -q -m gpu 2>&1 | tail -8
+python tools/probe_kinds.py 64 > gpurun_out/kinds_quick.log 2>&1; cat gpurun_out/kinds_quick.log
+python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -c 1500 gpurun_out/bench_quick.json; tail -3 gpurun_out/bench_quick.err

@@ -612,11 +612,6 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     ZTS_CUDA(ctx, cudaMemcpyAsync(d_chunks, h_chunks, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t),
                                   cudaMemcpyHostToDevice, ctx->stream));
     ZTS_CUDA(ctx, cudaMemsetAsync(d_running, 0, n * 8, ctx->stream));
-    if (n_sets == 2) {
-        rc = zts_host_streams(ctx);
-        if (rc) return rc;
-        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 4 * n_waves), ctx->stream));
-    }
     ZTS_CUDA(ctx, cudaFuncSetAttribute(bitpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(PACK_STAGE_WORDS * 4)));
 
@@ -640,6 +635,10 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         if (!pipe_in)
             ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
     }
+    // Everything the second stream reads must be on the device before it starts: the tables uploaded above and, when
+    // the input is not pipelined wave by wave (items not laid out in ascending order), the whole-input copy just
+    // queued on ctx->stream. The event is recorded behind both.
+    if (n_sets == 2) ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 4 * n_waves), ctx->stream));
     auto wave_in_copy = [&](size_t k) -> int {  // input bytes of wave k: one contiguous hull (chunks are in order)
         const size_t a = wstart[k], b = wstart[k + 1] - 1;
         const uint64_t lo = h_chunks[a].in_off, hi = h_chunks[b].in_off + h_chunks[b].len;

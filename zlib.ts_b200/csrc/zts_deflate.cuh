@@ -5,15 +5,14 @@
 #define LZ_THREADS 1024
 #define LZ_WARPS 32
 #define LZ_MAX_CHUNK 65536u
-// Speculative parse tiles (warps take them from a counter in order). Sizes shrink towards the end of the chunk --
-// 96 x 512, 48 x 256, 32 x 128 positions -- so that the last tiles to finish are small ones and the warps reach
-// the barrier behind the speculative parse close together.
-#define LZ_TILE 512u                    // largest tile
-// measured on the C2 data (lz77 ms per 64 MiB mixed): 96/48/32 3.03, 80/64/64 3.04, 112/16/32 3.08, 120/8/16 3.11
+// Speculative parse tiles (8-lane groups take them from a counter in order, 128 groups per CTA). Sizes shrink
+// towards the end of the chunk -- 64 x 512, 64 x 256, 128 x 128 positions -- so that the last tiles to finish are
+// small ones and the groups run out of work close together.
+#define LZ_TILE 512u                    // largest tile (a group keeps 8 x 64 visited bits in registers)
 #ifndef LZ_TA
-#define LZ_TA 96u                       // tiles of 512 positions
-#define LZ_TB 48u                       // then tiles of 256
-#define LZ_TC 32u                       // then tiles of 128
+#define LZ_TA 64u                       // tiles of 512 positions
+#define LZ_TB 64u                       // then tiles of 256
+#define LZ_TC 128u                      // then tiles of 128
 #endif
 #define LZ_NTILES (LZ_TA + LZ_TB + LZ_TC)
 static_assert(LZ_TA * 512u + LZ_TB * 256u + LZ_TC * 128u == 65536u, "the tiles must cover a 64 KiB chunk");

@@ -9,14 +9,17 @@
 //   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
 //   2. all positions are radix-sorted (stable, 2 LSD passes, ballot-based ranking inside a warp, no atomics)
 //      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
-//   3. the chunk is cut into 176 tiles (512, then 256, then 128 positions) which the 32 warps take from a counter
-//      (segments of different entropy cost very different time) and parse speculatively, each from
-//      its tile start. A parse step first probes 32 positions at once, one per lane, for "has any
-//      earlier position with the same 3 bytes": runs of positions without one are literals and are
-//      emitted together. A position that may have candidates gets the warp-cooperative search:
-//      32 candidates per step (newest first), exact-key filter, tail-byte filter against the best
-//      so far, word-wise extension, REDUX.MAX over (len << 16 | q);
-//   4. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
+//   3. every position gets a 16-bit info word (L2-resident scratch): its rank inside its bucket (how many earlier
+//      positions the bucket holds) and a "may have a candidate" bit -- an earlier position with the same 3 bytes
+//      inside the window, found by walking back over the few hash collisions in front of the position's slot;
+//   4a. the chunk is cut into tiles (512, then 256, then 128 positions) which are parsed speculatively, each from
+//      its tile start, by GROUPS OF 8 LANES: a warp works on four tiles at once. A group reads the info words of
+//      32 positions with one coalesced load; runs of positions without a candidate are literals and are emitted
+//      together; a position with few earlier bucket entries (the common case: the median is below 8) is searched
+//      by the group, 8 candidates per step (newest first), exact-key filter, tail-byte filter against the best so
+//      far, word-wise extension, REDUX.MAX over (len << 16 | q) inside the group; positions behind long candidate
+//      lists are handed to the whole warp, 32 (or 128) candidates per step;
+//   4b. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
 //      of the previous one and is re-parsed only until it meets a speculatively parsed position
 //      (a visited-bit per position); the remainder of the speculative tokens is reused. All tiles
 //      re-enter in parallel assuming their predecessor exits where its speculative parse did; the
@@ -59,6 +62,7 @@ struct LzMisc {
     uint32_t hist[316];
     uint32_t n_tokens;
     uint8_t spec_done[LZ_NTILES];    // set (release) when a tile's speculative parse and its tables are complete
+    uint16_t tile_start[LZ_NTILES];  // where the tile's speculative parse starts
 };
 
 // The radix scratch T is the one global buffer a CTA keeps re-using (256 KiB per chunk, written and read twice):
@@ -208,12 +212,75 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
     return min(k, maxlen);
 }
 
+// ---- per-position info words -----------------------------------------------------------------------------------
+// P[slot(p)] = rank of p inside its bucket (earlier bucket entries, saturating) | "may have a candidate" << 15.
+// Inside a block of 32 positions the words are permuted so that lane s of an 8-lane group finds the words of
+// positions s, s + 8, s + 16, s + 24 of the block in one aligned 8-byte load.
+#define LZ_INFO_HAS 0x8000u
+#define LZ_RANK_SAT 0x7FFFu
+#define LZ_HAS_WALK 16u        // hash collisions walked over before a position is declared "may have a candidate"
+#ifndef LZ_GROUP_MAX
+#define LZ_GROUP_MAX 32u       // searches with at most this many earlier bucket entries stay inside the 8-lane group
+#endif
+__device__ __forceinline__ uint32_t lz_info_slot(uint32_t p) { return (p & ~31u) | ((p & 7u) << 2) | ((p >> 3) & 3u); }
+__device__ __forceinline__ void st_u16_hint(uint16_t* p, uint32_t v, unsigned long long pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"((unsigned short)v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_u64_hint(const void* p, unsigned long long pol)
+{
+    unsigned long long v;
+    asm volatile("ld.global.cg.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_u16_hint(const uint16_t* p, unsigned long long pol)
+{
+    unsigned short v;
+    asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+
+// one thread per slot of the sorted index (all threads of the block call it, barrier behind it is the caller's)
+__device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __restrict__ sorted,
+                                              const uint16_t* __restrict__ bstart, uint32_t m, uint32_t n, uint16_t* P,
+                                              unsigned long long keep)
+{
+    const unsigned tid = threadIdx.x;
+    // positions without a slot, and the padding block-wise readers touch: no candidate
+    const uint32_t npad = ((n + 31u) & ~31u) + 32u;
+    for (uint32_t p = m + tid; p < npad; p += LZ_THREADS) st_u16_hint(&P[lz_info_slot(p)], 0u, keep);
+    for (uint32_t i = tid; i < m; i += LZ_THREADS) {
+        const uint32_t p = sorted[i];
+        const uint32_t key = ld_u32(S, p) & 0xFFFFFFu;
+        const uint32_t lo = bstart[hash13(key)];
+        uint32_t has = 0;
+        if (p + 3u < n) {  // src/LZ77.ts:228: the last three positions are never searched
+            // the nearest earlier position with the same 3 bytes sits a few slots back (hash collisions in between);
+            // it decides: older ones are further away
+            uint32_t j = i, steps = 0;
+            while (j > lo) {
+                --j;
+                const uint32_t q = sorted[j];
+                if ((ld_u32(S, q) & 0xFFFFFFu) == key) {
+                    has = (p - q <= LZ_WINDOW) ? LZ_INFO_HAS : 0u;
+                    break;
+                }
+                if (++steps >= LZ_HAS_WALK) {
+                    has = LZ_INFO_HAS;  // undecided: the search will tell
+                    break;
+                }
+            }
+        }
+        st_u16_hint(&P[lz_info_slot(p)], min(i - lo, LZ_RANK_SAT) | has, keep);
+    }
+}
+
 // ---- warp-cooperative longest/nearest match search at position p (requires p + 3 < n) ----------
 // returns (len << 16) | dist, or 0 when no candidate exists (src/LZ77.ts:157-194 + :242)
-// `depth` = how many candidates (newest first) are looked at: 0xFFFFFFFF in the reference-compatible mode (all of
-// them, like the reference), a small multiple of 32 in the fast mode.
+// `rank` = earlier entries of p's bucket (LZ_RANK_SAT: unknown, found by a 32-way search);
+// `depth` = how many candidates (newest first) are looked at: 0xFFFFFFFF = all of them, like the reference.
 __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __restrict__ sorted,
-                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n, uint32_t depth)
+                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n, uint32_t depth, uint32_t rank)
 {
     const unsigned lane = zts_lane();
     const uint32_t pw = ld_u32(S, p);
@@ -240,54 +307,24 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
     }
     const uint32_t h = hash13(pw & 0xFFFFFFu);
     const uint32_t lo = bstart[h];
-    uint32_t a = lo, b = bstart[h + 1];
-    if (b - lo <= 32u) {
-        // the whole bucket fits one step (the common case): lane j takes entry j, whatever its position; entries at
-        // or behind p and outside the window drop out, REDUX.MAX over len << 16 | q picks longest, then nearest
-        const uint32_t pw1s = ld_u32(S, p + 4);
-        uint32_t key = 0;
-        if (lo + lane < b) {
-            const uint32_t q = sorted[lo + lane];
-            if (q < p && p - q <= LZ_WINDOW) key = (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q;
+    uint32_t cur = lo + rank;
+    if (rank >= LZ_RANK_SAT) {
+        // slot of p inside its bucket (positions ascending): 32-way search
+        uint32_t a = lo, b = bstart[h + 1];
+        while (b - a > 32) {
+            const uint32_t step = (b - a + 31) >> 5;
+            const uint32_t s = a + lane * step;
+            const bool less = (s < b) && (sorted[s] < p);
+            const uint32_t k = __popc(__ballot_sync(0xFFFFFFFFu, less));
+            if (k == 0) {
+                b = a;
+                break;
+            }
+            const uint32_t na = a + (k - 1) * step + 1;
+            const uint32_t nb = min(b, a + k * step);
+            a = na;
+            b = nb;
         }
-        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
-        if ((m >> 16) < 3u) return 0;
-        return (m & 0xFFFF0000u) | (p - (m & 0xFFFFu));
-    }
-    if (b - lo <= 64u) {
-        // up to 64 entries: two per lane in one step, no slot search -- cheaper than ranking p inside the bucket and
-        // stepping through the candidates in front of it (measured against 3 and 4 entries per lane: no better)
-        const uint32_t pw1s = ld_u32(S, p + 4);
-        uint32_t key = 0;
-        {
-            const uint32_t q = sorted[lo + lane];  // lo + lane < b: the bucket has more than 32 entries
-            if (q < p && p - q <= LZ_WINDOW) key = (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q;
-        }
-        if (lo + 32u + lane < b) {
-            const uint32_t q = sorted[lo + 32u + lane];
-            if (q < p && p - q <= LZ_WINDOW) key = max(key, (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q);
-        }
-        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
-        if ((m >> 16) < 3u) return 0;
-        return (m & 0xFFFF0000u) | (p - (m & 0xFFFFu));
-    }
-    // slot of p inside its bucket (positions ascending): 32-way search
-    while (b - a > 32) {
-        const uint32_t step = (b - a + 31) >> 5;
-        const uint32_t s = a + lane * step;
-        const bool less = (s < b) && (sorted[s] < p);
-        const uint32_t k = __popc(__ballot_sync(0xFFFFFFFFu, less));
-        if (k == 0) {
-            b = a;
-            break;
-        }
-        const uint32_t na = a + (k - 1) * step + 1;
-        const uint32_t nb = min(b, a + k * step);
-        a = na;
-        b = nb;
-    }
-    uint32_t cur;
-    {
         const uint32_t s = a + lane;
         const bool less = (s < b) && (sorted[s] < p);
         cur = a + __popc(__ballot_sync(0xFFFFFFFFu, less));
@@ -329,19 +366,50 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
         if (best_len >= maxlen) break;                          // :189 (258) or capped by the input end
         if (__any_sync(0xFFFFFFFFu, act && !inwin)) break;      // older ones are outside the window (:223)
         cur -= cnt;
-        if (depth <= 32u) break;                                // fast mode: candidate budget spent
+        if (depth <= 32u) break;                                // candidate budget spent
         depth -= 32u;
     }
     if (best_len < 3) return 0;
     return (best_len << 16) | (p - (best & 0xFFFFu));
 }
 
-// one greedy step at parse position p: emits the token, returns the next parse position
+// The same search by one 8-lane group (lanes gmask, this lane is number s of its group): `rank` earlier bucket
+// entries, newest first, 8 per step. Group-uniform control flow; every group of a warp may be somewhere else.
+__device__ __forceinline__ uint32_t lz_search_group(const LzS& S, const uint16_t* __restrict__ sorted, uint32_t lo,
+                                                    uint32_t rank, uint32_t p, uint32_t pw, uint32_t maxlen,
+                                                    unsigned gmask, unsigned s)
+{
+    const uint32_t pw1 = ld_u32(S, p + 4);
+    uint32_t cur = lo + rank, best = 0, best_len = 0;
+    while (cur > lo) {
+        const uint32_t cnt = min(8u, cur - lo);
+        const bool act = s < cnt;
+        const uint32_t q = act ? sorted[cur - 1 - s] : 0u;  // lane 0 of the group = newest candidate
+        const bool inwin = act && (p - q <= LZ_WINDOW);
+        uint32_t key = 0;
+        if (inwin && (best_len < 3 || S[q + best_len] == S[p + best_len]))
+            key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
+        const uint32_t m = __reduce_max_sync(gmask, key);  // longest, then nearest
+        if ((m >> 16) > best_len) {
+            best_len = m >> 16;
+            best = m;
+        }
+        if (best_len >= maxlen) break;
+        if (__any_sync(gmask, act && !inwin)) break;
+        cur -= cnt;
+    }
+    if (best_len < 3) return 0;
+    return (best_len << 16) | (p - (best & 0xFFFFu));
+}
+
+// one greedy step of the whole warp at parse position p: emits the token, returns the next parse position
 __device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                            uint32_t p, uint32_t n, uint32_t depth, uint32_t* tok_out)
+                                            const uint16_t* P, unsigned long long keep, uint32_t p, uint32_t n,
+                                            uint32_t depth, uint32_t* tok_out)
 {
     uint32_t r = 0;
-    if (p + 3 < n) r = lz_search(S, sorted, bstart, p, n, depth);  // src/LZ77.ts:228: no search in the last 3 bytes
+    const uint32_t info = ld_u16_hint(&P[lz_info_slot(p)], keep);  // 0 for the last three positions (src/LZ77.ts:228)
+    if (info & LZ_INFO_HAS) r = lz_search(S, sorted, bstart, p, n, depth, info & LZ_RANK_SAT);
     if (r) {
         const uint32_t len = r >> 16, dist = r & 0xFFFFu;
         *tok_out = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
@@ -349,25 +417,6 @@ __device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted
     }
     *tok_out = S[p];
     return p + 1;
-}
-
-// Lane-private probe: may position pl (pl + 3 < n) have a candidate, i.e. an earlier position inside the
-// window with the same 3 bytes (a non-empty table[key] list after pruning, src/LZ77.ts:211-225,242)?
-// Exact for buckets of at most LZ_PROBE_MAX entries, "maybe" (true) for longer ones.
-#define LZ_PROBE_MAX 20u  // measured 12 / 16 / 20 / 28: random data 2.92 / 1.86 / 1.76 / 1.76 ms per 64 MiB, text 3.72 / 3.75 / 3.79 / 3.85
-__device__ __forceinline__ bool lz_probe(const LzS& S, const uint16_t* __restrict__ sorted,
-                                         const uint16_t* __restrict__ bstart, uint32_t pl)
-{
-    const uint32_t pw = ld_u32(S, pl) & 0xFFFFFFu;
-    const uint32_t h = hash13(pw);
-    const uint32_t lo = bstart[h], hi = bstart[h + 1];
-    if (hi - lo > LZ_PROBE_MAX) return true;
-    for (uint32_t s = lo; s < hi; ++s) {
-        const uint32_t q = sorted[s];
-        if (q >= pl) break;  // ascending positions: the rest is not earlier
-        if (pl - q <= LZ_WINDOW && (ld_u32(S, q) & 0xFFFFFFu) == pw) return true;
-    }
-    return false;
 }
 
 // Where should the speculative parse of a tile that begins inside a run of one byte start? Inside such a run every
@@ -427,60 +476,11 @@ __device__ __forceinline__ uint32_t lz_run_aligned_start(const LzS& S, uint32_t 
     return p0;
 }
 
-// Speculative parse of tile [t_begin, t_end) from p0 >= t_begin: tokens to tok_out, visited bit per parsed position.
-// Returns the exit position (>= t_end); *count_out = tokens written.
-__device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                                  uint32_t t_begin, uint32_t t_end, uint32_t p0, uint32_t n,
-                                                  uint32_t depth, uint32_t* __restrict__ tok_out, uint32_t* visited,
-                                                  uint32_t* count_out)
-{
-    const unsigned lane = zts_lane();
-    uint32_t p = p0;                 // t_begin, or the first position behind the history inside the first tile
-    uint32_t* tp = tok_out;          // next token slot
-    uint32_t vis = 0;                // lane j keeps the visited bits of positions [t_begin + 32 j, + 32): 16 lanes
-    const uint32_t my_lo = lane * 32u;
-    uint32_t wbase = p - 32u, wmask = 0;  // forces a probe at the first step
-    while (p < t_end) {
-        if (p - wbase >= 32u) {
-            // probe the next 32 positions, one per lane
-            wbase = p;
-            const uint32_t pl = p + lane;
-            bool hc = false;
-            if (pl < t_end && pl + 3 < n) hc = lz_probe(S, sorted, bstart, pl);
-            wmask = __ballot_sync(0xFFFFFFFFu, hc);
-        }
-        const uint32_t off = p - wbase;
-        const uint32_t m = wmask >> off;  // bit 0 <-> position p
-        const uint32_t avail = min(32u - off, t_end - p);
-        const uint32_t k = m ? min((uint32_t)__ffs((int)m) - 1u, avail) : avail;
-        const uint32_t rel = p - t_begin;
-        if (k) {
-            // k positions without any candidate: k literals (src/LZ77.ts:267-272)
-            if (lane < k) tp[lane] = S[p + lane];
-            tp += k;
-            // bits [rel, rel + k) of the tile, cut to this lane's word
-            const uint32_t a = max(rel, my_lo), e = min(rel + k, my_lo + 32u);
-            if (a < e) vis |= (0xFFFFFFFFu >> (32u - (e - a))) << (a - my_lo);
-            p += k;
-            continue;
-        }
-        uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
-        if (lane == 0) *tp = tok;
-        ++tp;
-        if (lane == (rel >> 5)) vis |= 1u << (rel & 31u);
-        p = np;
-    }
-    if (lane < ((t_end - t_begin + 31u) >> 5)) visited[(t_begin >> 5) + lane] = vis;
-    *count_out = (uint32_t)(tp - tok_out);
-    return p;
-}
-
 // True parse of a tile entered at `entry` (>= the tile's begin is not required: entry may lie past it):
 // re-parse until a position the speculative parse visited, from there its tokens are reused.
 // Writes fix tokens, returns the exit; *nfix_out / *from_out describe the splice.
 __device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                                   uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
+                                                   const uint16_t* P, unsigned long long keep, uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
                                                    uint32_t depth, uint32_t* __restrict__ fix_out, const uint32_t* visited,
                                                    uint32_t spec_count, uint32_t spec_exit, uint32_t* nfix_out,
                                                    uint32_t* from_out)
@@ -502,7 +502,7 @@ __device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t*
             break;
         }
         uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
+        const uint32_t np = lz_step(S, sorted, bstart, P, keep, p, n, depth, &tok);
         if (lane == 0) fix_out[nfix] = tok;
         nfix++;
         p = np;
@@ -758,6 +758,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;  // per-CTA radix temp (L2 resident): pos | hash << 16
+    const unsigned long long keep = l2_policy_keep();
     uint32_t phase = 0;
 
     if (tid == 0) {
@@ -785,7 +786,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         (void)m;
         const uint32_t t0 = base ? lz_tile_of(base) : 0u;  // first tile with anything to parse
 
-        // ---- 3. speculative parse: warps take tiles from a shared counter
+        // ---- 3. per-position info words (rank inside the bucket, may-have-a-candidate bit) into the L2 scratch,
+        //         which the radix sort no longer needs
+        uint16_t* P = reinterpret_cast<uint16_t*>(T);
+        lz_build_info(SV, sorted, bstart, m, n, P, keep);
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
         if (tid < LZ_NTILES) M->spec_done[tid] = 0;
         if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
@@ -793,71 +797,207 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             M->tile_next = t0;
             M->tile_next2 = t0;
         }
-        __syncthreads();
         const uint32_t n_tiles = lz_tile_count(n);
+        // where the speculative parse of every tile starts (tiles inside a run of one byte: at the run's 258-byte phase)
+        for (uint32_t t = t0 + warp; t < n_tiles; t += LZ_WARPS) {
+            const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
+            uint32_t p0 = max(t_begin, base);  // the first tile starts where the parse starts
+            if (t != t0) p0 = lz_run_aligned_start(SV, t_begin, t_end, n);
+            if (lane == 0) M->tile_start[t] = (uint16_t)p0;  // p0 < n <= 65536 (lz_run_aligned_start stays 262 bytes clear of the end)
+        }
+        __threadfence_block();
+        __syncthreads();
         uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         uint32_t* fix_c = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         ZtsChunkInfo* ci = info + c;
-        for (;;) {
-            uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(&M->tile_next, 1u);
-            t = __shfl_sync(0xFFFFFFFFu, t, 0);
-            if (t >= n_tiles) break;
-            const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
-            uint32_t cnt;
-            uint32_t p0 = max(t_begin, base);
-            if (t != t0) p0 = lz_run_aligned_start(SV, t_begin, t_end, n);  // the first tile starts where the parse starts
-            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, p0, n, depth, spec_c + lz_tok_off(t),
-                                              visited, &cnt);
-            if (lane == 0) {
-                M->spec_exit[t] = ex;
-                M->spec_count[t] = (uint16_t)cnt;
-            }
-            // publish the tile: its visited bits and tables before the flag (no block barrier behind this loop)
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();  // release: the other lanes' writes, ordered before this point by the warp barrier
-                *(volatile uint8_t*)&M->spec_done[t] = 1;
-            }
-        }
 
-        // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel); this is already
-        //          the true parse wherever the predecessor did converge to its speculative parse. A warp that runs
-        //          out of speculative tiles starts here at once: a tile only needs itself and its predecessor parsed
-        //          (all tiles have been taken by then, so the ones it waits for are being worked on).
-        for (;;) {
-            uint32_t w = 0;
-            if (lane == 0) w = atomicAdd(&M->tile_next2, 1u);
-            w = __shfl_sync(0xFFFFFFFFu, w, 0);
-            if (w >= n_tiles) break;
-            {
-                uint32_t spins = 0;
-                while (*(volatile uint8_t*)&M->spec_done[w] == 0 || (w > t0 && *(volatile uint8_t*)&M->spec_done[w - 1] == 0)) {
-                    __nanosleep(40);
-                    if (++spins > (1u << 26)) __trap();  // never hang the device
+        // ---- 4a. speculative parse, then re-entry at the predecessor's speculative exit: both by 8-lane groups, four
+        //          tiles per warp. One loop iteration = one parse step of every group that has a tile: a run of literals,
+        //          a match found by the group, or a match found by the whole warp for the group (long candidate lists).
+        //          A group that runs out of speculative tiles starts re-entering at once; a re-entry tile only needs
+        //          itself and its predecessor parsed (per-tile ready flags, polled without blocking the other groups).
+        {
+            enum { G_IDLE = 0, G_SPEC = 1, G_RESYNC = 2, G_WAIT = 3, G_DONE = 4 };
+            const unsigned g8 = lane & ~7u, s = lane & 7u;
+            const unsigned gmask = 0xFFu << g8;
+            uint32_t mode = G_IDLE, t = 0, t_begin = 0, t_end = 0, p = 0, entry = 0, from = 0;
+            uint32_t* tp = nullptr;   // next token slot
+            uint32_t* tp0 = nullptr;  // first token slot of the tile
+            unsigned long long vis = 0;          // lane s: visited bits [64 s, 64 s + 64) of the tile (speculative parse)
+            uint32_t blk = 0xFFFFFFFEu;          // block of 32 positions the info words belong to (none yet, and no next one)
+            unsigned long long icur = 0, inxt = 0;  // lane s: info words of positions blk * 32 + s + 8 j; next block
+            uint32_t wmask = 0;                  // may-have-a-candidate bits of the block
+            bool spec_left = true;
+            for (;;) {
+                // -- work
+                if (mode == G_IDLE) {
+                    uint32_t nt = n_tiles;
+                    if (spec_left) {
+                        if (s == 0) nt = atomicAdd(&M->tile_next, 1u);
+                        nt = __shfl_sync(gmask, nt, g8);
+                    }
+                    if (nt < n_tiles) {
+                        t = nt;
+                        t_begin = lz_tile_begin(t);
+                        t_end = min(n, lz_tile_begin(t + 1));
+                        p = M->tile_start[t];
+                        tp0 = tp = spec_c + lz_tok_off(t);
+                        vis = 0;
+                        mode = G_SPEC;
+                    } else {
+                        spec_left = false;
+                        if (s == 0) nt = atomicAdd(&M->tile_next2, 1u);
+                        nt = __shfl_sync(gmask, nt, g8);
+                        t = nt;
+                        mode = nt < n_tiles ? G_WAIT : G_DONE;
+                    }
                 }
-                __threadfence_block();
-            }
-            if (w == t0) {  // the first tile needs no re-entry
-                if (lane == 0) {
-                    M->entry_used[t0] = base;
-                    M->fix_exit[t0] = M->spec_exit[t0];
-                    M->fix_count[t0] = 0;
-                    M->spec_from[t0] = 0;
+                if (mode == G_WAIT) {
+                    const bool ready = *(volatile uint8_t*)&M->spec_done[t] != 0 &&
+                                       (t == t0 || *(volatile uint8_t*)&M->spec_done[t - 1] != 0);
+                    if (ready) {
+                        __threadfence_block();
+                        if (t == t0) {  // the first tile needs no re-entry
+                            if (s == 0) {
+                                M->entry_used[t0] = base;
+                                M->fix_exit[t0] = M->spec_exit[t0];
+                                M->fix_count[t0] = 0;
+                                M->spec_from[t0] = 0;
+                            }
+                            mode = G_IDLE;
+                        } else {
+                            t_begin = lz_tile_begin(t);
+                            t_end = min(n, lz_tile_begin(t + 1));
+                            p = entry = M->spec_exit[t - 1];
+                            from = M->spec_count[t];
+                            tp0 = tp = fix_c + lz_tok_off(t);
+                            mode = G_RESYNC;
+                        }
+                    }
                 }
-                continue;
-            }
-            const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
-            const uint32_t entry = M->spec_exit[w - 1];
-            uint32_t nfix, from;
-            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
-                                               visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
-            if (lane == 0) {
-                M->entry_used[w] = entry;
-                M->fix_exit[w] = ex;
-                M->fix_count[w] = (uint16_t)nfix;
-                M->spec_from[w] = (uint16_t)from;
+                const bool active = mode == G_SPEC || mode == G_RESYNC;
+                if (!__any_sync(0xFFFFFFFFu, active)) {
+                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE)) break;
+                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE || mode == G_WAIT)) __nanosleep(64);
+                    continue;
+                }
+
+                // -- one parse step per active group
+                bool searched = false, need_warp = false;
+                uint32_t r = 0, rank = 0;
+                if (active) {
+                    bool finish = p >= t_end;
+                    uint32_t vlimit = 32u;
+                    if (!finish && mode == G_RESYNC) {
+                        const uint32_t vm = visited[p >> 5] >> (p & 31u);
+                        if (vm & 1u) {
+                            // met the speculative parse: its tokens from this position on are the true ones
+                            uint32_t idx = 0;
+                            for (uint32_t wd = (t_begin >> 5) + s; wd <= (p >> 5); wd += 8u) {
+                                uint32_t bits = visited[wd];
+                                if (wd == (p >> 5)) bits &= (1u << (p & 31u)) - 1u;
+                                idx += __popc(bits);
+                            }
+                            from = __reduce_add_sync(gmask, idx);
+                            p = M->spec_exit[t];
+                            finish = true;
+                        } else if (vm) {
+                            vlimit = (uint32_t)__ffs((int)vm) - 1u;  // a run of literals stops in front of a visited position
+                        }
+                    }
+                    if (finish) {
+                        if (mode == G_SPEC) {
+                            const uint32_t tl = t_end - t_begin;
+                            if (64u * s < tl) visited[(t_begin >> 5) + 2u * s] = (uint32_t)vis;
+                            if (64u * s + 32u < tl) visited[(t_begin >> 5) + 2u * s + 1u] = (uint32_t)(vis >> 32);
+                            if (s == 0) {
+                                M->spec_exit[t] = p;
+                                M->spec_count[t] = (uint16_t)(tp - tp0);
+                            }
+                            // publish the tile: its visited bits and tables before the flag
+                            __threadfence_block();
+                            __syncwarp(gmask);
+                            if (s == 0) {
+                                __threadfence_block();  // release: the other lanes' writes, ordered before this point by the group barrier
+                                *(volatile uint8_t*)&M->spec_done[t] = 1;
+                            }
+                        } else if (s == 0) {
+                            M->entry_used[t] = entry;
+                            M->fix_exit[t] = p;
+                            M->fix_count[t] = (uint16_t)(tp - tp0);
+                            M->spec_from[t] = (uint16_t)from;
+                        }
+                        mode = G_IDLE;
+                    } else {
+                        // info words of the block of 32 positions around p (the next block is already on its way)
+                        if ((p >> 5) != blk) {
+                            const uint32_t nb = p >> 5;
+                            const uint32_t nblocks = (n + 31u) >> 5;  // blocks [0, nblocks] are initialised
+                            icur = (nb == blk + 1u) ? inxt : ld_u64_hint(P + nb * 32u + s * 4u, keep);
+                            blk = nb;
+                            inxt = (nb + 1u <= nblocks) ? ld_u64_hint(P + (nb + 1u) * 32u + s * 4u, keep) : 0ull;
+                            const uint32_t b0 = __ballot_sync(gmask, (icur >> 15) & 1ull), b1 = __ballot_sync(gmask, (icur >> 31) & 1ull),
+                                           b2 = __ballot_sync(gmask, (icur >> 47) & 1ull), b3 = __ballot_sync(gmask, (icur >> 63) & 1ull);
+                            wmask = ((b0 >> g8) & 0xFFu) | (((b1 >> g8) & 0xFFu) << 8) | (((b2 >> g8) & 0xFFu) << 16) |
+                                    (((b3 >> g8) & 0xFFu) << 24);
+                        }
+                        const uint32_t off = p & 31u;
+                        const uint32_t mm = wmask >> off;  // bit 0 <-> position p
+                        const uint32_t avail = min(min(32u - off, t_end - p), vlimit);
+                        const uint32_t k = mm ? min((uint32_t)__ffs((int)mm) - 1u, avail) : avail;
+                        if (k) {
+                            // k positions without any candidate: k literals (src/LZ77.ts:267-272)
+                            for (uint32_t o = s; o < k; o += 8u) tp[o] = SV[p + o];
+                            tp += k;
+                            if (mode == G_SPEC) {
+                                // bits [rel, rel + k) of the tile, cut to this lane's 64
+                                const uint32_t rel = p - t_begin, lo64 = 64u * s;
+                                const uint32_t a = max(rel, lo64), e = min(rel + k, lo64 + 64u);
+                                if (a < e) vis |= (0xFFFFFFFFFFFFFFFFull >> (64u - (e - a))) << (a - lo64);
+                            }
+                            p += k;
+                        } else {
+                            searched = true;
+                            const uint32_t e = (uint32_t)(icur >> (16u * (off >> 3))) & LZ_RANK_SAT;
+                            rank = __shfl_sync(gmask, e, (int)(g8 + (off & 7u)));
+                            if (rank > LZ_GROUP_MAX) {
+                                need_warp = true;
+                            } else {
+                                const uint32_t pw = ld_u32(SV, p);
+                                r = lz_search_group(SV, sorted, bstart[hash13(pw & 0xFFFFFFu)], rank, p, pw,
+                                                    min(LZ_MAXLEN, n - p), gmask, s);
+                            }
+                        }
+                    }
+                }
+                // -- searches behind long candidate lists: the whole warp, one group's position after the other
+                unsigned bigm = __ballot_sync(0xFFFFFFFFu, need_warp) & 0x01010101u;
+                while (bigm) {
+                    const int src = __ffs((int)bigm) - 1;
+                    bigm &= bigm - 1u;
+                    const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, src), br = __shfl_sync(0xFFFFFFFFu, rank, src);
+                    const uint32_t rr = lz_search(SV, sorted, bstart, bp, n, depth, br);
+                    if (g8 == (unsigned)src) r = rr;
+                }
+                // -- the token of a searched position
+                if (searched) {
+                    uint32_t tok, np;
+                    if (r) {
+                        const uint32_t len = r >> 16, dist = r & 0xFFFFu;
+                        tok = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
+                        np = p + len;
+                    } else {
+                        tok = SV[p];  // the bit was a "maybe" (hash collisions) or everything lies outside the window
+                        np = p + 1;
+                    }
+                    if (s == 0) *tp = tok;
+                    ++tp;
+                    if (mode == G_SPEC) {
+                        const uint32_t rel = p - t_begin;
+                        if (s == (rel >> 6)) vis |= 1ull << (rel & 63u);
+                    }
+                    p = np;
+                }
             }
         }
         __syncthreads();
@@ -878,7 +1018,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 if (entry == M->entry_used[t]) break;
                 const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
                 uint32_t nfix, from;
-                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth,
+                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, P, keep, entry, t_begin, t_end, n, depth,
                                                    fix_c + lz_tok_off(t), visited, M->spec_count[t],
                                                    M->spec_exit[t], &nfix, &from);
                 if (lane == 0) {
@@ -904,7 +1044,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
                 uint32_t nfix, from;
                 const uint32_t entry = true_exit;
-                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
+                true_exit = lz_resync_tile(SV, sorted, bstart, P, keep, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
                                            visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[w] = entry;
