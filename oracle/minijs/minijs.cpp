@@ -1,6 +1,7 @@
 // minijs.cpp -- see minijs.h. TEST INFRASTRUCTURE ONLY (never part of the product path).
 #include "minijs.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -3220,6 +3221,40 @@ static Value string_indexOf(Interp& I, const Value& self, const Value* args, int
     return Value(p == U16::npos ? -1.0 : (double)p);
 }
 static Value string_toString(Interp& I, const Value& self, const Value*, int) { return Value::str(I.to_string(self)); }
+static Value string_split(Interp& I, const Value& self, const Value* args, int argc)
+{
+    U16 s = I.to_string(self);
+    ArrayObj* r = I.new_array();
+    Value rv = Value::obj(r);
+    if (ARG(0).is_undef()) {
+        r->el.push_back(Value::str(s));
+        return rv;
+    }
+    U16 sep = I.to_string(ARG(0));
+    if (sep.empty()) {
+        for (char16_t c : s) r->el.push_back(Value::str(U16(1, c)));
+        return rv;
+    }
+    size_t at = 0;
+    for (;;) {
+        size_t f = s.find(sep, at);
+        if (f == U16::npos) {
+            r->el.push_back(Value::str(s.substr(at)));
+            break;
+        }
+        r->el.push_back(Value::str(s.substr(at, f - at)));
+        at = f + sep.size();
+    }
+    return rv;
+}
+static Value string_trim(Interp& I, const Value& self, const Value*, int)
+{
+    U16 s = I.to_string(self);
+    size_t a = 0, b = s.size();
+    while (a < b && (s[a] == u' ' || s[a] == u'\t' || s[a] == u'\n' || s[a] == u'\r')) ++a;
+    while (b > a && (s[b - 1] == u' ' || s[b - 1] == u'\t' || s[b - 1] == u'\n' || s[b - 1] == u'\r')) --b;
+    return Value::str(s.substr(a, b - a));
+}
 static Value string_padStart(Interp& I, const Value& self, const Value* args, int argc)
 {
     U16 s = I.to_string(self);
@@ -3468,6 +3503,8 @@ void Interp::setup()
     def_native(string_proto, "indexOf", string_indexOf);
     def_native(string_proto, "toString", string_toString);
     def_native(string_proto, "padStart", string_padStart);
+    def_native(string_proto, "split", string_split);
+    def_native(string_proto, "trim", string_trim);
 
     // Error (+ the subclasses the interpreter itself throws)
     error_ctor = def_ctor("Error", error_ctor_fn, error_proto);
@@ -3506,6 +3543,9 @@ void Interp::setup()
     def_native(global, "readFile", host_readFile);
     def_native(global, "writeFile", host_writeFile);
     def_native(global, "clock", host_clock);
+    def_native(global, "Boolean", [](Interp& I, const Value&, const Value* args, int argc) {
+        return Value::boolean(argc > 0 && I.to_bool(args[0]));
+    });
     def_native(global, "isNaN", [](Interp& I, const Value&, const Value* args, int argc) {
         return Value::boolean(std::isnan(I.to_number(ARG(0))));
     });

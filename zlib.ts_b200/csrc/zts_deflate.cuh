@@ -5,14 +5,13 @@
 #define LZ_THREADS 1024
 #define LZ_WARPS 32
 #define LZ_MAX_CHUNK 65536u
-// Speculative parse tiles (8-lane groups take them from a counter in order, 128 groups per CTA). Sizes shrink
-// towards the end of the chunk -- 64 x 512, 64 x 256, 128 x 128 positions -- so that the last tiles to finish are
-// small ones and the groups run out of work close together.
-#define LZ_TILE 512u                    // largest tile (a group keeps 8 x 64 visited bits in registers)
+// Speculative parse tiles: every tile is owned by one lane (8 owners per warp, 256 per CTA, see zts_lz77.cu), so the
+// default is one tile of 256 positions per owner, all in flight at once. The three size classes (512, 256, 128
+// positions, in this order along the chunk) are kept for experiments.
 #ifndef LZ_TA
-#define LZ_TA 64u                       // tiles of 512 positions
-#define LZ_TB 64u                       // then tiles of 256
-#define LZ_TC 128u                      // then tiles of 128
+#define LZ_TA 0u                        // tiles of 512 positions
+#define LZ_TB 256u                      // then tiles of 256
+#define LZ_TC 0u                        // then tiles of 128
 #endif
 #define LZ_NTILES (LZ_TA + LZ_TB + LZ_TC)
 static_assert(LZ_TA * 512u + LZ_TB * 256u + LZ_TC * 128u == 65536u, "the tiles must cover a 64 KiB chunk");
@@ -41,6 +40,9 @@ struct ZtsChunk {      // host-built, one per chunk
     uint32_t pad1;
 };
 
+#ifdef __CUDACC__
+#pragma nv_diag_suppress 186  // a size class may be empty (LZ_TA == 0): the comparison with zero is intended
+#endif
 // first position of tile t (t == LZ_NTILES gives the chunk size)
 __host__ __device__ __forceinline__ uint32_t lz_tile_begin(uint32_t t)
 {

@@ -30,6 +30,8 @@
 // Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 14 KiB scratch.
 #include "zts_deflate.cuh"
 
+#define LZ_OWNERS_MAX 8u
+
 struct LzSmem {
     // byte offsets into dynamic shared memory
     static constexpr uint32_t S_OFF = 0;                          // chunk bytes (+ shift, + slack)
@@ -63,6 +65,15 @@ struct LzMisc {
     uint32_t n_tokens;
     uint8_t spec_done[LZ_NTILES];    // set (release) when a tile's speculative parse and its tables are complete
     uint16_t tile_start[LZ_NTILES];  // where the tile's speculative parse starts
+};
+
+struct LzBatch {  // one per warp: the searches its tile owners post in a round
+    uint32_t end[LZ_OWNERS_MAX];    // candidates of requests 0 .. r (inclusive running sum)
+    uint32_t start[LZ_OWNERS_MAX];  // candidates of requests 0 .. r-1
+    uint32_t p[LZ_OWNERS_MAX];      // position searched
+    uint32_t slot[LZ_OWNERS_MAX];   // its slot in the sorted index: the candidates sit in front of it, newest first
+    uint32_t pw[LZ_OWNERS_MAX], pw1[LZ_OWNERS_MAX];  // the 8 bytes at p
+    uint32_t best[LZ_OWNERS_MAX];   // max of len << 16 | q over the candidates
 };
 
 // The radix scratch T is the one global buffer a CTA keeps re-using (256 KiB per chunk, written and read twice):
@@ -212,75 +223,60 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
     return min(k, maxlen);
 }
 
-// ---- per-position info words -----------------------------------------------------------------------------------
-// P[slot(p)] = rank of p inside its bucket (earlier bucket entries, saturating) | "may have a candidate" << 15.
-// Inside a block of 32 positions the words are permuted so that lane s of an 8-lane group finds the words of
-// positions s, s + 8, s + 16, s + 24 of the block in one aligned 8-byte load.
-#define LZ_INFO_HAS 0x8000u
-#define LZ_RANK_SAT 0x7FFFu
-#define LZ_HAS_WALK 16u        // hash collisions walked over before a position is declared "may have a candidate"
-#ifndef LZ_GROUP_MAX
-#define LZ_GROUP_MAX 32u       // searches with at most this many earlier bucket entries stay inside the 8-lane group
+// ---- per-position info ------------------------------------------------------------------------------------------
+// Built once per chunk from the sorted index, one thread per slot:
+//   P[p]      = slot of p in the sorted index | rank of p inside its bucket << 16  (rank = earlier bucket entries; the
+//               candidates of p are the `rank` slots in front of its own). L2-resident scratch, 4 bytes per position.
+//   hasbits   = one bit per position in shared memory: "may have a candidate" -- an earlier position with the same
+//               3 bytes inside the window, found by walking back over the hash collisions in front of the slot.
+#define LZ_HAS_WALK 16u        // collisions walked over before a position is declared "may have a candidate"
+#ifndef LZ_OWNERS
+#define LZ_OWNERS 8u           // lanes of a warp that own a tile each (lanes 0 .. LZ_OWNERS-1): power of two, <= 16
 #endif
-__device__ __forceinline__ uint32_t lz_info_slot(uint32_t p) { return (p & ~31u) | ((p & 7u) << 2) | ((p >> 3) & 3u); }
-__device__ __forceinline__ void st_u16_hint(uint16_t* p, uint32_t v, unsigned long long pol)
-{
-    asm volatile("st.global.cg.L2::cache_hint.u16 [%0], %1, %2;" ::"l"(p), "h"((unsigned short)v), "l"(pol) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_u64_hint(const void* p, unsigned long long pol)
-{
-    unsigned long long v;
-    asm volatile("ld.global.cg.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint32_t ld_u16_hint(const uint16_t* p, unsigned long long pol)
-{
-    unsigned short v;
-    asm volatile("ld.global.cg.L2::cache_hint.u16 %0, [%1], %2;" : "=h"(v) : "l"(p), "l"(pol) : "memory");
-    return v;
-}
+#ifndef LZ_BATCH_CAP
+#define LZ_BATCH_CAP 64u       // a search over at most this many earlier bucket entries goes into the warp's batch
+#endif
 
-// one thread per slot of the sorted index (all threads of the block call it, barrier behind it is the caller's)
+// one thread per slot of the sorted index (all threads of the block call it; `hasbits` zeroed, barrier behind it)
 __device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __restrict__ sorted,
-                                              const uint16_t* __restrict__ bstart, uint32_t m, uint32_t n, uint16_t* P,
-                                              unsigned long long keep)
+                                              const uint16_t* __restrict__ bstart, uint32_t m, uint32_t n, uint32_t* P,
+                                              uint32_t* hasbits, unsigned long long keep)
 {
     const unsigned tid = threadIdx.x;
-    // positions without a slot, and the padding block-wise readers touch: no candidate
-    const uint32_t npad = ((n + 31u) & ~31u) + 32u;
-    for (uint32_t p = m + tid; p < npad; p += LZ_THREADS) st_u16_hint(&P[lz_info_slot(p)], 0u, keep);
+    for (uint32_t p = m + tid; p < n; p += LZ_THREADS) st_u32_hint(&P[p], 0u, keep);  // positions without a slot (P has LZ_MAX_CHUNK entries per CTA)
     for (uint32_t i = tid; i < m; i += LZ_THREADS) {
         const uint32_t p = sorted[i];
         const uint32_t key = ld_u32(S, p) & 0xFFFFFFu;
         const uint32_t lo = bstart[hash13(key)];
-        uint32_t has = 0;
         if (p + 3u < n) {  // src/LZ77.ts:228: the last three positions are never searched
             // the nearest earlier position with the same 3 bytes sits a few slots back (hash collisions in between);
             // it decides: older ones are further away
+            bool has = false;
             uint32_t j = i, steps = 0;
             while (j > lo) {
                 --j;
                 const uint32_t q = sorted[j];
                 if ((ld_u32(S, q) & 0xFFFFFFu) == key) {
-                    has = (p - q <= LZ_WINDOW) ? LZ_INFO_HAS : 0u;
+                    has = p - q <= LZ_WINDOW;
                     break;
                 }
                 if (++steps >= LZ_HAS_WALK) {
-                    has = LZ_INFO_HAS;  // undecided: the search will tell
+                    has = true;  // undecided: the search will tell
                     break;
                 }
             }
+            if (has) atomicOr(&hasbits[p >> 5], 1u << (p & 31u));
         }
-        st_u16_hint(&P[lz_info_slot(p)], min(i - lo, LZ_RANK_SAT) | has, keep);
+        st_u32_hint(&P[p], i | ((i - lo) << 16), keep);
     }
 }
 
 // ---- warp-cooperative longest/nearest match search at position p (requires p + 3 < n) ----------
 // returns (len << 16) | dist, or 0 when no candidate exists (src/LZ77.ts:157-194 + :242)
-// `rank` = earlier entries of p's bucket (LZ_RANK_SAT: unknown, found by a 32-way search);
-// `depth` = how many candidates (newest first) are looked at: 0xFFFFFFFF = all of them, like the reference.
-__device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __restrict__ sorted,
-                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n, uint32_t depth, uint32_t rank)
+// The candidates are the slots [lo, cur) of the sorted index, newest (cur - 1) first;
+// `depth` = how many of them are looked at: 0xFFFFFFFF = all, like the reference.
+__device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t* __restrict__ sorted, uint32_t lo,
+                                                   uint32_t cur, uint32_t p, uint32_t n, uint32_t depth)
 {
     const unsigned lane = zts_lane();
     const uint32_t pw = ld_u32(S, p);
@@ -304,30 +300,6 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
             }
             if (__all_sync(0xFFFFFFFFu, same)) return (maxlen << 16) | 1u;
         }
-    }
-    const uint32_t h = hash13(pw & 0xFFFFFFu);
-    const uint32_t lo = bstart[h];
-    uint32_t cur = lo + rank;
-    if (rank >= LZ_RANK_SAT) {
-        // slot of p inside its bucket (positions ascending): 32-way search
-        uint32_t a = lo, b = bstart[h + 1];
-        while (b - a > 32) {
-            const uint32_t step = (b - a + 31) >> 5;
-            const uint32_t s = a + lane * step;
-            const bool less = (s < b) && (sorted[s] < p);
-            const uint32_t k = __popc(__ballot_sync(0xFFFFFFFFu, less));
-            if (k == 0) {
-                b = a;
-                break;
-            }
-            const uint32_t na = a + (k - 1) * step + 1;
-            const uint32_t nb = min(b, a + k * step);
-            a = na;
-            b = nb;
-        }
-        const uint32_t s = a + lane;
-        const bool less = (s < b) && (sorted[s] < p);
-        cur = a + __popc(__ballot_sync(0xFFFFFFFFu, less));
     }
     const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
@@ -373,43 +345,17 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
     return (best_len << 16) | (p - (best & 0xFFFFu));
 }
 
-// The same search by one 8-lane group (lanes gmask, this lane is number s of its group): `rank` earlier bucket
-// entries, newest first, 8 per step. Group-uniform control flow; every group of a warp may be somewhere else.
-__device__ __forceinline__ uint32_t lz_search_group(const LzS& S, const uint16_t* __restrict__ sorted, uint32_t lo,
-                                                    uint32_t rank, uint32_t p, uint32_t pw, uint32_t maxlen,
-                                                    unsigned gmask, unsigned s)
-{
-    const uint32_t pw1 = ld_u32(S, p + 4);
-    uint32_t cur = lo + rank, best = 0, best_len = 0;
-    while (cur > lo) {
-        const uint32_t cnt = min(8u, cur - lo);
-        const bool act = s < cnt;
-        const uint32_t q = act ? sorted[cur - 1 - s] : 0u;  // lane 0 of the group = newest candidate
-        const bool inwin = act && (p - q <= LZ_WINDOW);
-        uint32_t key = 0;
-        if (inwin && (best_len < 3 || S[q + best_len] == S[p + best_len]))
-            key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
-        const uint32_t m = __reduce_max_sync(gmask, key);  // longest, then nearest
-        if ((m >> 16) > best_len) {
-            best_len = m >> 16;
-            best = m;
-        }
-        if (best_len >= maxlen) break;
-        if (__any_sync(gmask, act && !inwin)) break;
-        cur -= cnt;
-    }
-    if (best_len < 3) return 0;
-    return (best_len << 16) | (p - (best & 0xFFFFu));
-}
-
 // one greedy step of the whole warp at parse position p: emits the token, returns the next parse position
-__device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                            const uint16_t* P, unsigned long long keep, uint32_t p, uint32_t n,
+__device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint32_t* P,
+                                            const uint32_t* hasbits, unsigned long long keep, uint32_t p, uint32_t n,
                                             uint32_t depth, uint32_t* tok_out)
 {
     uint32_t r = 0;
-    const uint32_t info = ld_u16_hint(&P[lz_info_slot(p)], keep);  // 0 for the last three positions (src/LZ77.ts:228)
-    if (info & LZ_INFO_HAS) r = lz_search(S, sorted, bstart, p, n, depth, info & LZ_RANK_SAT);
+    if ((hasbits[p >> 5] >> (p & 31u)) & 1u) {  // never set for the last three positions (src/LZ77.ts:228)
+        const uint32_t info = ld_u32_hint(&P[p], keep);
+        const uint32_t slot = info & 0xFFFFu;
+        r = lz_search_from(S, sorted, slot - (info >> 16), slot, p, n, depth);
+    }
     if (r) {
         const uint32_t len = r >> 16, dist = r & 0xFFFFu;
         *tok_out = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
@@ -479,8 +425,9 @@ __device__ __forceinline__ uint32_t lz_run_aligned_start(const LzS& S, uint32_t 
 // True parse of a tile entered at `entry` (>= the tile's begin is not required: entry may lie past it):
 // re-parse until a position the speculative parse visited, from there its tokens are reused.
 // Writes fix tokens, returns the exit; *nfix_out / *from_out describe the splice.
-__device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                                   const uint16_t* P, unsigned long long keep, uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
+__device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted,
+                                                   const uint32_t* P, const uint32_t* hasbits, unsigned long long keep,
+                                                   uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
                                                    uint32_t depth, uint32_t* __restrict__ fix_out, const uint32_t* visited,
                                                    uint32_t spec_count, uint32_t spec_exit, uint32_t* nfix_out,
                                                    uint32_t* from_out)
@@ -502,7 +449,7 @@ __device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t*
             break;
         }
         uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, bstart, P, keep, p, n, depth, &tok);
+        const uint32_t np = lz_step(S, sorted, P, hasbits, keep, p, n, depth, &tok);
         if (lane == 0) fix_out[nfix] = tok;
         nfix++;
         p = np;
@@ -753,7 +700,11 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
     uint16_t* sorted = reinterpret_cast<uint16_t*>(smem + LzSmem::SORTED_OFF);
     uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);
     uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::AUX_OFF);   // [32 warps][128 digits]
-    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position
+    uint32_t* hasbits = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position (+ 1 padding word: the misc area follows)
+    // once the info words are built the bucket starts are dead: visited bits and the warps' batch tables take their place
+    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::BSTART_OFF); // [2048] bit per position
+    LzBatch* batch = reinterpret_cast<LzBatch*>(smem + LzSmem::BSTART_OFF + 8192);
+    static_assert(8192 + sizeof(LzBatch) * LZ_WARPS <= LzSmem::BSTART_BYTES, "batch tables must fit behind the visited bits");
     LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -786,17 +737,12 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         (void)m;
         const uint32_t t0 = base ? lz_tile_of(base) : 0u;  // first tile with anything to parse
 
-        // ---- 3. per-position info words (rank inside the bucket, may-have-a-candidate bit) into the L2 scratch,
-        //         which the radix sort no longer needs
-        uint16_t* P = reinterpret_cast<uint16_t*>(T);
-        lz_build_info(SV, sorted, bstart, m, n, P, keep);
-        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
-        if (tid < LZ_NTILES) M->spec_done[tid] = 0;
-        if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
-        if (tid == 0) {
-            M->tile_next = t0;
-            M->tile_next2 = t0;
-        }
+        // ---- 3. per-position info: slot and bucket rank into the L2 scratch (which the radix sort no longer needs),
+        //         may-have-a-candidate bits into shared memory
+        uint32_t* P = T;
+        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) hasbits[i] = 0;
+        __syncthreads();
+        lz_build_info(SV, sorted, bstart, m, n, P, hasbits, keep);
         const uint32_t n_tiles = lz_tile_count(n);
         // where the speculative parse of every tile starts (tiles inside a run of one byte: at the run's 258-byte phase)
         for (uint32_t t = t0 + warp; t < n_tiles; t += LZ_WARPS) {
@@ -805,49 +751,53 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (t != t0) p0 = lz_run_aligned_start(SV, t_begin, t_end, n);
             if (lane == 0) M->tile_start[t] = (uint16_t)p0;  // p0 < n <= 65536 (lz_run_aligned_start stays 262 bytes clear of the end)
         }
+        __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the batch tables
+        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
+        if (tid < LZ_NTILES) M->spec_done[tid] = 0;
+        if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
+        if (tid == 0) {
+            M->tile_next = t0;
+            M->tile_next2 = t0;
+        }
         __threadfence_block();
         __syncthreads();
         uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         uint32_t* fix_c = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         ZtsChunkInfo* ci = info + c;
 
-        // ---- 4a. speculative parse, then re-entry at the predecessor's speculative exit: both by 8-lane groups, four
-        //          tiles per warp. One loop iteration = one parse step of every group that has a tile: a run of literals,
-        //          a match found by the group, or a match found by the whole warp for the group (long candidate lists).
-        //          A group that runs out of speculative tiles starts re-entering at once; a re-entry tile only needs
-        //          itself and its predecessor parsed (per-tile ready flags, polled without blocking the other groups).
+        // ---- 4a. speculative parse of every tile, then re-entry at the predecessor's speculative exit.
+        //      Lanes 0 .. LZ_OWNERS-1 of every warp OWN a tile each: the parse state (position, token pointer) is
+        //      lane-private, a run of literals is written by its owner alone. What a parse step costs is the match
+        //      search, and that is shared: every round the owners post their positions, the candidates of all of them
+        //      (the `rank` slots in front of each position's own slot) form one list, and the 32 lanes of the warp
+        //      evaluate it 32 candidates at a time whatever request they belong to -- exact key, window, match length,
+        //      shared-memory atomicMax of (len << 16 | q) per request = longest, then nearest. Requests behind long
+        //      candidate lists (ends of runs, low-entropy records) go to the warp-cooperative search with its tail-byte
+        //      filter instead, one after the other. An owner that runs out of speculative tiles starts re-entering at
+        //      once; a re-entry tile only needs itself and its predecessor parsed (ready flags, polled once a round).
         {
             enum { G_IDLE = 0, G_SPEC = 1, G_RESYNC = 2, G_WAIT = 3, G_DONE = 4 };
-            const unsigned g8 = lane & ~7u, s = lane & 7u;
-            const unsigned gmask = 0xFFu << g8;
-            uint32_t mode = G_IDLE, t = 0, t_begin = 0, t_end = 0, p = 0, entry = 0, from = 0;
+            LzBatch* B = batch + warp;
+            const bool owner = lane < LZ_OWNERS;
+            uint32_t mode = owner ? G_IDLE : G_DONE, t = 0, t_begin = 0, t_end = 0, p = 0, entry = 0, from = 0;
             uint32_t* tp = nullptr;   // next token slot
             uint32_t* tp0 = nullptr;  // first token slot of the tile
-            unsigned long long vis = 0;          // lane s: visited bits [64 s, 64 s + 64) of the tile (speculative parse)
-            uint32_t blk = 0xFFFFFFFEu;          // block of 32 positions the info words belong to (none yet, and no next one)
-            unsigned long long icur = 0, inxt = 0;  // lane s: info words of positions blk * 32 + s + 8 j; next block
-            uint32_t wmask = 0;                  // may-have-a-candidate bits of the block
             bool spec_left = true;
             for (;;) {
                 // -- work
                 if (mode == G_IDLE) {
                     uint32_t nt = n_tiles;
-                    if (spec_left) {
-                        if (s == 0) nt = atomicAdd(&M->tile_next, 1u);
-                        nt = __shfl_sync(gmask, nt, g8);
-                    }
+                    if (spec_left) nt = atomicAdd(&M->tile_next, 1u);
                     if (nt < n_tiles) {
                         t = nt;
                         t_begin = lz_tile_begin(t);
                         t_end = min(n, lz_tile_begin(t + 1));
                         p = M->tile_start[t];
                         tp0 = tp = spec_c + lz_tok_off(t);
-                        vis = 0;
                         mode = G_SPEC;
                     } else {
                         spec_left = false;
-                        if (s == 0) nt = atomicAdd(&M->tile_next2, 1u);
-                        nt = __shfl_sync(gmask, nt, g8);
+                        nt = atomicAdd(&M->tile_next2, 1u);
                         t = nt;
                         mode = nt < n_tiles ? G_WAIT : G_DONE;
                     }
@@ -858,12 +808,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                     if (ready) {
                         __threadfence_block();
                         if (t == t0) {  // the first tile needs no re-entry
-                            if (s == 0) {
-                                M->entry_used[t0] = base;
-                                M->fix_exit[t0] = M->spec_exit[t0];
-                                M->fix_count[t0] = 0;
-                                M->spec_from[t0] = 0;
-                            }
+                            M->entry_used[t0] = base;
+                            M->fix_exit[t0] = M->spec_exit[t0];
+                            M->fix_count[t0] = 0;
+                            M->spec_from[t0] = 0;
                             mode = G_IDLE;
                         } else {
                             t_begin = lz_tile_begin(t);
@@ -882,23 +830,23 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                     continue;
                 }
 
-                // -- one parse step per active group
-                bool searched = false, need_warp = false;
-                uint32_t r = 0, rank = 0;
+                // -- owners: finish the tile, write a run of literals, or post a search
+                bool req = false;
+                uint32_t slot = 0, rank = 0;
                 if (active) {
                     bool finish = p >= t_end;
                     uint32_t vlimit = 32u;
                     if (!finish && mode == G_RESYNC) {
-                        const uint32_t vm = visited[p >> 5] >> (p & 31u);
+                        const uint32_t vm = __funnelshift_r(visited[p >> 5], visited[(p >> 5) + 1u], p & 31u);  // (one word of slack behind the bits)
                         if (vm & 1u) {
                             // met the speculative parse: its tokens from this position on are the true ones
                             uint32_t idx = 0;
-                            for (uint32_t wd = (t_begin >> 5) + s; wd <= (p >> 5); wd += 8u) {
+                            for (uint32_t wd = t_begin >> 5; wd <= (p >> 5); ++wd) {
                                 uint32_t bits = visited[wd];
                                 if (wd == (p >> 5)) bits &= (1u << (p & 31u)) - 1u;
                                 idx += __popc(bits);
                             }
-                            from = __reduce_add_sync(gmask, idx);
+                            from = idx;
                             p = M->spec_exit[t];
                             finish = true;
                         } else if (vm) {
@@ -907,21 +855,12 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                     }
                     if (finish) {
                         if (mode == G_SPEC) {
-                            const uint32_t tl = t_end - t_begin;
-                            if (64u * s < tl) visited[(t_begin >> 5) + 2u * s] = (uint32_t)vis;
-                            if (64u * s + 32u < tl) visited[(t_begin >> 5) + 2u * s + 1u] = (uint32_t)(vis >> 32);
-                            if (s == 0) {
-                                M->spec_exit[t] = p;
-                                M->spec_count[t] = (uint16_t)(tp - tp0);
-                            }
-                            // publish the tile: its visited bits and tables before the flag
+                            M->spec_exit[t] = p;
+                            M->spec_count[t] = (uint16_t)(tp - tp0);
+                            // publish the tile: its visited bits (this lane's own stores) and tables before the flag
                             __threadfence_block();
-                            __syncwarp(gmask);
-                            if (s == 0) {
-                                __threadfence_block();  // release: the other lanes' writes, ordered before this point by the group barrier
-                                *(volatile uint8_t*)&M->spec_done[t] = 1;
-                            }
-                        } else if (s == 0) {
+                            *(volatile uint8_t*)&M->spec_done[t] = 1;
+                        } else {
                             M->entry_used[t] = entry;
                             M->fix_exit[t] = p;
                             M->fix_count[t] = (uint16_t)(tp - tp0);
@@ -929,73 +868,94 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                         }
                         mode = G_IDLE;
                     } else {
-                        // info words of the block of 32 positions around p (the next block is already on its way)
-                        if ((p >> 5) != blk) {
-                            const uint32_t nb = p >> 5;
-                            const uint32_t nblocks = (n + 31u) >> 5;  // blocks [0, nblocks] are initialised
-                            icur = (nb == blk + 1u) ? inxt : ld_u64_hint(P + nb * 32u + s * 4u, keep);
-                            blk = nb;
-                            inxt = (nb + 1u <= nblocks) ? ld_u64_hint(P + (nb + 1u) * 32u + s * 4u, keep) : 0ull;
-                            const uint32_t b0 = __ballot_sync(gmask, (icur >> 15) & 1ull), b1 = __ballot_sync(gmask, (icur >> 31) & 1ull),
-                                           b2 = __ballot_sync(gmask, (icur >> 47) & 1ull), b3 = __ballot_sync(gmask, (icur >> 63) & 1ull);
-                            wmask = ((b0 >> g8) & 0xFFu) | (((b1 >> g8) & 0xFFu) << 8) | (((b2 >> g8) & 0xFFu) << 16) |
-                                    (((b3 >> g8) & 0xFFu) << 24);
-                        }
-                        const uint32_t off = p & 31u;
-                        const uint32_t mm = wmask >> off;  // bit 0 <-> position p
-                        const uint32_t avail = min(min(32u - off, t_end - p), vlimit);
+                        // may-have-a-candidate bits of the 32 positions from p on
+                        const uint32_t w = p >> 5, off = p & 31u;
+                        const uint32_t mm = __funnelshift_r(hasbits[w], hasbits[w + 1], off);  // w + 1 <= 2048: padding word
+                        const uint32_t avail = min(min(32u, t_end - p), vlimit);
                         const uint32_t k = mm ? min((uint32_t)__ffs((int)mm) - 1u, avail) : avail;
                         if (k) {
                             // k positions without any candidate: k literals (src/LZ77.ts:267-272)
-                            for (uint32_t o = s; o < k; o += 8u) tp[o] = SV[p + o];
+                            for (uint32_t o = 0; o < k; ++o) tp[o] = SV[p + o];
                             tp += k;
-                            if (mode == G_SPEC) {
-                                // bits [rel, rel + k) of the tile, cut to this lane's 64
-                                const uint32_t rel = p - t_begin, lo64 = 64u * s;
-                                const uint32_t a = max(rel, lo64), e = min(rel + k, lo64 + 64u);
-                                if (a < e) vis |= (0xFFFFFFFFFFFFFFFFull >> (64u - (e - a))) << (a - lo64);
+                            if (mode == G_SPEC) {  // visited bits [p, p + k): at most two words, this lane's own tile
+                                const unsigned long long bits = (0xFFFFFFFFFFFFFFFFull >> (64u - k)) << off;
+                                visited[w] |= (uint32_t)bits;
+                                if (bits >> 32) visited[w + 1] |= (uint32_t)(bits >> 32);
                             }
                             p += k;
                         } else {
-                            searched = true;
-                            const uint32_t e = (uint32_t)(icur >> (16u * (off >> 3))) & LZ_RANK_SAT;
-                            rank = __shfl_sync(gmask, e, (int)(g8 + (off & 7u)));
-                            if (rank > LZ_GROUP_MAX) {
-                                need_warp = true;
-                            } else {
-                                const uint32_t pw = ld_u32(SV, p);
-                                r = lz_search_group(SV, sorted, bstart[hash13(pw & 0xFFFFFFu)], rank, p, pw,
-                                                    min(LZ_MAXLEN, n - p), gmask, s);
-                            }
+                            const uint32_t info = ld_u32_hint(&P[p], keep);
+                            slot = info & 0xFFFFu;
+                            rank = info >> 16;
+                            req = true;
                         }
                     }
                 }
-                // -- searches behind long candidate lists: the whole warp, one group's position after the other
-                unsigned bigm = __ballot_sync(0xFFFFFFFFu, need_warp) & 0x01010101u;
+                // -- the batch: every request with a short candidate list
+                const bool in_batch = req && rank <= LZ_BATCH_CAP;
+                uint32_t incl = in_batch ? rank : 0u;
+#pragma unroll
+                for (uint32_t d = 1; d < LZ_OWNERS; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, LZ_OWNERS - 1);
+                if (total) {
+                    if (owner) {
+                        B->end[lane] = incl;
+                        B->start[lane] = incl - (in_batch ? rank : 0u);
+                        B->best[lane] = 0;
+                        if (in_batch) {
+                            B->p[lane] = p;
+                            B->slot[lane] = slot;
+                            B->pw[lane] = ld_u32(SV, p);
+                            B->pw1[lane] = ld_u32(SV, p + 4);
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t i = lane; i < total; i += 32u) {
+                        // request of candidate i: the first one whose list ends behind i
+                        uint32_t r = 0;
+#pragma unroll
+                        for (uint32_t h = LZ_OWNERS / 2; h >= 1; h >>= 1)
+                            if (B->end[r + h - 1] <= i) r += h;
+                        const uint32_t rp = B->p[r];
+                        const uint32_t q = sorted[B->slot[r] - 1u - (i - B->start[r])];  // start = newest candidate
+                        if (rp - q <= LZ_WINDOW) {
+                            const uint32_t len = lz_match_len(SV, q, rp, B->pw[r], B->pw1[r], min(LZ_MAXLEN, n - rp));
+                            if (len >= 3u) atomicMax(&B->best[r], (len << 16) | q);  // longest, then nearest
+                        }
+                    }
+                    __syncwarp();
+                }
+                uint32_t res = 0;
+                if (in_batch && rank) {  // rank == 0: nothing was posted (and the table may not have been reset)
+                    const uint32_t bm = B->best[lane];
+                    if (bm) res = (bm & 0xFFFF0000u) | (p - (bm & 0xFFFFu));
+                }
+                // -- searches behind long candidate lists: the whole warp, one request after the other
+                unsigned bigm = __ballot_sync(0xFFFFFFFFu, req && !in_batch);
                 while (bigm) {
                     const int src = __ffs((int)bigm) - 1;
                     bigm &= bigm - 1u;
-                    const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, src), br = __shfl_sync(0xFFFFFFFFu, rank, src);
-                    const uint32_t rr = lz_search(SV, sorted, bstart, bp, n, depth, br);
-                    if (g8 == (unsigned)src) r = rr;
+                    const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, src), bs = __shfl_sync(0xFFFFFFFFu, slot, src),
+                                   br = __shfl_sync(0xFFFFFFFFu, rank, src);
+                    const uint32_t rr = lz_search_from(SV, sorted, bs - br, bs, bp, n, depth);
+                    if (lane == (unsigned)src) res = rr;
                 }
                 // -- the token of a searched position
-                if (searched) {
+                if (req) {
                     uint32_t tok, np;
-                    if (r) {
-                        const uint32_t len = r >> 16, dist = r & 0xFFFFu;
+                    if (res) {
+                        const uint32_t len = res >> 16, dist = res & 0xFFFFu;
                         tok = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
                         np = p + len;
                     } else {
-                        tok = SV[p];  // the bit was a "maybe" (hash collisions) or everything lies outside the window
+                        tok = SV[p];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
                         np = p + 1;
                     }
-                    if (s == 0) *tp = tok;
-                    ++tp;
-                    if (mode == G_SPEC) {
-                        const uint32_t rel = p - t_begin;
-                        if (s == (rel >> 6)) vis |= 1ull << (rel & 63u);
-                    }
+                    *tp++ = tok;
+                    if (mode == G_SPEC) visited[p >> 5] |= 1u << (p & 31u);
                     p = np;
                 }
             }
@@ -1018,7 +978,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 if (entry == M->entry_used[t]) break;
                 const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
                 uint32_t nfix, from;
-                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, P, keep, entry, t_begin, t_end, n, depth,
+                const uint32_t ex = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth,
                                                    fix_c + lz_tok_off(t), visited, M->spec_count[t],
                                                    M->spec_exit[t], &nfix, &from);
                 if (lane == 0) {
@@ -1044,7 +1004,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
                 uint32_t nfix, from;
                 const uint32_t entry = true_exit;
-                true_exit = lz_resync_tile(SV, sorted, bstart, P, keep, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
+                true_exit = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
                                            visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[w] = entry;
