@@ -1,6 +1,7 @@
 """Python loader of the CPU oracle (oracle/zts_oracle.c). TEST INFRASTRUCTURE ONLY:
 only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
-PARITY UNPINNED (no JS engine in this image; see zts_oracle.h)."""
+Parity: pinned to the reference executed under oracle/minijs (tests/test_refjs.py, tests/golden/refjs_vectors.json;
+see zts_oracle.h)."""
 import ctypes
 import os
 import subprocess

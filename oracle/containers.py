@@ -2,8 +2,9 @@
 RawDeflate / CRC32 / Adler32 (oracle/zts_oracle.c). Only tests/, __graft_entry__.smoke() and bench.py's CPU
 baseline may import this; the product path never does.
 
-Parity status: unpinned, like the rest of the oracle (no JS engine in this image, the reference ships no golden
-vectors for these classes); cross-checked in tests/ against CPython's zlib / gzip / zipfile readers.
+Parity status: pinned -- tests/test_refjs.py compares these functions with the bytes the reference's own Deflate /
+GZip / Zip classes produce when dist/Zlib-main.js is executed under oracle/minijs (tests/golden/refjs_vectors.json);
+also cross-checked in tests/ against CPython's zlib / gzip / zipfile readers.
 
 Where the reference's own behaviour is a bug the intended bytes are restated instead, as listed in SURVEY.md
 Appendix B (B-1: Deflate.compress throws a RangeError for outputs > 32 KiB; restated as header + body + Adler-32).

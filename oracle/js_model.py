@@ -1,9 +1,9 @@
 """js_model.py -- independent, statement-by-statement Python model of the reference's hot path with
 JavaScript semantics made explicit (TEST INFRASTRUCTURE: pins oracle/zts_oracle.c; never shipped).
 
-Why it exists: the reference (ExaGraphica/zlib.ts) ships no golden vectors and no JavaScript engine
-exists in this image, so the C oracle cannot be replayed against the real reference ("parity
-unpinned"). This file is a second, separately written restatement that keeps the reference's own
+Why it exists: it was written before oracle/minijs could execute the reference itself, as a second witness for
+the C oracle; it is kept as an independent statement-level model (the executed reference, tests/test_refjs.py, is
+what pins parity now). This file is a second, separately written restatement that keeps the reference's own
 control flow -- typed-array wrap-around, `undefined`/NaN comparisons, signed shifts, the per-bit
 BitStream loop, the per-key candidate arrays of LZ77 -- so that a slip in either restatement shows
 up as a disagreement. It is slow (pure Python) and only used on small inputs.

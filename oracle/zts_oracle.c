@@ -1,6 +1,6 @@
 /*
  * zts_oracle.c -- CPU restatement of the zlib.ts hot path. TEST INFRASTRUCTURE ONLY
- * (see zts_oracle.h: PARITY UNPINNED, how it is cross-checked, and who may load it).
+ * (see zts_oracle.h: pinned to the executed reference through oracle/minijs, and who may load it).
  *
  * Every function cites the reference lines it restates (paths under /root/reference).
  * JavaScript semantics that matter are made explicit: Uint16Array / Uint8Array wrap-around,

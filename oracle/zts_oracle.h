@@ -7,12 +7,17 @@
  * It is NOT part of the product: only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY UNPINNED: the reference ships no golden vectors and no JavaScript
- * engine exists in this image, so the oracle cannot be replayed against the
- * real reference. It is pinned instead against (1) the provisional known-answer
- * vectors of SURVEY.md Appendix C (an independent transliteration), (2) an
- * independent line-by-line Python model of the trap-heavy functions
- * (oracle/js_model.py) and (3) CPython zlib as RFC-1950/1951/1952 cross-oracle.
+ * PARITY PINNED TO THE EXECUTED REFERENCE: the reference ships no golden vectors
+ * and the image has no JavaScript engine, so one was written as test
+ * infrastructure (oracle/minijs/, C++): it runs /root/reference/dist/Zlib-main.js
+ * UNMODIFIED. tests/golden/refjs_vectors.json holds what the reference computes
+ * under it (tests/golden/make_refjs_vectors.py regenerates the file) and
+ * tests/test_refjs.py holds this oracle to those vectors -- 240 fuzz inputs,
+ * 64 KiB benchmark chunks, the 1 MiB single block of config C1, getLengths,
+ * RawInflate's .ip, the zlib / gzip / zip containers -- plus a live differential
+ * fuzz against the interpreter wherever the reference sources are present.
+ * Further witnesses: oracle/js_model.py (independent Python model), SURVEY.md
+ * Appendix C (reproduced by the executed reference bit for bit) and CPython zlib.
  */
 #ifndef ZTS_ORACLE_H
 #define ZTS_ORACLE_H

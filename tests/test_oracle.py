@@ -1,7 +1,7 @@
 """CPU: pins the C oracle (oracle/zts_oracle.c) -- the checker every GPU parity test leans on.
 
-The reference ships no golden vectors and no JS engine exists here ("parity unpinned"), so the C
-restatement is held against three independent witnesses:
+The executed reference pins the oracle in tests/test_refjs.py (dist/Zlib-main.js under oracle/minijs). This file
+holds the C restatement against three further, independent witnesses:
   1. oracle/js_model.py, a separately written statement-by-statement Python model of the TS sources;
   2. the provisional known-answer vectors of SURVEY.md Appendix C (tests/golden/appendix_c.json);
   3. CPython zlib as the RFC 1950/1951 cross-oracle (decodes every stream, produces streams to decode,

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libzlibts_b200.so")
+LIB_PATH = os.environ.get("ZLB_LIB_OVERRIDE") or os.path.join(_HERE, "libzlibts_b200.so")  # override: kernel-variant experiments (tools/build_variants.sh)
 
 ITEM_DTYPE = np.dtype([("in_off", "<u8"), ("in_len", "<u8"), ("out_off", "<u8"), ("out_cap", "<u8")])
 RESULT_DTYPE = np.dtype([("status", "<u4"), ("crc32", "<u4"), ("adler32", "<u4"), ("blocks", "<u4"),

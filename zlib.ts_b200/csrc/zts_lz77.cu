@@ -9,17 +9,14 @@
 //   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
 //   2. all positions are radix-sorted (stable, 2 LSD passes, ballot-based ranking inside a warp, no atomics)
 //      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
-//   3. every position gets a 16-bit info word (L2-resident scratch): its rank inside its bucket (how many earlier
-//      positions the bucket holds) and a "may have a candidate" bit -- an earlier position with the same 3 bytes
-//      inside the window, found by walking back over the few hash collisions in front of the position's slot;
-//   4a. the chunk is cut into tiles (512, then 256, then 128 positions) which are parsed speculatively, each from
-//      its tile start, by GROUPS OF 8 LANES: a warp works on four tiles at once. A group reads the info words of
-//      32 positions with one coalesced load; runs of positions without a candidate are literals and are emitted
-//      together; a position with few earlier bucket entries (the common case: the median is below 8) is searched
-//      by the group, 8 candidates per step (newest first), exact-key filter, tail-byte filter against the best so
-//      far, word-wise extension, REDUX.MAX over (len << 16 | q) inside the group; positions behind long candidate
-//      lists are handed to the whole warp, 32 (or 128) candidates per step;
-//   4b. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
+//   3. the chunk is cut into 176 tiles (512, then 256, then 128 positions) which the 32 warps take from a counter
+//      (segments of different entropy cost very different time) and parse speculatively, each from
+//      its tile start. A parse step first probes 32 positions at once, one per lane, for "has any
+//      earlier position with the same 3 bytes": runs of positions without one are literals and are
+//      emitted together. A position that may have candidates gets the warp-cooperative search:
+//      32 candidates per step (newest first), exact-key filter, tail-byte filter against the best
+//      so far, word-wise extension, REDUX.MAX over (len << 16 | q);
+//   4. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
 //      of the previous one and is re-parsed only until it meets a speculatively parsed position
 //      (a visited-bit per position); the remainder of the speculative tokens is reused. All tiles
 //      re-enter in parallel assuming their predecessor exits where its speculative parse did; the
@@ -29,8 +26,6 @@
 //
 // Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 14 KiB scratch.
 #include "zts_deflate.cuh"
-
-#define LZ_OWNERS_MAX 8u
 
 struct LzSmem {
     // byte offsets into dynamic shared memory
@@ -64,16 +59,6 @@ struct LzMisc {
     uint32_t hist[316];
     uint32_t n_tokens;
     uint8_t spec_done[LZ_NTILES];    // set (release) when a tile's speculative parse and its tables are complete
-    uint16_t tile_start[LZ_NTILES];  // where the tile's speculative parse starts
-};
-
-struct LzBatch {  // one per warp: the searches its tile owners post in a round
-    uint32_t end[LZ_OWNERS_MAX];    // candidates of requests 0 .. r (inclusive running sum)
-    uint32_t start[LZ_OWNERS_MAX];  // candidates of requests 0 .. r-1
-    uint32_t p[LZ_OWNERS_MAX];      // position searched
-    uint32_t slot[LZ_OWNERS_MAX];   // its slot in the sorted index: the candidates sit in front of it, newest first
-    uint32_t pw[LZ_OWNERS_MAX], pw1[LZ_OWNERS_MAX];  // the 8 bytes at p
-    uint32_t best[LZ_OWNERS_MAX];   // max of len << 16 | q over the candidates
 };
 
 // The radix scratch T is the one global buffer a CTA keeps re-using (256 KiB per chunk, written and read twice):
@@ -223,60 +208,12 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
     return min(k, maxlen);
 }
 
-// ---- per-position info ------------------------------------------------------------------------------------------
-// Built once per chunk from the sorted index, one thread per slot:
-//   P[p]      = slot of p in the sorted index | rank of p inside its bucket << 16  (rank = earlier bucket entries; the
-//               candidates of p are the `rank` slots in front of its own). L2-resident scratch, 4 bytes per position.
-//   hasbits   = one bit per position in shared memory: "may have a candidate" -- an earlier position with the same
-//               3 bytes inside the window, found by walking back over the hash collisions in front of the slot.
-#define LZ_HAS_WALK 16u        // collisions walked over before a position is declared "may have a candidate"
-#ifndef LZ_OWNERS
-#define LZ_OWNERS 8u           // lanes of a warp that own a tile each (lanes 0 .. LZ_OWNERS-1): power of two, <= 16
-#endif
-#ifndef LZ_BATCH_CAP
-#define LZ_BATCH_CAP 64u       // a search over at most this many earlier bucket entries goes into the warp's batch
-#endif
-
-// one thread per slot of the sorted index (all threads of the block call it; `hasbits` zeroed, barrier behind it)
-__device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __restrict__ sorted,
-                                              const uint16_t* __restrict__ bstart, uint32_t m, uint32_t n, uint32_t* P,
-                                              uint32_t* hasbits, unsigned long long keep)
-{
-    const unsigned tid = threadIdx.x;
-    for (uint32_t p = m + tid; p < n; p += LZ_THREADS) st_u32_hint(&P[p], 0u, keep);  // positions without a slot (P has LZ_MAX_CHUNK entries per CTA)
-    for (uint32_t i = tid; i < m; i += LZ_THREADS) {
-        const uint32_t p = sorted[i];
-        const uint32_t key = ld_u32(S, p) & 0xFFFFFFu;
-        const uint32_t lo = bstart[hash13(key)];
-        if (p + 3u < n) {  // src/LZ77.ts:228: the last three positions are never searched
-            // the nearest earlier position with the same 3 bytes sits a few slots back (hash collisions in between);
-            // it decides: older ones are further away
-            bool has = false;
-            uint32_t j = i, steps = 0;
-            while (j > lo) {
-                --j;
-                const uint32_t q = sorted[j];
-                if ((ld_u32(S, q) & 0xFFFFFFu) == key) {
-                    has = p - q <= LZ_WINDOW;
-                    break;
-                }
-                if (++steps >= LZ_HAS_WALK) {
-                    has = true;  // undecided: the search will tell
-                    break;
-                }
-            }
-            if (has) atomicOr(&hasbits[p >> 5], 1u << (p & 31u));
-        }
-        st_u32_hint(&P[p], i | ((i - lo) << 16), keep);
-    }
-}
-
 // ---- warp-cooperative longest/nearest match search at position p (requires p + 3 < n) ----------
 // returns (len << 16) | dist, or 0 when no candidate exists (src/LZ77.ts:157-194 + :242)
-// The candidates are the slots [lo, cur) of the sorted index, newest (cur - 1) first;
-// `depth` = how many of them are looked at: 0xFFFFFFFF = all, like the reference.
-__device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t* __restrict__ sorted, uint32_t lo,
-                                                   uint32_t cur, uint32_t p, uint32_t n, uint32_t depth)
+// `depth` = how many candidates (newest first) are looked at: 0xFFFFFFFF in the reference-compatible mode (all of
+// them, like the reference), a small multiple of 32 in the fast mode.
+__device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __restrict__ sorted,
+                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n, uint32_t depth)
 {
     const unsigned lane = zts_lane();
     const uint32_t pw = ld_u32(S, p);
@@ -300,6 +237,60 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
             }
             if (__all_sync(0xFFFFFFFFu, same)) return (maxlen << 16) | 1u;
         }
+    }
+    const uint32_t h = hash13(pw & 0xFFFFFFu);
+    const uint32_t lo = bstart[h];
+    uint32_t a = lo, b = bstart[h + 1];
+    if (b - lo <= 32u) {
+        // the whole bucket fits one step (the common case): lane j takes entry j, whatever its position; entries at
+        // or behind p and outside the window drop out, REDUX.MAX over len << 16 | q picks longest, then nearest
+        const uint32_t pw1s = ld_u32(S, p + 4);
+        uint32_t key = 0;
+        if (lo + lane < b) {
+            const uint32_t q = sorted[lo + lane];
+            if (q < p && p - q <= LZ_WINDOW) key = (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q;
+        }
+        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
+        if ((m >> 16) < 3u) return 0;
+        return (m & 0xFFFF0000u) | (p - (m & 0xFFFFu));
+    }
+    if (b - lo <= 64u) {
+        // up to 64 entries: two per lane in one step, no slot search -- cheaper than ranking p inside the bucket and
+        // stepping through the candidates in front of it (measured against 3 and 4 entries per lane: no better)
+        const uint32_t pw1s = ld_u32(S, p + 4);
+        uint32_t key = 0;
+        {
+            const uint32_t q = sorted[lo + lane];  // lo + lane < b: the bucket has more than 32 entries
+            if (q < p && p - q <= LZ_WINDOW) key = (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q;
+        }
+        if (lo + 32u + lane < b) {
+            const uint32_t q = sorted[lo + 32u + lane];
+            if (q < p && p - q <= LZ_WINDOW) key = max(key, (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q);
+        }
+        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
+        if ((m >> 16) < 3u) return 0;
+        return (m & 0xFFFF0000u) | (p - (m & 0xFFFFu));
+    }
+    // slot of p inside its bucket (positions ascending): 32-way search
+    while (b - a > 32) {
+        const uint32_t step = (b - a + 31) >> 5;
+        const uint32_t s = a + lane * step;
+        const bool less = (s < b) && (sorted[s] < p);
+        const uint32_t k = __popc(__ballot_sync(0xFFFFFFFFu, less));
+        if (k == 0) {
+            b = a;
+            break;
+        }
+        const uint32_t na = a + (k - 1) * step + 1;
+        const uint32_t nb = min(b, a + k * step);
+        a = na;
+        b = nb;
+    }
+    uint32_t cur;
+    {
+        const uint32_t s = a + lane;
+        const bool less = (s < b) && (sorted[s] < p);
+        cur = a + __popc(__ballot_sync(0xFFFFFFFFu, less));
     }
     const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
@@ -338,24 +329,19 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
         if (best_len >= maxlen) break;                          // :189 (258) or capped by the input end
         if (__any_sync(0xFFFFFFFFu, act && !inwin)) break;      // older ones are outside the window (:223)
         cur -= cnt;
-        if (depth <= 32u) break;                                // candidate budget spent
+        if (depth <= 32u) break;                                // fast mode: candidate budget spent
         depth -= 32u;
     }
     if (best_len < 3) return 0;
     return (best_len << 16) | (p - (best & 0xFFFFu));
 }
 
-// one greedy step of the whole warp at parse position p: emits the token, returns the next parse position
-__device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint32_t* P,
-                                            const uint32_t* hasbits, unsigned long long keep, uint32_t p, uint32_t n,
-                                            uint32_t depth, uint32_t* tok_out)
+// one greedy step at parse position p: emits the token, returns the next parse position
+__device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
+                                            uint32_t p, uint32_t n, uint32_t depth, uint32_t* tok_out)
 {
     uint32_t r = 0;
-    if ((hasbits[p >> 5] >> (p & 31u)) & 1u) {  // never set for the last three positions (src/LZ77.ts:228)
-        const uint32_t info = ld_u32_hint(&P[p], keep);
-        const uint32_t slot = info & 0xFFFFu;
-        r = lz_search_from(S, sorted, slot - (info >> 16), slot, p, n, depth);
-    }
+    if (p + 3 < n) r = lz_search(S, sorted, bstart, p, n, depth);  // src/LZ77.ts:228: no search in the last 3 bytes
     if (r) {
         const uint32_t len = r >> 16, dist = r & 0xFFFFu;
         *tok_out = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
@@ -363,6 +349,25 @@ __device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted
     }
     *tok_out = S[p];
     return p + 1;
+}
+
+// Lane-private probe: may position pl (pl + 3 < n) have a candidate, i.e. an earlier position inside the
+// window with the same 3 bytes (a non-empty table[key] list after pruning, src/LZ77.ts:211-225,242)?
+// Exact for buckets of at most LZ_PROBE_MAX entries, "maybe" (true) for longer ones.
+#define LZ_PROBE_MAX 20u  // measured 12 / 16 / 20 / 28: random data 2.92 / 1.86 / 1.76 / 1.76 ms per 64 MiB, text 3.72 / 3.75 / 3.79 / 3.85
+__device__ __forceinline__ bool lz_probe(const LzS& S, const uint16_t* __restrict__ sorted,
+                                         const uint16_t* __restrict__ bstart, uint32_t pl)
+{
+    const uint32_t pw = ld_u32(S, pl) & 0xFFFFFFu;
+    const uint32_t h = hash13(pw);
+    const uint32_t lo = bstart[h], hi = bstart[h + 1];
+    if (hi - lo > LZ_PROBE_MAX) return true;
+    for (uint32_t s = lo; s < hi; ++s) {
+        const uint32_t q = sorted[s];
+        if (q >= pl) break;  // ascending positions: the rest is not earlier
+        if (pl - q <= LZ_WINDOW && (ld_u32(S, q) & 0xFFFFFFu) == pw) return true;
+    }
+    return false;
 }
 
 // Where should the speculative parse of a tile that begins inside a run of one byte start? Inside such a run every
@@ -422,11 +427,59 @@ __device__ __forceinline__ uint32_t lz_run_aligned_start(const LzS& S, uint32_t 
     return p0;
 }
 
+// Speculative parse of tile [t_begin, t_end) from p0 >= t_begin: tokens to tok_out, visited bit per parsed position.
+// Returns the exit position (>= t_end); *count_out = tokens written.
+__device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
+                                                  uint32_t t_begin, uint32_t t_end, uint32_t p0, uint32_t n,
+                                                  uint32_t depth, uint32_t* __restrict__ tok_out, uint32_t* visited,
+                                                  uint32_t* count_out)
+{
+    const unsigned lane = zts_lane();
+    uint32_t p = p0;                 // t_begin, or the first position behind the history inside the first tile
+    uint32_t* tp = tok_out;          // next token slot
+    uint32_t vis = 0;                // lane j keeps the visited bits of positions [t_begin + 32 j, + 32): 16 lanes
+    const uint32_t my_lo = lane * 32u;
+    uint32_t wbase = p - 32u, wmask = 0;  // forces a probe at the first step
+    while (p < t_end) {
+        if (p - wbase >= 32u) {
+            // probe the next 32 positions, one per lane
+            wbase = p;
+            const uint32_t pl = p + lane;
+            bool hc = false;
+            if (pl < t_end && pl + 3 < n) hc = lz_probe(S, sorted, bstart, pl);
+            wmask = __ballot_sync(0xFFFFFFFFu, hc);
+        }
+        const uint32_t off = p - wbase;
+        const uint32_t m = wmask >> off;  // bit 0 <-> position p
+        const uint32_t avail = min(32u - off, t_end - p);
+        const uint32_t k = m ? min((uint32_t)__ffs((int)m) - 1u, avail) : avail;
+        const uint32_t rel = p - t_begin;
+        if (k) {
+            // k positions without any candidate: k literals (src/LZ77.ts:267-272)
+            if (lane < k) tp[lane] = S[p + lane];
+            tp += k;
+            // bits [rel, rel + k) of the tile, cut to this lane's word
+            const uint32_t a = max(rel, my_lo), e = min(rel + k, my_lo + 32u);
+            if (a < e) vis |= (0xFFFFFFFFu >> (32u - (e - a))) << (a - my_lo);
+            p += k;
+            continue;
+        }
+        uint32_t tok;
+        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
+        if (lane == 0) *tp = tok;
+        ++tp;
+        if (lane == (rel >> 5)) vis |= 1u << (rel & 31u);
+        p = np;
+    }
+    if (lane < ((t_end - t_begin + 31u) >> 5)) visited[(t_begin >> 5) + lane] = vis;
+    *count_out = (uint32_t)(tp - tok_out);
+    return p;
+}
+
 // True parse of a tile entered at `entry` (>= the tile's begin is not required: entry may lie past it):
 // re-parse until a position the speculative parse visited, from there its tokens are reused.
 // Writes fix tokens, returns the exit; *nfix_out / *from_out describe the splice.
-__device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted,
-                                                   const uint32_t* P, const uint32_t* hasbits, unsigned long long keep,
+__device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
                                                    uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
                                                    uint32_t depth, uint32_t* __restrict__ fix_out, const uint32_t* visited,
                                                    uint32_t spec_count, uint32_t spec_exit, uint32_t* nfix_out,
@@ -449,7 +502,7 @@ __device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t*
             break;
         }
         uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, P, hasbits, keep, p, n, depth, &tok);
+        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
         if (lane == 0) fix_out[nfix] = tok;
         nfix++;
         p = np;
@@ -700,16 +753,11 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
     uint16_t* sorted = reinterpret_cast<uint16_t*>(smem + LzSmem::SORTED_OFF);
     uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);
     uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::AUX_OFF);   // [32 warps][128 digits]
-    uint32_t* hasbits = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position (+ 1 padding word: the misc area follows)
-    // once the info words are built the bucket starts are dead: visited bits and the warps' batch tables take their place
-    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::BSTART_OFF); // [2048] bit per position
-    LzBatch* batch = reinterpret_cast<LzBatch*>(smem + LzSmem::BSTART_OFF + 8192);
-    static_assert(8192 + sizeof(LzBatch) * LZ_WARPS <= LzSmem::BSTART_BYTES, "batch tables must fit behind the visited bits");
+    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position
     LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;  // per-CTA radix temp (L2 resident): pos | hash << 16
-    const unsigned long long keep = l2_policy_keep();
     uint32_t phase = 0;
 
     if (tid == 0) {
@@ -737,21 +785,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         (void)m;
         const uint32_t t0 = base ? lz_tile_of(base) : 0u;  // first tile with anything to parse
 
-        // ---- 3. per-position info: slot and bucket rank into the L2 scratch (which the radix sort no longer needs),
-        //         may-have-a-candidate bits into shared memory
-        uint32_t* P = T;
-        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) hasbits[i] = 0;
-        __syncthreads();
-        lz_build_info(SV, sorted, bstart, m, n, P, hasbits, keep);
-        const uint32_t n_tiles = lz_tile_count(n);
-        // where the speculative parse of every tile starts (tiles inside a run of one byte: at the run's 258-byte phase)
-        for (uint32_t t = t0 + warp; t < n_tiles; t += LZ_WARPS) {
-            const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
-            uint32_t p0 = max(t_begin, base);  // the first tile starts where the parse starts
-            if (t != t0) p0 = lz_run_aligned_start(SV, t_begin, t_end, n);
-            if (lane == 0) M->tile_start[t] = (uint16_t)p0;  // p0 < n <= 65536 (lz_run_aligned_start stays 262 bytes clear of the end)
-        }
-        __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the batch tables
+        // ---- 3. speculative parse: warps take tiles from a shared counter
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
         if (tid < LZ_NTILES) M->spec_done[tid] = 0;
         if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
@@ -759,205 +793,71 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             M->tile_next = t0;
             M->tile_next2 = t0;
         }
-        __threadfence_block();
         __syncthreads();
+        const uint32_t n_tiles = lz_tile_count(n);
         uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         uint32_t* fix_c = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
         ZtsChunkInfo* ci = info + c;
+        for (;;) {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(&M->tile_next, 1u);
+            t = __shfl_sync(0xFFFFFFFFu, t, 0);
+            if (t >= n_tiles) break;
+            const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
+            uint32_t cnt;
+            uint32_t p0 = max(t_begin, base);
+            if (t != t0) p0 = lz_run_aligned_start(SV, t_begin, t_end, n);  // the first tile starts where the parse starts
+            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, p0, n, depth, spec_c + lz_tok_off(t),
+                                              visited, &cnt);
+            if (lane == 0) {
+                M->spec_exit[t] = ex;
+                M->spec_count[t] = (uint16_t)cnt;
+            }
+            // publish the tile: its visited bits and tables before the flag (no block barrier behind this loop)
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();  // release: the other lanes' writes, ordered before this point by the warp barrier
+                *(volatile uint8_t*)&M->spec_done[t] = 1;
+            }
+        }
 
-        // ---- 4a. speculative parse of every tile, then re-entry at the predecessor's speculative exit.
-        //      Lanes 0 .. LZ_OWNERS-1 of every warp OWN a tile each: the parse state (position, token pointer) is
-        //      lane-private, a run of literals is written by its owner alone. What a parse step costs is the match
-        //      search, and that is shared: every round the owners post their positions, the candidates of all of them
-        //      (the `rank` slots in front of each position's own slot) form one list, and the 32 lanes of the warp
-        //      evaluate it 32 candidates at a time whatever request they belong to -- exact key, window, match length,
-        //      shared-memory atomicMax of (len << 16 | q) per request = longest, then nearest. Requests behind long
-        //      candidate lists (ends of runs, low-entropy records) go to the warp-cooperative search with its tail-byte
-        //      filter instead, one after the other. An owner that runs out of speculative tiles starts re-entering at
-        //      once; a re-entry tile only needs itself and its predecessor parsed (ready flags, polled once a round).
-        {
-            enum { G_IDLE = 0, G_SPEC = 1, G_RESYNC = 2, G_WAIT = 3, G_DONE = 4 };
-            LzBatch* B = batch + warp;
-            const bool owner = lane < LZ_OWNERS;
-            uint32_t mode = owner ? G_IDLE : G_DONE, t = 0, t_begin = 0, t_end = 0, p = 0, entry = 0, from = 0;
-            uint32_t* tp = nullptr;   // next token slot
-            uint32_t* tp0 = nullptr;  // first token slot of the tile
-            bool spec_left = true;
-            for (;;) {
-                // -- work
-                if (mode == G_IDLE) {
-                    uint32_t nt = n_tiles;
-                    if (spec_left) nt = atomicAdd(&M->tile_next, 1u);
-                    if (nt < n_tiles) {
-                        t = nt;
-                        t_begin = lz_tile_begin(t);
-                        t_end = min(n, lz_tile_begin(t + 1));
-                        p = M->tile_start[t];
-                        tp0 = tp = spec_c + lz_tok_off(t);
-                        mode = G_SPEC;
-                    } else {
-                        spec_left = false;
-                        nt = atomicAdd(&M->tile_next2, 1u);
-                        t = nt;
-                        mode = nt < n_tiles ? G_WAIT : G_DONE;
-                    }
+        // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel); this is already
+        //          the true parse wherever the predecessor did converge to its speculative parse. A warp that runs
+        //          out of speculative tiles starts here at once: a tile only needs itself and its predecessor parsed
+        //          (all tiles have been taken by then, so the ones it waits for are being worked on).
+        for (;;) {
+            uint32_t w = 0;
+            if (lane == 0) w = atomicAdd(&M->tile_next2, 1u);
+            w = __shfl_sync(0xFFFFFFFFu, w, 0);
+            if (w >= n_tiles) break;
+            {
+                uint32_t spins = 0;
+                while (*(volatile uint8_t*)&M->spec_done[w] == 0 || (w > t0 && *(volatile uint8_t*)&M->spec_done[w - 1] == 0)) {
+                    __nanosleep(40);
+                    if (++spins > (1u << 26)) __trap();  // never hang the device
                 }
-                if (mode == G_WAIT) {
-                    const bool ready = *(volatile uint8_t*)&M->spec_done[t] != 0 &&
-                                       (t == t0 || *(volatile uint8_t*)&M->spec_done[t - 1] != 0);
-                    if (ready) {
-                        __threadfence_block();
-                        if (t == t0) {  // the first tile needs no re-entry
-                            M->entry_used[t0] = base;
-                            M->fix_exit[t0] = M->spec_exit[t0];
-                            M->fix_count[t0] = 0;
-                            M->spec_from[t0] = 0;
-                            mode = G_IDLE;
-                        } else {
-                            t_begin = lz_tile_begin(t);
-                            t_end = min(n, lz_tile_begin(t + 1));
-                            p = entry = M->spec_exit[t - 1];
-                            from = M->spec_count[t];
-                            tp0 = tp = fix_c + lz_tok_off(t);
-                            mode = G_RESYNC;
-                        }
-                    }
+                __threadfence_block();
+            }
+            if (w == t0) {  // the first tile needs no re-entry
+                if (lane == 0) {
+                    M->entry_used[t0] = base;
+                    M->fix_exit[t0] = M->spec_exit[t0];
+                    M->fix_count[t0] = 0;
+                    M->spec_from[t0] = 0;
                 }
-                const bool active = mode == G_SPEC || mode == G_RESYNC;
-                if (!__any_sync(0xFFFFFFFFu, active)) {
-                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE)) break;
-                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE || mode == G_WAIT)) __nanosleep(64);
-                    continue;
-                }
-
-                // -- owners: finish the tile, write a run of literals, or post a search
-                bool req = false;
-                uint32_t slot = 0, rank = 0;
-                if (active) {
-                    bool finish = p >= t_end;
-                    uint32_t vlimit = 32u;
-                    if (!finish && mode == G_RESYNC) {
-                        const uint32_t vm = __funnelshift_r(visited[p >> 5], visited[(p >> 5) + 1u], p & 31u);  // (one word of slack behind the bits)
-                        if (vm & 1u) {
-                            // met the speculative parse: its tokens from this position on are the true ones
-                            uint32_t idx = 0;
-                            for (uint32_t wd = t_begin >> 5; wd <= (p >> 5); ++wd) {
-                                uint32_t bits = visited[wd];
-                                if (wd == (p >> 5)) bits &= (1u << (p & 31u)) - 1u;
-                                idx += __popc(bits);
-                            }
-                            from = idx;
-                            p = M->spec_exit[t];
-                            finish = true;
-                        } else if (vm) {
-                            vlimit = (uint32_t)__ffs((int)vm) - 1u;  // a run of literals stops in front of a visited position
-                        }
-                    }
-                    if (finish) {
-                        if (mode == G_SPEC) {
-                            M->spec_exit[t] = p;
-                            M->spec_count[t] = (uint16_t)(tp - tp0);
-                            // publish the tile: its visited bits (this lane's own stores) and tables before the flag
-                            __threadfence_block();
-                            *(volatile uint8_t*)&M->spec_done[t] = 1;
-                        } else {
-                            M->entry_used[t] = entry;
-                            M->fix_exit[t] = p;
-                            M->fix_count[t] = (uint16_t)(tp - tp0);
-                            M->spec_from[t] = (uint16_t)from;
-                        }
-                        mode = G_IDLE;
-                    } else {
-                        // may-have-a-candidate bits of the 32 positions from p on
-                        const uint32_t w = p >> 5, off = p & 31u;
-                        const uint32_t mm = __funnelshift_r(hasbits[w], hasbits[w + 1], off);  // w + 1 <= 2048: padding word
-                        const uint32_t avail = min(min(32u, t_end - p), vlimit);
-                        const uint32_t k = mm ? min((uint32_t)__ffs((int)mm) - 1u, avail) : avail;
-                        if (k) {
-                            // k positions without any candidate: k literals (src/LZ77.ts:267-272)
-                            for (uint32_t o = 0; o < k; ++o) tp[o] = SV[p + o];
-                            tp += k;
-                            if (mode == G_SPEC) {  // visited bits [p, p + k): at most two words, this lane's own tile
-                                const unsigned long long bits = (0xFFFFFFFFFFFFFFFFull >> (64u - k)) << off;
-                                visited[w] |= (uint32_t)bits;
-                                if (bits >> 32) visited[w + 1] |= (uint32_t)(bits >> 32);
-                            }
-                            p += k;
-                        } else {
-                            const uint32_t info = ld_u32_hint(&P[p], keep);
-                            slot = info & 0xFFFFu;
-                            rank = info >> 16;
-                            req = true;
-                        }
-                    }
-                }
-                // -- the batch: every request with a short candidate list
-                const bool in_batch = req && rank <= LZ_BATCH_CAP;
-                uint32_t incl = in_batch ? rank : 0u;
-#pragma unroll
-                for (uint32_t d = 1; d < LZ_OWNERS; d <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += u;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, LZ_OWNERS - 1);
-                if (total) {
-                    if (owner) {
-                        B->end[lane] = incl;
-                        B->start[lane] = incl - (in_batch ? rank : 0u);
-                        B->best[lane] = 0;
-                        if (in_batch) {
-                            B->p[lane] = p;
-                            B->slot[lane] = slot;
-                            B->pw[lane] = ld_u32(SV, p);
-                            B->pw1[lane] = ld_u32(SV, p + 4);
-                        }
-                    }
-                    __syncwarp();
-                    for (uint32_t i = lane; i < total; i += 32u) {
-                        // request of candidate i: the first one whose list ends behind i
-                        uint32_t r = 0;
-#pragma unroll
-                        for (uint32_t h = LZ_OWNERS / 2; h >= 1; h >>= 1)
-                            if (B->end[r + h - 1] <= i) r += h;
-                        const uint32_t rp = B->p[r];
-                        const uint32_t q = sorted[B->slot[r] - 1u - (i - B->start[r])];  // start = newest candidate
-                        if (rp - q <= LZ_WINDOW) {
-                            const uint32_t len = lz_match_len(SV, q, rp, B->pw[r], B->pw1[r], min(LZ_MAXLEN, n - rp));
-                            if (len >= 3u) atomicMax(&B->best[r], (len << 16) | q);  // longest, then nearest
-                        }
-                    }
-                    __syncwarp();
-                }
-                uint32_t res = 0;
-                if (in_batch && rank) {  // rank == 0: nothing was posted (and the table may not have been reset)
-                    const uint32_t bm = B->best[lane];
-                    if (bm) res = (bm & 0xFFFF0000u) | (p - (bm & 0xFFFFu));
-                }
-                // -- searches behind long candidate lists: the whole warp, one request after the other
-                unsigned bigm = __ballot_sync(0xFFFFFFFFu, req && !in_batch);
-                while (bigm) {
-                    const int src = __ffs((int)bigm) - 1;
-                    bigm &= bigm - 1u;
-                    const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, src), bs = __shfl_sync(0xFFFFFFFFu, slot, src),
-                                   br = __shfl_sync(0xFFFFFFFFu, rank, src);
-                    const uint32_t rr = lz_search_from(SV, sorted, bs - br, bs, bp, n, depth);
-                    if (lane == (unsigned)src) res = rr;
-                }
-                // -- the token of a searched position
-                if (req) {
-                    uint32_t tok, np;
-                    if (res) {
-                        const uint32_t len = res >> 16, dist = res & 0xFFFFu;
-                        tok = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
-                        np = p + len;
-                    } else {
-                        tok = SV[p];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
-                        np = p + 1;
-                    }
-                    *tp++ = tok;
-                    if (mode == G_SPEC) visited[p >> 5] |= 1u << (p & 31u);
-                    p = np;
-                }
+                continue;
+            }
+            const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
+            const uint32_t entry = M->spec_exit[w - 1];
+            uint32_t nfix, from;
+            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
+                                               visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
+            if (lane == 0) {
+                M->entry_used[w] = entry;
+                M->fix_exit[w] = ex;
+                M->fix_count[w] = (uint16_t)nfix;
+                M->spec_from[w] = (uint16_t)from;
             }
         }
         __syncthreads();
@@ -978,7 +878,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 if (entry == M->entry_used[t]) break;
                 const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
                 uint32_t nfix, from;
-                const uint32_t ex = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth,
+                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth,
                                                    fix_c + lz_tok_off(t), visited, M->spec_count[t],
                                                    M->spec_exit[t], &nfix, &from);
                 if (lane == 0) {
@@ -1004,7 +904,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
                 uint32_t nfix, from;
                 const uint32_t entry = true_exit;
-                true_exit = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
+                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
                                            visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[w] = entry;
