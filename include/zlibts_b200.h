@@ -139,6 +139,18 @@ int zlb_abi_version(void);
 /* the cudaStream_t all work of this ctx is ordered on */
 void* zlb_stream(const zlb_ctx* ctx);
 
+/* ---- page-locked host memory ----------------------------------------------------------------
+ * The "_host" entry points run at full speed on page-locked buffers (their copies overlap the kernels wave by wave).
+ * A caller that owns its allocations -- an N-API addon handing out external ArrayBuffers (napi/addon.cc), a C
+ * program -- gets such buffers here. Buffers that are NOT page-locked (a JS-heap Uint8Array, malloc) are accepted
+ * just the same: the library then goes through page-locked shadows of its own, filled and drained by a few copy
+ * threads while the pipeline runs (one more memcpy per byte; blobs above 4 GiB take the driver's pageable path).
+ * Replaces nothing in the reference -- `new Uint8Array(n)` (src/RawDeflate.ts:58, src/RawInflate.ts:100-106) is what
+ * a binding would swap for it. */
+int zlb_host_alloc(size_t bytes, void** out);
+void zlb_host_free(void* p);
+int zlb_host_is_pinned(const void* p);  /* 1 when the "_host" entry points can copy from / to p directly */
+
 /* ---- raw deflate (replaces RawDeflate.compress, src/RawDeflate.ts:87-114) -------------------
  * Each item is cut into chunks of `chunk_bytes` (<= 65536; 0 = 65536); every chunk becomes one
  * block of `block_type`. Chunks of an item are joined with an empty stored block that byte-aligns

@@ -43,6 +43,7 @@ EXPORTS = [
     "zlb_archive", "zlb_archive_host", "zlb_archive_bound",
     "zlb_profile_enable", "zlb_profile_read", "zlb_profile_reset", "zlb_launch_count",
     "zlb_debug_lz77", "zlb_debug_code_lengths",
+    "zlb_host_alloc", "zlb_host_free", "zlb_host_is_pinned",
 ]
 
 _lib = None
@@ -105,8 +106,53 @@ def load_library():
     lib.zlb_debug_lz77.restype = i32
     lib.zlb_debug_code_lengths.argtypes = [vp, vp, i32, i32, vp]
     lib.zlb_debug_code_lengths.restype = i32
+    lib.zlb_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
+    lib.zlb_host_alloc.restype = i32
+    lib.zlb_host_free.argtypes = [vp]
+    lib.zlb_host_free.restype = None
+    lib.zlb_host_is_pinned.argtypes = [vp]
+    lib.zlb_host_is_pinned.restype = i32
     _lib = lib
     return lib
+
+
+class _Pinned:
+    """Owner of one zlb_host_alloc block; the numpy views made over it keep it alive."""
+
+    def __init__(self, nbytes):
+        lib = load_library()
+        p = ctypes.c_void_p()
+        rc = lib.zlb_host_alloc(nbytes, ctypes.byref(p))
+        if rc != 0 or not p.value:
+            raise MemoryError(f"zlb_host_alloc({nbytes}) failed ({rc})")
+        self.ptr, self.nbytes = p.value, nbytes
+
+    def __del__(self):
+        if getattr(self, "ptr", None) and _lib is not None:
+            _lib.zlb_host_free(self.ptr)
+            self.ptr = None
+
+
+def host_alloc(nbytes):
+    """uint8 numpy array over page-locked memory from zlb_host_alloc (what an addon hands out as external ArrayBuffers)."""
+    owner = _Pinned(max(1, int(nbytes)))
+    buf = (ctypes.c_uint8 * owner.nbytes).from_address(owner.ptr)
+    arr = np.frombuffer(buf, dtype=np.uint8)[:int(nbytes)]
+    _PIN_OWNERS[owner.ptr] = owner   # freed by host_free() or at interpreter exit
+    return arr
+
+
+_PIN_OWNERS = {}
+
+
+def host_free(arr):
+    owner = _PIN_OWNERS.pop(arr.ctypes.data, None)
+    if owner is not None:
+        del owner
+
+
+def host_is_pinned(arr):
+    return bool(load_library().zlb_host_is_pinned(arr.ctypes.data))
 
 
 def crc32_combine(crc_a, crc_b, len_b):

@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libzlibts_b200.so")
 SYNTH_LIB = os.path.join(HERE, "libzts_synth.so")
 
-CU_SOURCES = ["zts_ctx.cu", "zts_checksum.cu", "zts_inflate.cu", "zts_lz77.cu", "zts_huffman.cu", "zts_deflate.cu",
+CU_SOURCES = ["zts_ctx.cu", "zts_hoststage.cu", "zts_checksum.cu", "zts_inflate.cu", "zts_lz77.cu", "zts_huffman.cu", "zts_deflate.cu",
               "zts_container.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

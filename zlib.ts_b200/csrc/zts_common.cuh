@@ -66,6 +66,14 @@ struct zlb_ctx {
     cudaStream_t s_in = nullptr, s_out = nullptr, s_aux[3] = {nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> sync_events;  // disable-timing events, reused across calls
 
+    // "_host" entry points with pageable caller buffers: page-locked shadows + copy threads (zts_hoststage.cu)
+    void* copy_pool = nullptr;
+    void* h_shadow_in = nullptr;
+    size_t h_shadow_in_cap = 0;
+    void* h_shadow_out = nullptr;
+    size_t h_shadow_out_cap = 0;
+    std::vector<cudaEvent_t> stage_ev_pool;
+
     // profiling
     bool prof = false;
     std::vector<ZtsProfRec> pending;
@@ -81,6 +89,19 @@ int zts_reserve_pinned(zlb_ctx* ctx, size_t bytes);
 int zts_reserve_pinned2(zlb_ctx* ctx, size_t bytes);
 int zts_host_streams(zlb_ctx* ctx);                 // creates s_in / s_out / s_aux
 cudaEvent_t zts_sync_event(zlb_ctx* ctx, size_t k);  // k-th reusable ordering event (nullptr on failure)
+// host staging for pageable caller buffers (zts_hoststage.cu); every function accepts st == nullptr / unstaged sides
+struct ZtsHostStage;
+int zts_stage_begin(zlb_ctx* ctx, const void* h_in, size_t in_bytes, void* h_out, size_t out_bytes, ZtsHostStage** out);
+const uint8_t* zts_stage_in_ptr(const ZtsHostStage* st);   // where H2D copies read from (shadow or the caller's buffer)
+uint8_t* zts_stage_out_ptr(const ZtsHostStage* st);        // where D2H copies write to
+void zts_stage_wait_in(ZtsHostStage* st, size_t lo, size_t hi);  // blocks until [lo, hi) of the input may be copied from
+int zts_stage_out_ready(zlb_ctx* ctx, ZtsHostStage* st, cudaStream_t s, size_t off, size_t len);
+int zts_stage_end(zlb_ctx* ctx, ZtsHostStage* st);
+void zts_stage_destroy_ctx(zlb_ctx* ctx);
+// D2H of what items [a, b) wrote (adjacent ranges merged; see zts_ctx.cu); h_out = zts_stage_out_ptr() when staged
+int zts_copy_back(zlb_ctx* ctx, ZtsHostStage* st, cudaStream_t s, const uint8_t* d_out, uint8_t* h_out,
+                  const zlb_item* h_items, const zlb_result* h_res, const zlb_item* d_items, const zlb_result* d_res,
+                  size_t a, size_t b);
 void zts_prof_begin(zlb_ctx* ctx, int slot);
 void zts_prof_end(zlb_ctx* ctx, int slot);
 

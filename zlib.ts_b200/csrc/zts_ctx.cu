@@ -126,6 +126,58 @@ static void prof_resolve(zlb_ctx* ctx)
     ctx->pending.clear();
 }
 
+// ---- reading results back to the host: only what was written ------------------------------------------------------
+// The "_host" entry points stage the output blob in a device buffer that is reused from call to call. Copying whole
+// slots (or one span over all of them) back would put stale bytes of earlier calls between the items' outputs, so
+// only [out_off, out_off + out_len) of every item travels; adjacent ranges are merged into one copy (a batch of
+// streams that fill their slots is one copy). Should that still take more than ZTS_COPYBACK_MAX copies, the slack
+// behind every item is zeroed on the device and one span is copied instead.
+#define ZTS_COPYBACK_MAX 2048u
+
+__global__ void __launch_bounds__(256)
+zero_slack_kernel(uint8_t* __restrict__ out, const zlb_item* __restrict__ items, const zlb_result* __restrict__ res)
+{
+    const zlb_item it = items[blockIdx.x];
+    const zlb_result r = res[blockIdx.x];
+    const unsigned long long len = r.out_len <= it.out_cap ? r.out_len : 0ull;
+    uint8_t* p = out + it.out_off;
+    for (unsigned long long i = len + threadIdx.x; i < it.out_cap; i += 256) p[i] = 0;
+}
+
+int zts_copy_back(zlb_ctx* ctx, ZtsHostStage* st, cudaStream_t s, const uint8_t* d_out, uint8_t* h_out,
+                  const zlb_item* h_items, const zlb_result* h_res, const zlb_item* d_items, const zlb_result* d_res,
+                  size_t a, size_t b)
+{
+    struct Run {
+        uint64_t off, len;
+    };
+    std::vector<Run> runs;
+    uint64_t lo = ~0ull, hi = 0;
+    for (size_t i = a; i < b; ++i) {
+        const uint64_t len = h_res[i].out_len <= h_items[i].out_cap ? h_res[i].out_len : 0;  // an overflowed item wrote nothing usable
+        const uint64_t off = h_items[i].out_off;
+        if (off < lo) lo = off;
+        if (off + h_items[i].out_cap > hi) hi = off + h_items[i].out_cap;
+        if (!len) continue;
+        if (!runs.empty() && runs.back().off + runs.back().len == off)
+            runs.back().len += len;
+        else
+            runs.push_back({off, len});
+    }
+    if (runs.size() > ZTS_COPYBACK_MAX && d_items && d_res) {
+        zero_slack_kernel<<<(unsigned)(b - a), 256, 0, s>>>(const_cast<uint8_t*>(d_out), d_items + a, d_res + a);
+        ZTS_CUDA(ctx, cudaGetLastError());
+        runs.clear();
+        runs.push_back({lo, hi - lo});
+    }
+    for (const Run& r : runs) {
+        ZTS_CUDA(ctx, cudaMemcpyAsync(h_out + r.off, d_out + r.off, r.len, cudaMemcpyDeviceToHost, s));
+        int rc = zts_stage_out_ready(ctx, st, s, r.off, r.len);
+        if (rc) return rc;
+    }
+    return ZLB_OK;
+}
+
 extern "C" {
 
 int zlb_abi_version(void) { return ZLB_ABI_VERSION; }
@@ -174,6 +226,7 @@ void zlb_destroy(zlb_ctx* ctx)
                          &ctx->d_body,  &ctx->d_frames};
     for (ZtsDevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
+    zts_stage_destroy_ctx(ctx);
     if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
     if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
     for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);

@@ -434,10 +434,11 @@ static int deflate_stored(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
 // Host buffers of the "_host" entry point. The device path below then also moves the data: the input of
 // wave k+1 travels while wave k is compressed, and what wave k produced travels while wave k+1 runs.
 struct HostIO {
-    const uint8_t* h_in;
-    uint8_t* h_out;
+    const uint8_t* h_in;   // where H2D copies read from: the caller's page-locked buffer, or the library's shadow
+    uint8_t* h_out;        // where D2H copies write to
     size_t in_bytes, out_bytes;
     bool out_done;  // set when the output has already been copied wave by wave
+    ZtsHostStage* stage;   // copy threads behind the shadows (pageable caller buffers), see zts_hoststage.cu
 };
 #define HOST_DELTA_MAX_ITEMS 256u  // per-wave output read-back is done item by item up to this many items
 
@@ -475,8 +476,10 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (flags & ZLB_DEFLATE_WANT_CRC32) kinds |= ZLB_SUM_CRC32;
     if (flags & ZLB_DEFLATE_WANT_ADLER32) kinds |= ZLB_SUM_ADLER32;
 
-    if (hio && block_type == ZLB_NONE)
+    if (hio && block_type == ZLB_NONE) {
+        zts_stage_wait_in(hio->stage, 0, hio->in_bytes);
         ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
     if (block_type == ZLB_NONE) {
         rc = deflate_stored(ctx, d_in, d_out, h_items, h_results, n, d_items);
         if (rc) return rc;
@@ -632,8 +635,10 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             h_run = (unsigned long long*)ctx->h_pin2;
             copied.assign(n, 0ull);
         }
-        if (!pipe_in)
+        if (!pipe_in) {
+            zts_stage_wait_in(hio->stage, 0, hio->in_bytes);
             ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     // Everything the second stream reads must be on the device before it starts: the tables uploaded above and, when
     // the input is not pipelined wave by wave (items not laid out in ascending order), the whole-input copy just
@@ -642,8 +647,10 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     auto wave_in_copy = [&](size_t k) -> int {  // input bytes of wave k: one contiguous hull (chunks are in order)
         const size_t a = wstart[k], b = wstart[k + 1] - 1;
         const uint64_t lo = h_chunks[a].in_off, hi = h_chunks[b].in_off + h_chunks[b].len;
-        if (hi > lo)
+        if (hi > lo) {
+            zts_stage_wait_in(hio->stage, lo, hi);  // pageable caller buffer: its copy threads have filled the shadow up to here
             ZTS_CUDA(ctx, cudaMemcpyAsync((void*)(d_in + lo), hio->h_in + lo, hi - lo, cudaMemcpyHostToDevice, ctx->s_in));
+        }
         ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * k), ctx->s_in));
         return ZLB_OK;
     };
@@ -657,6 +664,8 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                 const uint64_t off = h_items[i].out_off + copied[i];
                 ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out + off, d_out + off, now - copied[i], cudaMemcpyDeviceToHost,
                                               ctx->s_out));
+                int rc2 = zts_stage_out_ready(ctx, hio->stage, ctx->s_out, off, now - copied[i]);
+                if (rc2) return rc2;
                 copied[i] = now;
             }
         }
@@ -674,10 +683,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         ctx->work = st;
         if (n_sets == 2 && k == 1)  // the tables uploaded on ctx->stream must be there before the second stream starts
             ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 4 * n_waves), 0));
-        if (pipe_in) {
-            if (k + 1 < n_waves && (rc = wave_in_copy(k + 1))) return rc;
-            ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * k), 0));
-        }
+        if (pipe_in) ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * k), 0));
         if (fast)
             rc = zts_lz77_fast_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.spec, S.fastT, S.hist, S.sortT, S.counter, g,
                                       depth);
@@ -701,9 +707,12 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, st>>>(
                        d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_STAGE_WORDS,
                        PACK_SMALL_WORDS, d_in));
+        // wave k is queued: the input of wave k+1 follows (with a pageable caller buffer this waits for the copy
+        // threads, so it comes behind the launches), then the output of wave k-1
+        if (pipe_in && k + 1 < n_waves && (rc = wave_in_copy(k + 1))) return rc;
         if (delta_out) {
             ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * k + 1), st));
-            if (k > 0 && (rc = wave_out_copy(k - 1))) return rc;  // wave k is queued: now wait for wave k-1
+            if (k > 0 && (rc = wave_out_copy(k - 1))) return rc;
         }
     }
     ctx->work = ctx->stream;
@@ -755,21 +764,21 @@ extern "C" int zlb_deflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_stage_out, out_bytes + 256);
     if (rc) return rc;
-    HostIO hio = {(const uint8_t*)h_in, (uint8_t*)h_out, in_bytes, out_bytes, false};
-    rc = deflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, mode,
-                        block_type, chunk_bytes, flags, &hio);
-    if (rc) return rc;
-    if (hio.out_done) return ZLB_OK;
-    // many items: copy back the span up to the furthest written byte in one piece
-    uint64_t hi = 0;
-    for (size_t i = 0; i < n; ++i) {
-        uint64_t e = items[i].out_off + (results[i].status == ZLB_ST_OK ? results[i].out_len : 0);
-        if (e > hi) hi = e;
+    ZtsHostStage* stage = nullptr;
+    rc = zts_stage_begin(ctx, h_in, in_bytes, h_out, out_bytes, &stage);
+    if (!rc) {
+        HostIO hio = {zts_stage_in_ptr(stage), zts_stage_out_ptr(stage), in_bytes, out_bytes, false, stage};
+        rc = deflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, mode,
+                            block_type, chunk_bytes, flags, &hio);
+        if (!rc && !hio.out_done) {
+            // many items: what each of them wrote, adjacent ranges merged
+            rc = zts_copy_back(ctx, stage, ctx->stream, (const uint8_t*)ctx->d_stage_out.p, hio.h_out, items, results,
+                               (const zlb_item*)ctx->d_items.p, (const zlb_result*)ctx->d_results.p, 0, n);
+            if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = zts_fail(ctx, ZLB_E_CUDA, "synchronize failed");
+        }
     }
-    if (hi)
-        ZTS_CUDA(ctx, cudaMemcpyAsync(h_out, ctx->d_stage_out.p, hi, cudaMemcpyDeviceToHost, ctx->stream));
-    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return ZLB_OK;
+    zts_stage_end(ctx, stage);  // also on errors: the copy threads hold pointers into the caller's buffers
+    return rc;
 }
 
 // ---- test hooks ---------------------------------------------------------------------------------------

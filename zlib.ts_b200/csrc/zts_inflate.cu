@@ -619,6 +619,7 @@ static int inflate_launch(zlb_ctx* ctx, cudaStream_t st, const uint8_t* d_in, ui
 #define SPLIT_MIN_BYTES (256u << 10)   // items at least this large are worth splitting
 #define SPLIT_SLOT (128u << 10)        // scratch bytes per piece (pieces of this engine's streams are <= 64 KiB)
 #define SPLIT_MAX_MARKS (1u << 22)
+#define SPLIT_MIN_PIECE 64u            // compressed bytes a piece has at least (64 KiB of zeros deflate to 78 + the marker)
 
 __global__ void __launch_bounds__(256)
 marker_scan_kernel(const uint8_t* __restrict__ in, unsigned long long n, unsigned long long* __restrict__ marks,
@@ -716,7 +717,9 @@ static int inflate_split_batch(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out
             pieces.push_back({(uint32_t)k, 0ull});
             for (; mi < marks.size() && (marks[mi] >> SPLIT_TAG_SHIFT) == k; ++mi) {
                 const unsigned long long m = marks[mi] & ((1ull << SPLIT_TAG_SHIFT) - 1);
-                if (m < n && m != pieces.back().start) pieces.push_back({(uint32_t)k, m});
+                // a piece of this engine's streams holds a whole block: never closer than SPLIT_MIN_PIECE bytes to the
+                // previous cut (a hostile stream of empty stored blocks would otherwise ask for a slot per 5 bytes)
+                if (m < n && m >= pieces.back().start + SPLIT_MIN_PIECE) pieces.push_back({(uint32_t)k, m});
             }
             if (pieces.size() - first[k] < 2) pieces.resize(first[k]);  // no marker inside: nothing to gain
         }
@@ -724,22 +727,48 @@ static int inflate_split_batch(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out
     }
     const size_t np = pieces.size();
     if (np == 0) return ZLB_OK;
-    rc = zts_reserve(ctx, &ctx->d_split, np * (size_t)SPLIT_SLOT + np * (sizeof(zlb_item) + sizeof(zlb_result) + sizeof(ZtsGather)) + 1024);
-    if (rc) return rc;
-    uint8_t* d_scratch = (uint8_t*)ctx->d_split.p;
-    zlb_item* d_seg = (zlb_item*)(d_scratch + np * (size_t)SPLIT_SLOT);
-    zlb_result* d_segres = (zlb_result*)(d_seg + np);
-    ZtsGather* d_gather = (ZtsGather*)(d_segres + np);
+    // slots: a piece of L compressed bytes cannot inflate to more than ~1032 L (258 bytes per 2 bits at best), and a
+    // piece of this engine's streams holds at most one 64 KiB chunk
     std::vector<zlb_item> seg(np);
+    size_t scratch = 0, big_in = 0;
     for (size_t k = 0; k < nb; ++k) {
         const zlb_item& it = h_items[big[k]];
+        if (first[k + 1] > first[k]) big_in += it.in_len;
         for (size_t j = first[k]; j < first[k + 1]; ++j) {
             seg[j].in_off = it.in_off + pieces[j].start;
             seg[j].in_len = (j + 1 < first[k + 1] ? pieces[j + 1].start : it.in_len) - pieces[j].start;
-            seg[j].out_off = j * (size_t)SPLIT_SLOT;
-            seg[j].out_cap = SPLIT_SLOT;
+            size_t slot = (size_t)seg[j].in_len * 1032u + 512u;
+            if (slot > SPLIT_SLOT) slot = SPLIT_SLOT;
+            slot = (slot + 255) & ~(size_t)255;
+            seg[j].out_off = scratch;
+            seg[j].out_cap = slot;
+            scratch += slot;
         }
     }
+    {
+        // the scratch is bounded: what the input could legitimately inflate to (2048 x, floor 64 MiB), a quarter of
+        // what the device has free right now, 16 GiB at most. Whatever does not fit (or cannot be allocated) is simply
+        // not split -- the one-warp decoder gives the same result.
+        const size_t need = ((scratch + 255) & ~(size_t)255) + np * (sizeof(zlb_item) + sizeof(zlb_result) + sizeof(ZtsGather)) + 1024;
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = 0;
+        size_t budget = (free_b + ctx->d_split.cap) / 4;
+        if (budget > ((size_t)16 << 30)) budget = (size_t)16 << 30;
+        size_t by_input = big_in * 2048u;
+        if (by_input < ((size_t)64 << 20)) by_input = (size_t)64 << 20;
+        if (budget > by_input) budget = by_input;
+        if (need > budget) return ZLB_OK;
+        rc = zts_reserve(ctx, &ctx->d_split, need);
+        if (rc == ZLB_E_NOMEM) {
+            ctx->err[0] = 0;
+            return ZLB_OK;
+        }
+        if (rc) return rc;
+    }
+    uint8_t* d_scratch = (uint8_t*)ctx->d_split.p;
+    zlb_item* d_seg = (zlb_item*)(d_scratch + ((scratch + 255) & ~(size_t)255));
+    zlb_result* d_segres = (zlb_result*)(d_seg + np);
+    ZtsGather* d_gather = (ZtsGather*)(d_segres + np);
     ZTS_CUDA(ctx, cudaMemcpyAsync(d_seg, seg.data(), np * sizeof(zlb_item), cudaMemcpyHostToDevice, st));
     ZTS_CUDA(ctx, cudaMemsetAsync(d_segres, 0, np * sizeof(zlb_result), st));
     rc = inflate_launch(ctx, st, d_in, d_scratch, d_seg, d_segres, np,
@@ -793,9 +822,10 @@ static int inflate_split_batch(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out
 // previous waves are decoded (one compute stream per wave: a wave is latency-bound, so the waves run side by side) and its output
 // travels back as soon as it is done.
 struct InfHostIO {
-    const uint8_t* h_in;
-    uint8_t* h_out;
+    const uint8_t* h_in;   // where H2D copies read from: the caller's page-locked buffer, or the library's shadow
+    uint8_t* h_out;        // where D2H copies write to
     size_t in_bytes, out_bytes;
+    ZtsHostStage* stage;   // copy threads behind the shadows (pageable caller buffers), see zts_hoststage.cu
 };
 
 static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, const zlb_item* h_items,
@@ -820,7 +850,10 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         for (size_t i = 0; i < n; ++i)
             if (h_items[i].in_len >= SPLIT_MIN_BYTES) big.push_back(i);
         if (!big.empty()) {
-            if (hio) ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            if (hio) {
+                zts_stage_wait_in(hio->stage, 0, hio->in_bytes);
+                ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            }
             std::vector<zlb_item> rest_items;
             std::vector<size_t> rest_idx;
             std::vector<char> is_done(n, 0);
@@ -866,66 +899,100 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                 rc = zts_checksum_device(ctx, d_out, d_items, d_results, h_items, n, kinds, 1);
                 if (rc) return rc;
             }
-            if (hio) ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out, d_out, hio->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
             ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+            if (hio) {
+                ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the sizes decide what travels
+                rc = zts_copy_back(ctx, hio->stage, ctx->stream, d_out, hio->h_out, h_items, h_results, d_items, d_results, 0, n);
+                if (rc) return rc;
+            }
             return ZLB_OK;
         }
     }
     // waves only pay when the items are laid out in order on both sides (then a wave is one contiguous copy each way)
     size_t n_waves = 1;
     if (hio && n >= 1024) {
-        n_waves = 4;
+        n_waves = n >= 8192 ? 8 : 4;
         for (size_t i = 1; i < n && n_waves > 1; ++i)
             if (h_items[i].in_off < h_items[i - 1].in_off + h_items[i - 1].in_len ||
                 h_items[i].out_off < h_items[i - 1].out_off + h_items[i - 1].out_cap)
                 n_waves = 1;
     }
-    if (!hio || n_waves == 1) {
-        if (hio)
-            ZTS_CUDA(ctx, cudaMemcpyAsync((void*)d_in, hio->h_in, hio->in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!hio) {
         rc = inflate_launch(ctx, ctx->stream, d_in, d_out, d_items, d_results, n, flags);
         if (rc) return rc;
         if (kinds) {
             rc = zts_checksum_device(ctx, d_out, d_items, d_results, h_items, n, kinds, 1);
             if (rc) return rc;
         }
-        if (hio)
-            ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out, d_out, hio->out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
         return ZLB_OK;
     }
 
+    // Host buffers: the waves are decoded one after the other on the context's stream; the input of wave k+1 travels
+    // on a copy stream while wave k is decoded, and as soon as the sizes of wave k are known (its results are read
+    // back behind it, wave k+1 is already queued) what it wrote travels back on the other copy stream.
     rc = zts_host_streams(ctx);
     if (rc) return rc;
-    // event 0: item table is on the device; 1+3k: input of wave k arrived; 2+3k: wave k decoded; 3+3k: spare
+    rc = zts_reserve_pinned2(ctx, n * sizeof(zlb_result));
+    if (rc) return rc;
+    zlb_result* pin_res = (zlb_result*)ctx->h_pin2;
+    const size_t per = (n + n_waves - 1) / n_waves;
+    // events: 0 = item table on the device; 1 + 2k = input of wave k arrived; 2 + 2k = wave k decoded, results read back
     cudaEvent_t ev_tab = zts_sync_event(ctx, 0);
     ZTS_CUDA(ctx, cudaEventRecord(ev_tab, ctx->stream));
-    for (int i = 0; i < 3; ++i) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_aux[i], ev_tab, 0));
-    const size_t per = (n + n_waves - 1) / n_waves;
+    auto wave_range = [&](size_t k, size_t& a, size_t& b) {
+        a = k * per;
+        b = a + per < n ? a + per : n;
+        if (a > n) a = n;
+    };
+    auto wave_in = [&](size_t k) -> int {
+        size_t a, b;
+        wave_range(k, a, b);
+        if (a < b) {
+            uint64_t ilo, ihi;
+            if (n_waves == 1) {  // items in any order: the whole blob
+                ilo = 0;
+                ihi = hio->in_bytes;
+            } else {
+                ilo = h_items[a].in_off;
+                ihi = h_items[b - 1].in_off + h_items[b - 1].in_len;
+            }
+            if (ihi > ilo) {
+                zts_stage_wait_in(hio->stage, ilo, ihi);
+                ZTS_CUDA(ctx, cudaMemcpyAsync((void*)(d_in + ilo), hio->h_in + ilo, ihi - ilo, cudaMemcpyHostToDevice, ctx->s_in));
+            }
+        }
+        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 1 + 2 * k), ctx->s_in));
+        return ZLB_OK;
+    };
+    auto wave_out = [&](size_t k) -> int {
+        size_t a, b;
+        wave_range(k, a, b);
+        ZTS_CUDA(ctx, cudaEventSynchronize(zts_sync_event(ctx, 2 + 2 * k)));
+        if (a >= b) return ZLB_OK;
+        memcpy(h_results + a, pin_res + a, (b - a) * sizeof(zlb_result));
+        return zts_copy_back(ctx, hio->stage, ctx->s_out, d_out, hio->h_out, h_items, h_results, d_items, d_results, a, b);
+    };
+    if ((rc = wave_in(0))) return rc;
     for (size_t k = 0; k < n_waves; ++k) {
-        const size_t a = k * per, b = (a + per < n ? a + per : n);
-        if (a >= b) break;
-        const uint64_t ilo = h_items[a].in_off, ihi = h_items[b - 1].in_off + h_items[b - 1].in_len;
-        const uint64_t olo = h_items[a].out_off, ohi = h_items[b - 1].out_off + h_items[b - 1].out_cap;
-        cudaEvent_t ev_in = zts_sync_event(ctx, 1 + 3 * k), ev_done = zts_sync_event(ctx, 2 + 3 * k);
-        if (ihi > ilo)
-            ZTS_CUDA(ctx, cudaMemcpyAsync((void*)(d_in + ilo), hio->h_in + ilo, ihi - ilo, cudaMemcpyHostToDevice, ctx->s_in));
-        ZTS_CUDA(ctx, cudaEventRecord(ev_in, ctx->s_in));
-        cudaStream_t st = k ? ctx->s_aux[(k - 1) % 3] : ctx->stream;  // all waves may be in flight together
-        ZTS_CUDA(ctx, cudaStreamWaitEvent(st, ev_in, 0));
-        rc = inflate_launch(ctx, st, d_in, d_out, d_items + a, d_results + a, b - a, flags);
-        if (rc) return rc;
-        ZTS_CUDA(ctx, cudaEventRecord(ev_done, st));
-        ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->s_out, ev_done, 0));
-        if (ohi > olo)
-            ZTS_CUDA(ctx, cudaMemcpyAsync(hio->h_out + olo, d_out + olo, ohi - olo, cudaMemcpyDeviceToHost, ctx->s_out));
-        if (st != ctx->stream) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ev_done, 0));  // results / checksums follow on ctx->stream
+        size_t a, b;
+        wave_range(k, a, b);
+        ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 1 + 2 * k), 0));
+        if (a < b) {
+            rc = inflate_launch(ctx, ctx->stream, d_in, d_out, d_items + a, d_results + a, b - a, flags);
+            if (rc) return rc;
+            if (kinds) {
+                rc = zts_checksum_device(ctx, d_out, d_items + a, d_results + a, h_items + a, b - a, kinds, 1);
+                if (rc) return rc;
+            }
+            ZTS_CUDA(ctx, cudaMemcpyAsync(pin_res + a, d_results + a, (b - a) * sizeof(zlb_result), cudaMemcpyDeviceToHost,
+                                          ctx->stream));
+        }
+        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 + 2 * k), ctx->stream));
+        if (k + 1 < n_waves && (rc = wave_in(k + 1))) return rc;  // behind the launches: may wait for the copy threads
+        if (k > 0 && (rc = wave_out(k - 1))) return rc;
     }
-    if (kinds) {
-        rc = zts_checksum_device(ctx, d_out, d_items, d_results, h_items, n, kinds, 1);
-        if (rc) return rc;
-    }
-    ZTS_CUDA(ctx, cudaMemcpyAsync(h_results, d_results, n * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = wave_out(n_waves - 1))) return rc;
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return ZLB_OK;
 }
@@ -958,10 +1025,14 @@ extern "C" int zlb_inflate_batch_host(zlb_ctx* ctx, const void* h_in, size_t in_
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_stage_out, out_bytes + 256);
     if (rc) return rc;
-    InfHostIO hio = {(const uint8_t*)h_in, (uint8_t*)h_out, in_bytes, out_bytes};
-    rc = inflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, flags,
-                        &hio);
-    if (rc) return rc;
-    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return ZLB_OK;
+    ZtsHostStage* stage = nullptr;
+    rc = zts_stage_begin(ctx, h_in, in_bytes, h_out, out_bytes, &stage);
+    if (!rc) {
+        InfHostIO hio = {zts_stage_in_ptr(stage), zts_stage_out_ptr(stage), in_bytes, out_bytes, stage};
+        rc = inflate_device(ctx, (const uint8_t*)ctx->d_stage_in.p, (uint8_t*)ctx->d_stage_out.p, items, results, n, flags,
+                            &hio);
+        if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = zts_fail(ctx, ZLB_E_CUDA, "synchronize failed");
+    }
+    zts_stage_end(ctx, stage);  // also on errors: the copy threads hold pointers into the caller's buffers
+    return rc;
 }
