@@ -1,18 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200 DEFLATE engine (BASELINE.json metric / configs[1]).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--configs all|none|c1,c3,...]
 
 A "step" is one chunk-parallel raw deflate (DYNAMIC blocks, 64 KiB chunks, reference-compatible bytes)
 of one 256 MiB `mixed(268435456, seed)` buffer per GPU. The same JSON line also
-carries the batched-inflate leg (the 4096 independent 64 KiB streams of that buffer, C3-shaped) under
-"inflate". Multi-GPU: one process per GPU (torchrun), every rank owns its own buffer (weak scaling),
-no data-path collective; the only exchange is the exclusive scan of the per-rank output sizes.
+carries: the end-to-end figures through the C-ABI host entry points (page-locked and pageable caller buffers), the
+batched-inflate leg (the 4096 independent 64 KiB streams of that buffer), fast / primed modes, an adversarial leg
+(2-symbol random, period-3, 8-byte records), and BASELINE's other configs C1, C3, C4, C5 at full size with their
+parity checks (`configs`; C5 is sharded over the ranks under --gpus N). Multi-GPU: one process per GPU (torchrun),
+every rank owns its own buffer (weak scaling), no data-path collective; the only exchange is the exclusive scan of
+the per-rank output sizes.
 
-`--impl reference` times the reference's CPU algorithm (oracle/: C restatement of RawDeflate, because no
-JavaScript engine exists in this image) on all host threads, on bounded samples of the same workload.
+`--impl reference` times the reference's CPU algorithm (oracle/: C restatement of RawDeflate, pinned to the executed
+reference by tests/test_refjs.py; Node is absent from this image) on all host threads over the SAME 256 MiB buffer
+per step. That arm neither builds, imports nor loads the CUDA library.
 """
 import argparse
+import ctypes
+import importlib.util
 import json
 import os
 import subprocess
@@ -43,6 +49,8 @@ def parse_args():
     ap.add_argument("--bytes", type=int, default=WORKLOAD_BYTES, help="per-GPU workload bytes (default = C2)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--configs", default="all", help="BASELINE configs to add to the line: all | none | c1,c3,c4,c5")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fast / primed / pageable / adversarial legs")
     return ap.parse_args()
 
 
@@ -54,6 +62,13 @@ def peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _load_py(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 class ClockSampler:
@@ -131,8 +146,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU arm: the reference algorithm (oracle port) on the host cores
+# CPU arm: the reference algorithm (oracle port) on the host cores -- no CUDA library anywhere near it
 # ------------------------------------------------------------------------------------------------
+def _synth_lib():
+    """libzts_synth.so alone (plain C generators of SURVEY Appendix D): built and loaded without the engine."""
+    build = _load_py(os.path.join(ROOT, "zlib.ts_b200", "build.py"), "_zts_build")
+    build.build_synth()
+    lib = ctypes.CDLL(build.SYNTH_LIB)
+    lib.zts_gen_mixed.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint32]
+    return lib
+
+
+def _mixed_no_engine(n, seed):
+    buf = np.empty(n, dtype=np.uint8)
+    _synth_lib().zts_gen_mixed(buf.ctypes.data, n, seed & 0xFFFFFFFF, 4096)
+    return buf
+
+
 def cpu_deflate_rate(data, threads, target_s, max_bytes=None):
     """Times oracle RawDeflate per 64 KiB chunk over a bounded prefix sample of `data`.
     Returns (GB/s, sample bytes, compressed bytes of the sample, seconds)."""
@@ -157,31 +187,30 @@ def run_reference(args, rank, world):
         return
     import oracle
     oracle.build()
-    from zlibts_b200 import synth
     threads = os.cpu_count() or 1
-    # a prefix of the C2 buffer is enough for the bounded samples
-    data = synth.mixed(min(args.bytes, max(64 << 20, threads * (4 << 20))), 2)
-    per_step_s = max(2.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))
-    # size the sample once, then time K steps on it
-    _, sample, _, _ = cpu_deflate_rate(data, threads, per_step_s)
+    n = args.bytes // CHUNK * CHUNK
+    data = _mixed_no_engine(n, 2)          # the very buffer rank 0 of the GPU arm compresses
     for _ in range(args.warmup):
-        oracle.deflate_chunks_mt(data[:sample], CHUNK, oracle.DYNAMIC, threads)
+        oracle.deflate_chunks_mt(data, CHUNK, oracle.DYNAMIC, threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cbytes = oracle.deflate_chunks_mt(data[:sample], CHUNK, oracle.DYNAMIC, threads)
+        cbytes = oracle.deflate_chunks_mt(data, CHUNK, oracle.DYNAMIC, threads)
     dt = time.perf_counter() - t0
-    gbs = sample * args.steps / dt / 1e9
+    gbs = n * args.steps / dt / 1e9
     # single-thread figure (north_star: "both single-threaded and across all stated cores")
     st_gbs, st_sample, _, _ = cpu_deflate_rate(data, 1, 3.0)
-    sample_txt = f"first {sample >> 10} KiB of the C2 buffer ({sample // CHUNK} chunks) per step, {threads} threads"
+    sample_txt = f"the whole C2 buffer ({n >> 20} MiB, {n // CHUNK} chunks) per step, {threads} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "chunk_bytes": CHUNK, "sampled": sample_txt,
-                   "note": "reference = C restatement of zlib.ts RawDeflate (oracle/); Node is absent from this image"},
+        "config": {"workload": WORKLOAD, "bytes_per_gpu": n, "chunk_bytes": CHUNK, "chunks_per_gpu": n // CHUNK,
+                   "mode": "compat", "block_type": "DYNAMIC",
+                   "note": "reference = C restatement of zlib.ts RawDeflate (oracle/, pinned to the executed reference "
+                           "by tests/test_refjs.py); Node is absent from this image; this arm does not load the CUDA library"},
+        "ratio": cbytes / n,
         "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt,
-                         "single_thread_value": st_gbs, "ratio": cbytes / sample},
+                         "single_thread_value": st_gbs, "single_thread_sample_bytes": st_sample},
         "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -191,6 +220,19 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def adversarial_inputs(n):
+    """SURVEY's worst cases for an exhaustive matcher: 2-symbol random (every 3-byte key has thousands of candidates),
+    period-3 ("abcabc..."), 8-byte low-entropy records."""
+    rng = np.random.default_rng(20261018)
+    r = np.zeros((n // 8, 8), dtype=np.uint8)
+    v = (7 * np.arange(n // 8, dtype=np.uint64)).astype(np.uint32)
+    for k in range(4):
+        r[:, k] = (v >> (8 * k)) & 0xFF
+    r[:, 4] = rng.integers(0, 16, n // 8)
+    return {"rand2": rng.integers(0, 2, n, dtype=np.uint8), "period3": np.resize(np.frombuffer(b"abc", dtype=np.uint8), n),
+            "records8": r.reshape(-1)}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import zlibts_b200 as z
@@ -273,38 +315,50 @@ def run_b200(args, rank, world, local_rank):
     clen = int(r["out_len"][0])
     value = world * n * args.steps / (ms * 1e-3) / 1e9
 
-    # ---- fast mode (bounded candidate depth; valid stream, not byte-identical): speed and ratio beside compat ----
-    for _ in range(2):
-        rf = eng.deflate_batch(d_in, d_out, items, flags=dflags, mode=z.MODE_FAST)
-    ms_f = timed(lambda: res.__setitem__("f", eng.deflate_batch(d_in, d_out, items, flags=dflags, mode=z.MODE_FAST)),
-                 max(1, min(args.steps, 5)))
-    fast_steps = max(1, min(args.steps, 5))
-    fast = {"value": world * n * fast_steps / (ms_f * 1e-3) / 1e9, "unit": UNIT, "chain_depth": 16,
-            "ratio": int(res["f"]["out_len"][0]) / n, "ratio_vs_compat": int(res["f"]["out_len"][0]) / clen,
-            "note": "ratio tolerance vs reference RawDeflate per chunk: 3 % (north_star); compat ratio == reference"}
-    # ---- primed mode (32 KiB of history in front of every 32 KiB chunk): ratio recovered, speed paid
-    items_p = items.copy()
-    items_p["out_cap"] = cap_primed
-    primed = {}
-    for name, mode in (("exhaustive", z.MODE_PRIMED), ("fast", z.MODE_FAST | z.MODE_PRIMED)):
+    extras = not args.no_extras
+    few = max(1, min(args.steps, 5))
+    fast = primed = None
+    if extras:
+        # ---- fast mode (bounded candidate depth; valid stream, not byte-identical): speed and ratio beside compat ----
         for _ in range(2):
-            eng.deflate_batch(d_in, d_out, items_p, flags=dflags, mode=mode)
-        ms_p = timed(lambda: res.__setitem__("p", eng.deflate_batch(d_in, d_out, items_p, flags=dflags, mode=mode)),
-                     fast_steps)
-        assert int(res["p"]["status"][0]) == 0
-        primed[name] = {"value": world * n * fast_steps / (ms_p * 1e-3) / 1e9, "unit": UNIT,
-                        "ratio": int(res["p"]["out_len"][0]) / n, "ratio_vs_compat": int(res["p"]["out_len"][0]) / clen}
-    primed["note"] = ("32 KiB chunks, each searching the 32 KiB before it as well; exhaustive = the reference's matcher "
-                      "(blocks equal the oracle's block construction with that history), fast = depth 16")
-    step_device()  # leave the compat output in d_out
+            eng.deflate_batch(d_in, d_out, items, flags=dflags, mode=z.MODE_FAST)
+        ms_f = timed(lambda: res.__setitem__("f", eng.deflate_batch(d_in, d_out, items, flags=dflags, mode=z.MODE_FAST)), few)
+        fast = {"value": world * n * few / (ms_f * 1e-3) / 1e9, "unit": UNIT, "chain_depth": 16, "steps": few,
+                "ratio": int(res["f"]["out_len"][0]) / n, "ratio_vs_compat": int(res["f"]["out_len"][0]) / clen,
+                "note": "ratio tolerance vs reference RawDeflate per chunk: 3 % (north_star); compat ratio == reference"}
+        # ---- primed mode (32 KiB of history in front of every 32 KiB chunk): ratio recovered, speed paid
+        items_p = items.copy()
+        items_p["out_cap"] = cap_primed
+        primed = {}
+        for name, mode in (("exhaustive", z.MODE_PRIMED), ("fast", z.MODE_FAST | z.MODE_PRIMED)):
+            for _ in range(2):
+                eng.deflate_batch(d_in, d_out, items_p, flags=dflags, mode=mode)
+            ms_p = timed(lambda: res.__setitem__("p", eng.deflate_batch(d_in, d_out, items_p, flags=dflags, mode=mode)), few)
+            assert int(res["p"]["status"][0]) == 0
+            primed[name] = {"value": world * n * few / (ms_p * 1e-3) / 1e9, "unit": UNIT, "steps": few,
+                            "ratio": int(res["p"]["out_len"][0]) / n, "ratio_vs_compat": int(res["p"]["out_len"][0]) / clen}
+        primed["note"] = ("32 KiB chunks, each searching the 32 KiB before it as well; exhaustive = the reference's matcher "
+                          "(blocks equal the oracle's block construction with that history), fast = depth 16")
+        step_device()  # leave the compat output in d_out
 
-    # ---- end-to-end leg: host buffers through the C-ABI host entry point (H2D + D2H inside) -----------
+    # ---- end-to-end leg: host buffers through the C-ABI host entry point (H2D + D2H inside), as many steps as `value`
     for _ in range(max(1, min(2, args.warmup))):
         step_host()
-    e2e_steps = max(1, min(args.steps, 5))
-    ms_h = timed(step_host, e2e_steps)
+    ms_h = timed(step_host, args.steps)
     assert int(res["h"]["status"][0]) == 0 and int(res["h"]["out_len"][0]) == clen
-    e2e_value = world * n * e2e_steps / (ms_h * 1e-3) / 1e9
+    e2e_value = world * n * args.steps / (ms_h * 1e-3) / 1e9
+    # the same through PAGEABLE caller buffers (what a binding without zlb_host_alloc passes): the library stages them
+    e2e_pageable = None
+    if extras:
+        pg_in, pg_out = data.copy(), np.empty(cap, dtype=np.uint8)
+        for _ in range(2):
+            eng.deflate_batch_host(pg_in, pg_out, items, flags=dflags)
+        ms_pg = timed(lambda: res.__setitem__("hp", eng.deflate_batch_host(pg_in, pg_out, items, flags=dflags)), few)
+        assert int(res["hp"]["out_len"][0]) == clen and np.array_equal(pg_out[:clen], h_out.numpy()[:clen])
+        e2e_pageable = {"value": world * n * few / (ms_pg * 1e-3) / 1e9, "unit": UNIT, "steps": few,
+                        "ms_per_step": ms_pg / few, "ratio_to_pinned": (ms_h / args.steps) / (ms_pg / few),
+                        "api": "zlb_deflate_batch_host on pageable numpy buffers (page-locked shadows + copy threads inside)"}
+        del pg_in, pg_out
 
     # ---- inflate leg: the chunks as independent streams (C3-shaped), device resident + host e2e -------
     slot = z.deflate_bound(CHUNK)
@@ -355,9 +409,19 @@ def run_b200(args, rank, world, local_rank):
     assert torch.equal(d_plain, d_in), "inflate(deflate(x)) != x"
     inf_value = world * n * args.steps / (ms_i * 1e-3) / 1e9
     inf_host()
-    ms_ih = timed(inf_host, e2e_steps)
+    ms_ih = timed(inf_host, args.steps)
     assert torch.equal(h_plain, h_in)
-    inf_e2e = world * n * e2e_steps / (ms_ih * 1e-3) / 1e9
+    inf_e2e = world * n * args.steps / (ms_ih * 1e-3) / 1e9
+    inf_pageable = None
+    if extras:
+        pg_c, pg_p = h_packed.numpy().copy(), np.empty(n, dtype=np.uint8)
+        for _ in range(2):
+            eng.inflate_batch_host(pg_c, pg_p, it_i)
+        ms_ipg = timed(lambda: eng.inflate_batch_host(pg_c, pg_p, it_i), few)
+        assert np.array_equal(pg_p, data)
+        inf_pageable = {"value": world * n * few / (ms_ipg * 1e-3) / 1e9, "unit": UNIT, "steps": few,
+                        "ms_per_step": ms_ipg / few, "ratio_to_pinned": (ms_ih / args.steps) / (ms_ipg / few)}
+        del pg_c, pg_p
 
     # ---- the one cross-rank exchange: exclusive scan of the per-rank output sizes ----------------------
     rank_off = 0
@@ -383,21 +447,54 @@ def run_b200(args, rank, world, local_rank):
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "avg_launch_ms": avg_launch_ms,
                 "kernel_share_of_step": top_ms / max(step_kernel_ms, 1e-9),
-                "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]}}
+                "kernels_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if v["launches"]},
+                "note": "the kernel is issue-bound, not HBM-bound: see issue_frac"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             tj = json.load(open(traffic_file))
-            # the capture may be of a smaller launch than this run's: traffic scales with the chunks per launch
+            units = n_chunks * args.steps / max(1, top_launches)   # chunks per launch of this run
             per_unit = tj.get(top_name, 0) / max(1, tj.get("_units_per_launch", 1))
-            roofline["traffic"] = per_unit * (n_chunks * args.steps / max(1, top_launches)) or None
-            roofline["traffic_source"] = tj.get("_note")
+            roofline["traffic"] = per_unit * units or None
+            roofline["traffic_source"] = "carried from profiles/ (not measured in this run): " + str(tj.get("_note"))
+            inst = tj.get("_inst_executed", {}).get(top_name)
+            if inst and clk.get("sm_mhz"):
+                # warp instructions issued / issue slots of the device during the launch (4 schedulers per SM, 1 per clock)
+                sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
+                per_launch = inst / max(1, tj.get("_units_per_launch", 1)) * units
+                slots = sm_count * 4 * clk["sm_mhz"] * 1e6 * avg_launch_ms * 1e-3
+                roofline["issue_frac"] = per_launch / slots
+                roofline["warp_instructions_per_input_byte"] = per_launch / (n * args.steps / max(1, top_launches))
+                roofline["issue_frac_source"] = "smsp__inst_executed.sum carried from profiles/ (ncu), clocks and time of this run"
         except Exception:
             pass
     inf_top_ms = prof_i["inflate_warp_kernel"]["ms"] / max(1, prof_i["inflate_warp_kernel"]["launches"])
     inf_roofline = {"bound": "hbm", "kernel": "inflate_warp_kernel",
                     "achieved": (n + total_c) / (inf_top_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"}
     inf_roofline["frac"] = inf_roofline["achieved"] / peak
+
+    # ---- adversarial inputs (rank 0, N = 1): throughput on 64 MiB of each and the time of ONE chunk --------------
+    adversarial = None
+    if extras and rank == 0 and world == 1:
+        adversarial = {}
+        an = 64 << 20
+        it_a = z.make_items(1)
+        it_a["in_len"], it_a["out_cap"] = an, z.deflate_bound(an)
+        it_1 = z.make_items(1)
+        it_1["in_len"], it_1["out_cap"] = CHUNK, z.deflate_bound(CHUNK)
+        for name, arr in adversarial_inputs(an).items():
+            with torch.cuda.stream(stream):
+                d_a = torch.from_numpy(np.ascontiguousarray(arr)).cuda()
+            for _ in range(2):
+                ra = eng.deflate_batch(d_a, d_out, it_a)
+            ms_a = timed(lambda: eng.deflate_batch(d_a, d_out, it_a), 3)
+            eng.deflate_batch(d_a, d_out, it_1)
+            ms_1 = timed(lambda: eng.deflate_batch(d_a, d_out, it_1), 5)
+            adversarial[name] = {"value": an * 3 / (ms_a * 1e-3) / 1e9, "unit": UNIT, "ratio": int(ra["out_len"][0]) / an,
+                                 "one_chunk_ms": ms_1 / 5}
+            del d_a
+        adversarial["note"] = ("64 MiB each, compat mode; one_chunk_ms = a single 64 KiB chunk through the whole pipeline "
+                               "(one CTA): what the slowest chunk of a wave can cost")
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): oracle port on a bounded sample ------------------
     cpu = None
@@ -415,6 +512,23 @@ def run_b200(args, rank, world, local_rank):
                "single_thread_value": st_gbs, "sample_ratio": cbytes / sample,
                "gpu_bytes_equal_on_sample": bool(gpu_sample == cbytes)}
 
+    # ---- BASELINE's other configs at full size, with their parity checks ------------------------------------------
+    configs = None
+    want = [] if args.configs == "none" else (["c1", "c3", "c4", "c5"] if args.configs == "all" else args.configs.split(","))
+    if want:
+        del d_packed, d_plain, h_plain
+        torch.cuda.empty_cache()
+        bc = _load_py(os.path.join(ROOT, "tools", "bench_configs.py"), "_bench_configs")
+        configs = {}
+        for name in want:
+            try:
+                if name == "c5":
+                    configs["c5"] = bc.c5_sharded(eng, stream, rank, world, dist)    # every rank takes part
+                elif rank == 0 and world == 1:
+                    configs[name] = getattr(bc, name)(eng)
+            except Exception as e:  # a config that cannot run here (host memory, ...) must not take the headline down
+                configs[name] = {"error": repr(e)[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -422,12 +536,15 @@ def run_b200(args, rank, world, local_rank):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": WORKLOAD, "bytes_per_gpu": n, "chunk_bytes": CHUNK, "chunks_per_gpu": n_chunks,
                        "mode": "compat", "block_type": "DYNAMIC", "parallelism": f"shard{world}",
-                       "l2": "inputs (256 MiB) larger than L2 (126 MB), no flush"},
+                       "l2": "inputs (256 MiB) larger than L2 (126 MB), no flush",
+                       "timers": "value: CUDA events around K calls with the per-kernel event timers on (they feed roofline)"},
             "ratio": clen / n,
             "fast_mode": fast,
             "primed_mode": primed,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": clen,
-                    "ms_per_step": ms_h / e2e_steps, "api": "zlb_deflate_batch_host (pinned host buffers)"},
+                    "ms_per_step": ms_h / args.steps, "steps": args.steps,
+                    "api": "zlb_deflate_batch_host (page-locked host buffers)"},
+            "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                        "samples": clk["samples"], "window": clk.get("window")},
@@ -436,8 +553,11 @@ def run_b200(args, rank, world, local_rank):
             "inflate": {"metric": "inflate_output_GBps", "value": inf_value, "unit": UNIT, "streams_per_gpu": n_chunks,
                         "ms_per_step": ms_i / args.steps, "gpu_launches": int(inf_launches),
                         "e2e": {"value": inf_e2e, "unit": UNIT, "h2d_bytes_per_step": total_c,
-                                "d2h_bytes_per_step": n, "ms_per_step": ms_ih / e2e_steps},
+                                "d2h_bytes_per_step": n, "ms_per_step": ms_ih / args.steps, "steps": args.steps},
+                        "e2e_pageable": inf_pageable,
                         "roofline": inf_roofline},
+            "adversarial": adversarial,
+            "configs": configs,
             "multi_gpu": {"output_bytes_total": total_clen, "rank0_offset": rank_off,
                           "exchange": "exclusive scan of per-rank output sizes (8-byte all-reduce), no data-path collective"},
         }
@@ -470,12 +590,12 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)   # builds the oracle and the generators only; never touches the CUDA library
+        return
     import __graft_entry__ as g
     if rank == 0 or not os.path.exists(os.path.join(ROOT, "zlib.ts_b200", "libzlibts_b200.so")):
         g.build()
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
     run_b200(args, rank, world, local_rank)
 
 

@@ -53,6 +53,8 @@ def lib():
         L.zo_deflate_chunks_mt.restype = i32
         L.zo_inflate_streams_mt.argtypes = [vp, vp, vp, sz, vp, sz, i32, ctypes.POINTER(ctypes.c_uint64)]
         L.zo_inflate_streams_mt.restype = i32
+        L.zo_zlib_chunks_keep_mt.argtypes = [vp, sz, sz, i32, vp, sz, vp]
+        L.zo_zlib_chunks_keep_mt.restype = i32
         _lib = L
     return _lib
 
@@ -166,6 +168,20 @@ def deflate_chunks_mt(data, chunk=65536, compression_type=DYNAMIC, threads=1):
     if rc:
         raise OracleError(rc)
     return int(total.value)
+
+
+def zlib_chunks_keep_mt(data, chunk=65536, threads=1):
+    """Zlib stream (78 9C | RawDeflate(chunk) | Adler-32 BE) of every chunk, kept: returns (slots array, slot size,
+    lengths). Used to make config C3's input, "zlib streams produced by the reference"."""
+    a = _u8(data)
+    n_chunks = (a.size + chunk - 1) // chunk
+    slot = int(lib().zo_raw_deflate_bound(chunk)) + 6
+    out = np.empty(n_chunks * slot, dtype=np.uint8)
+    lens = np.zeros(n_chunks, dtype=np.uint64)
+    rc = lib().zo_zlib_chunks_keep_mt(a.ctypes.data, a.size, chunk, threads, out.ctypes.data, slot, lens.ctypes.data)
+    if rc:
+        raise OracleError(rc)
+    return out, slot, lens
 
 
 def inflate_streams_mt(comp, offs, lens, out_stride, threads=1):

@@ -29,6 +29,17 @@ def _newer(target, sources):
     return all(os.path.getmtime(s) <= t for s in sources)
 
 
+def build_synth(force=False):
+    """libzts_synth.so alone: plain-C generators, no CUDA (bench.py's reference arm builds nothing else of this package)."""
+    synth_src = os.path.join(CSRC, "zts_synth.c")
+    if force or not _newer(SYNTH_LIB, [synth_src]):
+        gcc = shutil.which("gcc") or "gcc"
+        tmp = SYNTH_LIB + ".tmp%d" % os.getpid()
+        subprocess.run([gcc, "-O2", "-fPIC", "-shared", "-std=c11", "-o", tmp, synth_src], check=True)
+        os.replace(tmp, SYNTH_LIB)
+    return SYNTH_LIB
+
+
 def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     srcs = [os.path.join(CSRC, s) for s in CU_SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -39,12 +50,7 @@ def build(force=False, verbose=False):
         cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + srcs
         subprocess.run(cmd, check=True, cwd=CSRC)
         os.replace(tmp, LIB)
-    synth_src = os.path.join(CSRC, "zts_synth.c")
-    if force or not _newer(SYNTH_LIB, [synth_src]):
-        gcc = shutil.which("gcc") or "gcc"
-        tmp = SYNTH_LIB + ".tmp%d" % os.getpid()
-        subprocess.run([gcc, "-O2", "-fPIC", "-shared", "-std=c11", "-o", tmp, synth_src], check=True)
-        os.replace(tmp, SYNTH_LIB)
+    build_synth(force)
     return LIB
 
 

@@ -16,12 +16,13 @@
 #include "zts_deflate.cuh"
 
 size_t zts_lz77_smem_bytes();
+size_t zts_lz77_scratch_bytes(int sm_count);   // per-CTA tile token scratch of the reference-compatible kernel
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
-                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint32_t* d_sortT,
+                    ZtsChunkInfo* d_info, uint32_t* d_tile_tok, uint32_t* d_list, uint32_t* d_hist, uint32_t* d_sortT,
                     uint32_t* d_counter, uint32_t grid, uint32_t depth);
 size_t zts_lz77_fast_scratch_bytes(int sm_count);
 int zts_lz77_fast_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
-                         ZtsChunkInfo* d_info, uint32_t* d_tok, uint32_t* d_tile_tok, uint32_t* d_hist,
+                         ZtsChunkInfo* d_info, uint32_t* d_list, uint32_t* d_tile_tok, uint32_t* d_hist,
                          uint32_t* d_sortT, uint32_t* d_counter, uint32_t grid, uint32_t depth);
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type, int smallest);
@@ -98,16 +99,11 @@ __global__ void deflate_finalize_kernel(const zlb_item* __restrict__ items, zlb_
 }
 
 // ---- bit packer: one CTA per chunk ------------------------------------------------------------------------
-// Every warp owns a contiguous range of the chunk's tokens. Pass 1 adds up the bits of each range, a 16-entry
-// scan gives every range its first bit, pass 2 re-derives the codes and ORs them into a shared-memory image of the
-// block with warp-level prefix sums only (no block barrier per batch of tokens). Launched twice per wave with two
-// image sizes: a CTA whose block fits the small image runs in the small launch (4 CTAs per SM), the others in
-// the large one; the CTA of the other class exits at once.
-struct PackSeg {
-    uint32_t prefix;      // tokens before this segment
-    uint32_t src;         // index into the fix (bit 31 clear) or spec (bit 31 set) token buffer
-};
-
+// The chunk's tokens are one contiguous list (both LZ77 kernels write it). Every warp owns a contiguous range of
+// it. Pass 1 adds up the bits of each range, a 16-entry scan gives every range its first bit, pass 2 re-derives the
+// codes and ORs them into a shared-memory image of the block with warp-level prefix sums only (no block barrier per
+// batch of tokens). Launched twice per wave with two image sizes: a CTA whose block fits the small image runs in the
+// small launch (4 CTAs per SM), the others in the large one; the CTA of the other class exits at once.
 #define PACK_WARPS (PACK_THREADS / 32)
 #define PACK_SMALL_WORDS 13312u  // 52 KiB image: 4 CTAs per SM
 
@@ -116,20 +112,15 @@ struct PackTok {
     uint32_t nb;
 };
 
-// Token g of the chunk (g == n_tok is the end-of-block symbol, g >= g_end nothing); `seg` is the lane's segment
-// hint. Loads are issued two batches ahead of their use (the loop bodies are short next to a trip to L2 / DRAM).
+// Token g of the chunk (g == n_tok is the end-of-block symbol, g >= g_end nothing). Loads are issued two batches
+// ahead of their use (the loop bodies are short next to a trip to L2 / DRAM).
 #define PACK_TOK_EOB 0x7F000000u   // bits 24..30 are zero in every real token
 #define PACK_TOK_NONE 0x7E000000u
-__device__ __forceinline__ uint32_t fetch_token(uint32_t g, uint32_t g_end, uint32_t n_tok, uint32_t& seg,
-                                                const PackSeg* s_seg, const uint32_t* __restrict__ sp,
-                                                const uint32_t* __restrict__ fx)
+__device__ __forceinline__ uint32_t fetch_token(uint32_t g, uint32_t g_end, uint32_t n_tok, const uint32_t* __restrict__ list)
 {
     if (g >= g_end) return PACK_TOK_NONE;
     if (g >= n_tok) return PACK_TOK_EOB;
-    while (s_seg[seg + 1].prefix <= g) ++seg;  // g only grows: the hint moves forward a slot or two per call
-    const uint32_t src = s_seg[seg].src;
-    const uint32_t idx = (src & 0x7FFFFFFFu) + (g - s_seg[seg].prefix);
-    return (src & 0x80000000u) ? __ldg(sp + idx) : __ldg(fx + idx);
+    return __ldg(list + g);
 }
 
 // code bits of a token
@@ -160,15 +151,13 @@ __device__ __forceinline__ PackTok encode_token(uint32_t tok, const uint32_t* s_
 
 __global__ void __launch_bounds__(PACK_THREADS)
 bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restrict__ info,
-               const ZtsChunkCodes* __restrict__ codes, const uint32_t* __restrict__ spec_tok,
-               const uint32_t* __restrict__ fix_tok, const zlb_item* __restrict__ items, uint8_t* __restrict__ out,
+               const ZtsChunkCodes* __restrict__ codes, const uint32_t* __restrict__ tok_list,
+               const zlb_item* __restrict__ items, uint8_t* __restrict__ out,
                uint32_t stage_words, uint32_t min_words, const uint8_t* __restrict__ in)
 {
     extern __shared__ __align__(16) uint32_t stage[];  // stage_words
     __shared__ uint32_t s_ll[286];
     __shared__ uint32_t s_d[30];
-    __shared__ PackSeg s_seg[2 * LZ_NTILES + 2];
-    __shared__ uint32_t warp_tot[PACK_WARPS];
     __shared__ unsigned long long range_bits[PACK_WARPS];
 
     const uint32_t c = blockIdx.x;
@@ -180,8 +169,8 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     const unsigned long long rel = ci->out_off - it.out_off;
     if (rel + out_bytes > it.out_cap) return;  // item overflows its slot: status is set by the finalize kernel
     uint8_t* dst = out + ci->out_off;
-    const uint32_t shift = (uint32_t)((uintptr_t)dst & 3u);  // image word j <-> aligned global word j
-    const uint32_t n_words = (shift + out_bytes + 3) >> 2;
+    const uint32_t shift = (uint32_t)((uintptr_t)dst & 15u);  // image byte j <-> byte j of the 16-byte aligned block dst sits in
+    const uint32_t n_words = ((shift + out_bytes + 15) >> 4) << 2;  // whole 16-byte groups: the image leaves in 128-bit stores
     if (n_words > stage_words || n_words <= min_words) return;  // the other launch's size class
 
     if (ci->hdr_bits == ZTS_HDR_STORED) {
@@ -213,52 +202,6 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     for (uint32_t i = tid; i < 286; i += PACK_THREADS) s_ll[i] = codes[c].ll[i];
     if (tid < 30) s_d[tid] = codes[c].d[tid];
     const uint32_t n_tok = ci->n_tokens;
-    // token segments in stream order: per tile the re-parsed tokens, then the reused speculative ones.
-    // Slot 2w = fix tokens of tile w, slot 2w+1 = its speculative tail; an empty slot shares the prefix of its
-    // successor, so "last slot with prefix <= g" always lands on a non-empty one.
-    {
-        static_assert(2 * LZ_NTILES <= PACK_THREADS, "one thread per token segment");
-        uint32_t cnt = 0, src = 0;
-        if (ci->pad) {  // fast mode: one contiguous token list (kept in the "speculative" buffer)
-            if (tid == 1) cnt = n_tok;
-            src = 0x80000000u;
-        } else if (tid < 2 * LZ_NTILES) {
-            const ZtsTile t = ci->tiles[tid >> 1];
-            if (tid & 1) {
-                cnt = (uint32_t)t.spec_count - t.spec_from;
-                src = 0x80000000u | (lz_tok_off(tid >> 1) + t.spec_from);
-            } else {
-                cnt = t.fix_count;
-                src = lz_tok_off(tid >> 1);
-            }
-        }
-        uint32_t inc = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= (unsigned)d) inc += t;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            uint32_t w = lane < PACK_WARPS ? warp_tot[lane] : 0u, winc = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, winc, d);
-                if (lane >= (unsigned)d) winc += t;
-            }
-            if (lane < PACK_WARPS) warp_tot[lane] = winc - w;
-        }
-        __syncthreads();
-        if (tid < 2 * LZ_NTILES) {
-            s_seg[tid].prefix = warp_tot[warp] + inc - cnt;
-            s_seg[tid].src = src;
-        }
-        if (tid < 2) {  // two sentinels end the forward walk of the hint
-            s_seg[2 * LZ_NTILES + tid].prefix = 0xFFFFFFFFu;
-            s_seg[2 * LZ_NTILES + tid].src = 0;
-        }
-    }
     __syncthreads();
     // header bits
     const uint32_t hdr_bits = ci->hdr_bits;
@@ -268,31 +211,17 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
         const uint32_t bit = base_bit + i * 8;
         if (b) atomicOr(&stage[bit >> 5], b << (bit & 31));  // byte-aligned inside a word: never straddles
     }
-    const uint32_t* sp = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
-    const uint32_t* fx = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
+    const uint32_t* list = tok_list + (size_t)c * LZ_LIST_PER_CHUNK;
 
     // tokens 0 .. n_tok-1, then the end-of-block symbol: warp w owns [w * per, (w + 1) * per)
     const uint32_t per = (((n_tok + 1 + PACK_WARPS - 1) / PACK_WARPS) + 31u) & ~31u;
     const uint32_t g_begin = warp * per, g_end = min(n_tok + 1, g_begin + per);
-    uint32_t seg0 = 0;
-    if (g_begin < n_tok) {  // last slot with prefix <= g_begin
-        uint32_t lo = 0, hi = 2 * LZ_NTILES;
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (s_seg[mid].prefix <= g_begin)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        seg0 = lo;
-    }
     {
         unsigned long long tot = 0;
-        uint32_t seg = seg0;
-        uint32_t t0 = fetch_token(g_begin + lane, g_end, n_tok, seg, s_seg, sp, fx);
-        uint32_t t1 = fetch_token(g_begin + 32 + lane, g_end, n_tok, seg, s_seg, sp, fx);
+        uint32_t t0 = fetch_token(g_begin + lane, g_end, n_tok, list);
+        uint32_t t1 = fetch_token(g_begin + 32 + lane, g_end, n_tok, list);
         for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
-            const uint32_t t2 = fetch_token(g0 + 64 + lane, g_end, n_tok, seg, s_seg, sp, fx);
+            const uint32_t t2 = fetch_token(g0 + 64 + lane, g_end, n_tok, list);
             tot += encode_token(t0, s_ll, s_d).nb;
             t0 = t1;
             t1 = t2;
@@ -305,11 +234,10 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     unsigned long long bitpos = (unsigned long long)base_bit + hdr_bits;
     for (uint32_t w = 0; w < warp; ++w) bitpos += range_bits[w];
     {
-        uint32_t seg = seg0;
-        uint32_t t0 = fetch_token(g_begin + lane, g_end, n_tok, seg, s_seg, sp, fx);
-        uint32_t t1 = fetch_token(g_begin + 32 + lane, g_end, n_tok, seg, s_seg, sp, fx);
+        uint32_t t0 = fetch_token(g_begin + lane, g_end, n_tok, list);
+        uint32_t t1 = fetch_token(g_begin + 32 + lane, g_end, n_tok, list);
         for (uint32_t g0 = g_begin; g0 < g_end; g0 += 32) {
-            const uint32_t t2 = fetch_token(g0 + 64 + lane, g_end, n_tok, seg, s_seg, sp, fx);
+            const uint32_t t2 = fetch_token(g0 + 64 + lane, g_end, n_tok, list);
             const PackTok t = encode_token(t0, s_ll, s_d);
             t0 = t1;
             t1 = t2;
@@ -342,18 +270,21 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
         atomicOr(&stage[(b0 + 1) >> 2], 0xFFu << (((b0 + 1) & 3) * 8));
     }
     __syncthreads();
-    // copy the image out: whole aligned words in the middle, own bytes only at the two edges
-    uint32_t* gw = reinterpret_cast<uint32_t*>(dst - shift);
+    // copy the image out: 128-bit stores for the 16-byte groups that lie inside the chunk's bytes (coalesced, 512
+    // bytes per warp instruction), own bytes only in the two edge groups
+    uint4* g4 = reinterpret_cast<uint4*>(dst - shift);
+    const uint4* s4 = reinterpret_cast<const uint4*>(stage);
     const uint32_t end_byte = shift + out_bytes;
-    for (uint32_t j = tid; j < n_words; j += PACK_THREADS) {
-        const uint32_t w = stage[j];
-        const uint32_t b_lo = j * 4, b_hi = b_lo + 4;
+    for (uint32_t j = tid; j < (n_words >> 2); j += PACK_THREADS) {
+        const uint4 q = s4[j];
+        const uint32_t b_lo = j * 16, b_hi = b_lo + 16;
         if (b_lo >= shift && b_hi <= end_byte) {
-            gw[j] = w;
+            g4[j] = q;
         } else {
-            uint8_t* gb = reinterpret_cast<uint8_t*>(gw + j);
-            for (uint32_t k = 0; k < 4; ++k)
-                if (b_lo + k >= shift && b_lo + k < end_byte) gb[k] = (uint8_t)(w >> (8 * k));
+            uint8_t* gb = reinterpret_cast<uint8_t*>(g4 + j);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            for (uint32_t k = 0; k < 16; ++k)
+                if (b_lo + k >= shift && b_lo + k < end_byte) gb[k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
         }
     }
 }
@@ -571,7 +502,8 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     rc = zts_reserve(ctx, &ctx->d_chunks, n_chunks * sizeof(ZtsChunk) + n * sizeof(uint32_t) + 64);
     if (rc) return rc;
     const size_t info_b = (wave * sizeof(ZtsChunkInfo) + 255) & ~(size_t)255;
-    const size_t tok_b = (wave * (size_t)LZ_TOK_PER_CHUNK * 4 + 255) & ~(size_t)255;
+    const size_t list_b = (wave * (size_t)LZ_LIST_PER_CHUNK * 4 + 255) & ~(size_t)255;   // token list of every chunk
+    const size_t tile_b = (zts_lz77_scratch_bytes(ctx->sm_count) + 255) & ~(size_t)255;  // per-CTA tile token scratch
     const size_t hist_b = (wave * 316 * 4 + 255) & ~(size_t)255;
     const size_t codes_b = (wave * sizeof(ZtsChunkCodes) + 255) & ~(size_t)255;
     const size_t sort_b = ((size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 255) & ~(size_t)255;
@@ -579,10 +511,9 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     const size_t gpos_b = (wave * 8 + 256 + 255) & ~(size_t)255;  // chunk offsets of the wave + the work counter
     rc = zts_reserve(ctx, &ctx->d_chunk_info, n_sets * info_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_tokens, n_sets * tok_b + 64);
+    rc = zts_reserve(ctx, &ctx->d_tokens, n_sets * list_b + 64);
     if (rc) return rc;
-    rc = zts_reserve(ctx, &ctx->d_spec, n_sets * tok_b + 64);
-    if (rc) return rc;
+    if (!fast && (rc = zts_reserve(ctx, &ctx->d_spec, n_sets * tile_b + 64))) return rc;
     rc = zts_reserve(ctx, &ctx->d_hist, n_sets * hist_b + 64);
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_codes, n_sets * codes_b + 64);
@@ -597,14 +528,14 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     unsigned long long* d_running = (unsigned long long*)ctx->d_misc.p;
     struct Set {
         ZtsChunkInfo* info;
-        uint32_t *fix, *spec, *hist, *sortT, *fastT, *counter;
+        uint32_t *list, *tile_tok, *hist, *sortT, *fastT, *counter;
         ZtsChunkCodes* codes;
         unsigned long long* gpos;
     } sets[2];
     for (int b = 0; b < n_sets; ++b) {
         sets[b].info = (ZtsChunkInfo*)((uint8_t*)ctx->d_chunk_info.p + b * info_b);
-        sets[b].fix = (uint32_t*)((uint8_t*)ctx->d_tokens.p + b * tok_b);
-        sets[b].spec = (uint32_t*)((uint8_t*)ctx->d_spec.p + b * tok_b);
+        sets[b].list = (uint32_t*)((uint8_t*)ctx->d_tokens.p + b * list_b);
+        sets[b].tile_tok = fast ? nullptr : (uint32_t*)((uint8_t*)ctx->d_spec.p + b * tile_b);
         sets[b].hist = (uint32_t*)((uint8_t*)ctx->d_hist.p + b * hist_b);
         sets[b].codes = (ZtsChunkCodes*)((uint8_t*)ctx->d_codes.p + b * codes_b);
         sets[b].sortT = (uint32_t*)((uint8_t*)ctx->d_sortT.p + b * sort_b);
@@ -685,10 +616,11 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 4 * n_waves), 0));
         if (pipe_in) ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * k), 0));
         if (fast)
-            rc = zts_lz77_fast_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.spec, S.fastT, S.hist, S.sortT, S.counter, g,
+            rc = zts_lz77_fast_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.list, S.fastT, S.hist, S.sortT, S.counter, g,
                                       depth);
         else
-            rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.spec, S.fix, S.hist, S.sortT, S.counter, g, depth);
+            rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.tile_tok, S.list, S.hist, S.sortT, S.counter, g,
+                                 depth);
         if (rc) return rc;
         rc = zts_huffman_launch(ctx, d_chunks + w0, wn, S.hist, S.info, S.codes, block_type, smallest ? 1 : 0);
         if (rc) return rc;
@@ -702,11 +634,11 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         if (n_sets == 2) ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * n_waves + k), st));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_SMALL_WORDS * 4, st>>>(
-                       d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_SMALL_WORDS, 0u, d_in));
+                       d_chunks + w0, S.info, S.codes, S.list, d_items, d_out, PACK_SMALL_WORDS, 0u, d_in));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_STAGE_WORDS * 4, st>>>(
-                       d_chunks + w0, S.info, S.codes, S.spec, S.fix, d_items, d_out, PACK_STAGE_WORDS,
-                       PACK_SMALL_WORDS, d_in));
+                       d_chunks + w0, S.info, S.codes, S.list, d_items, d_out, PACK_STAGE_WORDS, PACK_SMALL_WORDS,
+                       d_in));
         // wave k is queued: the input of wave k+1 follows (with a pageable caller buffer this waits for the copy
         // threads, so it comes behind the launches), then the output of wave k-1
         if (pipe_in && k + 1 < n_waves && (rc = wave_in_copy(k + 1))) return rc;
@@ -790,8 +722,8 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
     int rc;
     if ((rc = zts_reserve(ctx, &ctx->d_chunks, sizeof(ZtsChunk) + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_chunk_info, sizeof(ZtsChunkInfo) + 64))) return rc;
-    if ((rc = zts_reserve(ctx, &ctx->d_tokens, (size_t)LZ_TOK_PER_CHUNK * 4 + 64))) return rc;
-    if ((rc = zts_reserve(ctx, &ctx->d_spec, (size_t)LZ_TOK_PER_CHUNK * 4 + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_tokens, (size_t)LZ_LIST_PER_CHUNK * 4 + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_spec, zts_lz77_scratch_bytes(ctx->sm_count) + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_hist, 316 * 4 + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_sortT, (size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 64))) return rc;
     if ((rc = zts_reserve(ctx, &ctx->d_misc, 256))) return rc;
@@ -802,21 +734,14 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
                          (uint32_t*)ctx->d_spec.p, (uint32_t*)ctx->d_tokens.p, (uint32_t*)ctx->d_hist.p,
                          (uint32_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1, 0xFFFFFFFFu);
     if (rc) return rc;
-    std::vector<uint32_t> spec(LZ_TOK_PER_CHUNK), fix(LZ_TOK_PER_CHUNK);
     ZtsChunkInfo ci;
-    ZTS_CUDA(ctx, cudaMemcpyAsync(spec.data(), ctx->d_spec.p, spec.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    ZTS_CUDA(ctx, cudaMemcpyAsync(fix.data(), ctx->d_tokens.p, fix.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZTS_CUDA(ctx, cudaMemcpyAsync(&ci, ctx->d_chunk_info.p, sizeof ci, cudaMemcpyDeviceToHost, ctx->stream));
     ZTS_CUDA(ctx, cudaMemcpyAsync(h_hist_out, ctx->d_hist.p, 316 * 4, cudaMemcpyDeviceToHost, ctx->stream));
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    uint32_t k = 0;
-    for (uint32_t w = 0; w < LZ_NTILES; ++w) {
-        const ZtsTile t = ci.tiles[w];
-        for (uint32_t i = 0; i < t.fix_count && k <= n; ++i) h_tokens_out[k++] = fix[lz_tok_off(w) + i];
-        for (uint32_t i = t.spec_from; i < t.spec_count && k <= n; ++i) h_tokens_out[k++] = spec[lz_tok_off(w) + i];
-    }
-    *n_tokens = k;
-    if (k != ci.n_tokens) return zts_fail(ctx, ZLB_E_CUDA, "token count mismatch %u vs %u", k, ci.n_tokens);
+    if (ci.n_tokens > n) return zts_fail(ctx, ZLB_E_CUDA, "token count %u for %u bytes", ci.n_tokens, n);
+    ZTS_CUDA(ctx, cudaMemcpyAsync(h_tokens_out, ctx->d_tokens.p, (size_t)ci.n_tokens * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_tokens = ci.n_tokens;
     return ZLB_OK;
 }
 

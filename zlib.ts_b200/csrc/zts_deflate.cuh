@@ -5,15 +5,14 @@
 #define LZ_THREADS 1024
 #define LZ_WARPS 32
 #define LZ_MAX_CHUNK 65536u
-// Speculative parse tiles (warps take them from a counter in order). Sizes shrink towards the end of the chunk --
-// 96 x 512, 48 x 256, 32 x 128 positions -- so that the last tiles to finish are small ones and the warps reach
-// the barrier behind the speculative parse close together.
-#define LZ_TILE 512u                    // largest tile
-// measured on the C2 data (lz77 ms per 64 MiB mixed): 96/48/32 3.03, 80/64/64 3.04, 112/16/32 3.08, 120/8/16 3.11
+// Speculative parse tiles: every tile is parsed by one lane that owns it (8 owners per warp, 256 per CTA, see
+// zts_lz77.cu); owners take tiles from a counter, so more tiles than owners keep the warps' search batches filled
+// when the tiles of a chunk cost very different amounts (mixed data). Default: 512 tiles of 128 positions. The three
+// size classes (512, 256, 128 positions, in this order along the chunk) are kept for experiments.
 #ifndef LZ_TA
-#define LZ_TA 96u                       // tiles of 512 positions
-#define LZ_TB 48u                       // then tiles of 256
-#define LZ_TC 32u                       // then tiles of 128
+#define LZ_TA 0u                        // tiles of 512 positions
+#define LZ_TB 0u                        // then tiles of 256
+#define LZ_TC 512u                      // then tiles of 128
 #endif
 #define LZ_NTILES (LZ_TA + LZ_TB + LZ_TC)
 static_assert(LZ_TA * 512u + LZ_TB * 256u + LZ_TC * 128u == 65536u, "the tiles must cover a 64 KiB chunk");
@@ -22,7 +21,8 @@ static_assert(LZ_TA * 512u + LZ_TB * 256u + LZ_TC * 128u == 65536u, "the tiles m
 #define LZ_NB (1u << LZ_HASH_BITS)
 #define LZ_WINDOW 32768u                // WindowSize, src/LZ77.ts:8
 #define LZ_MAXLEN 258u                  // LZ77MaxLength, src/LZ77.ts:5
-#define LZ_TOK_PER_CHUNK (LZ_MAX_CHUNK + 8u * LZ_NTILES + 8u)  // token slots per chunk in the spec / fix buffers
+#define LZ_TOK_PER_CHUNK (LZ_MAX_CHUNK + 8u * LZ_NTILES + 8u)  // token slots of the per-CTA spec / fix scratch (tile t at lz_tok_off(t))
+#define LZ_LIST_PER_CHUNK (LZ_MAX_CHUNK + 8u)                  // token slots per chunk in the token list both LZ77 kernels write
 
 #define TOK_MATCH 0x80000000u           // literal: byte ; match: TOK_MATCH | (len-3) << 16 | (dist-1)
 
@@ -42,6 +42,9 @@ struct ZtsChunk {      // host-built, one per chunk
     uint32_t pad1;
 };
 
+#ifdef __CUDACC__
+#pragma nv_diag_suppress 186  // a size class may be empty (LZ_TA == 0): the comparison with zero is intended
+#endif
 // first position of tile t (t == LZ_NTILES gives the chunk size)
 __host__ __device__ __forceinline__ uint32_t lz_tile_begin(uint32_t t)
 {
@@ -65,16 +68,8 @@ __host__ __device__ __forceinline__ uint32_t lz_tile_of(uint32_t pos)
 // first token slot of tile t: a tile never holds more tokens than positions
 __host__ __device__ __forceinline__ uint32_t lz_tok_off(uint32_t t) { return lz_tile_begin(t) + 8u * t; }
 
-struct ZtsTile {
-    uint16_t fix_count;   // tokens re-parsed from the true entry point until it met the speculative parse
-    uint16_t spec_from;   // first speculative token that belongs to the true parse
-    uint16_t spec_count;  // speculative tokens of the tile
-    uint16_t pad;
-};
-
 struct ZtsChunkInfo {  // device-produced, one per chunk
-    ZtsTile tiles[LZ_NTILES];
-    uint32_t n_tokens;   // tokens of the true parse (without end-of-block)
+    uint32_t n_tokens;   // tokens of the parse (without end-of-block), contiguous at the start of the chunk's list
     uint32_t hdr_bits;   // block header bits incl. BFINAL/BTYPE
     unsigned long long body_bits;  // token bits incl. end-of-block
     uint32_t out_bytes;  // bytes this chunk contributes (incl. the join marker)

@@ -911,7 +911,7 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     // waves only pay when the items are laid out in order on both sides (then a wave is one contiguous copy each way)
     size_t n_waves = 1;
     if (hio && n >= 1024) {
-        n_waves = n >= 8192 ? 8 : 4;
+        n_waves = n >= 16384 ? 8 : 4;
         for (size_t i = 1; i < n && n_waves > 1; ++i)
             if (h_items[i].in_off < h_items[i - 1].in_off + h_items[i - 1].in_len ||
                 h_items[i].out_off < h_items[i - 1].out_off + h_items[i - 1].out_cap)
@@ -928,9 +928,12 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         return ZLB_OK;
     }
 
-    // Host buffers: the waves are decoded one after the other on the context's stream; the input of wave k+1 travels
-    // on a copy stream while wave k is decoded, and as soon as the sizes of wave k are known (its results are read
-    // back behind it, wave k+1 is already queued) what it wrote travels back on the other copy stream.
+    // Host buffers: the input of wave k+1 travels on a copy stream while wave k is decoded, and as soon as the sizes of
+    // wave k are known (its results are read back behind it, wave k+1 is already queued) what it wrote travels back on
+    // the other copy stream. The waves are launched on up to four compute streams in turn: a stream is decoded by one
+    // warp from start to end (milliseconds, whatever the batch size), so waves that do not fill the device by
+    // themselves run side by side, staggered by their input copies, and their outputs leave as each one finishes;
+    // waves that do fill it simply take over the SMs as their predecessor drains.
     rc = zts_host_streams(ctx);
     if (rc) return rc;
     rc = zts_reserve_pinned2(ctx, n * sizeof(zlb_result));
@@ -977,18 +980,23 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     for (size_t k = 0; k < n_waves; ++k) {
         size_t a, b;
         wave_range(k, a, b);
-        ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 1 + 2 * k), 0));
+        // checksums are computed on the context's stream (their tables are staged there): then every wave runs on it
+        cudaStream_t st = (kinds || k % 4 == 0) ? ctx->stream : ctx->s_aux[k % 4 - 1];
+        if (st != ctx->stream && k < 4) ZTS_CUDA(ctx, cudaStreamWaitEvent(st, ev_tab, 0));  // the item table
+        ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 1 + 2 * k), 0));
         if (a < b) {
-            rc = inflate_launch(ctx, ctx->stream, d_in, d_out, d_items + a, d_results + a, b - a, flags);
+            ctx->work = st;
+            rc = inflate_launch(ctx, st, d_in, d_out, d_items + a, d_results + a, b - a, flags);
+            ctx->work = ctx->stream;
             if (rc) return rc;
             if (kinds) {
                 rc = zts_checksum_device(ctx, d_out, d_items + a, d_results + a, h_items + a, b - a, kinds, 1);
                 if (rc) return rc;
             }
-            ZTS_CUDA(ctx, cudaMemcpyAsync(pin_res + a, d_results + a, (b - a) * sizeof(zlb_result), cudaMemcpyDeviceToHost,
-                                          ctx->stream));
+            ZTS_CUDA(ctx, cudaMemcpyAsync(pin_res + a, d_results + a, (b - a) * sizeof(zlb_result), cudaMemcpyDeviceToHost, st));
         }
-        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 + 2 * k), ctx->stream));
+        ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 + 2 * k), st));
+        if (st != ctx->stream) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 + 2 * k), 0));  // the call ends on ctx->stream
         if (k + 1 < n_waves && (rc = wave_in(k + 1))) return rc;  // behind the launches: may wait for the copy threads
         if (k > 0 && (rc = wave_out(k - 1))) return rc;
     }

@@ -9,14 +9,17 @@
 //   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
 //   2. all positions are radix-sorted (stable, 2 LSD passes, ballot-based ranking inside a warp, no atomics)
 //      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
-//   3. the chunk is cut into 176 tiles (512, then 256, then 128 positions) which the 32 warps take from a counter
-//      (segments of different entropy cost very different time) and parse speculatively, each from
-//      its tile start. A parse step first probes 32 positions at once, one per lane, for "has any
-//      earlier position with the same 3 bytes": runs of positions without one are literals and are
-//      emitted together. A position that may have candidates gets the warp-cooperative search:
-//      32 candidates per step (newest first), exact-key filter, tail-byte filter against the best
-//      so far, word-wise extension, REDUX.MAX over (len << 16 | q);
-//   4. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
+//   3. every position gets a 16-bit info word (L2-resident scratch): its rank inside its bucket (how many earlier
+//      positions the bucket holds) and a "may have a candidate" bit -- an earlier position with the same 3 bytes
+//      inside the window, found by walking back over the few hash collisions in front of the position's slot;
+//   4a. the chunk is cut into tiles (512, then 256, then 128 positions) which are parsed speculatively, each from
+//      its tile start, by GROUPS OF 8 LANES: a warp works on four tiles at once. A group reads the info words of
+//      32 positions with one coalesced load; runs of positions without a candidate are literals and are emitted
+//      together; a position with few earlier bucket entries (the common case: the median is below 8) is searched
+//      by the group, 8 candidates per step (newest first), exact-key filter, tail-byte filter against the best so
+//      far, word-wise extension, REDUX.MAX over (len << 16 | q) inside the group; positions behind long candidate
+//      lists are handed to the whole warp, 32 (or 128) candidates per step;
+//   4b. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
 //      of the previous one and is re-parsed only until it meets a speculatively parsed position
 //      (a visited-bit per position); the remainder of the speculative tokens is reused. All tiles
 //      re-enter in parallel assuming their predecessor exits where its speculative parse did; the
@@ -25,7 +28,16 @@
 //   5. litlen / dist histograms are taken over the surviving tokens.
 //
 // Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 14 KiB scratch.
+#include <stddef.h>
+
 #include "zts_deflate.cuh"
+
+#define LZ_OWNERS_MAX 8u
+#if LZ_TA == 0 && LZ_TB == 0
+typedef uint8_t LZ_COUNT_T;    // tokens of a 128-position tile
+#else
+typedef uint16_t LZ_COUNT_T;
+#endif
 
 struct LzSmem {
     // byte offsets into dynamic shared memory
@@ -42,6 +54,9 @@ struct LzSmem {
     static constexpr uint32_t TOTAL = MISC_OFF + MISC_BYTES;
 };
 
+// Per-tile tables. Positions are kept relative to the tile's first position (an exit lies at most a maximum match
+// behind the tile: < 128 + 258; an entry at most 257 behind its first position), counts fit a byte (<= 128 tokens per
+// tile when the default 128-position tiles are used; larger tiles are checked by the static_assert below).
 struct LzMisc {
     unsigned long long mbar;
     uint32_t chunk;
@@ -49,16 +64,26 @@ struct LzMisc {
     uint32_t tile_next2;             // next tile of the re-entry pass
     uint32_t warp_tot[32];
     uint32_t warp_min[32];
-    uint32_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)
-    uint32_t fix_exit[LZ_NTILES];    // exit of the tile for the entry it was last parsed from
-    uint32_t entry_used[LZ_NTILES];  // that entry
+    uint16_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)   } the two arrays double as
+    uint16_t fix_exit[LZ_NTILES];    // exit of the tile for the entry it was last parsed from      } u32 tok_off[] in phase 5
+    uint16_t entry_used[LZ_NTILES];  // that entry
+    uint16_t tile_start[LZ_NTILES];  // where the tile's speculative parse starts
     uint32_t start_mask[(LZ_NTILES + 31) / 32];  // tiles that start a chain of wrongly entered tiles
-    uint16_t spec_count[LZ_NTILES];
-    uint16_t fix_count[LZ_NTILES];
-    uint16_t spec_from[LZ_NTILES];
+    LZ_COUNT_T spec_count[LZ_NTILES];
+    LZ_COUNT_T fix_count[LZ_NTILES];
+    LZ_COUNT_T spec_from[LZ_NTILES];
+    uint8_t spec_done[LZ_NTILES];    // set (release) when a tile's speculative parse and its tables are complete
     uint32_t hist[316];
     uint32_t n_tokens;
-    uint8_t spec_done[LZ_NTILES];    // set (release) when a tile's speculative parse and its tables are complete
+};
+
+struct LzBatch {  // one per warp: the searches its tile owners post in a round
+    uint32_t end[LZ_OWNERS_MAX];    // candidates of requests 0 .. r (inclusive running sum)
+    uint32_t start[LZ_OWNERS_MAX];  // candidates of requests 0 .. r-1
+    uint32_t p[LZ_OWNERS_MAX];      // position searched
+    uint32_t slot[LZ_OWNERS_MAX];   // its slot in the sorted index: the candidates sit in front of it, newest first
+    uint32_t pw[LZ_OWNERS_MAX], pw1[LZ_OWNERS_MAX];  // the 8 bytes at p
+    uint32_t best[LZ_OWNERS_MAX];   // max of len << 16 | q over the candidates
 };
 
 // The radix scratch T is the one global buffer a CTA keeps re-using (256 KiB per chunk, written and read twice):
@@ -208,12 +233,73 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
     return min(k, maxlen);
 }
 
+// ---- per-position info ------------------------------------------------------------------------------------------
+// Built once per chunk from the sorted index, one thread per slot:
+//   P[p]      = slot of p in the sorted index | rank of p inside its bucket << 16  (rank = earlier bucket entries; the
+//               candidates of p are the `rank` slots in front of its own). L2-resident scratch, 4 bytes per position.
+//   hasbits   = one bit per position in shared memory: "may have a candidate" -- an earlier position with the same
+//               3 bytes inside the window, found by walking back over the hash collisions in front of the slot.
+#define LZ_HAS_WALK 16u        // collisions walked over before a position is declared "may have a candidate"
+#ifndef LZ_OWNERS
+#define LZ_OWNERS 8u           // lanes of a warp that own a tile each (lanes 0 .. LZ_OWNERS-1): power of two, <= 16
+#endif
+#ifndef LZ_BATCH_CAP
+#define LZ_BATCH_CAP 64u       // a search over at most this many earlier bucket entries goes into the warp's batch
+#endif
+
+// one thread per slot of the sorted index (all threads of the block call it; `hasbits` zeroed, barrier behind it)
+__device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __restrict__ sorted,
+                                              const uint16_t* __restrict__ bstart, uint32_t m, uint32_t n, uint32_t* P,
+                                              uint32_t* hasbits, unsigned long long keep)
+{
+    const unsigned tid = threadIdx.x;
+    for (uint32_t p = m + tid; p < n; p += LZ_THREADS) st_u32_hint(&P[p], 0u, keep);  // positions without a slot (P has LZ_MAX_CHUNK entries per CTA)
+    for (uint32_t i0 = 0; i0 < m; i0 += LZ_THREADS) {  // whole warps stay in the loop (warp votes below)
+        const uint32_t i = i0 + tid;
+        const bool valid = i < m;
+        bool has = false;
+        uint32_t p = 0xFFFFFFFFu;
+        if (valid) {
+            p = sorted[i];
+            const uint32_t key = ld_u32(S, p) & 0xFFFFFFu;
+            const uint32_t lo = bstart[hash13(key)];
+            if (p + 3u < n) {  // src/LZ77.ts:228: the last three positions are never searched
+                // the nearest earlier position with the same 3 bytes sits a few slots back (hash collisions in
+                // between); it decides: older ones are further away
+                uint32_t j = i, steps = 0;
+                while (j > lo) {
+                    --j;
+                    const uint32_t q = sorted[j];
+                    if (S[q] == (uint8_t)key && (ld_u32(S, q) & 0xFFFFFFu) == key) {  // one byte decides for most collisions
+                        has = p - q <= LZ_WINDOW;
+                        break;
+                    }
+                    if (++steps >= LZ_HAS_WALK) {
+                        has = true;  // undecided: the search will tell
+                        break;
+                    }
+                }
+            }
+            st_u32_hint(&P[p], i | ((i - lo) << 16), keep);
+        }
+        // inside a long bucket consecutive slots are consecutive positions (runs of one byte): one atomic per warp then
+        const uint32_t w = p >> 5, w0 = __shfl_sync(0xFFFFFFFFu, w, 0);
+        const uint32_t bit = has ? 1u << (p & 31u) : 0u;
+        if (__all_sync(0xFFFFFFFFu, w == w0)) {
+            const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, bit);
+            if ((tid & 31u) == 0 && bits) atomicOr(&hasbits[w0], bits);
+        } else if (bit) {
+            atomicOr(&hasbits[w], bit);
+        }
+    }
+}
+
 // ---- warp-cooperative longest/nearest match search at position p (requires p + 3 < n) ----------
 // returns (len << 16) | dist, or 0 when no candidate exists (src/LZ77.ts:157-194 + :242)
-// `depth` = how many candidates (newest first) are looked at: 0xFFFFFFFF in the reference-compatible mode (all of
-// them, like the reference), a small multiple of 32 in the fast mode.
-__device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __restrict__ sorted,
-                              const uint16_t* __restrict__ bstart, uint32_t p, uint32_t n, uint32_t depth)
+// The candidates are the slots [lo, cur) of the sorted index, newest (cur - 1) first;
+// `depth` = how many of them are looked at: 0xFFFFFFFF = all, like the reference.
+__device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t* __restrict__ sorted, uint32_t lo,
+                                                   uint32_t cur, uint32_t p, uint32_t n, uint32_t depth)
 {
     const unsigned lane = zts_lane();
     const uint32_t pw = ld_u32(S, p);
@@ -237,60 +323,6 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
             }
             if (__all_sync(0xFFFFFFFFu, same)) return (maxlen << 16) | 1u;
         }
-    }
-    const uint32_t h = hash13(pw & 0xFFFFFFu);
-    const uint32_t lo = bstart[h];
-    uint32_t a = lo, b = bstart[h + 1];
-    if (b - lo <= 32u) {
-        // the whole bucket fits one step (the common case): lane j takes entry j, whatever its position; entries at
-        // or behind p and outside the window drop out, REDUX.MAX over len << 16 | q picks longest, then nearest
-        const uint32_t pw1s = ld_u32(S, p + 4);
-        uint32_t key = 0;
-        if (lo + lane < b) {
-            const uint32_t q = sorted[lo + lane];
-            if (q < p && p - q <= LZ_WINDOW) key = (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q;
-        }
-        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
-        if ((m >> 16) < 3u) return 0;
-        return (m & 0xFFFF0000u) | (p - (m & 0xFFFFu));
-    }
-    if (b - lo <= 64u) {
-        // up to 64 entries: two per lane in one step, no slot search -- cheaper than ranking p inside the bucket and
-        // stepping through the candidates in front of it (measured against 3 and 4 entries per lane: no better)
-        const uint32_t pw1s = ld_u32(S, p + 4);
-        uint32_t key = 0;
-        {
-            const uint32_t q = sorted[lo + lane];  // lo + lane < b: the bucket has more than 32 entries
-            if (q < p && p - q <= LZ_WINDOW) key = (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q;
-        }
-        if (lo + 32u + lane < b) {
-            const uint32_t q = sorted[lo + 32u + lane];
-            if (q < p && p - q <= LZ_WINDOW) key = max(key, (lz_match_len(S, q, p, pw, pw1s, maxlen) << 16) | q);
-        }
-        const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
-        if ((m >> 16) < 3u) return 0;
-        return (m & 0xFFFF0000u) | (p - (m & 0xFFFFu));
-    }
-    // slot of p inside its bucket (positions ascending): 32-way search
-    while (b - a > 32) {
-        const uint32_t step = (b - a + 31) >> 5;
-        const uint32_t s = a + lane * step;
-        const bool less = (s < b) && (sorted[s] < p);
-        const uint32_t k = __popc(__ballot_sync(0xFFFFFFFFu, less));
-        if (k == 0) {
-            b = a;
-            break;
-        }
-        const uint32_t na = a + (k - 1) * step + 1;
-        const uint32_t nb = min(b, a + k * step);
-        a = na;
-        b = nb;
-    }
-    uint32_t cur;
-    {
-        const uint32_t s = a + lane;
-        const bool less = (s < b) && (sorted[s] < p);
-        cur = a + __popc(__ballot_sync(0xFFFFFFFFu, less));
     }
     const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
@@ -329,19 +361,24 @@ __device__ __forceinline__ uint32_t lz_search(const LzS& S, const uint16_t* __re
         if (best_len >= maxlen) break;                          // :189 (258) or capped by the input end
         if (__any_sync(0xFFFFFFFFu, act && !inwin)) break;      // older ones are outside the window (:223)
         cur -= cnt;
-        if (depth <= 32u) break;                                // fast mode: candidate budget spent
+        if (depth <= 32u) break;                                // candidate budget spent
         depth -= 32u;
     }
     if (best_len < 3) return 0;
     return (best_len << 16) | (p - (best & 0xFFFFu));
 }
 
-// one greedy step at parse position p: emits the token, returns the next parse position
-__device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                            uint32_t p, uint32_t n, uint32_t depth, uint32_t* tok_out)
+// one greedy step of the whole warp at parse position p: emits the token, returns the next parse position
+__device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted, const uint32_t* P,
+                                            const uint32_t* hasbits, unsigned long long keep, uint32_t p, uint32_t n,
+                                            uint32_t depth, uint32_t* tok_out)
 {
     uint32_t r = 0;
-    if (p + 3 < n) r = lz_search(S, sorted, bstart, p, n, depth);  // src/LZ77.ts:228: no search in the last 3 bytes
+    if ((hasbits[p >> 5] >> (p & 31u)) & 1u) {  // never set for the last three positions (src/LZ77.ts:228)
+        const uint32_t info = ld_u32_hint(&P[p], keep);
+        const uint32_t slot = info & 0xFFFFu;
+        r = lz_search_from(S, sorted, slot - (info >> 16), slot, p, n, depth);
+    }
     if (r) {
         const uint32_t len = r >> 16, dist = r & 0xFFFFu;
         *tok_out = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
@@ -349,25 +386,6 @@ __device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted
     }
     *tok_out = S[p];
     return p + 1;
-}
-
-// Lane-private probe: may position pl (pl + 3 < n) have a candidate, i.e. an earlier position inside the
-// window with the same 3 bytes (a non-empty table[key] list after pruning, src/LZ77.ts:211-225,242)?
-// Exact for buckets of at most LZ_PROBE_MAX entries, "maybe" (true) for longer ones.
-#define LZ_PROBE_MAX 20u  // measured 12 / 16 / 20 / 28: random data 2.92 / 1.86 / 1.76 / 1.76 ms per 64 MiB, text 3.72 / 3.75 / 3.79 / 3.85
-__device__ __forceinline__ bool lz_probe(const LzS& S, const uint16_t* __restrict__ sorted,
-                                         const uint16_t* __restrict__ bstart, uint32_t pl)
-{
-    const uint32_t pw = ld_u32(S, pl) & 0xFFFFFFu;
-    const uint32_t h = hash13(pw);
-    const uint32_t lo = bstart[h], hi = bstart[h + 1];
-    if (hi - lo > LZ_PROBE_MAX) return true;
-    for (uint32_t s = lo; s < hi; ++s) {
-        const uint32_t q = sorted[s];
-        if (q >= pl) break;  // ascending positions: the rest is not earlier
-        if (pl - q <= LZ_WINDOW && (ld_u32(S, q) & 0xFFFFFFu) == pw) return true;
-    }
-    return false;
 }
 
 // Where should the speculative parse of a tile that begins inside a run of one byte start? Inside such a run every
@@ -427,59 +445,11 @@ __device__ __forceinline__ uint32_t lz_run_aligned_start(const LzS& S, uint32_t 
     return p0;
 }
 
-// Speculative parse of tile [t_begin, t_end) from p0 >= t_begin: tokens to tok_out, visited bit per parsed position.
-// Returns the exit position (>= t_end); *count_out = tokens written.
-__device__ __forceinline__ uint32_t lz_parse_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
-                                                  uint32_t t_begin, uint32_t t_end, uint32_t p0, uint32_t n,
-                                                  uint32_t depth, uint32_t* __restrict__ tok_out, uint32_t* visited,
-                                                  uint32_t* count_out)
-{
-    const unsigned lane = zts_lane();
-    uint32_t p = p0;                 // t_begin, or the first position behind the history inside the first tile
-    uint32_t* tp = tok_out;          // next token slot
-    uint32_t vis = 0;                // lane j keeps the visited bits of positions [t_begin + 32 j, + 32): 16 lanes
-    const uint32_t my_lo = lane * 32u;
-    uint32_t wbase = p - 32u, wmask = 0;  // forces a probe at the first step
-    while (p < t_end) {
-        if (p - wbase >= 32u) {
-            // probe the next 32 positions, one per lane
-            wbase = p;
-            const uint32_t pl = p + lane;
-            bool hc = false;
-            if (pl < t_end && pl + 3 < n) hc = lz_probe(S, sorted, bstart, pl);
-            wmask = __ballot_sync(0xFFFFFFFFu, hc);
-        }
-        const uint32_t off = p - wbase;
-        const uint32_t m = wmask >> off;  // bit 0 <-> position p
-        const uint32_t avail = min(32u - off, t_end - p);
-        const uint32_t k = m ? min((uint32_t)__ffs((int)m) - 1u, avail) : avail;
-        const uint32_t rel = p - t_begin;
-        if (k) {
-            // k positions without any candidate: k literals (src/LZ77.ts:267-272)
-            if (lane < k) tp[lane] = S[p + lane];
-            tp += k;
-            // bits [rel, rel + k) of the tile, cut to this lane's word
-            const uint32_t a = max(rel, my_lo), e = min(rel + k, my_lo + 32u);
-            if (a < e) vis |= (0xFFFFFFFFu >> (32u - (e - a))) << (a - my_lo);
-            p += k;
-            continue;
-        }
-        uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
-        if (lane == 0) *tp = tok;
-        ++tp;
-        if (lane == (rel >> 5)) vis |= 1u << (rel & 31u);
-        p = np;
-    }
-    if (lane < ((t_end - t_begin + 31u) >> 5)) visited[(t_begin >> 5) + lane] = vis;
-    *count_out = (uint32_t)(tp - tok_out);
-    return p;
-}
-
 // True parse of a tile entered at `entry` (>= the tile's begin is not required: entry may lie past it):
 // re-parse until a position the speculative parse visited, from there its tokens are reused.
 // Writes fix tokens, returns the exit; *nfix_out / *from_out describe the splice.
-__device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted, const uint16_t* bstart,
+__device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t* sorted,
+                                                   const uint32_t* P, const uint32_t* hasbits, unsigned long long keep,
                                                    uint32_t entry, uint32_t t_begin, uint32_t t_end, uint32_t n,
                                                    uint32_t depth, uint32_t* __restrict__ fix_out, const uint32_t* visited,
                                                    uint32_t spec_count, uint32_t spec_exit, uint32_t* nfix_out,
@@ -502,7 +472,7 @@ __device__ __forceinline__ uint32_t lz_resync_tile(const LzS& S, const uint16_t*
             break;
         }
         uint32_t tok;
-        const uint32_t np = lz_step(S, sorted, bstart, p, n, depth, &tok);
+        const uint32_t np = lz_step(S, sorted, P, hasbits, keep, p, n, depth, &tok);
         if (lane == 0) fix_out[nfix] = tok;
         nfix++;
         p = np;
@@ -744,7 +714,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
 
 __global__ void __launch_bounds__(LZ_THREADS, 1)
 lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ chunks, uint32_t n_chunks,
-                  ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ spec_tok, uint32_t* __restrict__ fix_tok,
+                  ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ tile_tok, uint32_t* __restrict__ list_out,
                   uint32_t* __restrict__ hist_out, uint32_t* __restrict__ sortT, uint32_t* __restrict__ work_counter,
                   uint32_t depth)
 {
@@ -753,11 +723,16 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
     uint16_t* sorted = reinterpret_cast<uint16_t*>(smem + LzSmem::SORTED_OFF);
     uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);
     uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::AUX_OFF);   // [32 warps][128 digits]
-    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position
+    uint32_t* hasbits = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position (+ 1 padding word: the misc area follows)
+    // once the info words are built the bucket starts are dead: visited bits and the warps' batch tables take their place
+    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::BSTART_OFF); // [2048] bit per position
+    LzBatch* batch = reinterpret_cast<LzBatch*>(smem + LzSmem::BSTART_OFF + 8192);
+    static_assert(8192 + sizeof(LzBatch) * LZ_WARPS <= LzSmem::BSTART_BYTES, "batch tables must fit behind the visited bits");
     LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint32_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;  // per-CTA radix temp (L2 resident): pos | hash << 16
+    const unsigned long long keep = l2_policy_keep();
     uint32_t phase = 0;
 
     if (tid == 0) {
@@ -785,7 +760,81 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         (void)m;
         const uint32_t t0 = base ? lz_tile_of(base) : 0u;  // first tile with anything to parse
 
-        // ---- 3. speculative parse: warps take tiles from a shared counter
+        // ---- 3. per-position info: slot and bucket rank into the L2 scratch (which the radix sort no longer needs),
+        //         may-have-a-candidate bits into shared memory
+        uint32_t* P = T;
+        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) hasbits[i] = 0;
+        __syncthreads();
+        lz_build_info(SV, sorted, bstart, m, n, P, hasbits, keep);
+        const uint32_t n_tiles = lz_tile_count(n);
+        __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the batch tables
+        // Where the speculative parse of every tile starts. A tile that begins inside a run of one byte starts at the
+        // run's 258-byte phase: inside such a run every match is a maximum-length distance-1 match, so the true parse
+        // visits run_start + 1 + 258 k, and starting there makes the predecessor's exit land on a parsed position (no
+        // chain of wrongly entered tiles across the run). Purely a heuristic choice: any start >= the tile's first
+        // position is a valid speculative parse. The run boundaries ("change points": S[p] != S[p - 1]) around every
+        // tile boundary come from two block scans over 64-byte blocks: the last change point at or before the end of a
+        // block, the first one at or behind its start.
+        {
+            uint16_t* lastcp = reinterpret_cast<uint16_t*>(batch);  // [1024] (the batch tables are not in use yet)
+            uint16_t* nextcp = lastcp + LZ_THREADS;                 // [1024]; 0xFFFF = none
+            static_assert(4u * LZ_THREADS <= sizeof(LzBatch) * LZ_WARPS, "scan arrays must fit the batch area");
+            const uint32_t lo = 64u * tid;
+            uint32_t last = 0xFFFFu, next = 0xFFFFu;
+            if (lo < n) {
+                uint32_t prevb = lo ? SV[lo - 1] : ~(uint32_t)SV[0];  // position 0 is a change point
+#pragma unroll 4
+                for (uint32_t k = 0; k < 16; ++k) {
+                    const uint32_t at = lo + 4u * k;
+                    if (at >= n) break;
+                    const uint32_t w = ld_u32(SV, at);
+                    uint32_t x = w ^ ((w << 8) | (prevb & 0xFFu));  // byte j != 0  <=>  S[at + j] != S[at + j - 1]
+                    const uint32_t nb = n - at;
+                    if (nb < 4u) x &= (1u << (8u * nb)) - 1u;
+                    if (x) {
+                        if (next == 0xFFFFu) next = at + (((uint32_t)__ffs((int)x) - 1u) >> 3);
+                        last = at + ((31u - (uint32_t)__clz((int)x)) >> 3);
+                    }
+                    prevb = w >> 24;
+                }
+            }
+            // inclusive prefix "last" (max, with none = 0xFFFF treated as -1) and suffix "next" (min) over the threads
+            int lastv = last == 0xFFFFu ? -1 : (int)last;
+            uint32_t nextv = next;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int a = __shfl_up_sync(0xFFFFFFFFu, lastv, d);
+                const uint32_t b = __shfl_down_sync(0xFFFFFFFFu, nextv, d);
+                if ((int)lane >= d) lastv = max(lastv, a);
+                if ((int)lane + d < 32) nextv = min(nextv, b);
+            }
+            if (lane == 31) M->warp_tot[warp] = (uint32_t)lastv;
+            if (lane == 0) M->warp_min[warp] = nextv;
+            __syncthreads();
+            int carry = -1;
+            uint32_t carry_n = 0xFFFFu;
+            for (uint32_t w2 = 0; w2 < warp; ++w2) carry = max(carry, (int)M->warp_tot[w2]);
+            for (uint32_t w2 = warp + 1; w2 < LZ_WARPS; ++w2) carry_n = min(carry_n, M->warp_min[w2]);
+            lastcp[tid] = (uint16_t)max(lastv, carry);  // -1 -> 0xFFFF
+            nextcp[tid] = (uint16_t)min(nextv, carry_n);
+            __syncthreads();
+            for (uint32_t t = t0 + tid; t < n_tiles; t += LZ_THREADS) {
+                const uint32_t t_begin = lz_tile_begin(t);
+                uint32_t p0 = max(t_begin, base);  // the first tile starts where the parse starts
+                if (t != t0 && t_begin >= 4u && t_begin + LZ_MAXLEN + 4u <= n) {
+                    const uint32_t r0 = lastcp[(t_begin - 1u) >> 6];   // first byte of the run that holds t_begin - 1
+                    uint32_t nx = nextcp[t_begin >> 6];                // first change point at or behind t_begin
+                    if (nx == 0xFFFFu) nx = n;
+                    if (r0 != 0xFFFFu && nx >= t_begin + 3u) {
+                        const uint32_t phase = (t_begin - (r0 + 1u)) % LZ_MAXLEN;
+                        const uint32_t cand = t_begin + (LZ_MAXLEN - phase);
+                        if (phase && cand + 3u <= nx) p0 = cand;       // the run reaches the aligned position and 3 bytes on
+                    }
+                }
+                M->tile_start[t] = (uint16_t)(p0 - t_begin);  // < 258
+            }
+        }
+        __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the batch tables
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
         if (tid < LZ_NTILES) M->spec_done[tid] = 0;
         if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
@@ -793,79 +842,218 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             M->tile_next = t0;
             M->tile_next2 = t0;
         }
+        __threadfence_block();
         __syncthreads();
-        const uint32_t n_tiles = lz_tile_count(n);
-        uint32_t* spec_c = spec_tok + (size_t)c * LZ_TOK_PER_CHUNK;
-        uint32_t* fix_c = fix_tok + (size_t)c * LZ_TOK_PER_CHUNK;
+        uint32_t* spec_c = tile_tok + (size_t)blockIdx.x * (2u * LZ_TOK_PER_CHUNK);  // per-CTA scratch: speculative tokens per tile,
+        uint32_t* fix_c = spec_c + LZ_TOK_PER_CHUNK;                                  // re-parsed tokens per tile
+        uint32_t* list_c = list_out + (size_t)c * LZ_LIST_PER_CHUNK;                   // the chunk's token list (phase 5)
         ZtsChunkInfo* ci = info + c;
-        for (;;) {
-            uint32_t t = 0;
-            if (lane == 0) t = atomicAdd(&M->tile_next, 1u);
-            t = __shfl_sync(0xFFFFFFFFu, t, 0);
-            if (t >= n_tiles) break;
-            const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
-            uint32_t cnt;
-            uint32_t p0 = max(t_begin, base);
-            if (t != t0) p0 = lz_run_aligned_start(SV, t_begin, t_end, n);  // the first tile starts where the parse starts
-            const uint32_t ex = lz_parse_tile(SV, sorted, bstart, t_begin, t_end, p0, n, depth, spec_c + lz_tok_off(t),
-                                              visited, &cnt);
-            if (lane == 0) {
-                M->spec_exit[t] = ex;
-                M->spec_count[t] = (uint16_t)cnt;
-            }
-            // publish the tile: its visited bits and tables before the flag (no block barrier behind this loop)
-            __threadfence_block();
-            __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();  // release: the other lanes' writes, ordered before this point by the warp barrier
-                *(volatile uint8_t*)&M->spec_done[t] = 1;
-            }
-        }
 
-        // ---- 4a. every tile re-enters at its predecessor's speculative exit (in parallel); this is already
-        //          the true parse wherever the predecessor did converge to its speculative parse. A warp that runs
-        //          out of speculative tiles starts here at once: a tile only needs itself and its predecessor parsed
-        //          (all tiles have been taken by then, so the ones it waits for are being worked on).
-        for (;;) {
-            uint32_t w = 0;
-            if (lane == 0) w = atomicAdd(&M->tile_next2, 1u);
-            w = __shfl_sync(0xFFFFFFFFu, w, 0);
-            if (w >= n_tiles) break;
-            {
-                uint32_t spins = 0;
-                while (*(volatile uint8_t*)&M->spec_done[w] == 0 || (w > t0 && *(volatile uint8_t*)&M->spec_done[w - 1] == 0)) {
-                    __nanosleep(40);
-                    if (++spins > (1u << 26)) __trap();  // never hang the device
+        // ---- 4a. speculative parse of every tile, then re-entry at the predecessor's speculative exit.
+        //      Lanes 0 .. LZ_OWNERS-1 of every warp OWN a tile each: the parse state (position, token pointer) is
+        //      lane-private, a run of literals is written by its owner alone. What a parse step costs is the match
+        //      search, and that is shared: every round the owners post their positions, the candidates of all of them
+        //      (the `rank` slots in front of each position's own slot) form one list, and the 32 lanes of the warp
+        //      evaluate it 32 candidates at a time whatever request they belong to -- exact key, window, match length,
+        //      shared-memory atomicMax of (len << 16 | q) per request = longest, then nearest. Requests behind long
+        //      candidate lists (ends of runs, low-entropy records) go to the warp-cooperative search with its tail-byte
+        //      filter instead, one after the other. An owner that runs out of speculative tiles starts re-entering at
+        //      once; a re-entry tile only needs itself and its predecessor parsed (ready flags, polled once a round).
+        {
+            enum { G_IDLE = 0, G_SPEC = 1, G_RESYNC = 2, G_WAIT = 3, G_DONE = 4 };
+            LzBatch* B = batch + warp;
+            const bool owner = lane < LZ_OWNERS;
+            uint32_t mode = owner ? G_IDLE : G_DONE, t = 0, t_begin = 0, t_end = 0, p = 0, entry = 0, from = 0;
+            uint32_t* tp = nullptr;   // next token slot
+            uint32_t* tp0 = nullptr;  // first token slot of the tile
+            uint32_t pinfo = 0;       // P[p], requested as soon as p is known (a round ahead of its use)
+            bool spec_left = true;
+            for (;;) {
+                // -- work
+                if (mode == G_IDLE) {
+                    uint32_t nt = n_tiles;
+                    if (spec_left) nt = atomicAdd(&M->tile_next, 1u);
+                    if (nt < n_tiles) {
+                        t = nt;
+                        t_begin = lz_tile_begin(t);
+                        t_end = min(n, lz_tile_begin(t + 1));
+                        p = t_begin + M->tile_start[t];
+                        if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                        tp0 = tp = spec_c + lz_tok_off(t);
+                        mode = G_SPEC;
+                    } else {
+                        spec_left = false;
+                        nt = atomicAdd(&M->tile_next2, 1u);
+                        t = nt;
+                        mode = nt < n_tiles ? G_WAIT : G_DONE;
+                    }
                 }
-                __threadfence_block();
-            }
-            if (w == t0) {  // the first tile needs no re-entry
-                if (lane == 0) {
-                    M->entry_used[t0] = base;
-                    M->fix_exit[t0] = M->spec_exit[t0];
-                    M->fix_count[t0] = 0;
-                    M->spec_from[t0] = 0;
+                if (mode == G_WAIT) {
+                    const bool ready = *(volatile uint8_t*)&M->spec_done[t] != 0 &&
+                                       (t == t0 || *(volatile uint8_t*)&M->spec_done[t - 1] != 0);
+                    if (ready) {
+                        __threadfence_block();
+                        if (t == t0) {  // the first tile needs no re-entry
+                            M->entry_used[t0] = (uint16_t)(base - lz_tile_begin(t0));
+                            M->fix_exit[t0] = M->spec_exit[t0];
+                            M->fix_count[t0] = 0;
+                            M->spec_from[t0] = 0;
+                            mode = G_IDLE;
+                        } else {
+                            t_begin = lz_tile_begin(t);
+                            t_end = min(n, lz_tile_begin(t + 1));
+                            p = entry = lz_tile_begin(t - 1) + M->spec_exit[t - 1];
+                            if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                            from = M->spec_count[t];
+                            tp0 = tp = fix_c + lz_tok_off(t);
+                            mode = G_RESYNC;
+                        }
+                    }
                 }
-                continue;
-            }
-            const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
-            const uint32_t entry = M->spec_exit[w - 1];
-            uint32_t nfix, from;
-            const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
-                                               visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
-            if (lane == 0) {
-                M->entry_used[w] = entry;
-                M->fix_exit[w] = ex;
-                M->fix_count[w] = (uint16_t)nfix;
-                M->spec_from[w] = (uint16_t)from;
+                const bool active = mode == G_SPEC || mode == G_RESYNC;
+                if (!__any_sync(0xFFFFFFFFu, active)) {
+                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE)) break;
+                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE || mode == G_WAIT)) __nanosleep(256);
+                    continue;
+                }
+
+                // -- owners: finish the tile, write a run of literals, or post a search
+                bool req = false;
+                uint32_t slot = 0, rank = 0;
+                if (active) {
+                    bool finish = p >= t_end;
+                    uint32_t vlimit = 32u;
+                    if (!finish && mode == G_RESYNC) {
+                        const uint32_t vm = __funnelshift_r(visited[p >> 5], visited[(p >> 5) + 1u], p & 31u);  // (one word of slack behind the bits)
+                        if (vm & 1u) {
+                            // met the speculative parse: its tokens from this position on are the true ones
+                            uint32_t idx = 0;
+                            for (uint32_t wd = t_begin >> 5; wd <= (p >> 5); ++wd) {
+                                uint32_t bits = visited[wd];
+                                if (wd == (p >> 5)) bits &= (1u << (p & 31u)) - 1u;
+                                idx += __popc(bits);
+                            }
+                            from = idx;
+                            p = t_begin + M->spec_exit[t];
+                            finish = true;
+                        } else if (vm) {
+                            vlimit = (uint32_t)__ffs((int)vm) - 1u;  // a run of literals stops in front of a visited position
+                        }
+                    }
+                    if (finish) {
+                        if (mode == G_SPEC) {
+                            M->spec_exit[t] = (uint16_t)(p - t_begin);
+                            M->spec_count[t] = (LZ_COUNT_T)(tp - tp0);
+                            // publish the tile: its visited bits (this lane's own stores) and tables before the flag
+                            __threadfence_block();
+                            *(volatile uint8_t*)&M->spec_done[t] = 1;
+                        } else {
+                            M->entry_used[t] = (uint16_t)(entry - t_begin);
+                            M->fix_exit[t] = (uint16_t)(p - t_begin);
+                            M->fix_count[t] = (LZ_COUNT_T)(tp - tp0);
+                            M->spec_from[t] = (LZ_COUNT_T)from;
+                        }
+                        mode = G_IDLE;
+                    } else {
+                        // may-have-a-candidate bits of the 32 positions from p on
+                        const uint32_t w = p >> 5, off = p & 31u;
+                        const uint32_t mm = __funnelshift_r(hasbits[w], hasbits[w + 1], off);  // w + 1 <= 2048: padding word
+                        const uint32_t avail = min(min(32u, t_end - p), vlimit);
+                        const uint32_t k = mm ? min((uint32_t)__ffs((int)mm) - 1u, avail) : avail;
+                        if (k) {
+                            // k positions without any candidate: k literals (src/LZ77.ts:267-272)
+                            for (uint32_t o = 0; o < k; ++o) tp[o] = SV[p + o];
+                            tp += k;
+                            if (mode == G_SPEC) {  // visited bits [p, p + k): at most two words, this lane's own tile
+                                const unsigned long long bits = (0xFFFFFFFFFFFFFFFFull >> (64u - k)) << off;
+                                visited[w] |= (uint32_t)bits;
+                                if (bits >> 32) visited[w + 1] |= (uint32_t)(bits >> 32);
+                            }
+                            p += k;
+                            if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                        } else {
+                            slot = pinfo & 0xFFFFu;
+                            rank = pinfo >> 16;
+                            req = true;
+                        }
+                    }
+                }
+                // -- the batch: every request with a short candidate list
+                const bool in_batch = req && rank <= LZ_BATCH_CAP;
+                uint32_t incl = in_batch ? rank : 0u;
+#pragma unroll
+                for (uint32_t d = 1; d < LZ_OWNERS; d <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+                    if (lane >= d) incl += u;
+                }
+                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, LZ_OWNERS - 1);
+                if (total) {
+                    if (owner) {
+                        B->end[lane] = incl;
+                        B->start[lane] = incl - (in_batch ? rank : 0u);
+                        B->best[lane] = 0;
+                        if (in_batch) {
+                            B->p[lane] = p;
+                            B->slot[lane] = slot;
+                            B->pw[lane] = ld_u32(SV, p);
+                            B->pw1[lane] = ld_u32(SV, p + 4);
+                        }
+                    }
+                    __syncwarp();
+                    for (uint32_t i = lane; i < total; i += 32u) {
+                        // request of candidate i: the first one whose list ends behind i
+                        uint32_t r = 0;
+#pragma unroll
+                        for (uint32_t h = LZ_OWNERS / 2; h >= 1; h >>= 1)
+                            if (B->end[r + h - 1] <= i) r += h;
+                        const uint32_t rp = B->p[r];
+                        const uint32_t q = sorted[B->slot[r] - 1u - (i - B->start[r])];  // start = newest candidate
+                        if (rp - q <= LZ_WINDOW) {
+                            const uint32_t len = lz_match_len(SV, q, rp, B->pw[r], B->pw1[r], min(LZ_MAXLEN, n - rp));
+                            if (len >= 3u) atomicMax(&B->best[r], (len << 16) | q);  // longest, then nearest
+                        }
+                    }
+                    __syncwarp();
+                }
+                uint32_t res = 0;
+                if (in_batch && rank) {  // rank == 0: nothing was posted (and the table may not have been reset)
+                    const uint32_t bm = B->best[lane];
+                    if (bm) res = (bm & 0xFFFF0000u) | (p - (bm & 0xFFFFu));
+                }
+                // -- searches behind long candidate lists: the whole warp, one request after the other
+                unsigned bigm = __ballot_sync(0xFFFFFFFFu, req && !in_batch);
+                while (bigm) {
+                    const int src = __ffs((int)bigm) - 1;
+                    bigm &= bigm - 1u;
+                    const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, src), bs = __shfl_sync(0xFFFFFFFFu, slot, src),
+                                   br = __shfl_sync(0xFFFFFFFFu, rank, src);
+                    const uint32_t rr = lz_search_from(SV, sorted, bs - br, bs, bp, n, depth);
+                    if (lane == (unsigned)src) res = rr;
+                }
+                // -- the token of a searched position
+                if (req) {
+                    uint32_t tok, np;
+                    if (res) {
+                        const uint32_t len = res >> 16, dist = res & 0xFFFFu;
+                        tok = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
+                        np = p + len;
+                    } else {
+                        tok = SV[p];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
+                        np = p + 1;
+                    }
+                    *tp++ = tok;
+                    if (mode == G_SPEC) visited[p >> 5] |= 1u << (p & 31u);
+                    p = np;
+                    if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                }
             }
         }
         __syncthreads();
         // ---- 4b. tiles entered at the wrong place form chains (consecutive tiles inside one long run of
         //          matches that never meets the speculative parse); chains are independent, one warp each
         for (uint32_t w = t0 + 1 + tid; w < n_tiles; w += LZ_THREADS) {
-            const bool bad = M->fix_exit[w - 1] != M->entry_used[w];
-            const bool bad_prev = w >= t0 + 2 && M->fix_exit[w - 2] != M->entry_used[w - 1];
+            const bool bad = lz_tile_begin(w - 1) + M->fix_exit[w - 1] != lz_tile_begin(w) + M->entry_used[w];
+            const bool bad_prev = w >= t0 + 2 && lz_tile_begin(w - 2) + M->fix_exit[w - 2] != lz_tile_begin(w - 1) + M->entry_used[w - 1];
             if (bad && !bad_prev) atomicOr(&M->start_mask[w >> 5], 1u << (w & 31));
         }
         __syncthreads();
@@ -873,19 +1061,19 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (!((M->start_mask[w >> 5] >> (w & 31)) & 1u)) continue;
             uint32_t end = w + 1;  // next chain start (or the end of the chunk)
             while (end < n_tiles && !((M->start_mask[end >> 5] >> (end & 31)) & 1u)) ++end;
-            uint32_t entry = M->fix_exit[w - 1];
+            uint32_t entry = lz_tile_begin(w - 1) + M->fix_exit[w - 1];
             for (uint32_t t = w; t < end; ++t) {
-                if (entry == M->entry_used[t]) break;
+                if (entry == lz_tile_begin(t) + M->entry_used[t]) break;
                 const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
                 uint32_t nfix, from;
-                const uint32_t ex = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth,
+                const uint32_t ex = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth,
                                                    fix_c + lz_tok_off(t), visited, M->spec_count[t],
-                                                   M->spec_exit[t], &nfix, &from);
+                                                   t_begin + M->spec_exit[t], &nfix, &from);
                 if (lane == 0) {
-                    M->entry_used[t] = entry;
-                    M->fix_exit[t] = ex;
-                    M->fix_count[t] = (uint16_t)nfix;
-                    M->spec_from[t] = (uint16_t)from;
+                    M->entry_used[t] = (uint16_t)(entry - t_begin);
+                    M->fix_exit[t] = (uint16_t)(ex - t_begin);
+                    M->fix_count[t] = (LZ_COUNT_T)nfix;
+                    M->spec_from[t] = (LZ_COUNT_T)from;
                 }
                 __syncwarp();
                 entry = ex;
@@ -895,22 +1083,22 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         // ---- 4c. walk the chain of true exits once; anything still entered at the wrong place is redone here
         //          (normally nothing: this pass is what makes 4a/4b safe to run optimistically)
         if (warp == 0 && t0 < n_tiles) {
-            uint32_t true_exit = M->fix_exit[t0];
+            uint32_t true_exit = lz_tile_begin(t0) + M->fix_exit[t0];
             for (uint32_t w = t0 + 1; w < n_tiles; ++w) {
-                if (true_exit == M->entry_used[w]) {
-                    true_exit = M->fix_exit[w];
+                if (true_exit == lz_tile_begin(w) + M->entry_used[w]) {
+                    true_exit = lz_tile_begin(w) + M->fix_exit[w];
                     continue;
                 }
                 const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
                 uint32_t nfix, from;
                 const uint32_t entry = true_exit;
-                true_exit = lz_resync_tile(SV, sorted, bstart, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
-                                           visited, M->spec_count[w], M->spec_exit[w], &nfix, &from);
+                true_exit = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
+                                           visited, M->spec_count[w], t_begin + M->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
-                    M->entry_used[w] = entry;
-                    M->fix_exit[w] = true_exit;
-                    M->fix_count[w] = (uint16_t)nfix;
-                    M->spec_from[w] = (uint16_t)from;
+                    M->entry_used[w] = (uint16_t)(entry - t_begin);
+                    M->fix_exit[w] = (uint16_t)(true_exit - t_begin);
+                    M->fix_count[w] = (LZ_COUNT_T)nfix;
+                    M->spec_from[w] = (LZ_COUNT_T)from;
                 }
             }
         }
@@ -919,38 +1107,41 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         __threadfence_block();
         __syncthreads();
 
-        // ---- 5. tile table + histograms over the surviving tokens (src/LZ77.ts:126-128,141-142,236,251,271,279)
-        for (uint32_t w = warp; w < LZ_NTILES; w += LZ_WARPS) {
-            ZtsTile t = {0, 0, 0, 0};
-            if (w >= t0 && w < n_tiles) {
-                t.fix_count = M->fix_count[w];
-                t.spec_from = M->spec_from[w];
-                t.spec_count = M->spec_count[w];
+        // ---- 5. the chunk's token list + histograms (src/LZ77.ts:126-128,141-142,236,251,271,279): per tile the
+        //         re-parsed tokens, then the speculative ones from the splice on, tiles in order -- one contiguous list,
+        //         written once (streaming stores) and read once by the bit packer
+        uint32_t* tok_off = reinterpret_cast<uint32_t*>(M->spec_exit);  // the two exit tables are dead now: u32 per tile
+        static_assert(offsetof(LzMisc, fix_exit) == offsetof(LzMisc, spec_exit) + sizeof(uint16_t) * LZ_NTILES,
+                      "spec_exit and fix_exit must be adjacent");
+        {
+            uint32_t cnt = 0;
+            if (tid < LZ_NTILES && tid >= t0 && tid < n_tiles)
+                cnt = (uint32_t)M->fix_count[tid] + ((uint32_t)M->spec_count[tid] - (uint32_t)M->spec_from[tid]);
+            const uint32_t off = block_excl_sum(cnt, M->warp_tot, &M->n_tokens);
+            if (tid < LZ_NTILES) tok_off[tid] = off;  // (block_excl_sum ends with a barrier: the exit tables were read before it)
+        }
+        __syncthreads();
+        {
+            const unsigned long long stream = l2_policy_stream();
+            for (uint32_t w = t0 + warp; w < n_tiles; w += LZ_WARPS) {
+                const uint32_t nf = M->fix_count[w], from = M->spec_from[w], sc = M->spec_count[w];
+                uint32_t* dst = list_c + tok_off[w];
+                const uint32_t* fx = fix_c + lz_tok_off(w);
+                const uint32_t* sp = spec_c + lz_tok_off(w) + from;
+                const uint32_t ns = sc - from;
+                for (uint32_t k = lane; k < nf + ns; k += 32) {
+                    const uint32_t tok = k < nf ? fx[k] : sp[k - nf];
+                    st_u32_hint(&dst[k], tok, stream);
+                    hist_token(tok, M->hist);
+                }
             }
-            if (lane == 0) {
-                ci->tiles[w] = t;
-                atomicAdd(&M->n_tokens, (uint32_t)t.fix_count + (t.spec_count - t.spec_from));
-            }
-            const uint32_t* fx = fix_c + lz_tok_off(w);
-            const uint32_t* sp = spec_c + lz_tok_off(w);
-            for (uint32_t k = lane; k < t.fix_count; k += 32) hist_token(fx[k], M->hist);
-            // the surviving speculative tokens come back from L2: four loads in flight before they are counted
-            uint32_t k = t.spec_from + lane;
-            for (; k + 96u < t.spec_count; k += 128u) {
-                const uint32_t a0 = sp[k], a1 = sp[k + 32u], a2 = sp[k + 64u], a3 = sp[k + 96u];
-                hist_token(a0, M->hist);
-                hist_token(a1, M->hist);
-                hist_token(a2, M->hist);
-                hist_token(a3, M->hist);
-            }
-            for (; k < t.spec_count; k += 32u) hist_token(sp[k], M->hist);
         }
         __syncthreads();
         for (uint32_t i = tid; i < 316; i += LZ_THREADS)
             hist_out[(size_t)c * 316 + i] = M->hist[i] + (i == 256 ? 2u : 0u);  // freqsLitLen[256] ends at 2
         if (tid == 0) {
             ci->n_tokens = M->n_tokens;
-            ci->pad = 0;  // tokens are in tile segments
+            ci->pad = 0;
         }
         __syncthreads();
     }
@@ -1154,7 +1345,7 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
             mine = nfix + (sc - from);
         }
         const uint32_t tbase = block_excl_sum(mine, M->warp_tot, &M->n_tokens);
-        uint32_t* out = tok_out + (size_t)c * LZ_TOK_PER_CHUNK;
+        uint32_t* out = tok_out + (size_t)c * LZ_LIST_PER_CHUNK;
         {
             // the 32 tiles of a warp are copied one after the other by the whole warp: coalesced, no dependent loads
             const unsigned lane = tid & 31;
@@ -1185,18 +1376,21 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
 
 size_t zts_lz77_smem_bytes() { return LzSmem::TOTAL; }
 
+size_t zts_lz77_scratch_bytes(int sm_count) { return (size_t)sm_count * 2u * LZ_TOK_PER_CHUNK * 4u; }
+
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
-                    ZtsChunkInfo* d_info, uint32_t* d_spec, uint32_t* d_fix, uint32_t* d_hist, uint32_t* d_sortT,
+                    ZtsChunkInfo* d_info, uint32_t* d_tile_tok, uint32_t* d_list, uint32_t* d_hist, uint32_t* d_sortT,
                     uint32_t* d_counter, uint32_t grid, uint32_t depth)
 {
     static_assert(sizeof(LzMisc) <= LzSmem::MISC_BYTES, "misc area too small");
     static_assert(LzSmem::TOTAL <= 232448, "exceeds 227 KiB of dynamic shared memory");
+    if (grid > (uint32_t)ctx->sm_count) grid = (uint32_t)ctx->sm_count;  // the tile scratch holds one slot per SM
     ZTS_CUDA(ctx, cudaFuncSetAttribute(lz77_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)LzSmem::TOTAL));
     ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->work));
     ZTS_LAUNCH(ctx, ZK_LZ77,
                lz77_chunk_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->work>>>(
-                   d_in, d_chunks, n_chunks, d_info, d_spec, d_fix, d_hist, d_sortT, d_counter, depth));
+                   d_in, d_chunks, n_chunks, d_info, d_tile_tok, d_list, d_hist, d_sortT, d_counter, depth));
     return ZLB_OK;
 }
 
