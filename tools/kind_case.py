@@ -14,6 +14,8 @@ if kind == "random":
     data = rng.integers(0, 256, n, dtype=np.uint8)
 elif kind == "text":
     data = synth.text(n, 1)
+elif kind == "mixed":
+    data = synth.mixed(n, 2)
 elif kind == "runs":
     data = np.repeat(rng.integers(0, 256, n // 4096, dtype=np.uint8), 4096)
 else:

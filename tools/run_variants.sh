@@ -1,3 +1,4 @@
-python -m pytest tests/test_deflate_gpu.py -x -q -m gpu 2>&1 | tail -3
+#!/bin/bash
+# Development aid (on the GPU box): LZ77 time per kind of data for the built library and every variants/*.so
 echo "== base"; python tools/probe_kinds.py 64 2>&1 | grep compat
-for v in r4 cap32 cap128; do echo "== $v"; ZLB_LIB_OVERRIDE=$PWD/variants/$v.so python tools/probe_kinds.py 64 2>&1 | grep compat; done
+for f in variants/*.so; do v=$(basename $f .so); echo "== $v"; ZLB_LIB_OVERRIDE=$PWD/$f python tools/probe_kinds.py 64 2>&1 | grep compat; done

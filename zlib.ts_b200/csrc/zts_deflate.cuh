@@ -5,20 +5,13 @@
 #define LZ_THREADS 1024
 #define LZ_WARPS 32
 #define LZ_MAX_CHUNK 65536u
-// Speculative parse tiles: every tile is parsed by one lane that owns it (8 owners per warp, 256 per CTA, see
-// zts_lz77.cu); owners take tiles from a counter, so more tiles than owners keep the warps' search batches filled
-// when the tiles of a chunk cost very different amounts (mixed data). Default: 512 tiles of 128 positions. The three
-// size classes (512, 256, 128 positions, in this order along the chunk) are kept for experiments.
-#ifndef LZ_TA
-#define LZ_TA 0u                        // tiles of 512 positions
-#define LZ_TB 0u                        // then tiles of 256
-#define LZ_TC 512u                      // then tiles of 128
-#endif
-#define LZ_NTILES (LZ_TA + LZ_TB + LZ_TC)
-static_assert(LZ_TA * 512u + LZ_TB * 256u + LZ_TC * 128u == 65536u, "the tiles must cover a 64 KiB chunk");
+// Speculative parse tiles: the chunk is cut into 1024 tiles of 64 positions and every thread of the CTA owns one
+// (see zts_lz77.cu): it parses its tile from the tile's start, then carries on into the next tile until it meets
+// that tile's own parse.
+#define LZ_TILE_POS 64u
+#define LZ_NTILES (LZ_MAX_CHUNK / LZ_TILE_POS)
 #define LZ_SORT_TILE 2048u              // positions ranked by one warp in a radix pass
-#define LZ_HASH_BITS 13
-#define LZ_NB (1u << LZ_HASH_BITS)
+#define LZ_HASH_BITS 16                 // positions are grouped by a 16-bit hash of their 3-byte key
 #define LZ_WINDOW 32768u                // WindowSize, src/LZ77.ts:8
 #define LZ_MAXLEN 258u                  // LZ77MaxLength, src/LZ77.ts:5
 #define LZ_TOK_PER_CHUNK (LZ_MAX_CHUNK + 8u * LZ_NTILES + 8u)  // token slots of the per-CTA spec / fix scratch (tile t at lz_tok_off(t))
@@ -42,29 +35,12 @@ struct ZtsChunk {      // host-built, one per chunk
     uint32_t pad1;
 };
 
-#ifdef __CUDACC__
-#pragma nv_diag_suppress 186  // a size class may be empty (LZ_TA == 0): the comparison with zero is intended
-#endif
 // first position of tile t (t == LZ_NTILES gives the chunk size)
-__host__ __device__ __forceinline__ uint32_t lz_tile_begin(uint32_t t)
-{
-    return t < LZ_TA ? t * 512u : t < LZ_TA + LZ_TB ? LZ_TA * 512u + (t - LZ_TA) * 256u
-                                                    : LZ_TA * 512u + LZ_TB * 256u + (t - LZ_TA - LZ_TB) * 128u;
-}
+__host__ __device__ __forceinline__ uint32_t lz_tile_begin(uint32_t t) { return t * LZ_TILE_POS; }
 // tiles that a chunk of n bytes has
-__host__ __device__ __forceinline__ uint32_t lz_tile_count(uint32_t n)
-{
-    return n <= LZ_TA * 512u ? (n + 511u) / 512u
-         : n <= LZ_TA * 512u + LZ_TB * 256u ? LZ_TA + (n - LZ_TA * 512u + 255u) / 256u
-                                            : LZ_TA + LZ_TB + (n - LZ_TA * 512u - LZ_TB * 256u + 127u) / 128u;
-}
+__host__ __device__ __forceinline__ uint32_t lz_tile_count(uint32_t n) { return (n + LZ_TILE_POS - 1u) / LZ_TILE_POS; }
 // tile that holds position pos
-__host__ __device__ __forceinline__ uint32_t lz_tile_of(uint32_t pos)
-{
-    return pos < LZ_TA * 512u ? pos / 512u
-         : pos < LZ_TA * 512u + LZ_TB * 256u ? LZ_TA + (pos - LZ_TA * 512u) / 256u
-                                             : LZ_TA + LZ_TB + (pos - LZ_TA * 512u - LZ_TB * 256u) / 128u;
-}
+__host__ __device__ __forceinline__ uint32_t lz_tile_of(uint32_t pos) { return pos / LZ_TILE_POS; }
 // first token slot of tile t: a tile never holds more tokens than positions
 __host__ __device__ __forceinline__ uint32_t lz_tok_off(uint32_t t) { return lz_tile_begin(t) + 8u * t; }
 

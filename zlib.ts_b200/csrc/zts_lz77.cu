@@ -12,19 +12,20 @@
 //   3. every position gets a 16-bit info word (L2-resident scratch): its rank inside its bucket (how many earlier
 //      positions the bucket holds) and a "may have a candidate" bit -- an earlier position with the same 3 bytes
 //      inside the window, found by walking back over the few hash collisions in front of the position's slot;
-//   4a. the chunk is cut into tiles (512, then 256, then 128 positions) which are parsed speculatively, each from
-//      its tile start, by GROUPS OF 8 LANES: a warp works on four tiles at once. A group reads the info words of
-//      32 positions with one coalesced load; runs of positions without a candidate are literals and are emitted
-//      together; a position with few earlier bucket entries (the common case: the median is below 8) is searched
-//      by the group, 8 candidates per step (newest first), exact-key filter, tail-byte filter against the best so
-//      far, word-wise extension, REDUX.MAX over (len << 16 | q) inside the group; positions behind long candidate
-//      lists are handed to the whole warp, 32 (or 128) candidates per step;
-//   4b. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit
-//      of the previous one and is re-parsed only until it meets a speculatively parsed position
-//      (a visited-bit per position); the remainder of the speculative tokens is reused. All tiles
-//      re-enter in parallel assuming their predecessor exits where its speculative parse did; the
-//      few whose predecessor exits elsewhere (chains inside long runs) are redone chain by chain,
-//      one warp per chain, and a final walk over the true exits verifies every splice;
+//   4a. the chunk is cut into 1024 tiles of 64 positions and EVERY THREAD OWNS ONE: it parses its tile speculatively
+//      from the tile's start, all by itself -- runs of positions without a candidate are literals and are emitted
+//      together; at a position with candidates the thread walks the `rank` slots in front of the position's own slot,
+//      newest first: window test, tail-byte filter against the best so far, exact key, word-wise extension; strictly
+//      longer wins, so ties stay with the nearest. A warp iterates "a few candidate steps for every lane that is
+//      searching, then one token / next-position step for the lanes that are not", so lanes with short and long
+//      candidate lists do not wait for each other. Positions behind long candidate lists (ends of runs, low-entropy
+//      records) are handed to the whole warp, 32 (or 128) candidates per step;
+//   4b. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit of the previous
+//      one and only has to be re-parsed until it meets a speculatively parsed position (a visited-bit per
+//      position); the remainder of the speculative tokens is reused. The owner of tile t does this for tile t + 1
+//      as soon as its own tile is done, assuming tile t exits where its speculative parse did; the few tiles whose
+//      predecessor exits elsewhere (a match that jumps a whole tile, chains inside long runs) are redone chain by
+//      chain, one warp per chain, and a final check over the true exits verifies every splice;
 //   5. litlen / dist histograms are taken over the surviving tokens.
 //
 // Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 14 KiB scratch.
@@ -32,12 +33,7 @@
 
 #include "zts_deflate.cuh"
 
-#define LZ_OWNERS_MAX 8u
-#if LZ_TA == 0 && LZ_TB == 0
-typedef uint8_t LZ_COUNT_T;    // tokens of a 128-position tile
-#else
-typedef uint16_t LZ_COUNT_T;
-#endif
+typedef uint8_t LZ_COUNT_T;    // tokens of a 64-position tile
 
 struct LzSmem {
     // byte offsets into dynamic shared memory
@@ -45,8 +41,8 @@ struct LzSmem {
     static constexpr uint32_t S_BYTES = LZ_MAX_CHUNK + 64;
     static constexpr uint32_t SORTED_OFF = S_OFF + S_BYTES;       // u16[65536]
     static constexpr uint32_t SORTED_BYTES = LZ_MAX_CHUNK * 2;
-    static constexpr uint32_t BSTART_OFF = SORTED_OFF + SORTED_BYTES;  // u16[LZ_NB + 2]
-    static constexpr uint32_t BSTART_BYTES = (LZ_NB + 8) * 2;
+    static constexpr uint32_t BSTART_OFF = SORTED_OFF + SORTED_BYTES;  // 16 KiB: radix running offsets | visited bits + tile table
+    static constexpr uint32_t BSTART_BYTES = 16384 + 16;
     static constexpr uint32_t AUX_OFF = BSTART_OFF + BSTART_BYTES;     // 8 KiB: radix counters | visited bits
     static constexpr uint32_t AUX_BYTES = 8192;
     static constexpr uint32_t MISC_OFF = AUX_OFF + AUX_BYTES;
@@ -55,36 +51,29 @@ struct LzSmem {
 };
 
 // Per-tile tables. Positions are kept relative to the tile's first position (an exit lies at most a maximum match
-// behind the tile: < 128 + 258; an entry at most 257 behind its first position), counts fit a byte (<= 128 tokens per
-// tile when the default 128-position tiles are used; larger tiles are checked by the static_assert below).
+// behind the tile: < 64 + 258; an entry at most 257 behind its first position), counts fit a byte (<= 64 tokens per
+// tile). LzMisc lives in the misc area, LzTiles2 in the second half of the bucket-start area (dead once the info
+// words are built).
 struct LzMisc {
     unsigned long long mbar;
     uint32_t chunk;
-    uint32_t tile_next;              // next tile of the speculative parse
-    uint32_t tile_next2;             // next tile of the re-entry pass
+    uint32_t n_tokens;
     uint32_t warp_tot[32];
     uint32_t warp_min[32];
-    uint16_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)   } the two arrays double as
-    uint16_t fix_exit[LZ_NTILES];    // exit of the tile for the entry it was last parsed from      } u32 tok_off[] in phase 5
-    uint16_t entry_used[LZ_NTILES];  // that entry
-    uint16_t tile_start[LZ_NTILES];  // where the tile's speculative parse starts
+    uint32_t hist[316];
     uint32_t start_mask[(LZ_NTILES + 31) / 32];  // tiles that start a chain of wrongly entered tiles
+    uint16_t tile_start[LZ_NTILES];  // where the tile's speculative parse starts
+    uint16_t entry_used[LZ_NTILES];  // the entry the tile was last parsed from
     LZ_COUNT_T spec_count[LZ_NTILES];
     LZ_COUNT_T fix_count[LZ_NTILES];
-    LZ_COUNT_T spec_from[LZ_NTILES];
-    uint8_t spec_done[LZ_NTILES];    // set (release) when a tile's speculative parse and its tables are complete
-    uint32_t hist[316];
-    uint32_t n_tokens;
 };
-
-struct LzBatch {  // one per warp: the searches its tile owners post in a round
-    uint32_t end[LZ_OWNERS_MAX];    // candidates of requests 0 .. r (inclusive running sum)
-    uint32_t start[LZ_OWNERS_MAX];  // candidates of requests 0 .. r-1
-    uint32_t p[LZ_OWNERS_MAX];      // position searched
-    uint32_t slot[LZ_OWNERS_MAX];   // its slot in the sorted index: the candidates sit in front of it, newest first
-    uint32_t pw[LZ_OWNERS_MAX], pw1[LZ_OWNERS_MAX];  // the 8 bytes at p
-    uint32_t best[LZ_OWNERS_MAX];   // max of len << 16 | q over the candidates
+struct LzTiles2 {
+    uint16_t spec_exit[LZ_NTILES];   // where the speculative parse of a tile ended (>= tile end)   } the two arrays double as
+    uint16_t fix_exit[LZ_NTILES];    // exit of the tile for the entry it was last parsed from      } u32 tok_off[] in phase 5
+    LZ_COUNT_T spec_from[LZ_NTILES]; // first speculative token that belongs to the true parse (4a: the position of the splice)
 };
+#define LZ_NO_SPLICE 0xFFu          // LzTiles2::spec_from during 4a: the re-entry parse did not meet the speculative one
+#define LZ_EXIT_SPLICED 0xFFFFu     // LzTiles2::fix_exit during 4a: the tile exits where its speculative parse does
 
 // The radix scratch T is the one global buffer a CTA keeps re-using (256 KiB per chunk, written and read twice):
 // it is marked evict_last in L2 so that the streaming traffic next to it (input, tokens) does not push it out to
@@ -146,7 +135,7 @@ __device__ __forceinline__ void ld_u128(const LzS& V, uint32_t i, uint32_t (&o)[
     o[3] = __funnelshift_r(w3, w4, sh);
 }
 
-__device__ __forceinline__ uint32_t hash13(uint32_t key3) { return (key3 * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
+__device__ __forceinline__ uint32_t lz_hash(uint32_t key3) { return (key3 * 0x9E3779B1u) >> (32 - LZ_HASH_BITS); }
 
 // lanes holding the same NBITS-bit digit as this lane (invalid lanes only match each other). Same result as
 // __match_any_sync, built from NBITS + 1 ballots: MATCH.ANY issues far too slowly on sm_100 to sit in a loop that
@@ -240,29 +229,78 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
 //   hasbits   = one bit per position in shared memory: "may have a candidate" -- an earlier position with the same
 //               3 bytes inside the window, found by walking back over the hash collisions in front of the slot.
 #define LZ_HAS_WALK 16u        // collisions walked over before a position is declared "may have a candidate"
-#ifndef LZ_OWNERS
-#define LZ_OWNERS 8u           // lanes of a warp that own a tile each (lanes 0 .. LZ_OWNERS-1): power of two, <= 16
+#ifndef LZ_PRIV_CAP
+#define LZ_PRIV_CAP 64u        // a search over more earlier bucket entries than this is handed to the whole warp
 #endif
-#ifndef LZ_BATCH_CAP
-#define LZ_BATCH_CAP 64u       // a search over at most this many earlier bucket entries goes into the warp's batch
+#ifndef LZ_WAIT_MUL
+#define LZ_WAIT_MUL 1u         // ... which happens when LZ_WAIT_MUL x (lanes waiting) >= lanes searching
+#endif
+#ifndef LZ_KMAX
+#define LZ_KMAX 16u            // candidate steps in a row before the lanes that wait for their next position are served
 #endif
 
-// one thread per slot of the sorted index (all threads of the block call it; `hasbits` zeroed, barrier behind it)
-__device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __restrict__ sorted,
-                                              const uint16_t* __restrict__ bstart, uint32_t m, uint32_t n, uint32_t* P,
-                                              uint32_t* hasbits, unsigned long long keep)
+// Every warp walks the 2048 slots of the sorted index it ranked in the last radix sweep, 32 per step. Bucket starts
+// are the slots whose hash differs from their predecessor's; a position's rank is its distance to the last start (a
+// ballot + the start carried from the earlier steps) -- no table of bucket starts exists.
+//   FAST == false: P[] and `hasbits` (zeroed by the caller, barrier behind it) as described above;
+//   FAST == true : only `startbits` (64 Ki bits): bit i set where slot i starts a bucket.
+template <bool FAST>
+__device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __restrict__ sorted, uint32_t m, uint32_t n,
+                                              uint32_t* P, uint32_t* hasbits, uint32_t* startbits, unsigned long long keep)
 {
-    const unsigned tid = threadIdx.x;
-    for (uint32_t p = m + tid; p < n; p += LZ_THREADS) st_u32_hint(&P[p], 0u, keep);  // positions without a slot (P has LZ_MAX_CHUNK entries per CTA)
-    for (uint32_t i0 = 0; i0 < m; i0 += LZ_THREADS) {  // whole warps stay in the loop (warp votes below)
-        const uint32_t i = i0 + tid;
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!FAST)
+        for (uint32_t p = m + tid; p < n; p += LZ_THREADS) st_u32_hint(&P[p], 0u, keep);  // positions without a slot (P has LZ_MAX_CHUNK entries per CTA)
+    const uint32_t i0 = warp * LZ_SORT_TILE;
+    if (i0 >= m) {
+        if (FAST)
+            for (uint32_t k = lane; k < LZ_SORT_TILE / 32; k += 32) startbits[i0 / 32 + k] = 0;
+        return;
+    }
+    // the bucket that holds slot i0 may begin in an earlier warp's range: look back for its first slot
+    uint32_t carry = i0;          // first slot of the bucket that is open at the current step
+    uint32_t hlast = 0xFFFFFFFFu; // hash of the slot in front of the current step
+    if (i0) {
+        const uint32_t h0 = lz_hash(ld_u32(S, sorted[i0]) & 0xFFFFFFu);
+        hlast = lz_hash(ld_u32(S, sorted[i0 - 1]) & 0xFFFFFFu);
+        if (hlast == h0) {
+            uint32_t at = i0;  // slots [at, i0) are known to share h0
+            for (;;) {
+                const bool in = at > lane;  // slot at - 1 - lane exists
+                const uint32_t hl = in ? lz_hash(ld_u32(S, sorted[at - 1 - lane]) & 0xFFFFFFu) : 0xFFFFFFFFu;
+                const unsigned mism = __ballot_sync(0xFFFFFFFFu, hl != h0);
+                if (mism) {
+                    at -= (uint32_t)__ffs((int)mism) - 1u;
+                    break;
+                }
+                at -= 32u;
+            }
+            carry = at;
+        }
+    }
+    for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {  // whole warps stay in the loop (warp votes below)
+        const uint32_t i = i0 + it * 32 + lane;
         const bool valid = i < m;
-        bool has = false;
-        uint32_t p = 0xFFFFFFFFu;
+        uint32_t p = 0xFFFFFFFFu, key = 0, h = 0xFFFFFFFEu;
         if (valid) {
             p = sorted[i];
-            const uint32_t key = ld_u32(S, p) & 0xFFFFFFu;
-            const uint32_t lo = bstart[hash13(key)];
+            key = ld_u32(S, p) & 0xFFFFFFu;
+            h = lz_hash(key);
+        }
+        uint32_t hprev = __shfl_up_sync(0xFFFFFFFFu, h, 1);
+        if (lane == 0) hprev = hlast;
+        hlast = __shfl_sync(0xFFFFFFFFu, h, 31);
+        const bool start = valid && (i == 0 || h != hprev);
+        const unsigned sm = __ballot_sync(0xFFFFFFFFu, start);
+        const unsigned below = sm & (zts_lanemask_lt() | (1u << lane));
+        const uint32_t lo = below ? (i - lane) + (31u - (uint32_t)__clz((int)below)) : carry;  // first slot of i's bucket
+        if (sm) carry = (i - lane) + (31u - (uint32_t)__clz((int)sm));
+        if (FAST) {
+            if (lane == 0) startbits[i >> 5] = sm;
+            continue;
+        }
+        bool has = false;
+        if (valid) {
             if (p + 3u < n) {  // src/LZ77.ts:228: the last three positions are never searched
                 // the nearest earlier position with the same 3 bytes sits a few slots back (hash collisions in
                 // between); it decides: older ones are further away
@@ -287,7 +325,7 @@ __device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __re
         const uint32_t bit = has ? 1u << (p & 31u) : 0u;
         if (__all_sync(0xFFFFFFFFu, w == w0)) {
             const uint32_t bits = __reduce_or_sync(0xFFFFFFFFu, bit);
-            if ((tid & 31u) == 0 && bits) atomicOr(&hasbits[w0], bits);
+            if (lane == 0 && bits) atomicOr(&hasbits[w0], bits);
         } else if (bit) {
             atomicOr(&hasbits[w], bit);
         }
@@ -496,17 +534,16 @@ __device__ __forceinline__ void hist_token(uint32_t tok, uint32_t* hist)
 }
 
 // ---- stages 1 and 2 of both kernels: the chunk into shared memory, the position index over it ----------------
-// On return S holds the chunk (+ zeroed slack), `sorted` the positions grouped by hash13 of their 3-byte key
-// (ascending inside a bucket), `bstart` the first slot of every bucket (empty buckets point at the next one).
-// With `startbits` (64 Ki bits, may alias cnt16) bit i is set where slot i starts a bucket.
+// On return S holds the chunk (+ zeroed slack), `sorted` the positions grouped by the 16-bit hash of their 3-byte key
+// (ascending inside a bucket). `cnt16` = 16 KiB of scratch for the radix sort.
 struct LzIndexed {
     LzS SV;
     uint32_t m;  // positions that own a 3-byte key
 };
 
 __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restrict__ src, uint32_t n, uint8_t* Sbuf,
-                                                        uint16_t* sorted, uint16_t* bstart, uint16_t* cnt16, LzMisc* M,
-                                                        uint32_t* T, uint32_t& phase, uint32_t* startbits)
+                                                        uint16_t* sorted, uint16_t* cnt16, LzMisc* M, uint32_t* T,
+                                                        uint32_t& phase)
 {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned long long keep = l2_policy_keep();
@@ -547,89 +584,74 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
 
     const uint32_t m = n >= 3 ? n - 2 : 0;  // positions that own a 3-byte key
 
-    // ---- 2. stable LSD radix sort of positions by hash13(key), low 7 bits then high 6 bits, three sweeps:
+    // ---- 2. stable LSD radix sort of positions by lz_hash(key), low 8 bits then high 8 bits, three sweeps:
     //   A  count the low digits per (warp range, digit)            -- shared-memory atomics, order irrelevant
     //   B  scatter by low digit into T (global, L2 resident) as pos | hash << 16, stable (ballot ranking),
     //      and count the high digits per (destination range, digit) on the way
     //   C  scatter by high digit from T into `sorted`, stable
     // The u32 counters of A and B live in the `sorted` area, which is not written before sweep C.
     {
-        uint32_t* cntA = reinterpret_cast<uint32_t*>(sorted);   // [32 ranges][128 digits]
-        uint32_t* cntB = cntA + 32 * 128;                       // [32 ranges][64 digits]
-        for (uint32_t i = tid; i < 32u * 128u + 32u * 64u; i += LZ_THREADS) cntA[i] = 0;
+        uint32_t* cntA = reinterpret_cast<uint32_t*>(sorted);   // [32 ranges][256 digits]
+        uint32_t* cntB = cntA + 32 * 256;                       // [32 ranges][256 digits]
+        for (uint32_t i = tid; i < 2u * 32u * 256u; i += LZ_THREADS) cntA[i] = 0;
         __syncthreads();
         const uint32_t w_begin = warp * LZ_SORT_TILE;
         // sweep A
         if (w_begin < m) {
             for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
                 const uint32_t i = w_begin + it * 32 + lane;
-                if (i < m) atomicAdd(&cntA[warp * 128u + (hash13(ld_u32(SV, i) & 0xFFFFFFu) & 127u)], 1u);
+                if (i < m) atomicAdd(&cntA[warp * 256u + (lz_hash(ld_u32(SV, i) & 0xFFFFFFu) & 255u)], 1u);
             }
         }
         __syncthreads();
         // exclusive scan in (digit major, range minor) order: entry e = d * 32 + w  ->  u16 running offsets
-        {
-            uint32_t vals[4];
-            uint32_t sum = 0;
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
-                const uint32_t e = tid * 4 + k;
-                vals[k] = cntA[(e & 31u) * 128u + (e >> 5)];
-                sum += vals[k];
-            }
-            uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
-#pragma unroll
-            for (uint32_t k = 0; k < 4; ++k) {
-                const uint32_t e = tid * 4 + k;
-                cnt16[(e & 31u) * 128u + (e >> 5)] = (uint16_t)base;
-                base += vals[k];
-            }
-        }
-        __syncthreads();
-        // sweep B
-        if (w_begin < m) {
-            uint16_t* wc = cnt16 + warp * 128u;
-            for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
-                const uint32_t i = w_begin + it * 32 + lane;
-                const bool v = i < m;
-                uint32_t hh = 0x1FFFu;
-                if (v) hh = hash13(ld_u32(SV, i) & 0xFFFFFFu);
-                const uint32_t d = hh & 127u;
-                const unsigned peers = peers_of<7>(d, v);
-                uint32_t dst = 0;
-                if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
-                __syncwarp();
-                if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
-                if (v) {
-                    st_u32_hint(&T[dst], i | (hh << 16), keep);
-                    atomicAdd(&cntB[(dst >> 11) * 64u + (hh >> 7)], 1u);
+        for (int pass = 0; pass < 2; ++pass) {
+            uint32_t* cnt = pass ? cntB : cntA;
+            if (pass) {
+                // sweep B
+                if (w_begin < m) {
+                    uint16_t* wc = cnt16 + warp * 256u;
+                    for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
+                        const uint32_t i = w_begin + it * 32 + lane;
+                        const bool v = i < m;
+                        uint32_t hh = 0xFFFFu;
+                        if (v) hh = lz_hash(ld_u32(SV, i) & 0xFFFFFFu);
+                        const uint32_t d = hh & 255u;
+                        const unsigned peers = peers_of<8>(d, v);
+                        uint32_t dst = 0;
+                        if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
+                        __syncwarp();
+                        if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                        if (v) {
+                            st_u32_hint(&T[dst], i | (hh << 16), keep);
+                            atomicAdd(&cntB[(dst >> 11) * 256u + (hh >> 8)], 1u);
+                        }
+                        __syncwarp();
+                    }
                 }
-                __syncwarp();
+                __threadfence_block();
+                __syncthreads();
             }
-        }
-        __threadfence_block();
-        __syncthreads();
-        {
-            uint32_t vals[2];
+            uint32_t vals[8];
             uint32_t sum = 0;
 #pragma unroll
-            for (uint32_t k = 0; k < 2; ++k) {
-                const uint32_t e = tid * 2 + k;
-                vals[k] = cntB[(e & 31u) * 64u + (e >> 5)];
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t e = tid * 8 + k;
+                vals[k] = cnt[(e & 31u) * 256u + (e >> 5)];
                 sum += vals[k];
             }
             uint32_t base = block_excl_sum(sum, M->warp_tot, nullptr);
 #pragma unroll
-            for (uint32_t k = 0; k < 2; ++k) {
-                const uint32_t e = tid * 2 + k;
-                cnt16[(e & 31u) * 64u + (e >> 5)] = (uint16_t)base;
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t e = tid * 8 + k;
+                cnt16[(e & 31u) * 256u + (e >> 5)] = (uint16_t)base;
                 base += vals[k];
             }
+            __syncthreads();
         }
-        __syncthreads();
         // sweep C (overwrites the counters, which are dead now)
         if (w_begin < m) {
-            uint16_t* wc = cnt16 + warp * 64u;
+            uint16_t* wc = cnt16 + warp * 256u;
             // the entries come back from L2: the loads run four batches ahead of the ranking that consumes them
             uint32_t pre[4];
 #pragma unroll
@@ -646,8 +668,8 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                     const uint32_t i4 = i + 4u * 32u;
                     pre[it & 3u] = (it + 4u < LZ_SORT_TILE / 32 && i4 < m) ? ld_u32_hint(&T[i4], keep) : 0xFFFFFFFFu;
                 }
-                const uint32_t d = (e >> 23) & 63u;
-                const unsigned peers = peers_of<6>(d, v);
+                const uint32_t d = e >> 24;
+                const unsigned peers = peers_of<8>(d, v);
                 uint32_t dst = 0;
                 if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
                 __syncwarp();
@@ -658,55 +680,6 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
         }
         __syncthreads();
     }
-
-    // ---- bucket starts: first slot of every hash, empty buckets point at the next one
-    for (uint32_t i = tid; i < LZ_NB + 1; i += LZ_THREADS) bstart[i] = 0xFFFF;
-    if (startbits)
-        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) startbits[i] = 0;
-    __syncthreads();
-    for (uint32_t i0 = 0; i0 < m; i0 += LZ_THREADS) {  // whole warps stay in the loop: the shuffle below needs them
-        const uint32_t i = i0 + tid;
-        const uint32_t hcur = i < m ? hash13(ld_u32(SV, sorted[i]) & 0xFFFFFFu) : 0xFFFFFFFFu;
-        // the predecessor's hash is the neighbouring lane's; only lane 0 has to compute it
-        uint32_t hprev = __shfl_up_sync(0xFFFFFFFFu, hcur, 1);
-        if (lane == 0) hprev = (i && i < m) ? hash13(ld_u32(SV, sorted[i - 1]) & 0xFFFFFFu) : 0xFFFFFFFFu;
-        if (i < m && hcur != hprev) {
-            bstart[hcur] = (uint16_t)i;
-            if (startbits) atomicOr(&startbits[i >> 5], 1u << (i & 31));
-        }
-    }
-    if (tid == 0) bstart[LZ_NB] = (uint16_t)m;
-    __syncthreads();
-    {
-        // suffix-min over bstart[0 .. LZ_NB]: thread t owns 8 consecutive entries
-        uint32_t v[8];
-        uint32_t mn = 0xFFFFu;
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            v[k] = bstart[tid * 8 + k];
-            mn = min(mn, v[k]);
-        }
-        // suffix-min across threads (exclusive: the minimum of everything to the right)
-        uint32_t inc = mn;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t t = __shfl_down_sync(0xFFFFFFFFu, inc, d);
-            if (lane + d < 32) inc = min(inc, t);
-        }
-        if (lane == 0) M->warp_min[warp] = inc;
-        __syncthreads();
-        uint32_t right = m;  // bstart[LZ_NB]
-        for (uint32_t w = warp + 1; w < 32; ++w) right = min(right, M->warp_min[w]);
-        uint32_t nxt = __shfl_down_sync(0xFFFFFFFFu, inc, 1);
-        if (lane < 31) right = min(right, nxt);
-        uint32_t run = right;
-#pragma unroll
-        for (int k = 7; k >= 0; --k) {
-            run = min(run, v[k]);
-            bstart[tid * 8 + k] = (uint16_t)run;
-        }
-    }
-    __syncthreads();
 
     LzIndexed r = {SV, m};
     return r;
@@ -721,13 +694,12 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
     extern __shared__ __align__(128) unsigned char smem[];
     uint8_t* Sbuf = smem + LzSmem::S_OFF;
     uint16_t* sorted = reinterpret_cast<uint16_t*>(smem + LzSmem::SORTED_OFF);
-    uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);
-    uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::AUX_OFF);   // [32 warps][128 digits]
+    uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);  // [32 warps][256 digits] running offsets of the radix sort
     uint32_t* hasbits = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF); // [2048] bit per position (+ 1 padding word: the misc area follows)
-    // once the info words are built the bucket starts are dead: visited bits and the warps' batch tables take their place
-    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::BSTART_OFF); // [2048] bit per position
-    LzBatch* batch = reinterpret_cast<LzBatch*>(smem + LzSmem::BSTART_OFF + 8192);
-    static_assert(8192 + sizeof(LzBatch) * LZ_WARPS <= LzSmem::BSTART_BYTES, "batch tables must fit behind the visited bits");
+    // once the info words are built the bucket starts are dead: visited bits and the second tile table take their place
+    uint32_t* visited = reinterpret_cast<uint32_t*>(smem + LzSmem::BSTART_OFF); // [2048] bit per position (+ slack: the table follows)
+    LzTiles2* M2 = reinterpret_cast<LzTiles2*>(smem + LzSmem::BSTART_OFF + 8192);
+    static_assert(8192 + sizeof(LzTiles2) <= LzSmem::BSTART_BYTES, "second tile table must fit behind the visited bits");
     LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -754,7 +726,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         const uint8_t* src = in + ch.in_off - base;
 
         // ---- 1 + 2. stage the chunk (TMA bulk copy) and index its positions (radix sort by key hash)
-        const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, bstart, cnt16, M, T, phase, nullptr);
+        const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, cnt16, M, T, phase);
         const LzS SV = ix.SV;
         const uint32_t m = ix.m;
         (void)m;
@@ -765,9 +737,9 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         uint32_t* P = T;
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) hasbits[i] = 0;
         __syncthreads();
-        lz_build_info(SV, sorted, bstart, m, n, P, hasbits, keep);
+        lz_build_info<false>(SV, sorted, m, n, P, hasbits, nullptr, keep);
         const uint32_t n_tiles = lz_tile_count(n);
-        __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the batch tables
+        __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the second tile table
         // Where the speculative parse of every tile starts. A tile that begins inside a run of one byte starts at the
         // run's 258-byte phase: inside such a run every match is a maximum-length distance-1 match, so the true parse
         // visits run_start + 1 + 258 k, and starting there makes the predecessor's exit land on a parsed position (no
@@ -776,9 +748,9 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         // tile boundary come from two block scans over 64-byte blocks: the last change point at or before the end of a
         // block, the first one at or behind its start.
         {
-            uint16_t* lastcp = reinterpret_cast<uint16_t*>(batch);  // [1024] (the batch tables are not in use yet)
+            uint16_t* lastcp = reinterpret_cast<uint16_t*>(M2);     // [1024] (the second tile table is not in use yet)
             uint16_t* nextcp = lastcp + LZ_THREADS;                 // [1024]; 0xFFFF = none
-            static_assert(4u * LZ_THREADS <= sizeof(LzBatch) * LZ_WARPS, "scan arrays must fit the batch area");
+            static_assert(4u * LZ_THREADS <= sizeof(LzTiles2), "scan arrays must fit the second tile table");
             const uint32_t lo = 64u * tid;
             uint32_t last = 0xFFFFu, next = 0xFFFFu;
             if (lo < n) {
@@ -834,126 +806,180 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 M->tile_start[t] = (uint16_t)(p0 - t_begin);  // < 258
             }
         }
-        __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the batch tables
+        __syncthreads();  // the scan arrays are dead: the second tile table takes their place
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) visited[i] = 0;
-        if (tid < LZ_NTILES) M->spec_done[tid] = 0;
         if (tid < (LZ_NTILES + 31) / 32) M->start_mask[tid] = 0;
-        if (tid == 0) {
-            M->tile_next = t0;
-            M->tile_next2 = t0;
-        }
-        __threadfence_block();
         __syncthreads();
         uint32_t* spec_c = tile_tok + (size_t)blockIdx.x * (2u * LZ_TOK_PER_CHUNK);  // per-CTA scratch: speculative tokens per tile,
         uint32_t* fix_c = spec_c + LZ_TOK_PER_CHUNK;                                  // re-parsed tokens per tile
         uint32_t* list_c = list_out + (size_t)c * LZ_LIST_PER_CHUNK;                   // the chunk's token list (phase 5)
         ZtsChunkInfo* ci = info + c;
 
-        // ---- 4a. speculative parse of every tile, then re-entry at the predecessor's speculative exit.
-        //      Lanes 0 .. LZ_OWNERS-1 of every warp OWN a tile each: the parse state (position, token pointer) is
-        //      lane-private, a run of literals is written by its owner alone. What a parse step costs is the match
-        //      search, and that is shared: every round the owners post their positions, the candidates of all of them
-        //      (the `rank` slots in front of each position's own slot) form one list, and the 32 lanes of the warp
-        //      evaluate it 32 candidates at a time whatever request they belong to -- exact key, window, match length,
-        //      shared-memory atomicMax of (len << 16 | q) per request = longest, then nearest. Requests behind long
-        //      candidate lists (ends of runs, low-entropy records) go to the warp-cooperative search with its tail-byte
-        //      filter instead, one after the other. An owner that runs out of speculative tiles starts re-entering at
-        //      once; a re-entry tile only needs itself and its predecessor parsed (ready flags, polled once a round).
+        // ---- 4a. every thread parses the tile it owns from the tile's start (speculative), then carries on into the
+        //      next tile from its own exit (the re-entry parse of that tile) until it meets a position the next tile's
+        //      owner has visited, or leaves that tile. The visited bits of a tile are written by its owner alone and
+        //      read by its predecessor while they are being written: a bit seen too late only means a few more
+        //      re-parsed tokens (the parse is memoryless in p: both threads produce the same tokens from a common
+        //      position on), the splice itself is taken from the final bits behind the barrier.
+        //      A lane is in one of four states: looking for its next position (ST_ADV), walking a candidate list
+        //      (ST_SRCH), waiting for the warp to search a long list for it (ST_COOP), holding a result (ST_RES).
         {
-            enum { G_IDLE = 0, G_SPEC = 1, G_RESYNC = 2, G_WAIT = 3, G_DONE = 4 };
-            LzBatch* B = batch + warp;
-            const bool owner = lane < LZ_OWNERS;
-            uint32_t mode = owner ? G_IDLE : G_DONE, t = 0, t_begin = 0, t_end = 0, p = 0, entry = 0, from = 0;
-            uint32_t* tp = nullptr;   // next token slot
-            uint32_t* tp0 = nullptr;  // first token slot of the tile
-            uint32_t pinfo = 0;       // P[p], requested as soon as p is known (a round ahead of its use)
-            bool spec_left = true;
+            enum { ST_ADV = 0, ST_SRCH = 1, ST_COOP = 2, ST_RES = 3, ST_DONE = 4 };
+#ifndef LZ_INTERLEAVE
+            const uint32_t t = tid;
+#else
+            // the 32 tiles of a warp lie 2 KiB apart: neighbouring tiles cost alike (they hold the same kind of data),
+            // so this spreads expensive stretches of the chunk over all the warps
+            const uint32_t t = lane * LZ_WARPS + warp;
+#endif
+            const uint32_t t_begin = t * LZ_TILE_POS;
+            uint32_t st = ST_DONE;
+            bool resync = false;      // false: own tile; true: tile t + 1, entered at `entry`
+            uint32_t p = 0, t_end = 0, entry = 0;
+            uint32_t tok_i = 0, tok_0 = 0;   // next / first token slot of the parse in hand
+            uint32_t* tbuf = spec_c;
+            uint32_t pinfo = 0;       // P[p], requested as soon as p is known
+            uint32_t s_cur = 0, s_left = 0, best = 0, ptail = 0, pw = 0, pw1 = 0, maxlen = 0;
+            if (t >= t0 && t < n_tiles) {
+                p = t_begin + M->tile_start[t];
+                t_end = min(n, t_begin + LZ_TILE_POS);
+                tok_0 = tok_i = lz_tok_off(t);
+                if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                st = ST_ADV;
+            }
             for (;;) {
-                // -- work
-                if (mode == G_IDLE) {
-                    uint32_t nt = n_tiles;
-                    if (spec_left) nt = atomicAdd(&M->tile_next, 1u);
-                    if (nt < n_tiles) {
-                        t = nt;
-                        t_begin = lz_tile_begin(t);
-                        t_end = min(n, lz_tile_begin(t + 1));
-                        p = t_begin + M->tile_start[t];
-                        if (p < n) pinfo = ld_u32_hint(&P[p], keep);
-                        tp0 = tp = spec_c + lz_tok_off(t);
-                        mode = G_SPEC;
-                    } else {
-                        spec_left = false;
-                        nt = atomicAdd(&M->tile_next2, 1u);
-                        t = nt;
-                        mode = nt < n_tiles ? G_WAIT : G_DONE;
+                // -- candidate steps of the searching lanes; left when a quarter of the lanes in work wait to be served
+                {
+                    unsigned busy = __ballot_sync(0xFFFFFFFFu, st == ST_SRCH);
+                    uint32_t it = 0;
+                    while (busy) {
+                        if (st == ST_SRCH) {
+                            const uint32_t bl = best >> 16;
+                            bool end;
+                            if (bl < 3u) {
+                                // nothing found yet: the newest candidate not yet looked at, exact test
+                                const uint32_t q = sorted[--s_cur];
+                                --s_left;
+                                end = s_left == 0u;
+                                if (p - q > LZ_WINDOW) {
+                                    end = true;  // older ones are outside the window too (src/LZ77.ts:223)
+                                } else {
+                                    const uint32_t len = lz_match_len(SV, q, p, pw, pw1, maxlen);
+                                    if (len) {
+                                        best = (len << 16) | q;
+                                        ptail = SV[p + len];
+                                        end = end || len >= maxlen;  // :189 (258) or capped by the input end
+                                    }
+                                }
+                            } else {
+                                // only a strictly longer match replaces the best of the nearer ones (:183): its byte at
+                                // best_len must match. Four candidates per step through that test alone; the nearest
+                                // that passes gets the exact comparison
+                                const uint32_t c4 = min(4u, s_left);
+                                const uint32_t q0 = sorted[s_cur - 1u], q1 = c4 > 1u ? sorted[s_cur - 2u] : 0u,
+                                               q2 = c4 > 2u ? sorted[s_cur - 3u] : 0u, q3 = c4 > 3u ? sorted[s_cur - 4u] : 0u;
+                                const bool h0 = SV[q0 + bl] == ptail, h1 = c4 > 1u && SV[q1 + bl] == ptail,
+                                           h2 = c4 > 2u && SV[q2 + bl] == ptail, h3 = c4 > 3u && SV[q3 + bl] == ptail;
+                                uint32_t used = c4, q = 0xFFFFFFFFu;
+                                if (h0) {
+                                    used = 1u;
+                                    q = q0;
+                                } else if (h1) {
+                                    used = 2u;
+                                    q = q1;
+                                } else if (h2) {
+                                    used = 3u;
+                                    q = q2;
+                                } else if (h3) {
+                                    q = q3;
+                                }
+                                // the oldest candidate looked at decides about the window (ascending positions)
+                                const uint32_t qo = used == 1u ? q0 : used == 2u ? q1 : used == 3u ? q2 : q3;
+                                s_cur -= used;
+                                s_left -= used;
+                                end = s_left == 0u || p - qo > LZ_WINDOW;
+                                if (q != 0xFFFFFFFFu && p - q <= LZ_WINDOW) {
+                                    const uint32_t len = lz_match_len(SV, q, p, pw, pw1, maxlen);
+                                    if (len > bl) {
+                                        best = (len << 16) | q;
+                                        ptail = SV[p + len];
+                                        end = end || len >= maxlen;
+                                    }
+                                }
+                            }
+                            if (end) st = ST_RES;
+                        }
+                        busy = __ballot_sync(0xFFFFFFFFu, st == ST_SRCH);
+                        const unsigned waiting = __ballot_sync(0xFFFFFFFFu, st == ST_RES || st == ST_ADV);
+                        if (++it >= LZ_KMAX || LZ_WAIT_MUL * __popc(waiting) >= __popc(busy)) break;
                     }
                 }
-                if (mode == G_WAIT) {
-                    const bool ready = *(volatile uint8_t*)&M->spec_done[t] != 0 &&
-                                       (t == t0 || *(volatile uint8_t*)&M->spec_done[t - 1] != 0);
-                    if (ready) {
-                        __threadfence_block();
-                        if (t == t0) {  // the first tile needs no re-entry
-                            M->entry_used[t0] = (uint16_t)(base - lz_tile_begin(t0));
-                            M->fix_exit[t0] = M->spec_exit[t0];
-                            M->fix_count[t0] = 0;
-                            M->spec_from[t0] = 0;
-                            mode = G_IDLE;
-                        } else {
-                            t_begin = lz_tile_begin(t);
-                            t_end = min(n, lz_tile_begin(t + 1));
-                            p = entry = lz_tile_begin(t - 1) + M->spec_exit[t - 1];
-                            if (p < n) pinfo = ld_u32_hint(&P[p], keep);
-                            from = M->spec_count[t];
-                            tp0 = tp = fix_c + lz_tok_off(t);
-                            mode = G_RESYNC;
+                // -- searches behind long candidate lists: the whole warp, one request after the other
+                {
+                    unsigned cm = __ballot_sync(0xFFFFFFFFu, st == ST_COOP);
+                    while (cm) {
+                        const int src = __ffs((int)cm) - 1;
+                        cm &= cm - 1u;
+                        const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, src), bs = __shfl_sync(0xFFFFFFFFu, s_cur, src),
+                                       br = __shfl_sync(0xFFFFFFFFu, s_left, src);
+                        const uint32_t rr = lz_search_from(SV, sorted, bs - br, bs, bp, n, depth);
+                        if (lane == (unsigned)src) {
+                            best = rr ? (rr & 0xFFFF0000u) | (p - (rr & 0xFFFFu)) : 0u;
+                            st = ST_RES;
                         }
                     }
                 }
-                const bool active = mode == G_SPEC || mode == G_RESYNC;
-                if (!__any_sync(0xFFFFFFFFu, active)) {
-                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE)) break;
-                    if (__all_sync(0xFFFFFFFFu, mode == G_DONE || mode == G_WAIT)) __nanosleep(256);
-                    continue;
+                // -- the token of a searched position
+                if (st == ST_RES) {
+                    uint32_t tok, np;
+                    if (best >= (3u << 16)) {
+                        const uint32_t len = best >> 16, dist = p - (best & 0xFFFFu);
+                        tok = TOK_MATCH | ((len - 3u) << 16) | (dist - 1u);
+                        np = p + len;
+                    } else {
+                        tok = SV[p];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
+                        np = p + 1u;
+                    }
+                    tbuf[tok_i++] = tok;
+                    if (!resync) visited[p >> 5] |= 1u << (p & 31u);
+                    p = np;
+                    if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                    st = ST_ADV;
                 }
-
-                // -- owners: finish the tile, write a run of literals, or post a search
-                bool req = false;
-                uint32_t slot = 0, rank = 0;
-                if (active) {
-                    bool finish = p >= t_end;
+                // -- next position: end of the tile, the splice, a run of literals, or a search
+                if (st == ST_ADV) {
+                    bool fin = p >= t_end, spliced = false;
                     uint32_t vlimit = 32u;
-                    if (!finish && mode == G_RESYNC) {
-                        const uint32_t vm = __funnelshift_r(visited[p >> 5], visited[(p >> 5) + 1u], p & 31u);  // (one word of slack behind the bits)
+                    if (!fin && resync) {
+                        const volatile uint32_t* vv = visited;
+                        const uint32_t vm = __funnelshift_r(vv[p >> 5], vv[(p >> 5) + 1u], p & 31u);
                         if (vm & 1u) {
-                            // met the speculative parse: its tokens from this position on are the true ones
-                            uint32_t idx = 0;
-                            for (uint32_t wd = t_begin >> 5; wd <= (p >> 5); ++wd) {
-                                uint32_t bits = visited[wd];
-                                if (wd == (p >> 5)) bits &= (1u << (p & 31u)) - 1u;
-                                idx += __popc(bits);
-                            }
-                            from = idx;
-                            p = t_begin + M->spec_exit[t];
-                            finish = true;
+                            fin = spliced = true;  // met the speculative parse: its tokens from this position on are the true ones
                         } else if (vm) {
                             vlimit = (uint32_t)__ffs((int)vm) - 1u;  // a run of literals stops in front of a visited position
                         }
                     }
-                    if (finish) {
-                        if (mode == G_SPEC) {
-                            M->spec_exit[t] = (uint16_t)(p - t_begin);
-                            M->spec_count[t] = (LZ_COUNT_T)(tp - tp0);
-                            // publish the tile: its visited bits (this lane's own stores) and tables before the flag
-                            __threadfence_block();
-                            *(volatile uint8_t*)&M->spec_done[t] = 1;
+                    if (fin) {
+                        if (!resync) {
+                            M2->spec_exit[t] = (uint16_t)(p - t_begin);
+                            M->spec_count[t] = (LZ_COUNT_T)(tok_i - tok_0);
+                            if (t + 1u < n_tiles) {
+                                resync = true;
+                                entry = p;
+                                t_end = min(n, t_begin + 2u * LZ_TILE_POS);
+                                tbuf = fix_c;
+                                tok_0 = tok_i = lz_tok_off(t + 1u);
+                            } else {
+                                st = ST_DONE;
+                            }
                         } else {
-                            M->entry_used[t] = (uint16_t)(entry - t_begin);
-                            M->fix_exit[t] = (uint16_t)(p - t_begin);
-                            M->fix_count[t] = (LZ_COUNT_T)(tp - tp0);
-                            M->spec_from[t] = (LZ_COUNT_T)from;
+                            const uint32_t nb = t_begin + LZ_TILE_POS;  // first position of tile t + 1
+                            M->entry_used[t + 1u] = (uint16_t)(entry - nb);
+                            M->fix_count[t + 1u] = (LZ_COUNT_T)(tok_i - tok_0);
+                            M2->fix_exit[t + 1u] = spliced ? (uint16_t)LZ_EXIT_SPLICED : (uint16_t)(p - nb);
+                            M2->spec_from[t + 1u] = spliced ? (LZ_COUNT_T)(p - nb) : (LZ_COUNT_T)LZ_NO_SPLICE;
+                            st = ST_DONE;
                         }
-                        mode = G_IDLE;
                     } else {
                         // may-have-a-candidate bits of the 32 positions from p on
                         const uint32_t w = p >> 5, off = p & 31u;
@@ -962,89 +988,54 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                         const uint32_t k = mm ? min((uint32_t)__ffs((int)mm) - 1u, avail) : avail;
                         if (k) {
                             // k positions without any candidate: k literals (src/LZ77.ts:267-272)
-                            for (uint32_t o = 0; o < k; ++o) tp[o] = SV[p + o];
-                            tp += k;
-                            if (mode == G_SPEC) {  // visited bits [p, p + k): at most two words, this lane's own tile
+                            for (uint32_t o = 0; o < k; ++o) tbuf[tok_i + o] = SV[p + o];
+                            tok_i += k;
+                            if (!resync) {  // visited bits [p, p + k): at most two words, this lane's own tile
                                 const unsigned long long bits = (0xFFFFFFFFFFFFFFFFull >> (64u - k)) << off;
                                 visited[w] |= (uint32_t)bits;
                                 if (bits >> 32) visited[w + 1] |= (uint32_t)(bits >> 32);
                             }
                             p += k;
                             if (p < n) pinfo = ld_u32_hint(&P[p], keep);
-                        } else {
-                            slot = pinfo & 0xFFFFu;
-                            rank = pinfo >> 16;
-                            req = true;
+                        }
+                        if (k < avail) {  // p has candidates
+                            const uint32_t rank = pinfo >> 16;  // earlier entries of the bucket: the slots in front of p's own
+                            s_cur = pinfo & 0xFFFFu;
+                            maxlen = min(LZ_MAXLEN, n - p);
+                            best = 0;
+                            if (rank > LZ_PRIV_CAP && depth > LZ_PRIV_CAP) {
+                                s_left = rank;
+                                st = ST_COOP;
+                            } else {
+                                s_left = min(rank, depth);
+                                pw = ld_u32(SV, p);
+                                pw1 = ld_u32(SV, p + 4u);
+                                st = s_left ? ST_SRCH : ST_RES;
+                            }
                         }
                     }
                 }
-                // -- the batch: every request with a short candidate list
-                const bool in_batch = req && rank <= LZ_BATCH_CAP;
-                uint32_t incl = in_batch ? rank : 0u;
-#pragma unroll
-                for (uint32_t d = 1; d < LZ_OWNERS; d <<= 1) {
-                    const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-                    if (lane >= d) incl += u;
-                }
-                const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, LZ_OWNERS - 1);
-                if (total) {
-                    if (owner) {
-                        B->end[lane] = incl;
-                        B->start[lane] = incl - (in_batch ? rank : 0u);
-                        B->best[lane] = 0;
-                        if (in_batch) {
-                            B->p[lane] = p;
-                            B->slot[lane] = slot;
-                            B->pw[lane] = ld_u32(SV, p);
-                            B->pw1[lane] = ld_u32(SV, p + 4);
-                        }
-                    }
-                    __syncwarp();
-                    for (uint32_t i = lane; i < total; i += 32u) {
-                        // request of candidate i: the first one whose list ends behind i
-                        uint32_t r = 0;
-#pragma unroll
-                        for (uint32_t h = LZ_OWNERS / 2; h >= 1; h >>= 1)
-                            if (B->end[r + h - 1] <= i) r += h;
-                        const uint32_t rp = B->p[r];
-                        const uint32_t q = sorted[B->slot[r] - 1u - (i - B->start[r])];  // start = newest candidate
-                        if (rp - q <= LZ_WINDOW) {
-                            const uint32_t len = lz_match_len(SV, q, rp, B->pw[r], B->pw1[r], min(LZ_MAXLEN, n - rp));
-                            if (len >= 3u) atomicMax(&B->best[r], (len << 16) | q);  // longest, then nearest
-                        }
-                    }
-                    __syncwarp();
-                }
-                uint32_t res = 0;
-                if (in_batch && rank) {  // rank == 0: nothing was posted (and the table may not have been reset)
-                    const uint32_t bm = B->best[lane];
-                    if (bm) res = (bm & 0xFFFF0000u) | (p - (bm & 0xFFFFu));
-                }
-                // -- searches behind long candidate lists: the whole warp, one request after the other
-                unsigned bigm = __ballot_sync(0xFFFFFFFFu, req && !in_batch);
-                while (bigm) {
-                    const int src = __ffs((int)bigm) - 1;
-                    bigm &= bigm - 1u;
-                    const uint32_t bp = __shfl_sync(0xFFFFFFFFu, p, src), bs = __shfl_sync(0xFFFFFFFFu, slot, src),
-                                   br = __shfl_sync(0xFFFFFFFFu, rank, src);
-                    const uint32_t rr = lz_search_from(SV, sorted, bs - br, bs, bp, n, depth);
-                    if (lane == (unsigned)src) res = rr;
-                }
-                // -- the token of a searched position
-                if (req) {
-                    uint32_t tok, np;
-                    if (res) {
-                        const uint32_t len = res >> 16, dist = res & 0xFFFFu;
-                        tok = TOK_MATCH | ((len - 3) << 16) | (dist - 1);
-                        np = p + len;
-                    } else {
-                        tok = SV[p];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
-                        np = p + 1;
-                    }
-                    *tp++ = tok;
-                    if (mode == G_SPEC) visited[p >> 5] |= 1u << (p & 31u);
-                    p = np;
-                    if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                if (__all_sync(0xFFFFFFFFu, st == ST_DONE)) break;
+            }
+        }
+        __threadfence_block();
+        __syncthreads();
+        // the splices, from the final visited bits; the first tile needs no re-entry
+        if (tid >= t0 && tid < n_tiles) {
+            const uint32_t t = tid;
+            if (t == t0) {
+                M->entry_used[t] = (uint16_t)(base - lz_tile_begin(t0));
+                M->fix_count[t] = 0;
+                M2->fix_exit[t] = M2->spec_exit[t];
+                M2->spec_from[t] = 0;
+            } else {
+                const uint32_t x = M2->spec_from[t];
+                if (x == LZ_NO_SPLICE) {
+                    M2->spec_from[t] = M->spec_count[t];
+                } else {
+                    const unsigned long long vis = (unsigned long long)visited[2u * t] | ((unsigned long long)visited[2u * t + 1u] << 32);
+                    M2->spec_from[t] = (LZ_COUNT_T)__popcll(vis & ((1ull << x) - 1ull));
+                    M2->fix_exit[t] = M2->spec_exit[t];
                 }
             }
         }
@@ -1052,8 +1043,8 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         // ---- 4b. tiles entered at the wrong place form chains (consecutive tiles inside one long run of
         //          matches that never meets the speculative parse); chains are independent, one warp each
         for (uint32_t w = t0 + 1 + tid; w < n_tiles; w += LZ_THREADS) {
-            const bool bad = lz_tile_begin(w - 1) + M->fix_exit[w - 1] != lz_tile_begin(w) + M->entry_used[w];
-            const bool bad_prev = w >= t0 + 2 && lz_tile_begin(w - 2) + M->fix_exit[w - 2] != lz_tile_begin(w - 1) + M->entry_used[w - 1];
+            const bool bad = lz_tile_begin(w - 1) + M2->fix_exit[w - 1] != lz_tile_begin(w) + M->entry_used[w];
+            const bool bad_prev = w >= t0 + 2 && lz_tile_begin(w - 2) + M2->fix_exit[w - 2] != lz_tile_begin(w - 1) + M->entry_used[w - 1];
             if (bad && !bad_prev) atomicOr(&M->start_mask[w >> 5], 1u << (w & 31));
         }
         __syncthreads();
@@ -1061,19 +1052,19 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             if (!((M->start_mask[w >> 5] >> (w & 31)) & 1u)) continue;
             uint32_t end = w + 1;  // next chain start (or the end of the chunk)
             while (end < n_tiles && !((M->start_mask[end >> 5] >> (end & 31)) & 1u)) ++end;
-            uint32_t entry = lz_tile_begin(w - 1) + M->fix_exit[w - 1];
+            uint32_t entry = lz_tile_begin(w - 1) + M2->fix_exit[w - 1];
             for (uint32_t t = w; t < end; ++t) {
                 if (entry == lz_tile_begin(t) + M->entry_used[t]) break;
                 const uint32_t t_begin = lz_tile_begin(t), t_end = min(n, lz_tile_begin(t + 1));
                 uint32_t nfix, from;
                 const uint32_t ex = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth,
                                                    fix_c + lz_tok_off(t), visited, M->spec_count[t],
-                                                   t_begin + M->spec_exit[t], &nfix, &from);
+                                                   t_begin + M2->spec_exit[t], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[t] = (uint16_t)(entry - t_begin);
-                    M->fix_exit[t] = (uint16_t)(ex - t_begin);
+                    M2->fix_exit[t] = (uint16_t)(ex - t_begin);
                     M->fix_count[t] = (LZ_COUNT_T)nfix;
-                    M->spec_from[t] = (LZ_COUNT_T)from;
+                    M2->spec_from[t] = (LZ_COUNT_T)from;
                 }
                 __syncwarp();
                 entry = ex;
@@ -1082,23 +1073,26 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         __syncthreads();
         // ---- 4c. walk the chain of true exits once; anything still entered at the wrong place is redone here
         //          (normally nothing: this pass is what makes 4a/4b safe to run optimistically)
-        if (warp == 0 && t0 < n_tiles) {
-            uint32_t true_exit = lz_tile_begin(t0) + M->fix_exit[t0];
+        bool consistent = true;  // every tile entered where its predecessor exits: then the walk has nothing to find
+        for (uint32_t w = t0 + 1 + tid; w < n_tiles; w += LZ_THREADS)
+            consistent = consistent && lz_tile_begin(w - 1) + M2->fix_exit[w - 1] == lz_tile_begin(w) + M->entry_used[w];
+        if (!__syncthreads_and(consistent) && warp == 0 && t0 < n_tiles) {
+            uint32_t true_exit = lz_tile_begin(t0) + M2->fix_exit[t0];
             for (uint32_t w = t0 + 1; w < n_tiles; ++w) {
                 if (true_exit == lz_tile_begin(w) + M->entry_used[w]) {
-                    true_exit = lz_tile_begin(w) + M->fix_exit[w];
+                    true_exit = lz_tile_begin(w) + M2->fix_exit[w];
                     continue;
                 }
                 const uint32_t t_begin = lz_tile_begin(w), t_end = min(n, lz_tile_begin(w + 1));
                 uint32_t nfix, from;
                 const uint32_t entry = true_exit;
                 true_exit = lz_resync_tile(SV, sorted, P, hasbits, keep, entry, t_begin, t_end, n, depth, fix_c + lz_tok_off(w),
-                                           visited, M->spec_count[w], t_begin + M->spec_exit[w], &nfix, &from);
+                                           visited, M->spec_count[w], t_begin + M2->spec_exit[w], &nfix, &from);
                 if (lane == 0) {
                     M->entry_used[w] = (uint16_t)(entry - t_begin);
-                    M->fix_exit[w] = (uint16_t)(true_exit - t_begin);
+                    M2->fix_exit[w] = (uint16_t)(true_exit - t_begin);
                     M->fix_count[w] = (LZ_COUNT_T)nfix;
-                    M->spec_from[w] = (LZ_COUNT_T)from;
+                    M2->spec_from[w] = (LZ_COUNT_T)from;
                 }
             }
         }
@@ -1110,13 +1104,13 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         // ---- 5. the chunk's token list + histograms (src/LZ77.ts:126-128,141-142,236,251,271,279): per tile the
         //         re-parsed tokens, then the speculative ones from the splice on, tiles in order -- one contiguous list,
         //         written once (streaming stores) and read once by the bit packer
-        uint32_t* tok_off = reinterpret_cast<uint32_t*>(M->spec_exit);  // the two exit tables are dead now: u32 per tile
-        static_assert(offsetof(LzMisc, fix_exit) == offsetof(LzMisc, spec_exit) + sizeof(uint16_t) * LZ_NTILES,
+        uint32_t* tok_off = reinterpret_cast<uint32_t*>(M2->spec_exit);  // the two exit tables are dead now: u32 per tile
+        static_assert(offsetof(LzTiles2, fix_exit) == offsetof(LzTiles2, spec_exit) + sizeof(uint16_t) * LZ_NTILES,
                       "spec_exit and fix_exit must be adjacent");
         {
             uint32_t cnt = 0;
             if (tid < LZ_NTILES && tid >= t0 && tid < n_tiles)
-                cnt = (uint32_t)M->fix_count[tid] + ((uint32_t)M->spec_count[tid] - (uint32_t)M->spec_from[tid]);
+                cnt = (uint32_t)M->fix_count[tid] + ((uint32_t)M->spec_count[tid] - (uint32_t)M2->spec_from[tid]);
             const uint32_t off = block_excl_sum(cnt, M->warp_tot, &M->n_tokens);
             if (tid < LZ_NTILES) tok_off[tid] = off;  // (block_excl_sum ends with a barrier: the exit tables were read before it)
         }
@@ -1124,7 +1118,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         {
             const unsigned long long stream = l2_policy_stream();
             for (uint32_t w = t0 + warp; w < n_tiles; w += LZ_WARPS) {
-                const uint32_t nf = M->fix_count[w], from = M->spec_from[w], sc = M->spec_count[w];
+                const uint32_t nf = M->fix_count[w], from = M2->spec_from[w], sc = M->spec_count[w];
                 uint32_t* dst = list_c + tok_off[w];
                 const uint32_t* fx = fix_c + lz_tok_off(w);
                 const uint32_t* sp = spec_c + lz_tok_off(w) + from;
@@ -1230,9 +1224,8 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
     uint8_t* Sbuf = smem + LzSmem::S_OFF;
     uint16_t* sorted = reinterpret_cast<uint16_t*>(smem + LzSmem::SORTED_OFF);
     uint16_t* prev = sorted;  // the links replace the sorted index in place (via the global scratch)
-    uint16_t* bstart = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);
     LzFastTiles* TL = reinterpret_cast<LzFastTiles*>(smem + LzSmem::BSTART_OFF);
-    uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::AUX_OFF);
+    uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);  // radix offsets (dead before the tile table is written)
     uint32_t* bits = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF);  // bucket-start bits, then visited bits
     LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
 
@@ -1259,9 +1252,11 @@ lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ ch
         const uint32_t n = base + ch.len;
         const uint8_t* src = in + ch.in_off - base;
 
-        const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, bstart, cnt16, M, T, phase, bits);
+        const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, cnt16, M, T, phase);
         const LzS SV = ix.SV;
         const uint32_t m = ix.m;
+        lz_build_info<true>(SV, sorted, m, n, nullptr, nullptr, bits, keep);  // bucket-start bits
+        __syncthreads();
 
         // ---- hash-chain links: prev[pos] = the previous position of the same bucket (nearest earlier one).
         // The links replace the sorted index in place, so they take a detour through the global scratch: written
