@@ -133,10 +133,12 @@ def deflate_many(inputs, compression_type=CompressionType.DYNAMIC, chunk_bytes=0
     return outs, res
 
 
-def inflate_blob(blob, offs, lens, size_hints=None, want_crc32=False, want_adler32=False):
+def inflate_blob(blob, offs, lens, size_hints=None, want_crc32=False, want_adler32=False, split=True, tolerant=False):
     """Raw-inflates the streams blob[offs[i] : offs[i] + lens[i]] in one GPU batch; output slots that turn out
     too small are retried larger (the reference grows its buffer instead, src/RawInflate.ts:550-581).
-    Returns (list of uint8 arrays, results table); raises ZlibError with the reference's text on corrupt input."""
+    Returns (list of uint8 arrays, results table); raises ZlibError with the reference's text on corrupt input.
+    `tolerant`: nothing is raised or retried -- a stream that fails or overflows its slot comes back as None with its
+    status in the table (speculative decoding of gzip member candidates)."""
     blob = _u8(blob)
     n = len(offs)
     if n == 0:
@@ -148,7 +150,8 @@ def inflate_blob(blob, offs, lens, size_hints=None, want_crc32=False, want_adler
         hint = None if size_hints is None else size_hints[i]
         caps[i] = int(hint) if hint is not None else max(0x8000, 4 * int(lens[i]))  # DefaultInflateBufferSize
     # large streams written by this engine decode piecewise at their sync-flush markers (same result, see the header)
-    flags = (N.INFLATE_WANT_CRC32 if want_crc32 else 0) | (N.INFLATE_WANT_ADLER32 if want_adler32 else 0) | N.INFLATE_SPLIT
+    flags = ((N.INFLATE_WANT_CRC32 if want_crc32 else 0) | (N.INFLATE_WANT_ADLER32 if want_adler32 else 0) |
+             (N.INFLATE_SPLIT if split else 0))
     if blob.size == 0:
         blob = np.zeros(1, dtype=np.uint8)
     outs = [None] * n
@@ -165,6 +168,9 @@ def inflate_blob(blob, offs, lens, size_hints=None, want_crc32=False, want_adler
         again = []
         for k, i in enumerate(todo):
             st = int(res["status"][k])
+            if tolerant and st != N.ST_OK:
+                final[i] = res[k]
+                continue
             if st == N.ST_OUT_OVERFLOW:
                 caps[i] = max(int(caps[i]) * 4, 1 << 16)
                 again.append(i)
@@ -438,6 +444,14 @@ class GZip:
 
 
 class GUnzip:
+    """Multi-member files are decoded as ONE GPU batch: every `1F 8B 08` signature in the buffer is a candidate
+    member, all candidates are inflated speculatively side by side, and the chain of true members is then walked on
+    the host exactly as the reference's loop would (src/GUnzip.ts:56-58): member k + 1 begins where member k's trailer
+    ends; candidates that lie inside compressed data are never reached. Results, checks and error texts are those of
+    the member-by-member loop."""
+
+    BATCH_MIN_CANDIDATES = 2
+
     def __init__(self, input):
         self.input = _u8(input)
         self.ip = 0
@@ -451,13 +465,15 @@ class GUnzip:
         return list(self.members)
 
     def decompress(self):
+        if self.ip == 0 and not self.members:
+            self._decode_all_members()
         while self.ip < self.input.size:  # src/GUnzip.ts:56-58 (multi-member)
             self.decodeMember()
         self.decompressed = True
         return np.concatenate([m["data"] for m in self.members]) if self.members else np.zeros(0, dtype=np.uint8)
 
-    def decodeMember(self):  # src/GUnzip.ts:66-183
-        inp, p = self.input, self.ip
+    def _parse_header(self, p):  # src/GUnzip.ts:66-133; returns (member fields, offset of the deflate data)
+        inp = self.input
         m = {"id1": int(inp[p]), "id2": int(inp[p + 1])}
         if m["id1"] != 0x1F or m["id2"] != 0x8B:
             raise ZlibError("invalid file signature:%d,%d" % (m["id1"], m["id2"]))
@@ -483,14 +499,14 @@ class GUnzip:
             if m["crc16"] != (int(inp[p]) | (int(inp[p + 1]) << 8)):
                 raise ZlibError("invalid header crc16")
             p += 2
-        isize = struct.unpack("<I", inp[-4:].tobytes())[0]  # size hint from the last 4 bytes of the buffer (:135-149)
-        hint = isize if inp.size - p - 8 < isize * 512 else None
-        outs, res = inflate_many([inp], [p], [hint], want_crc32=True)
-        data = outs[0]
+        return m, p
+
+    def _finish_member(self, m, p, data, res_row):  # src/GUnzip.ts:151-183: trailer checks, member record
+        inp = self.input
         m["data"] = data
-        p += int(res["in_used"][0])
+        p += int(res_row["in_used"])
         crc32, isize2 = struct.unpack("<II", inp[p:p + 8].tobytes().ljust(8, b"\0"))
-        self.crc32 = int(res["crc32"][0])
+        self.crc32 = int(res_row["crc32"])
         if self.crc32 != crc32:
             raise ZlibError("invalid CRC-32 checksum: 0x%x / 0x%x" % (self.crc32, crc32))
         if (data.size & 0xFFFFFFFF) != isize2:
@@ -498,6 +514,78 @@ class GUnzip:
         m["crc32"], m["isize"] = crc32, isize2
         self.members.append(m)
         self.ip = p + 8
+
+    def decodeMember(self):  # src/GUnzip.ts:66-183
+        inp = self.input
+        m, p = self._parse_header(self.ip)
+        isize = struct.unpack("<I", inp[-4:].tobytes())[0]  # size hint from the last 4 bytes of the buffer (:135-149)
+        hint = isize if inp.size - p - 8 < isize * 512 else None
+        # only this member's bytes and what follows it travel; the marker split is for one large member, not for a
+        # tail of further members (they are decoded by the batch path above)
+        outs, res = inflate_many([inp[p:]], [0], [hint], want_crc32=True)
+        self._finish_member(m, p, outs[0], res[0])
+
+    def _decode_all_members(self):
+        """Batch path. Leaves self.ip at the first member it could not settle (the member loop carries on there and
+        reports whatever is wrong in the reference's words)."""
+        inp = self.input
+        if inp.size < 36:
+            return
+        sig = np.flatnonzero((inp[:-2] == 0x1F) & (inp[1:-1] == 0x8B) & (inp[2:] == 0x08))
+        if sig.size < self.BATCH_MIN_CANDIDATES or sig[0] != 0:
+            return
+        heads = {}
+        for c in sig.tolist():
+            try:
+                heads[c] = self._parse_header(c)
+            except (ZlibError, IndexError):
+                pass  # not a member start (or a broken one: the member loop will say so if the chain gets there)
+        starts = sorted(heads)
+        if len(starts) < self.BATCH_MIN_CANDIDATES:
+            return
+        offs = np.array([heads[c][1] for c in starts], dtype=np.uint64)
+        lens = np.uint64(inp.size) - offs
+        nxt = np.array(starts[1:] + [inp.size], dtype=np.int64)
+        gaps = np.maximum(nxt - offs.astype(np.int64), 0)
+        caps = np.maximum(0x8000, 4 * gaps)
+        index_of = {c: i for i, c in enumerate(starts)}
+        outs, res = [None] * len(starts), np.zeros(len(starts), dtype=N.RESULT_DTYPE)
+        g0 = 0
+        while g0 < len(starts):  # groups of candidates whose output slots stay below 2 GiB together
+            g1, tot = g0, 0
+            while g1 < len(starts) and (g1 == g0 or tot + int(caps[g1]) <= (2 << 30)):
+                tot += int(caps[g1])
+                g1 += 1
+            o1, r1 = inflate_blob(inp, offs[g0:g1], lens[g0:g1], list(caps[g0:g1]), want_crc32=True, split=False,
+                                  tolerant=True)
+            outs[g0:g1] = o1
+            res[g0:g1] = r1
+            g0 = g1
+        for _ in range(6):  # candidates on the chain whose slot was too small are decoded again, larger
+            pos, retry = 0, None
+            while pos < inp.size and pos in index_of:
+                i = index_of[pos]
+                st = int(res["status"][i])
+                if st == N.ST_OUT_OVERFLOW:
+                    retry = i
+                    break
+                if st != N.ST_OK:
+                    break
+                pos = int(offs[i]) + int(res["in_used"][i]) + 8
+            if retry is None:
+                break
+            again = [i for i in range(retry, len(starts)) if int(res["status"][i]) == N.ST_OUT_OVERFLOW]
+            caps[again] *= 4
+            o2, r2 = inflate_blob(inp, offs[again], lens[again], list(caps[again]), want_crc32=True, split=False,
+                                  tolerant=True)
+            for k, i in enumerate(again):
+                outs[i], res[i] = o2[k], r2[k]
+        while self.ip < inp.size and self.ip in index_of:
+            i = index_of[self.ip]
+            if int(res["status"][i]) != N.ST_OK:
+                return
+            m, p = heads[self.ip]
+            self._finish_member(dict(m), p, outs[i], res[i])
 
 
 # ------------------------------------------------------------------------------------------------------------

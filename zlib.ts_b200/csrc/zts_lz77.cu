@@ -364,43 +364,61 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
     }
     const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
-    uint32_t misses = 0;  // consecutive 32-wide steps in which the tail-byte filter rejected every candidate
-    while (cur > lo) {
-        // long candidate lists behind a known match (ends of runs, low-entropy records): 128 candidates per step
-        // through the tail-byte filter alone, four independent look-ups per lane in flight; the first group in
-        // which anything survives (or leaves the window) is handed to the exact 32-wide step below
-        if (misses >= 2u && cur - lo >= 128u) {  // misses > 0 implies a known match (best_len >= 3)
-            const uint8_t pt = S[p + best_len];
-            do {
-                const uint32_t c0 = sorted[cur - 1 - lane], c1 = sorted[cur - 33 - lane], c2 = sorted[cur - 65 - lane],
-                               c3 = sorted[cur - 97 - lane];
-                const bool hit = S[c0 + best_len] == pt || S[c1 + best_len] == pt || S[c2 + best_len] == pt ||
-                                 S[c3 + best_len] == pt || p - c3 > LZ_WINDOW;  // c3 is the oldest of the lane's four
-                if (__any_sync(0xFFFFFFFFu, hit)) break;
-                cur -= 128u;
-            } while (cur - lo >= 128u);
-            if (cur <= lo) break;
-        }
+    if (depth < cur - lo) lo = cur - depth;  // candidate budget
+    // until a match is known: 32 candidates per step, exact comparison
+    while (cur > lo && best_len < 3u) {
         const uint32_t cnt = min(32u, cur - lo);
         const bool act = lane < cnt;
         const uint32_t q = act ? sorted[cur - 1 - lane] : 0u;  // lane 0 = newest candidate
         const bool inwin = act && (p - q <= LZ_WINDOW);
-        const uint8_t ptail = S[p + best_len];
-        // only a strictly longer match can replace the best of the nearer blocks (:183): its byte at best_len
-        // must match, which is the cheapest test and rejects nearly everything once a match is known
         uint32_t key = 0;
-        if (inwin && (best_len < 3 || S[q + best_len] == ptail)) key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
+        if (inwin) key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
         const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);  // longest, then nearest
-        misses = m ? 0u : misses + 1u;
-        if ((m >> 16) > best_len) {
+        if (m >> 16) {
             best_len = m >> 16;
             best = m;
         }
-        if (best_len >= maxlen) break;                          // :189 (258) or capped by the input end
-        if (__any_sync(0xFFFFFFFFu, act && !inwin)) break;      // older ones are outside the window (:223)
         cur -= cnt;
-        if (depth <= 32u) break;                                // candidate budget spent
-        depth -= 32u;
+        if (__any_sync(0xFFFFFFFFu, act && !inwin)) cur = lo;  // older ones are outside the window (:223)
+    }
+    // behind a known match only a strictly longer one counts (:183): its byte at best_len must match, which is the
+    // cheapest test and rejects nearly everything. 128 candidates per step through that test (four independent
+    // look-ups per lane in flight); the few that pass get the exact comparison
+    while (cur > lo && best_len < maxlen) {  // :189 (258) or capped by the input end
+        const uint32_t cnt = min(128u, cur - lo);
+        const uint8_t pt = S[p + best_len];
+        uint32_t key = 0, hitq[4];
+        unsigned hm = 0;  // which of this lane's four candidates passed the test
+        bool out = false;
+#pragma unroll
+        for (uint32_t k = 0; k < 4u; ++k) {
+            const uint32_t o = k * 32u + lane;
+            hitq[k] = 0;
+            if (o < cnt) {
+                const uint32_t q = sorted[cur - 1u - o];
+                hitq[k] = q;
+                if (p - q > LZ_WINDOW)
+                    out = true;
+                else if (S[q + best_len] == pt)
+                    hm |= 1u << k;
+            }
+        }
+        while (hm) {
+            const uint32_t k = (uint32_t)__ffs((int)hm) - 1u;
+            hm &= hm - 1u;
+            const uint32_t q = k == 0u ? hitq[0] : k == 1u ? hitq[1] : k == 2u ? hitq[2] : hitq[3];
+            key = max(key, (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q);
+        }
+        const unsigned hits = __ballot_sync(0xFFFFFFFFu, key != 0u);
+        if (hits) {
+            const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
+            if ((m >> 16) > best_len) {
+                best_len = m >> 16;
+                best = m;
+            }
+        }
+        cur -= cnt;
+        if (__any_sync(0xFFFFFFFFu, out)) break;  // older ones are outside the window (:223)
     }
     if (best_len < 3) return 0;
     return (best_len << 16) | (p - (best & 0xFFFFu));
@@ -825,12 +843,12 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         //      (ST_SRCH), waiting for the warp to search a long list for it (ST_COOP), holding a result (ST_RES).
         {
             enum { ST_ADV = 0, ST_SRCH = 1, ST_COOP = 2, ST_RES = 3, ST_DONE = 4 };
-#ifndef LZ_INTERLEAVE
+#ifdef LZ_NO_INTERLEAVE
             const uint32_t t = tid;
 #else
             // the 32 tiles of a warp lie 2 KiB apart: neighbouring tiles cost alike (they hold the same kind of data),
             // so this spreads expensive stretches of the chunk over all the warps
-            const uint32_t t = lane * LZ_WARPS + warp;
+            const uint32_t t = lane * LZ_WARPS + ((lane + warp) & 31u);  // (33 tiles between neighbouring lanes: their table words fall into different banks)
 #endif
             const uint32_t t_begin = t * LZ_TILE_POS;
             uint32_t st = ST_DONE;
@@ -988,7 +1006,16 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                         const uint32_t k = mm ? min((uint32_t)__ffs((int)mm) - 1u, avail) : avail;
                         if (k) {
                             // k positions without any candidate: k literals (src/LZ77.ts:267-272)
-                            for (uint32_t o = 0; o < k; ++o) tbuf[tok_i + o] = SV[p + o];
+                            {
+                                uint32_t o = 0;  // single tokens up to a 16-byte boundary of the token slots, then four per store
+                                for (; o < k && ((tok_i + o) & 3u); ++o) tbuf[tok_i + o] = SV[p + o];
+                                for (; o + 4u <= k; o += 4u) {
+                                    const uint32_t w4 = ld_u32(SV, p + o);
+                                    *reinterpret_cast<uint4*>(tbuf + tok_i + o) =
+                                        make_uint4(w4 & 0xFFu, (w4 >> 8) & 0xFFu, (w4 >> 16) & 0xFFu, w4 >> 24);
+                                }
+                                for (; o < k; ++o) tbuf[tok_i + o] = SV[p + o];
+                            }
                             tok_i += k;
                             if (!resync) {  // visited bits [p, p + k): at most two words, this lane's own tile
                                 const unsigned long long bits = (0xFFFFFFFFFFFFFFFFull >> (64u - k)) << off;
