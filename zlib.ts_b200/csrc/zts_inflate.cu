@@ -998,9 +998,10 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 + 2 * k), st));
         if (st != ctx->stream) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 + 2 * k), 0));  // the call ends on ctx->stream
         if (k + 1 < n_waves && (rc = wave_in(k + 1))) return rc;  // behind the launches: may wait for the copy threads
-        if (k > 0 && (rc = wave_out(k - 1))) return rc;
     }
-    if ((rc = wave_out(n_waves - 1))) return rc;
+    // every wave is queued (none waits for the host): their outputs leave in order, each as soon as its wave is done
+    for (size_t k = 0; k < n_waves; ++k)
+        if ((rc = wave_out(k))) return rc;
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
     return ZLB_OK;
 }
