@@ -66,12 +66,14 @@ enum { ZLB_NONE = 0, ZLB_FIXED = 1, ZLB_DYNAMIC = 2 };
 /* deflate mode. COMPAT: every chunk's bytes equal the reference's RawDeflate run on that chunk
  * (lazy = 0, src/LZ77.ts:196-283 exhaustive longest/nearest match, src/RawDeflate.ts:484-571 code
  * lengths). */
-enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1, ZLB_MODE_PRIMED = 2, ZLB_MODE_SMALLEST = 4 };
-/* FAST: same pipeline and the same exact Huffman construction, but the match search follows only the nearest
- * `depth` links of a position's hash chain (default ZLB_FAST_DEFAULT_DEPTH), runs one position per lane, and
- * matches are cut at tile boundaries (at most ~127 bytes): still a valid stream for the reference's Inflate, no
- * longer byte-identical; the size stays within 3 % of the reference-compatible mode on the benchmark data
- * (bench.py reports it). A depth is passed as ZLB_MODE_FAST_DEPTH(d). */
+enum { ZLB_MODE_COMPAT = 0, ZLB_MODE_FAST = 1, ZLB_MODE_PRIMED = 2, ZLB_MODE_SMALLEST = 4, ZLB_MODE_LAZY = 8 };
+/* FAST: same kernels and the same exact Huffman construction, but a match search looks only at the `depth` nearest
+ * entries of the position's hash bucket (default ZLB_FAST_DEFAULT_DEPTH, at most 64): still the greedy parse and a
+ * valid stream for the reference's Inflate, no longer byte-identical; the size stays within 3 % of the
+ * reference-compatible mode on the benchmark data (bench.py reports it). A depth is passed as ZLB_MODE_FAST_DEPTH(d).
+ * LAZY (a flag for FAST): one-step lazy evaluation -- a match shorter than 32 is only taken if the next position
+ * has no longer one, otherwise the position becomes a literal (what src/LZ77.ts:243-256 meant to do; the reference's
+ * own `lazy` option corrupts data, SURVEY B-2, and is refused by the host mirror). */
 /* PRIMED (pigz-style dictionary priming; may be or-ed with FAST): the match search of a chunk also
  * reaches into the 32 KiB of the same item in front of it, which recovers the ratio independent chunks lose. History
  * and chunk share the 64 KiB a CTA indexes, so chunks are at most ZLB_PRIMED_CHUNK bytes (chunk_bytes 0 = that; pass

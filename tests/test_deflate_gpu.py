@@ -232,9 +232,9 @@ def test_not_final_shards_concatenate_into_one_stream(engine):
 
 
 def test_fast_mode_valid_streams_and_ratio_within_tolerance(engine):
-    """ZLB_MODE_FAST (lane-parallel bounded search): a valid stream for zlib and for the reference's decoder; size
-    within 3 % of the reference-compatible mode on the benchmark generators (north_star tolerance). Highly
-    repetitive input pays for the tile cut of its matches in relative, not in absolute terms."""
+    """ZLB_MODE_FAST (bounded search depth, optionally with lazy evaluation): a valid stream for zlib and for the
+    reference's decoder; size within 3 % of the reference-compatible mode on the benchmark generators (north_star
+    tolerance)."""
     import torch
     import zlibts_b200 as z
     from zlibts_b200 import synth
@@ -250,7 +250,8 @@ def test_fast_mode_valid_streams_and_ratio_within_tolerance(engine):
         it = z.make_items(1)
         it["in_len"], it["out_cap"] = n, cap
         sizes = {}
-        for mname, mode in (("compat", z.MODE_COMPAT), ("fast", z.MODE_FAST), ("fast8", z.mode_fast(8)), ("fast64", z.mode_fast(64))):
+        for mname, mode in (("compat", z.MODE_COMPAT), ("fast", z.MODE_FAST), ("fast8", z.mode_fast(8)), ("fast64", z.mode_fast(64)),
+                            ("lazy", z.MODE_FAST | z.MODE_LAZY), ("lazy64", z.mode_fast(64) | z.MODE_LAZY)):
             d_z = torch.zeros(cap, dtype=torch.uint8, device="cuda")
             r = engine.deflate_batch(d_in, d_z, it, mode=mode)
             assert int(r["status"][0]) == 0
@@ -262,6 +263,9 @@ def test_fast_mode_valid_streams_and_ratio_within_tolerance(engine):
         if tol:
             assert sizes["fast"] <= sizes["compat"] * tol, (name, sizes)
             assert sizes["fast64"] <= sizes["compat"] * tol, (name, sizes)
+            assert sizes["lazy"] <= sizes["fast"], (name, sizes)  # lazy evaluation never loses to the greedy parse here
+        if name == "text":  # ... and beats the reference's (exhaustive, greedy) parse where matches are short
+            assert sizes["lazy64"] < sizes["compat"], sizes
         else:
             assert sizes["fast"] <= max(3 * sizes["compat"], sizes["compat"] + n // 50), (name, sizes)
     # a batch of small items through the fast kernel (ragged sizes around the tile size)

@@ -20,12 +20,12 @@ assert ITEM_DTYPE.itemsize == 32 and RESULT_DTYPE.itemsize == 32 and ENTRY_DTYPE
 
 # CompressionType (src/RawDeflate.ts:12-17)
 NONE, FIXED, DYNAMIC = 0, 1, 2
-MODE_COMPAT, MODE_FAST, MODE_PRIMED, MODE_SMALLEST = 0, 1, 2, 4   # PRIMED / SMALLEST are flags (or-ed in)
+MODE_COMPAT, MODE_FAST, MODE_PRIMED, MODE_SMALLEST, MODE_LAZY = 0, 1, 2, 4, 8   # PRIMED / SMALLEST / LAZY are flags (or-ed in)
 PRIMED_CHUNK = 32768
 
 
 def mode_fast(depth=0):
-    """ZLB_MODE_FAST_DEPTH(depth); 0 = the library default (64 candidates)."""
+    """ZLB_MODE_FAST_DEPTH(depth); 0 = the library default (16 candidates)."""
     return MODE_FAST | (int(depth) << 8)
 
 DEFLATE_WANT_CRC32, DEFLATE_WANT_ADLER32, DEFLATE_NOT_FINAL = 1, 2, 4

@@ -90,7 +90,7 @@ def _b200(opts):
 # batch entry points (what the N-API addon exposes below the classes)
 # ------------------------------------------------------------------------------------------------------------
 def _mode_of(opts):
-    """engine-only knob `b200: {mode: 'compat' | 'fast' | 'primed' | 'fast-primed', depth: N}` (default:
+    """engine-only knob `b200: {mode: 'compat' | 'fast' | 'primed' | 'fast-primed', depth: N, lazy: bool}` (default:
     reference-compatible bytes). 'primed' = every chunk also searches the 32 KiB in front of it (better ratio,
     still one stream the reference inflates, no longer RawDeflate(chunk) per chunk)."""
     b = _b200(opts)
@@ -98,6 +98,12 @@ def _mode_of(opts):
     if name not in ("compat", "fast", "primed", "fast-primed"):
         raise ZlibError("unknown b200 mode: %s" % name)
     mode = N.mode_fast(int(b.get("depth", 0))) if name.startswith("fast") else N.MODE_COMPAT
+    # `lazy: true` (fast modes only): one-step lazy evaluation that is actually correct -- what src/LZ77.ts:243-256 meant
+    # to do; the reference's own `lazy` option corrupts data and stays refused
+    if b.get("lazy"):
+        if not name.startswith("fast"):
+            raise ZlibError("b200.lazy needs a fast mode: the compat mode is the reference's greedy parse")
+        mode |= N.MODE_LAZY
     # `smallest: true` lets every chunk fall back to a fixed or stored block when that is shorter
     return mode | (N.MODE_PRIMED if name.endswith("primed") else 0) | (N.MODE_SMALLEST if b.get("smallest") else 0)
 

@@ -23,7 +23,6 @@ enum ZtsKernelSlot {
     ZK_FINALIZE,
     ZK_MARKER_SCAN,
     ZK_GATHER,
-    ZK_LZ77_FAST,
     ZK_FRAME_BODY,
     ZK_FRAME_HEADER,
     ZK_COUNT
@@ -33,7 +32,7 @@ static const char* const kZtsKernelNames[ZK_COUNT] = {
     "inflate_warp_kernel", "checksum_slices_kernel", "checksum_combine_kernel",
     "lz77_chunk_kernel",   "huffman_build_kernel",   "chunk_scan_kernel",
     "bitpack_kernel",      "stored_block_kernel",    "deflate_finalize_kernel",
-    "marker_scan_kernel",  "segment_gather_kernel",  "lz77_fast_kernel",
+    "marker_scan_kernel",  "segment_gather_kernel",
     "frame_body_kernel",   "frame_header_kernel"};
 
 struct ZtsDevBuf {
@@ -56,7 +55,7 @@ struct zlb_ctx {
 
     // device arenas (grow-only, freed in zlb_destroy)
     ZtsDevBuf d_items, d_results, d_chunks, d_chunk_info, d_tokens, d_spec, d_hist, d_codes, d_sortT,
-        d_sums, d_misc, d_stage_in, d_stage_out, d_split, d_fast, d_body, d_frames;
+        d_sums, d_misc, d_stage_in, d_stage_out, d_split, d_body, d_frames;
     // pinned host staging for the small tables
     void* h_pin = nullptr;
     size_t h_pin_cap = 0;

@@ -19,11 +19,7 @@ size_t zts_lz77_smem_bytes();
 size_t zts_lz77_scratch_bytes(int sm_count);   // per-CTA tile token scratch of the reference-compatible kernel
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
                     ZtsChunkInfo* d_info, uint32_t* d_tile_tok, uint32_t* d_list, uint32_t* d_hist, uint32_t* d_sortT,
-                    uint32_t* d_counter, uint32_t grid, uint32_t depth);
-size_t zts_lz77_fast_scratch_bytes(int sm_count);
-int zts_lz77_fast_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
-                         ZtsChunkInfo* d_info, uint32_t* d_list, uint32_t* d_tile_tok, uint32_t* d_hist,
-                         uint32_t* d_sortT, uint32_t* d_counter, uint32_t grid, uint32_t depth);
+                    uint32_t* d_counter, uint32_t grid, uint32_t depth, uint32_t lazy);
 int zts_huffman_launch(zlb_ctx* ctx, const ZtsChunk* d_chunks, uint32_t n_chunks, const uint32_t* d_hist,
                        ZtsChunkInfo* d_info, ZtsChunkCodes* d_codes, int block_type, int smallest);
 int zts_huffman_lengths_debug(zlb_ctx* ctx, const uint32_t* d_freqs, int nsym, int limit, uint8_t* d_lengths);
@@ -378,13 +374,16 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                           zlb_result* h_results, size_t n, int mode, int block_type, uint32_t chunk_bytes,
                           uint32_t flags, HostIO* hio)
 {
-    if ((mode & 0xFF) & ~(ZLB_MODE_FAST | ZLB_MODE_PRIMED | ZLB_MODE_SMALLEST))
+    if ((mode & 0xFF) & ~(ZLB_MODE_FAST | ZLB_MODE_PRIMED | ZLB_MODE_SMALLEST | ZLB_MODE_LAZY))
         return zts_fail(ctx, ZLB_E_UNSUPPORTED, "unknown deflate mode %d", mode);
     uint32_t depth = 0xFFFFFFFFu;  // compat: every candidate, like the reference
+    // fast mode: the same kernel, but a search looks at the `depth` nearest entries of the position's bucket only
     const bool fast = (mode & ZLB_MODE_FAST) != 0;
     const bool primed = (mode & ZLB_MODE_PRIMED) != 0 && block_type != ZLB_NONE;
     const bool smallest = (mode & ZLB_MODE_SMALLEST) != 0 && block_type == ZLB_DYNAMIC;
     if (fast) depth = ((uint32_t)mode >> 8) ? ((uint32_t)mode >> 8) : ZLB_FAST_DEFAULT_DEPTH;
+    if (fast && depth > 64u) depth = 64u;  // (the lane-private search; longer lists belong to the exact mode)
+    const bool lazy = fast && (mode & ZLB_MODE_LAZY) != 0;  // a fast-mode option: the exact mode is the reference's greedy parse
     if (block_type != ZLB_NONE && block_type != ZLB_FIXED && block_type != ZLB_DYNAMIC)
         return zts_fail(ctx, ZLB_E_ARG, "invalid compression type");  // src/RawDeflate.ts:110
     // primed: history + chunk share the 64 KiB a CTA stages and indexes, so a chunk is at most 32 KiB
@@ -507,13 +506,12 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     const size_t hist_b = (wave * 316 * 4 + 255) & ~(size_t)255;
     const size_t codes_b = (wave * sizeof(ZtsChunkCodes) + 255) & ~(size_t)255;
     const size_t sort_b = ((size_t)ctx->sm_count * LZ_MAX_CHUNK * 4 + 255) & ~(size_t)255;
-    const size_t fast_b = (zts_lz77_fast_scratch_bytes(ctx->sm_count) + 255) & ~(size_t)255;
     const size_t gpos_b = (wave * 8 + 256 + 255) & ~(size_t)255;  // chunk offsets of the wave + the work counter
     rc = zts_reserve(ctx, &ctx->d_chunk_info, n_sets * info_b + 64);
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_tokens, n_sets * list_b + 64);
     if (rc) return rc;
-    if (!fast && (rc = zts_reserve(ctx, &ctx->d_spec, n_sets * tile_b + 64))) return rc;
+    if ((rc = zts_reserve(ctx, &ctx->d_spec, n_sets * tile_b + 64))) return rc;
     rc = zts_reserve(ctx, &ctx->d_hist, n_sets * hist_b + 64);
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_codes, n_sets * codes_b + 64);
@@ -522,24 +520,22 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     if (rc) return rc;
     rc = zts_reserve(ctx, &ctx->d_misc, n * 8 + n_sets * gpos_b + 256);
     if (rc) return rc;
-    if (fast && (rc = zts_reserve(ctx, &ctx->d_fast, n_sets * fast_b + 64))) return rc;
     ZtsChunk* d_chunks = (ZtsChunk*)ctx->d_chunks.p;
     uint32_t* d_blocks = (uint32_t*)(d_chunks + n_chunks);
     unsigned long long* d_running = (unsigned long long*)ctx->d_misc.p;
     struct Set {
         ZtsChunkInfo* info;
-        uint32_t *list, *tile_tok, *hist, *sortT, *fastT, *counter;
+        uint32_t *list, *tile_tok, *hist, *sortT, *counter;
         ZtsChunkCodes* codes;
         unsigned long long* gpos;
     } sets[2];
     for (int b = 0; b < n_sets; ++b) {
         sets[b].info = (ZtsChunkInfo*)((uint8_t*)ctx->d_chunk_info.p + b * info_b);
         sets[b].list = (uint32_t*)((uint8_t*)ctx->d_tokens.p + b * list_b);
-        sets[b].tile_tok = fast ? nullptr : (uint32_t*)((uint8_t*)ctx->d_spec.p + b * tile_b);
+        sets[b].tile_tok = (uint32_t*)((uint8_t*)ctx->d_spec.p + b * tile_b);
         sets[b].hist = (uint32_t*)((uint8_t*)ctx->d_hist.p + b * hist_b);
         sets[b].codes = (ZtsChunkCodes*)((uint8_t*)ctx->d_codes.p + b * codes_b);
         sets[b].sortT = (uint32_t*)((uint8_t*)ctx->d_sortT.p + b * sort_b);
-        sets[b].fastT = fast ? (uint32_t*)((uint8_t*)ctx->d_fast.p + b * fast_b) : nullptr;
         sets[b].gpos = (unsigned long long*)((uint8_t*)(d_running + n) + b * gpos_b);
         sets[b].counter = (uint32_t*)(sets[b].gpos + wave);
     }
@@ -615,12 +611,7 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         if (n_sets == 2 && k == 1)  // the tables uploaded on ctx->stream must be there before the second stream starts
             ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 4 * n_waves), 0));
         if (pipe_in) ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * k), 0));
-        if (fast)
-            rc = zts_lz77_fast_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.list, S.fastT, S.hist, S.sortT, S.counter, g,
-                                      depth);
-        else
-            rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.tile_tok, S.list, S.hist, S.sortT, S.counter, g,
-                                 depth);
+        rc = zts_lz77_launch(ctx, d_in, d_chunks + w0, wn, S.info, S.tile_tok, S.list, S.hist, S.sortT, S.counter, g, depth, lazy ? 1u : 0u);
         if (rc) return rc;
         rc = zts_huffman_launch(ctx, d_chunks + w0, wn, S.hist, S.info, S.codes, block_type, smallest ? 1 : 0);
         if (rc) return rc;
@@ -732,7 +723,7 @@ extern "C" int zlb_debug_lz77(zlb_ctx* ctx, const void* d_in, uint32_t n, uint32
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     rc = zts_lz77_launch(ctx, (const uint8_t*)d_in, (const ZtsChunk*)ctx->d_chunks.p, 1, (ZtsChunkInfo*)ctx->d_chunk_info.p,
                          (uint32_t*)ctx->d_spec.p, (uint32_t*)ctx->d_tokens.p, (uint32_t*)ctx->d_hist.p,
-                         (uint32_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1, 0xFFFFFFFFu);
+                         (uint32_t*)ctx->d_sortT.p, (uint32_t*)ctx->d_misc.p, 1, 0xFFFFFFFFu, 0u);
     if (rc) return rc;
     ZtsChunkInfo ci;
     ZTS_CUDA(ctx, cudaMemcpyAsync(&ci, ctx->d_chunk_info.p, sizeof ci, cudaMemcpyDeviceToHost, ctx->stream));

@@ -242,21 +242,14 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
 // Every warp walks the 2048 slots of the sorted index it ranked in the last radix sweep, 32 per step. Bucket starts
 // are the slots whose hash differs from their predecessor's; a position's rank is its distance to the last start (a
 // ballot + the start carried from the earlier steps) -- no table of bucket starts exists.
-//   FAST == false: P[] and `hasbits` (zeroed by the caller, barrier behind it) as described above;
-//   FAST == true : only `startbits` (64 Ki bits): bit i set where slot i starts a bucket.
-template <bool FAST>
+// P[] and `hasbits` (zeroed by the caller, barrier behind it) as described above.
 __device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __restrict__ sorted, uint32_t m, uint32_t n,
-                                              uint32_t* P, uint32_t* hasbits, uint32_t* startbits, unsigned long long keep)
+                                              uint32_t* P, uint32_t* hasbits, unsigned long long keep)
 {
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (!FAST)
-        for (uint32_t p = m + tid; p < n; p += LZ_THREADS) st_u32_hint(&P[p], 0u, keep);  // positions without a slot (P has LZ_MAX_CHUNK entries per CTA)
+    for (uint32_t p = m + tid; p < n; p += LZ_THREADS) st_u32_hint(&P[p], 0u, keep);  // positions without a slot (P has LZ_MAX_CHUNK entries per CTA)
     const uint32_t i0 = warp * LZ_SORT_TILE;
-    if (i0 >= m) {
-        if (FAST)
-            for (uint32_t k = lane; k < LZ_SORT_TILE / 32; k += 32) startbits[i0 / 32 + k] = 0;
-        return;
-    }
+    if (i0 >= m) return;
     // the bucket that holds slot i0 may begin in an earlier warp's range: look back for its first slot
     uint32_t carry = i0;          // first slot of the bucket that is open at the current step
     uint32_t hlast = 0xFFFFFFFFu; // hash of the slot in front of the current step
@@ -295,10 +288,6 @@ __device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __re
         const unsigned below = sm & (zts_lanemask_lt() | (1u << lane));
         const uint32_t lo = below ? (i - lane) + (31u - (uint32_t)__clz((int)below)) : carry;  // first slot of i's bucket
         if (sm) carry = (i - lane) + (31u - (uint32_t)__clz((int)sm));
-        if (FAST) {
-            if (lane == 0) startbits[i >> 5] = sm;
-            continue;
-        }
         bool has = false;
         if (valid) {
             if (p + 3u < n) {  // src/LZ77.ts:228: the last three positions are never searched
@@ -452,6 +441,7 @@ __device__ __forceinline__ uint32_t lz_step(const LzS& S, const uint16_t* sorted
 // speculative parse, the re-entry / chain / verification passes do not care where it came from.
 // Returns t_begin when the tile does not begin inside a run, the run's first byte is out of reach (LZ_RUN_LOOKBACK),
 // or the run ends before the aligned position.
+#define LZ_LAZY_MAX 32u        // lazy evaluation (ZLB_MODE_LAZY): matches at least this long are taken at once
 #define LZ_RUN_LOOKBACK 8192u
 __device__ __forceinline__ uint32_t lz_run_aligned_start(const LzS& S, uint32_t t_begin, uint32_t t_end, uint32_t n)
 {
@@ -707,7 +697,7 @@ __global__ void __launch_bounds__(LZ_THREADS, 1)
 lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ chunks, uint32_t n_chunks,
                   ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ tile_tok, uint32_t* __restrict__ list_out,
                   uint32_t* __restrict__ hist_out, uint32_t* __restrict__ sortT, uint32_t* __restrict__ work_counter,
-                  uint32_t depth)
+                  uint32_t depth, uint32_t lazy)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint8_t* Sbuf = smem + LzSmem::S_OFF;
@@ -755,7 +745,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         uint32_t* P = T;
         for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) hasbits[i] = 0;
         __syncthreads();
-        lz_build_info<false>(SV, sorted, m, n, P, hasbits, nullptr, keep);
+        lz_build_info(SV, sorted, m, n, P, hasbits, keep);
         const uint32_t n_tiles = lz_tile_count(n);
         __syncthreads();  // the bucket starts are dead from here on: their area holds the visited bits and the second tile table
         // Where the speculative parse of every tile starts. A tile that begins inside a run of one byte starts at the
@@ -858,6 +848,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             uint32_t* tbuf = spec_c;
             uint32_t pinfo = 0;       // P[p], requested as soon as p is known
             uint32_t s_cur = 0, s_left = 0, best = 0, ptail = 0, pw = 0, pw1 = 0, maxlen = 0;
+            uint32_t saved = 0;  // lazy evaluation: the match (len << 16 | q) found at p - 1, waiting for the search at p
             if (t >= t0 && t < n_tiles) {
                 p = t_begin + M->tile_start[t];
                 t_end = min(n, t_begin + LZ_TILE_POS);
@@ -949,20 +940,50 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 }
                 // -- the token of a searched position
                 if (st == ST_RES) {
-                    uint32_t tok, np;
-                    if (best >= (3u << 16)) {
-                        const uint32_t len = best >> 16, dist = p - (best & 0xFFFFu);
-                        tok = TOK_MATCH | ((len - 3u) << 16) | (dist - 1u);
-                        np = p + len;
-                    } else {
-                        tok = SV[p];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
-                        np = p + 1u;
+                    bool emit = true;
+                    uint32_t at = p, res = best;  // the token goes to position `at`
+                    if (saved) {
+                        // lazy evaluation: `saved` is the match at p - 1, `best` the one at p
+                        at = p - 1u;
+                        if ((best >> 16) > (saved >> 16)) {
+                            res = 0;        // the later match is longer: p - 1 becomes a literal, p is looked at again
+                            best = 0;       // (from the top: it may be the end of the tile or a visited position)
+                        } else {
+                            res = saved;
+                        }
+                        saved = 0;
+                    } else if (lazy && best >= (3u << 16) && best < (LZ_LAZY_MAX << 16) &&
+                               ((hasbits[(p + 1u) >> 5] >> ((p + 1u) & 31u)) & 1u)) {
+                        // a short match, and the next position has candidates too: decide after looking there
+                        saved = best;
+                        p += 1u;
+                        pinfo = ld_u32_hint(&P[p], keep);
+                        emit = false;
+                        const uint32_t rank = pinfo >> 16;
+                        s_cur = pinfo & 0xFFFFu;
+                        maxlen = min(LZ_MAXLEN, n - p);
+                        best = 0;
+                        s_left = min(rank, depth);
+                        pw = ld_u32(SV, p);
+                        pw1 = ld_u32(SV, p + 4u);
+                        st = s_left ? ST_SRCH : ST_RES;  // (lazy is a fast-mode option: depth <= LZ_PRIV_CAP, no warp searches)
                     }
-                    tbuf[tok_i++] = tok;
-                    if (!resync) visited[p >> 5] |= 1u << (p & 31u);
-                    p = np;
-                    if (p < n) pinfo = ld_u32_hint(&P[p], keep);
-                    st = ST_ADV;
+                    if (emit) {
+                        uint32_t tok, np;
+                        if (res >= (3u << 16)) {
+                            const uint32_t len = res >> 16, dist = at - (res & 0xFFFFu);
+                            tok = TOK_MATCH | ((len - 3u) << 16) | (dist - 1u);
+                            np = at + len;
+                        } else {
+                            tok = SV[at];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
+                            np = at + 1u;
+                        }
+                        tbuf[tok_i++] = tok;
+                        if (!resync) visited[at >> 5] |= 1u << (at & 31u);
+                        p = np;
+                        if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                        st = ST_ADV;
+                    }
                 }
                 // -- next position: end of the tile, the splice, a run of literals, or a search
                 if (st == ST_ADV) {
@@ -1168,241 +1189,13 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
     }
 }
 
-// =====================================================================================================
-// Fast mode (ZLB_MODE_FAST): same staging and position index, but the match search is bounded and runs one
-// position per LANE instead of one per warp. The chunk is cut into 1024 tiles of 64 positions, one per thread;
-// a thread parses its tile greedily, looking at the `depth` nearest entries of the position's hash chain
-// (prev[] links derived from the sorted index). A match may reach into the next tile but never to its last
-// position, so every tile is entered exactly once: the thread of tile t re-parses from its predecessor's exit until
-// it meets its own speculative parse, or lands exactly on its speculative exit (matches are cut to fit), after
-// which the tiles' tokens form one consistent cover of the chunk. Tokens are then compacted into one contiguous
-// list. The result is a valid DEFLATE block, not the reference's bytes; its size stays within the stated
-// tolerance of the reference-compatible mode (tests/test_deflate_gpu.py, bench.py "fast_mode").
-#define LZF_TILE 64u
-#define LZF_NTILES (LZ_MAX_CHUNK / LZF_TILE)
-#define LZF_SPEC_STRIDE 72u    // a tile's speculative parse has at most 64 tokens
-#define LZF_FIX_STRIDE 136u    // its re-entry parse at most 127
-#define LZF_NONE 0xFFFFu
-
-struct LzFastTiles {           // lives in the bucket-start area, which the fast parse no longer needs
-    uint32_t exit_a[LZF_NTILES];      // exit of the speculative parse (absolute position)
-    uint8_t spec_count[LZF_NTILES];
-    uint8_t spec_from[LZF_NTILES];
-    uint8_t fix_count[LZF_NTILES];
-};
-static_assert(sizeof(LzFastTiles) <= LzSmem::BSTART_BYTES, "tile table must fit the bucket-start area");
-
-__device__ __forceinline__ uint32_t lzf_search(const LzS& S, const uint16_t* __restrict__ prev, uint32_t p,
-                                               uint32_t maxlen, uint32_t depth)
-{
-    const uint32_t pw = ld_u32(S, p);
-    uint32_t best_len = 0, best_q = 0;
-    uint32_t q = prev[p];
-    for (uint32_t k = 0; k < depth && q != LZF_NONE; ++k) {
-        if (p - q > LZ_WINDOW) break;
-        const uint32_t x0 = ld_u32(S, q) ^ pw;
-        if ((x0 & 0xFFFFFFu) == 0) {
-            uint32_t l = 3;
-            if (x0 == 0) {
-                l = 4;
-                while (l < maxlen) {
-                    const uint32_t x = ld_u32(S, q + l) ^ ld_u32(S, p + l);
-                    if (x) {
-                        l += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                        break;
-                    }
-                    l += 4;
-                }
-            }
-            l = min(l, maxlen);
-            if (l > best_len) {
-                best_len = l;
-                best_q = q;
-                if (l >= maxlen) break;
-            }
-        }
-        q = prev[q];
-    }
-    return best_len >= 3 ? (best_len << 16) | (p - best_q) : 0u;
-}
-
-// one greedy step at p; a match ends at or before `limit`
-__device__ __forceinline__ uint32_t lzf_step(const LzS& S, const uint16_t* prev, uint32_t p, uint32_t n, uint32_t limit,
-                                             uint32_t depth, uint32_t* tok)
-{
-    const uint32_t maxlen = min(LZ_MAXLEN, limit - p);
-    uint32_t r = 0;
-    if (p + 3 < n && maxlen >= 3) r = lzf_search(S, prev, p, maxlen, depth);
-    if (r) {
-        *tok = TOK_MATCH | (((r >> 16) - 3) << 16) | ((r & 0xFFFFu) - 1);
-        return p + (r >> 16);
-    }
-    *tok = S[p];
-    return p + 1;
-}
-
-__global__ void __launch_bounds__(LZ_THREADS, 1)
-lz77_fast_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ chunks, uint32_t n_chunks,
-                 ZtsChunkInfo* __restrict__ info, uint32_t* __restrict__ tok_out, uint32_t* __restrict__ tile_tok,
-                 uint32_t* __restrict__ hist_out, uint32_t* __restrict__ sortT, uint32_t* __restrict__ work_counter,
-                 uint32_t depth)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint8_t* Sbuf = smem + LzSmem::S_OFF;
-    uint16_t* sorted = reinterpret_cast<uint16_t*>(smem + LzSmem::SORTED_OFF);
-    uint16_t* prev = sorted;  // the links replace the sorted index in place (via the global scratch)
-    LzFastTiles* TL = reinterpret_cast<LzFastTiles*>(smem + LzSmem::BSTART_OFF);
-    uint16_t* cnt16 = reinterpret_cast<uint16_t*>(smem + LzSmem::BSTART_OFF);  // radix offsets (dead before the tile table is written)
-    uint32_t* bits = reinterpret_cast<uint32_t*>(smem + LzSmem::AUX_OFF);  // bucket-start bits, then visited bits
-    LzMisc* M = reinterpret_cast<LzMisc*>(smem + LzSmem::MISC_OFF);
-
-    const unsigned tid = threadIdx.x;
-    const unsigned long long keep = l2_policy_keep(), stream = l2_policy_stream();
-    uint32_t* T = sortT + (size_t)blockIdx.x * LZ_MAX_CHUNK;
-    uint32_t* my_spec = tile_tok + (size_t)blockIdx.x * (LZF_NTILES * (LZF_SPEC_STRIDE + LZF_FIX_STRIDE));
-    uint32_t* my_fix = my_spec + LZF_NTILES * LZF_SPEC_STRIDE;
-    uint32_t phase = 0;
-
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&M->mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    for (;;) {
-        if (tid == 0) M->chunk = atomicAdd(work_counter, 1u);
-        __syncthreads();
-        const uint32_t c = M->chunk;
-        if (c >= n_chunks) break;
-        const ZtsChunk ch = chunks[c];
-        const uint32_t base = ch.dict_len;  // primed mode: history in front of the chunk, see lz77_chunk_kernel
-        const uint32_t n = base + ch.len;
-        const uint8_t* src = in + ch.in_off - base;
-
-        const LzIndexed ix = lz_stage_and_index(src, n, Sbuf, sorted, cnt16, M, T, phase);
-        const LzS SV = ix.SV;
-        const uint32_t m = ix.m;
-        lz_build_info<true>(SV, sorted, m, n, nullptr, nullptr, bits, keep);  // bucket-start bits
-        __syncthreads();
-
-        // ---- hash-chain links: prev[pos] = the previous position of the same bucket (nearest earlier one).
-        // The links replace the sorted index in place, so they take a detour through the global scratch: written
-        // coalesced as pos << 16 | prev in slot order, read back coalesced and scattered inside shared memory.
-        for (uint32_t i = tid; i < m; i += LZ_THREADS) {
-            const bool first = (bits[i >> 5] >> (i & 31)) & 1u;
-            const uint32_t pos = sorted[i];
-            st_u32_hint(&T[i], (pos << 16) | (first ? (uint32_t)LZF_NONE : (uint32_t)sorted[i - 1]), keep);
-        }
-        __threadfence_block();
-        __syncthreads();
-        for (uint32_t i = tid; i < m; i += LZ_THREADS) {
-            const uint32_t e = ld_u32_hint(&T[i], keep);
-            prev[e >> 16] = (uint16_t)e;
-        }
-        for (uint32_t i = tid; i < LZ_MAX_CHUNK / 32; i += LZ_THREADS) bits[i] = 0;  // now: visited bits
-        for (uint32_t i = tid; i < 316; i += LZ_THREADS) M->hist[i] = 0;
-        __syncthreads();
-
-        // ---- speculative parse: thread t parses tile t from its first position
-        const uint32_t n_tiles = (n + LZF_TILE - 1) / LZF_TILE;
-        const uint32_t t0 = base / LZF_TILE;  // first tile with anything to parse
-        const uint32_t t = tid;
-        const uint32_t t_begin = t * LZF_TILE, t_end = min(n, t_begin + LZF_TILE);
-        // a match of this tile may reach into the next one, but not to its last position
-        const uint32_t limit = (t + 1 < n_tiles) ? min(n, t_begin + 2 * LZF_TILE) - 1u : n;
-        if (t >= t0 && t < n_tiles) {
-            uint32_t p = max(t_begin, base), cnt = 0, v0 = 0, v1 = 0;
-            uint32_t* sp = my_spec + t * LZF_SPEC_STRIDE;
-            while (p < t_end) {
-                uint32_t tok;
-                const uint32_t np = lzf_step(SV, prev, p, n, limit, depth, &tok);
-                st_u32_hint(&sp[cnt++], tok, keep);
-                const uint32_t rel = p - t_begin;
-                if (rel < 32u)
-                    v0 |= 1u << rel;
-                else
-                    v1 |= 1u << (rel - 32u);
-                p = np;
-            }
-            bits[2 * t] = v0;
-            bits[2 * t + 1] = v1;
-            TL->exit_a[t] = p;
-            TL->spec_count[t] = (uint8_t)cnt;
-            TL->spec_from[t] = 0;
-            TL->fix_count[t] = 0;
-        }
-        __syncthreads();
-
-        // ---- re-entry: tile t starts where tile t-1 ended and must end where its own speculative parse ended
-        if (t > t0 && t < n_tiles) {
-            const uint32_t target = TL->exit_a[t];
-            const uint32_t v0 = bits[2 * t], v1 = bits[2 * t + 1];
-            uint32_t p = TL->exit_a[t - 1], nfix = 0, from = TL->spec_count[t];
-            uint32_t* fx = my_fix + t * LZF_FIX_STRIDE;
-            while (p < target) {
-                if (p < t_end) {
-                    const uint32_t rel = p - t_begin;
-                    const bool seen = rel < 32u ? ((v0 >> rel) & 1u) : ((v1 >> (rel - 32u)) & 1u);
-                    if (seen) {  // met the speculative parse: its tokens from here on are kept
-                        from = rel < 32u ? __popc(v0 & ((1u << rel) - 1u))
-                                         : __popc(v0) + __popc(v1 & ((1u << (rel - 32u)) - 1u));
-                        break;
-                    }
-                }
-                uint32_t tok;
-                p = lzf_step(SV, prev, p, n, target, depth, &tok);  // never past the speculative exit
-                st_u32_hint(&fx[nfix++], tok, keep);
-            }
-            TL->spec_from[t] = (uint8_t)from;
-            TL->fix_count[t] = (uint8_t)nfix;
-        }
-        __syncthreads();
-
-        // ---- compaction into one contiguous token list + histograms
-        uint32_t mine = 0, nfix = 0, from = 0, sc = 0;
-        if (t >= t0 && t < n_tiles) {
-            nfix = TL->fix_count[t];
-            from = TL->spec_from[t];
-            sc = TL->spec_count[t];
-            mine = nfix + (sc - from);
-        }
-        const uint32_t tbase = block_excl_sum(mine, M->warp_tot, &M->n_tokens);
-        uint32_t* out = tok_out + (size_t)c * LZ_LIST_PER_CHUNK;
-        {
-            // the 32 tiles of a warp are copied one after the other by the whole warp: coalesced, no dependent loads
-            const unsigned lane = tid & 31;
-            for (int j = 0; j < 32; ++j) {
-                const uint32_t jn = __shfl_sync(0xFFFFFFFFu, nfix, j), jf = __shfl_sync(0xFFFFFFFFu, from, j),
-                               js = __shfl_sync(0xFFFFFFFFu, sc, j), jb = __shfl_sync(0xFFFFFFFFu, tbase, j);
-                const uint32_t jt = (tid & ~31u) + (uint32_t)j;
-                const uint32_t* fx = my_fix + jt * LZF_FIX_STRIDE;
-                const uint32_t* sp = my_spec + jt * LZF_SPEC_STRIDE + jf;
-                const uint32_t ns = js - jf;
-                for (uint32_t k = lane; k < jn + ns; k += 32) {
-                    const uint32_t tok = ld_u32_hint(k < jn ? &fx[k] : &sp[k - jn], keep);
-                    st_u32_hint(&out[jb + k], tok, stream);
-                    hist_token(tok, M->hist);
-                }
-            }
-        }
-        __syncthreads();
-        for (uint32_t i = tid; i < 316; i += LZ_THREADS)
-            hist_out[(size_t)c * 316 + i] = M->hist[i] + (i == 256 ? 2u : 0u);  // same convention as the compat kernel
-        if (tid == 0) {
-            info[c].n_tokens = M->n_tokens;
-            info[c].pad = 1;  // tokens are one contiguous list at the start of the chunk's token buffer
-        }
-        __syncthreads();
-    }
-}
-
 size_t zts_lz77_smem_bytes() { return LzSmem::TOTAL; }
 
 size_t zts_lz77_scratch_bytes(int sm_count) { return (size_t)sm_count * 2u * LZ_TOK_PER_CHUNK * 4u; }
 
 int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
                     ZtsChunkInfo* d_info, uint32_t* d_tile_tok, uint32_t* d_list, uint32_t* d_hist, uint32_t* d_sortT,
-                    uint32_t* d_counter, uint32_t grid, uint32_t depth)
+                    uint32_t* d_counter, uint32_t grid, uint32_t depth, uint32_t lazy)
 {
     static_assert(sizeof(LzMisc) <= LzSmem::MISC_BYTES, "misc area too small");
     static_assert(LzSmem::TOTAL <= 232448, "exceeds 227 KiB of dynamic shared memory");
@@ -1412,24 +1205,6 @@ int zts_lz77_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks,
     ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->work));
     ZTS_LAUNCH(ctx, ZK_LZ77,
                lz77_chunk_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->work>>>(
-                   d_in, d_chunks, n_chunks, d_info, d_tile_tok, d_list, d_hist, d_sortT, d_counter, depth));
-    return ZLB_OK;
-}
-
-size_t zts_lz77_fast_scratch_bytes(int sm_count)
-{
-    return (size_t)sm_count * LZF_NTILES * (LZF_SPEC_STRIDE + LZF_FIX_STRIDE) * 4;
-}
-
-int zts_lz77_fast_launch(zlb_ctx* ctx, const uint8_t* d_in, const ZtsChunk* d_chunks, uint32_t n_chunks,
-                         ZtsChunkInfo* d_info, uint32_t* d_tok, uint32_t* d_tile_tok, uint32_t* d_hist,
-                         uint32_t* d_sortT, uint32_t* d_counter, uint32_t grid, uint32_t depth)
-{
-    ZTS_CUDA(ctx, cudaFuncSetAttribute(lz77_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)LzSmem::TOTAL));
-    ZTS_CUDA(ctx, cudaMemsetAsync(d_counter, 0, sizeof(uint32_t), ctx->work));
-    ZTS_LAUNCH(ctx, ZK_LZ77_FAST,
-               lz77_fast_kernel<<<grid, LZ_THREADS, LzSmem::TOTAL, ctx->work>>>(
-                   d_in, d_chunks, n_chunks, d_info, d_tok, d_tile_tok, d_hist, d_sortT, d_counter, depth));
+                   d_in, d_chunks, n_chunks, d_info, d_tile_tok, d_list, d_hist, d_sortT, d_counter, depth, lazy));
     return ZLB_OK;
 }
