@@ -326,6 +326,13 @@ def run_b200(args, rank, world, local_rank):
         fast = {"value": world * n * few / (ms_f * 1e-3) / 1e9, "unit": UNIT, "chain_depth": 16, "steps": few,
                 "ratio": int(res["f"]["out_len"][0]) / n, "ratio_vs_compat": int(res["f"]["out_len"][0]) / clen,
                 "note": "ratio tolerance vs reference RawDeflate per chunk: 3 % (north_star); compat ratio == reference"}
+        # ... with one-step lazy evaluation (ZLB_MODE_LAZY): the ratio falls below the reference's exhaustive greedy parse
+        for name, mode in (("lazy_depth16", z.MODE_FAST | z.MODE_LAZY), ("lazy_depth64", z.mode_fast(64) | z.MODE_LAZY)):
+            for _ in range(2):
+                eng.deflate_batch(d_in, d_out, items, flags=dflags, mode=mode)
+            ms_l = timed(lambda: res.__setitem__("l", eng.deflate_batch(d_in, d_out, items, flags=dflags, mode=mode)), few)
+            fast[name] = {"value": world * n * few / (ms_l * 1e-3) / 1e9, "unit": UNIT, "steps": few,
+                          "ratio": int(res["l"]["out_len"][0]) / n, "ratio_vs_compat": int(res["l"]["out_len"][0]) / clen}
         # ---- primed mode (32 KiB of history in front of every 32 KiB chunk): ratio recovered, speed paid
         items_p = items.copy()
         items_p["out_cap"] = cap_primed
@@ -340,6 +347,23 @@ def run_b200(args, rank, world, local_rank):
         primed["note"] = ("32 KiB chunks, each searching the 32 KiB before it as well; exhaustive = the reference's matcher "
                           "(blocks equal the oracle's block construction with that history), fast = depth 16")
         step_device()  # leave the compat output in d_out
+
+    # ---- what the host link alone allows: the copies of one step (H2D of the input, D2H of the output, side by side
+    #      on two streams, no kernels), every rank at the same time -- the denominator of the end-to-end figures
+    def copy_only(h_src, d_dst, d_src, h_dst):
+        s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+        def once():
+            s1.wait_stream(stream)
+            s2.wait_stream(stream)
+            with torch.cuda.stream(s1):
+                d_dst.copy_(h_src, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_dst.copy_(d_src, non_blocking=True)
+            stream.wait_stream(s1)
+            stream.wait_stream(s2)
+        once()
+        return timed(once, few) / few
+    ms_copy = copy_only(h_in, d_in, d_out[:clen], h_out[:clen])
 
     # ---- end-to-end leg: host buffers through the C-ABI host entry point (H2D + D2H inside), as many steps as `value`
     for _ in range(max(1, min(2, args.warmup))):
@@ -412,6 +436,7 @@ def run_b200(args, rank, world, local_rank):
     ms_ih = timed(inf_host, args.steps)
     assert torch.equal(h_plain, h_in)
     inf_e2e = world * n * args.steps / (ms_ih * 1e-3) / 1e9
+    ms_icopy = copy_only(h_packed, d_packed, d_plain, h_plain)
     inf_pageable = None
     if extras:
         pg_c, pg_p = h_packed.numpy().copy(), np.empty(n, dtype=np.uint8)
@@ -543,7 +568,11 @@ def run_b200(args, rank, world, local_rank):
             "primed_mode": primed,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": clen,
                     "ms_per_step": ms_h / args.steps, "steps": args.steps,
-                    "api": "zlb_deflate_batch_host (page-locked host buffers)"},
+                    "api": "zlb_deflate_batch_host (page-locked host buffers)",
+                    "copies_alone_ms": ms_copy, "copies_alone_value": world * n / (ms_copy * 1e-3) / 1e9,
+                    "frac_of_copies_alone": ms_copy / (ms_h / args.steps),
+                    "copies_alone_note": "H2D of the input and D2H of the output of one step on two streams, no kernels, "
+                                         "all ranks at once, max over ranks: the host link's ceiling for this leg"},
             "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches),
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
@@ -553,7 +582,9 @@ def run_b200(args, rank, world, local_rank):
             "inflate": {"metric": "inflate_output_GBps", "value": inf_value, "unit": UNIT, "streams_per_gpu": n_chunks,
                         "ms_per_step": ms_i / args.steps, "gpu_launches": int(inf_launches),
                         "e2e": {"value": inf_e2e, "unit": UNIT, "h2d_bytes_per_step": total_c,
-                                "d2h_bytes_per_step": n, "ms_per_step": ms_ih / args.steps, "steps": args.steps},
+                                "d2h_bytes_per_step": n, "ms_per_step": ms_ih / args.steps, "steps": args.steps,
+                                "copies_alone_ms": ms_icopy, "copies_alone_value": world * n / (ms_icopy * 1e-3) / 1e9,
+                                "frac_of_copies_alone": ms_icopy / (ms_ih / args.steps)},
                         "e2e_pageable": inf_pageable,
                         "roofline": inf_roofline},
             "adversarial": adversarial,

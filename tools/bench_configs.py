@@ -47,15 +47,20 @@ def c1(eng):
             "deflate_ms_host_api": (t1 - t0) * 1e3, "inflate_ms_host_api": (t2 - t1) * 1e3, "roundtrip_ok": True}
 
 
-def c3(eng, n_streams=65536):
+def c3(eng, n_streams=65536, host_leg=True):
+    """65 536 independent 64 KiB zlib streams PRODUCED BY THE REFERENCE's algorithm (oracle/, all host threads):
+    stream i = 78 9C | RawDeflate(text(65536, 1000 + i) for even i, mixed(65536, 1000 + i) for odd i) | Adler-32.
+    Batched inflate, device resident (4 GiB of output), then end to end through zlb_inflate_batch_host."""
     import oracle
+    oracle.build()
     stream = torch.cuda.Stream()
     eng2 = z.Engine(0, stream.cuda_stream)
     CH = 65536
-    slot = z.deflate_bound(CH) + 8
+    threads = os.cpu_count() or 1
     group = 4096  # generate + compress in groups, keep only the packed zlib streams
     packed, lens = [], []
-    samples = {}
+    gpu_equal = []
+    t_ref = 0.0
     for g0 in range(0, n_streams, group):
         g = min(group, n_streams - g0)
         h = np.empty(g * CH, dtype=np.uint8)
@@ -65,27 +70,25 @@ def c3(eng, n_streams=65536):
                 synth.text(CH, 1000 + i, out=h[k * CH:(k + 1) * CH])
             else:
                 synth.mixed(CH, 1000 + i, 4096, out=h[k * CH:(k + 1) * CH])
-        items = z.make_items(g)
-        items["in_off"] = np.arange(g, dtype=np.uint64) * CH
-        items["in_len"] = CH
-        items["out_off"] = np.arange(g, dtype=np.uint64) * slot + 2   # room for the 2-byte zlib header
-        items["out_cap"] = slot - 8
-        with torch.cuda.stream(stream):
-            d_in = torch.from_numpy(h).cuda()
-            d_out = torch.zeros(g * slot, dtype=torch.uint8, device="cuda")
-            r = eng2.deflate_batch(d_in, d_out, items, flags=z.DEFLATE_WANT_ADLER32)
-            ho = d_out.cpu().numpy()
-        assert int(r["status"].max()) == 0
+        t0 = time.perf_counter()
+        slots, slot, ln = oracle.zlib_chunks_keep_mt(h, CH, threads)
+        t_ref += time.perf_counter() - t0
         for k in range(g):
-            n = int(r["out_len"][k])
-            s = ho[k * slot:k * slot + 2 + n + 4]
-            s[0], s[1] = 0x78, 0x9C
-            s[2 + n:2 + n + 4] = np.frombuffer(int(r["adler32"][k]).to_bytes(4, "big"), dtype=np.uint8)
-            packed.append(s.copy())
-            lens.append(2 + n + 4)
-        for k in (0, 1):   # parity sample: the GPU encoder's bytes are the reference's
-            i = g0 + k
-            samples[i] = (bytes(packed[g0 + k][2:-4]) == oracle.raw_deflate(h[k * CH:(k + 1) * CH]))
+            packed.append(slots[k * slot:k * slot + int(ln[k])].copy())
+        lens.extend(int(x) for x in ln)
+        if g0 % (8 * group) == 0:   # parity sample: the GPU encoder writes the same bytes for 64 of these chunks
+            m = 64
+            items = z.make_items(m)
+            items["in_off"] = np.arange(m, dtype=np.uint64) * CH
+            items["in_len"] = CH
+            items["out_off"] = np.arange(m, dtype=np.uint64) * slot
+            items["out_cap"] = slot
+            with torch.cuda.stream(stream):
+                d_out = torch.zeros(m * slot, dtype=torch.uint8, device="cuda")
+                r = eng2.deflate_batch(torch.from_numpy(h[:m * CH]).cuda(), d_out, items)
+                ho = d_out.cpu().numpy()
+            for k in range(m):
+                gpu_equal.append(bytes(ho[k * slot:k * slot + int(r["out_len"][k])]) == bytes(packed[g0 + k][2:-4]))
         if g0 == 0:
             first_plain = h[:4 * CH].copy()
     lens = np.array(lens, dtype=np.uint64)
@@ -120,11 +123,32 @@ def c3(eng, n_streams=65536):
     assert np.array_equal(head, first_plain)
     best = min(ms)
     total_out = n_streams * CH
-    return {"config": "C3", "streams": n_streams, "out_bytes": total_out, "in_bytes": int(lens.sum()),
-            "inflate_ms": best, "inflate_output_GBps": total_out / best / 1e6,
-            "roofline_frac_hbm": (total_out + int(lens.sum())) / best / 1e6 / 6538.6,
-            "encoder_bytes_equal_oracle_on_samples": all(samples.values()), "samples": len(samples),
-            "adler32_of_all_outputs_match_trailers": True}
+    out = {"config": "C3", "streams": n_streams, "out_bytes": total_out, "in_bytes": int(lens.sum()),
+           "streams_made_by": "oracle RawDeflate (reference algorithm) on %d host threads, %.1f s" % (threads, t_ref),
+           "inflate_ms": best, "inflate_output_GBps": total_out / best / 1e6,
+           "roofline_frac_hbm": (total_out + int(lens.sum())) / best / 1e6 / 6538.6,
+           "gpu_encoder_bytes_equal_reference_streams": all(gpu_equal), "gpu_encoder_samples": len(gpu_equal),
+           "adler32_of_all_outputs_match_trailers": True}
+    if host_leg:
+        try:
+            del d_o
+            torch.cuda.empty_cache()
+            h_c = torch.from_numpy(blob).pin_memory()
+            h_o = torch.empty(total_out, dtype=torch.uint8).pin_memory()
+            with torch.cuda.stream(stream):
+                eng2.inflate_batch_host(h_c, h_o, items)
+                e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+                e0.record(stream)
+                rh = eng2.inflate_batch_host(h_c, h_o, items)
+                e1.record(stream)
+                e1.synchronize()
+            assert int(rh["status"].max()) == 0 and np.array_equal(h_o[:4 * CH].numpy(), first_plain)
+            msh = e0.elapsed_time(e1)
+            out["e2e"] = {"ms": msh, "inflate_output_GBps": total_out / msh / 1e6, "h2d_bytes": int(blob.size),
+                          "d2h_bytes": total_out, "api": "zlb_inflate_batch_host (page-locked buffers)"}
+        except Exception as e:  # host memory for 6 GiB of page-locked buffers may not be there
+            out["e2e"] = {"error": repr(e)[:200]}
+    return out
 
 
 def c4(eng, n_files=10000):
@@ -269,6 +293,86 @@ def c5(eng, gib=1):
             "gzip_multimember_bytes": tot, "cpython_gzip_reads_first_8_members": True,
             "gunzip_split_inflate_plus_crc_ms": best_d, "gunzip_GBps": n / best_d / 1e6, "roundtrip_ok": True,
             "crc32_matches_cpython": True, "cpython_gzip_reads_member_sample": True}
+
+
+def c5_sharded(eng, stream, rank, world, dist, gib_total=8, gib_cap_per_gpu=2):
+    """C5: `gib_total` GiB of 1 MiB shards (mixed(1 MiB, 5000 + s)) gzip-compressed and decompressed, the shards dealt
+    out over the ranks in contiguous runs (at most gib_cap_per_gpu GiB per GPU: a single GPU takes that much of the
+    8 GiB and says so). Every shard becomes one gzip member (header, raw deflate with the CRC-32 fused in, trailer,
+    framed and packed on the device: zlb_archive); the file is the members of all ranks back to back, so the only
+    exchange is the exclusive scan of the ranks' byte counts. Decompression: every member marker-split-inflated and
+    CRC-checked. Device resident; times are CUDA events, max over the ranks."""
+    import gzip
+    shards_total = gib_total << 10
+    per = shards_total // world
+    per = min(per, gib_cap_per_gpu << 10)
+    s0 = rank * per
+    n = per << 20
+    h = np.empty(n, dtype=np.uint8)
+    for k in range(per):
+        synth.mixed(1 << 20, 5000 + s0 + k, 4096, out=h[k << 20:(k + 1) << 20])
+    ent = z.make_entries(per)
+    ent["in_off"] = np.arange(per, dtype=np.uint64) << 20
+    ent["in_len"], ent["head_len"] = 1 << 20, 10
+    hdr = np.frombuffer(b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03", dtype=np.uint8).copy()
+
+    def timed(fn, reps=2):
+        best, r = 1e30, None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record(stream)
+            r = fn()
+            e1.record(stream)
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best, r
+
+    tot, ok, ms_c, ms_d, err = 0, False, 0.0, 0.0, None
+    try:  # a rank that fails still takes part in the one collective below
+        with torch.cuda.stream(stream):
+            d_in = torch.from_numpy(h).cuda()
+            d_meta = torch.from_numpy(hdr).cuda()
+            d_arc = torch.empty(z.archive_bound(z.FRAME_GZIP, ent), dtype=torch.uint8, device="cuda")
+            d_o = torch.empty(n, dtype=torch.uint8, device="cuda")
+            eng.archive(z.FRAME_GZIP, d_in, d_meta, ent, d_arc)
+            if world > 1:
+                dist.barrier()
+            ms_c, (tot, rm) = timed(lambda: eng.archive(z.FRAME_GZIP, d_in, d_meta, ent, d_arc))
+            assert int(rm["status"].max()) == 0
+            # members of this rank: [in_used, in_used + out_len) inside d_arc; deflate data sits behind the 10-byte header
+            it = z.make_items(per)
+            it["in_off"] = rm["in_used"].astype(np.uint64) + 10
+            it["in_len"] = rm["out_len"].astype(np.uint64) - 18
+            it["out_off"] = np.arange(per, dtype=np.uint64) << 20
+            it["out_cap"] = 1 << 20
+            eng.inflate_batch(d_arc, d_o, it, z.INFLATE_WANT_CRC32 | z.INFLATE_SPLIT)
+            ms_d, r2 = timed(lambda: eng.inflate_batch(d_arc, d_o, it, z.INFLATE_WANT_CRC32 | z.INFLATE_SPLIT))
+            same = bool(torch.equal(d_o, d_in))
+            first = bytes(d_arc[:int(rm["out_len"][:2].sum())].cpu().numpy())
+        ok = (same and int(r2["status"].max()) == 0 and np.array_equal(r2["crc32"], rm["crc32"]) and
+              gzip.decompress(first) == h[:2 << 20].tobytes())
+    except Exception as e:
+        err = repr(e)[:200]
+    mine = torch.tensor([int(tot), n, int(ok), int(ms_c * 1e3), int(ms_d * 1e3)], dtype=torch.int64, device="cuda")
+    gathered = [mine]
+    if world > 1:
+        gathered = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+    g = [[int(v) for v in t.tolist()] for t in gathered]
+    tot_c, tot_n = sum(x[0] for x in g), sum(x[1] for x in g)
+    ok_all = all(x[2] for x in g)
+    ms_c, ms_d = max(x[3] for x in g) / 1e3, max(x[4] for x in g) / 1e3    # max over the ranks
+    out = {"config": "C5", "n_gpus": world, "bytes": tot_n, "bytes_per_gpu": n, "members": per * world,
+           "note": ("8 GiB over the ranks" if per * world == shards_total else
+                    "capped at %d GiB per GPU: %d GiB of the 8 GiB" % (gib_cap_per_gpu, tot_n >> 30)),
+           "compressed": tot_c, "ratio": tot_c / max(tot_n, 1), "gzip_ms": ms_c, "gzip_GBps": tot_n / max(ms_c, 1e-9) / 1e6,
+           "gunzip_ms": ms_d, "gunzip_GBps": tot_n / max(ms_d, 1e-9) / 1e6,
+           "file_offset_of_rank": [sum(x[0] for x in g[:r]) for r in range(world)],
+           "roundtrip_and_crc32_ok_on_every_rank": bool(ok_all), "cpython_gzip_reads_first_members": bool(ok_all),
+           "exchange": "one all-gather of 5 integers per rank (member bytes -> file offsets, times); no data-path collective"}
+    if err:
+        out["error"] = err
+    return out
 
 
 def main():

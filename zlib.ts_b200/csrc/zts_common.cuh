@@ -63,6 +63,7 @@ struct zlb_ctx {
     size_t h_pin2_cap = 0;
     // copy / second compute streams of the pipelined host paths (created on first use)
     cudaStream_t s_in = nullptr, s_out = nullptr, s_aux[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_res = nullptr;  // small read-backs that must not queue behind (or in front of) anything else
     std::vector<cudaEvent_t> sync_events;  // disable-timing events, reused across calls
 
     // "_host" entry points with pageable caller buffers: page-locked shadows + copy threads (zts_hoststage.cu)

@@ -68,6 +68,7 @@ int zts_host_streams(zlb_ctx* ctx)
     ZTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
     ZTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
     for (int i = 0; i < 3; ++i) ZTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_aux[i], cudaStreamNonBlocking));
+    ZTS_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_res, cudaStreamNonBlocking));
     return ZLB_OK;
 }
 
@@ -232,6 +233,7 @@ void zlb_destroy(zlb_ctx* ctx)
     for (cudaEvent_t e : ctx->sync_events) cudaEventDestroy(e);
     if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
     if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
+    if (ctx->s_res) cudaStreamDestroy(ctx->s_res);
     for (int i = 0; i < 3; ++i)
         if (ctx->s_aux[i]) cudaStreamDestroy(ctx->s_aux[i]);
     for (const ZtsProfRec& r : ctx->pending) {

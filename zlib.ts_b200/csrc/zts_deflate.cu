@@ -94,6 +94,12 @@ __global__ void deflate_finalize_kernel(const zlb_item* __restrict__ items, zlb_
     results[i].status = total > items[i].out_cap ? ZLB_ST_OUT_OVERFLOW : ZLB_ST_OK;
 }
 
+__global__ void running_snapshot_kernel(unsigned long long* __restrict__ h_dst, const unsigned long long* __restrict__ src, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) h_dst[i] = src[i];  // h_dst is page-locked host memory (cudaMallocHost: device-accessible)
+}
+
 // ---- bit packer: one CTA per chunk ------------------------------------------------------------------------
 // The chunk's tokens are one contiguous list (both LZ77 kernels write it). Every warp owns a contiguous range of
 // it. Pass 1 adds up the bits of each range, a 16-entry scan gives every range its first bit, pass 2 re-derives the
@@ -619,9 +625,13 @@ static int deflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             ZTS_CUDA(ctx, cudaStreamWaitEvent(st, zts_sync_event(ctx, 2 * n_waves + k - 1), 0));
         ZTS_LAUNCH(ctx, ZK_SCAN,
                    chunk_scan_kernel<<<1, 1024, 0, st>>>(d_chunks + w0, S.info, wn, d_items, d_running, S.gpos));
-        if (delta_out)  // snapshot of the running totals before the next wave's scan moves them on
-            ZTS_CUDA(ctx, cudaMemcpyAsync(h_run + k * n, d_running, n * sizeof(unsigned long long),
-                                          cudaMemcpyDeviceToHost, st));
+        if (delta_out) {
+            // snapshot of the running totals before the next wave's scan moves them on: written straight into the
+            // page-locked table by a kernel. (A device-to-host copy queued here, behind kernels that are still
+            // running, would hold up the output copy of the wave before -- the copy engine serves its queue in order.)
+            running_snapshot_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h_run + k * n, d_running, (uint32_t)n);
+            ZTS_CUDA(ctx, cudaGetLastError());
+        }
         if (n_sets == 2) ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 * n_waves + k), st));
         ZTS_LAUNCH(ctx, ZK_BITPACK,
                    bitpack_kernel<<<wn, PACK_THREADS, PACK_SMALL_WORDS * 4, st>>>(

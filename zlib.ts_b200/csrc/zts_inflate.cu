@@ -22,7 +22,11 @@
 // replaces the reference's 2^15-entry single-level table.
 //
 // Algorithmic bytes per stream: C (compressed, read once) + N (output, written once).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 
 #include "zts_common.cuh"
 
@@ -968,11 +972,21 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
         ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 1 + 2 * k), ctx->s_in));
         return ZLB_OK;
     };
+    const bool trace = getenv("ZTS_TRACE_WAVES") != nullptr;  // development aid: when does the host see each wave
+    const auto t_begin = std::chrono::steady_clock::now();
     auto wave_out = [&](size_t k) -> int {
         size_t a, b;
         wave_range(k, a, b);
         ZTS_CUDA(ctx, cudaEventSynchronize(zts_sync_event(ctx, 2 + 2 * k)));
+        if (trace)
+            fprintf(stderr, "inflate wave %zu of %zu decoded at %.2f ms\n", k, n_waves,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
         if (a >= b) return ZLB_OK;
+        // The results are read back only now, on a stream of their own: a copy queued behind a kernel that is still
+        // running holds up every later copy of its direction (the copy engine serves its queue in order), and the
+        // outputs of the earlier waves would wait for the last wave's kernel.
+        ZTS_CUDA(ctx, cudaMemcpyAsync(pin_res + a, d_results + a, (b - a) * sizeof(zlb_result), cudaMemcpyDeviceToHost, ctx->s_res));
+        ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->s_res));
         memcpy(h_results + a, pin_res + a, (b - a) * sizeof(zlb_result));
         return zts_copy_back(ctx, hio->stage, ctx->s_out, d_out, hio->h_out, h_items, h_results, d_items, d_results, a, b);
     };
@@ -993,7 +1007,6 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
                 rc = zts_checksum_device(ctx, d_out, d_items + a, d_results + a, h_items + a, b - a, kinds, 1);
                 if (rc) return rc;
             }
-            ZTS_CUDA(ctx, cudaMemcpyAsync(pin_res + a, d_results + a, (b - a) * sizeof(zlb_result), cudaMemcpyDeviceToHost, st));
         }
         ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 + 2 * k), st));
         if (st != ctx->stream) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 + 2 * k), 0));  // the call ends on ctx->stream
@@ -1003,6 +1016,9 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     for (size_t k = 0; k < n_waves; ++k)
         if ((rc = wave_out(k))) return rc;
     ZTS_CUDA(ctx, cudaStreamSynchronize(ctx->s_out));
+    if (trace)
+        fprintf(stderr, "inflate outputs back at %.2f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
     return ZLB_OK;
 }
 
