@@ -52,9 +52,11 @@ enum {
     ZLB_ST_OK = 0,
     ZLB_ST_INPUT_BROKEN = 1,  /* 'input buffer is broken'                    src/RawInflate.ts:188,282 */
     ZLB_ST_BTYPE = 2,         /* 'unknown BTYPE: 3'                          src/RawInflate.ts:168 */
-    ZLB_ST_CODE_LENGTH = 3,   /* 'invalid code length: N'                    src/RawInflate.ts:238 */
+    ZLB_ST_CODE_LENGTH = 3,   /* 'invalid code length: N'                    src/RawInflate.ts:238; the input ends inside a
+                                 Huffman code of N bits: status = ZLB_ST_CODE_LENGTH | N << 8 (compare (status & 0xFF):
+                                 this status and ZLB_ST_STORED_LEN carry a detail above bit 7) */
     ZLB_ST_OUT_OVERFLOW = 4,  /* caller's out_cap too small (the reference grows its buffer instead) */
-    ZLB_ST_STORED_LEN = 5,    /* 'invalid uncompressed block header: LEN'    src/RawInflate.ts:266,272 */
+    ZLB_ST_STORED_LEN = 5,    /* 'invalid uncompressed block header: LEN'    src/RawInflate.ts:266; | 1 << 8: '... NLEN' (:272) */
     ZLB_ST_BAD_CODE = 6,      /* undefined Huffman code / distance beyond output start / bad symbol:
                                  the reference loops or emits zeros here; we stop */
     ZLB_ST_BAD_LENGTHS = 7    /* over-subscribed code-length set in a dynamic header */

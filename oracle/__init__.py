@@ -61,8 +61,16 @@ def lib():
 
 class OracleError(Exception):
     def __init__(self, code):
-        super().__init__(ERR_TEXT.get(code, f"oracle error {code}"))
+        detail = code >> 8   # the N of 'invalid code length: N'; 1 = NLEN for the uncompressed block header
+        code &= 0xFF
+        text = ERR_TEXT.get(code, f"oracle error {code}")
+        if code == 3 and detail:
+            text += ": %d" % detail
+        if code == 5 and detail:
+            text = "invalid uncompressed block header: NLEN"
+        super().__init__(text)
         self.code = code
+        self.detail = detail
 
 
 def _u8(data):

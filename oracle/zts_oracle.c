@@ -866,7 +866,7 @@ static int inf_read_code(inf_state* s, const inf_table* t) /* :214-246 */
     uint32_t cwl = t->table[s->bitsbuf & ((1u << t->max_len) - 1)];
     int code_length = (int)(cwl >> 16);
     if (code_length > s->bitsbuflen) {
-        s->err = ZO_E_CODE_LENGTH;
+        s->err = ZO_E_CODE_LENGTH | (code_length << 8); /* 'invalid code length: N' (:238): N rides above bit 7 */
         return 0;
     }
     if (code_length == 0) {
@@ -963,7 +963,7 @@ int zo_raw_inflate(const uint8_t* in, size_t in_len, size_t index, uint8_t* out,
             uint32_t len = s.in[s.ip] | ((uint32_t)s.in[s.ip + 1] << 8);
             s.ip += 2;
             if (s.ip + 1 >= s.in_len) {
-                s.err = ZO_E_STORED_LEN;
+                s.err = ZO_E_STORED_LEN | (1 << 8); /* '... header: NLEN' (:272); LEN (:266) has nothing above bit 7 */
                 break;
             }
             s.ip += 2; /* NLEN read but never effectively verified (:277 is always false) */

@@ -215,3 +215,33 @@ def test_primed_mode_option_through_the_api(Z):
         assert zf.read("t.txt") == d
     with pytest.raises(Z.ZlibError, match="unknown b200 mode"):
         Z.Deflate(d, {"b200": {"mode": "turbo"}}).compress()
+
+
+def test_gunzip_of_1024_members_is_one_batch(Z):
+    """src/GUnzip.ts:56-58 loops over the members; here every `1F 8B 08` in the buffer is a candidate, all candidates are
+    inflated in ONE call and the chain of true members is walked on the host. 1024 members (stock gzip + this engine's
+    own, signature bytes inside the data as decoys) cost a handful of launches, not a thousand."""
+    rng = np.random.default_rng(77)
+    parts, blob = [], []
+    for k in range(1024):
+        n = int(rng.integers(1, 3000))
+        d = rng.integers(0, 6, n, dtype=np.uint8).tobytes() + b"\x1f\x8b\x08\x00decoy" * int(k % 3 == 0)
+        parts.append(d)
+        blob.append(gzip.compress(d, mtime=k) if k % 2 else Z.GZip(d).compress().tobytes())
+    arc = b"".join(blob)
+    eng = Z.api.engine()
+    l0 = eng.launch_count
+    gu = Z.GUnzip(arc)
+    out = gu.decompress().tobytes()
+    launches = eng.launch_count - l0
+    assert out == b"".join(parts)
+    ms = gu.getMembers()
+    assert len(ms) == 1024 and all(m["data"].tobytes() == d for m, d in zip(ms, parts))
+    assert ms[3]["mtime"] == 3 and ms[5]["isize"] == len(parts[5]) and ms[7]["crc32"] == zlib.crc32(parts[7])
+    assert launches < 64, launches
+    # a member whose trailer is wrong is reported like the reference's loop would: at that member, same message
+    bad = bytearray(arc)
+    off = sum(len(b) for b in blob[:500]) + len(blob[500]) - 7
+    bad[off] ^= 0x55
+    with pytest.raises(Z.ZlibError, match="invalid CRC-32 checksum"):
+        Z.GUnzip(bytes(bad)).decompress()

@@ -581,3 +581,31 @@ def test_differential_fuzz_primed_and_smallest(engine):
                 raise AssertionError((mode, chunk, i, len(d), e.args))
             if i % 16 == 0:
                 assert zlib.decompress(o, -15) == d
+
+
+def test_repeated_runs_write_identical_bytes(engine):
+    """The LZ77 kernel's threads read each other's visited bits while they are being written and splice afterwards; a
+    race would show up as a run that differs. 64 MiB of the C2 data, 12 runs per mode, byte-identical every time, and
+    the first compat run decodes to the input (tools/stress_determinism.py is the long version)."""
+    import torch
+    import zlibts_b200 as z
+    from zlibts_b200 import synth
+    n = 64 << 20
+    data = synth.mixed(n, 2)
+    d_in = torch.from_numpy(data).cuda()
+    for name, mode in (("compat", z.MODE_COMPAT), ("primed", z.MODE_PRIMED), ("fast", z.MODE_FAST), ("lazy", z.MODE_FAST | z.MODE_LAZY)):
+        cap = z.deflate_bound(n, 0, z.DYNAMIC, mode)
+        d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        items = z.make_items(1)
+        items["in_len"], items["out_cap"] = n, cap
+        first = None
+        for k in range(12):
+            d_out.zero_()
+            r = engine.deflate_batch(d_in, d_out, items, mode=mode)
+            m = int(r["out_len"][0])
+            assert int(r["status"][0]) == 0
+            if first is None:
+                first = d_out[:m].clone()
+            assert m == first.numel() and torch.equal(d_out[:m], first), (name, k)
+        if name == "compat":
+            assert zlib.decompress(first.cpu().numpy().tobytes(), -15) == data.tobytes()

@@ -282,3 +282,24 @@ def test_container_restatement_is_read_by_cpython():
             assert zf.read(f["name"]) == f["data"]
             assert zf.getinfo(f["name"]).date_time == (2026, 10, 18, 12, 34, 56)
             assert zf.getinfo(f["name"]).comment == f["comment"].encode()
+
+
+def test_truncated_input_errors_equal_the_executed_reference():
+    """tests/golden/truncation_vectors.json: what the reference itself (dist/Zlib-main.js under oracle/minijs) throws for
+    EVERY cut of four streams -- 'input buffer is broken', 'invalid code length: N', '... header: LEN / NLEN'. The
+    oracle, with the reference's readBits end check mirrored, gives the same message at every cut."""
+    import json
+    import os
+    vec = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "truncation_vectors.json")))["vectors"]
+    n = 0
+    for v in vec:
+        s = bytes.fromhex(v["stream"])
+        for cut, want in enumerate(v["cuts"]):
+            try:
+                out, ip = oracle.raw_inflate(s[:cut], 0, out_cap=4096, mirror_readbits_quirk=True)
+                got = "OK %d %d" % (len(out), ip)
+            except oracle.OracleError as e:
+                got = "ERR " + str(e)
+            assert got == want, (v["name"], cut, got, want)
+            n += 1
+    assert n > 1200

@@ -47,11 +47,21 @@ class ZipCompressionMethod:  # src/Zip.ts:7-10
 _STATUS_TEXT = {  # zlb_result.status -> reference message (include/zlibts_b200.h)
     N.ST_INPUT_BROKEN: "input buffer is broken",
     N.ST_BTYPE: "unknown BTYPE: 3",
-    N.ST_CODE_LENGTH: "invalid code length",
     N.ST_STORED_LEN: "invalid uncompressed block header: LEN",
     N.ST_BAD_CODE: "invalid deflate stream: undefined code or distance",
     N.ST_BAD_LENGTHS: "invalid deflate stream: over-subscribed code lengths",
 }
+
+
+def status_text(st):
+    """The reference's message for a zlb_result.status (src/RawInflate.ts:168,188,238,266,272)."""
+    st = int(st)
+    if (st & 0xFF) == N.ST_CODE_LENGTH:
+        return "invalid code length: %d" % (st >> 8)
+    if (st & 0xFF) == N.ST_STORED_LEN and (st >> 8):
+        return "invalid uncompressed block header: NLEN"
+    return _STATUS_TEXT.get(st & 0xFF, "inflate failed with status %d" % st)
+
 
 _engine = None
 
@@ -182,7 +192,7 @@ def inflate_blob(blob, offs, lens, size_hints=None, want_crc32=False, want_adler
                 again.append(i)
                 continue
             if st != N.ST_OK:
-                raise ZlibError(_STATUS_TEXT.get(st, "inflate failed with status %d" % st))
+                raise ZlibError(status_text(st))
             outs[i] = out[int(out_off[k]):int(out_off[k]) + int(res["out_len"][k])]
             final[i] = res[k]
         if not again:

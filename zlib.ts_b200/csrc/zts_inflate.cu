@@ -255,6 +255,55 @@ __device__ __forceinline__ unsigned long long br_bits_used(const BitReader& br)
     return br.base_bits + br.words_taken * 32ull - br.skip_bits - (unsigned long long)br.cnt;
 }
 
+// ---- which error does the reference raise when the input ends early? ---------------------------------------------
+// readBits throws 'input buffer is broken' (src/RawInflate.ts:188), readCodeByTable looks the code up in what is left
+// (zero padded) and throws 'invalid code length: N' when the N bits of that code are not all there (:238). The decode
+// loops only notice that a batch ran past the end; these helpers replay from a known bit position, one symbol at a
+// time, and tell the two cases apart. Rare path, every lane computes the same.
+// 32 bits of the stream at bit position `pos`, zero padded behind the end of the input
+__device__ uint32_t inf_peek(const uint8_t* src, unsigned long long in_len, unsigned long long pos)
+{
+    const unsigned long long byte = pos >> 3;
+    unsigned long long v = 0;
+    for (uint32_t k = 0; k < 6; ++k)
+        if (byte + k < in_len) v |= (unsigned long long)src[byte + k] << (8u * k);
+    return (uint32_t)(v >> (pos & 7u));
+}
+// status of a Huffman code of the code-length alphabet read at `pos` (dynamic block header)
+__device__ uint32_t inf_classify_cl(const InfWarpSmem* S, const uint8_t* src, unsigned long long in_len, unsigned long long pos)
+{
+    const uint32_t e = S->cl_root[inf_peek(src, in_len, pos) & ((1u << CL_ROOT_BITS) - 1u)];
+    const uint32_t nb = e & 15u;
+    if (nb && pos + nb > in_len * 8ull) return ZLB_ST_CODE_LENGTH | (nb << 8);
+    return ZLB_ST_INPUT_BROKEN;  // the code was there: its repeat count was not
+}
+// replays the symbols of a block from `pos` until the input runs out
+__device__ uint32_t inf_classify_symbols(const InfWarpSmem* S, const uint8_t* src, unsigned long long in_len, unsigned long long pos)
+{
+    const unsigned long long in_bits = in_len * 8ull;
+    for (uint32_t k = 0; k < 64 && pos < in_bits + 64; ++k) {
+        uint32_t bits = inf_peek(src, in_len, pos);
+        uint32_t e = S->lit_root[bits & ((1u << LIT_ROOT_BITS) - 1u)];
+        if ((e & 15u) == 0) e = slow_decode(TAB_LITLEN, bits, LIT_ROOT_BITS, S->lit_sorted, &S->lit);
+        if (e == 0) return ZLB_ST_BAD_CODE;
+        if (pos + (e & 15u) > in_bits) return ZLB_ST_CODE_LENGTH | ((e & 15u) << 8);
+        pos += e & 15u;
+        if (!(e & 0x300u)) continue;              // literal
+        if ((e & 0x300u) != (KIND_BASE << 8)) break;  // end of block / invalid symbol: not an input problem
+        pos += (e >> 4) & 15u;                    // length extra bits (readBits)
+        if (pos > in_bits) return ZLB_ST_INPUT_BROKEN;
+        bits = inf_peek(src, in_len, pos);
+        uint32_t d = S->dist_root[bits & ((1u << DIST_ROOT_BITS) - 1u)];
+        if ((d & 15u) == 0) d = slow_decode(TAB_DIST, bits, DIST_ROOT_BITS, S->dist_sorted, &S->dist);
+        if (d == 0) return ZLB_ST_BAD_CODE;
+        if (pos + (d & 15u) > in_bits) return ZLB_ST_CODE_LENGTH | ((d & 15u) << 8);
+        pos += d & 15u;
+        pos += (d >> 4) & 15u;                    // distance extra bits (readBits)
+        if (pos > in_bits) return ZLB_ST_INPUT_BROKEN;
+    }
+    return ZLB_ST_INPUT_BROKEN;
+}
+
 __global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
 inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const zlb_item* __restrict__ items,
                     zlb_result* __restrict__ results, uint32_t n_items, uint32_t flags)
@@ -299,7 +348,8 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             unsigned long long used = br_bits_used(br);
             unsigned long long byte_pos = (used + 7) >> 3;
             if (byte_pos + 4 > it.in_len) {
-                status = ZLB_ST_STORED_LEN;
+                // src/RawInflate.ts:266 (LEN) / :272 (NLEN): which of the two 16-bit fields is cut short
+                status = byte_pos + 2 > it.in_len ? ZLB_ST_STORED_LEN : (ZLB_ST_STORED_LEN | (1u << 8));
                 break;
             }
             const uint8_t* p = src + byte_pos;
@@ -368,6 +418,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             uint32_t i = 0, prev = 0;
             while (i < total && status == ZLB_ST_OK) {
                 br_refill(br);
+                const unsigned long long cl_pos = br_bits_used(br);
                 uint32_t e = S->cl_root[(uint32_t)br.buf & ((1u << CL_ROOT_BITS) - 1u)];
                 uint32_t nb = e & 15u;
                 if (nb == 0) {
@@ -392,7 +443,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                     if (i + k < total) S->lens[32 + i + k] = (uint8_t)val;  // staging above the CL lengths
                 i += rep;
                 prev = val;
-                if (br_bits_used(br) > in_bits) status = ZLB_ST_INPUT_BROKEN;
+                if (br_bits_used(br) > in_bits) status = inf_classify_cl(S, src, it.in_len, cl_pos);
             }
             if (status != ZLB_ST_OK) break;
             __syncwarp();
@@ -413,6 +464,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             //    pointer to the per-warp slice gets rematerialised from %tid on every look-up otherwise).
             uint32_t mytok = 0, ntok = 0;
             uint32_t stop = 0;  // 1 = end of block, 2 = undefined code / symbol
+            const unsigned long long batch_pos = br_bits_used(br);  // (only looked at when the input ends inside the batch)
             {
                 uint32_t lit_s = (uint32_t)__cvta_generic_to_shared(S->lit_root);
                 uint32_t dist_s = (uint32_t)__cvta_generic_to_shared(S->dist_root);
@@ -505,8 +557,9 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             if (stop == 1) eob = true;
             if (stop == 2) status = ZLB_ST_BAD_CODE;
             if (br_bits_used(br) > in_bits) {
-                // the batch ran past the end of the input: nothing of it is trusted
-                status = ZLB_ST_INPUT_BROKEN;
+                // the batch ran past the end of the input: nothing of it is trusted; which error it is -- a code or
+                // extra bits cut short -- is found by replaying the batch
+                status = inf_classify_symbols(S, src, it.in_len, batch_pos);
                 break;
             }
             // -- output positions: exclusive prefix sum of the token lengths
