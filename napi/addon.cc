@@ -1,8 +1,14 @@
 // addon.cc -- Node.js N-API binding of libzlibts_b200.so (include/zlibts_b200.h).
 //
-// NOT COMPILED IN THIS IMAGE: there is no Node binary and no node_api.h here or on the GPU boxes (SURVEY.md
-// section 0.6). It is the binding a maintainer adds to the reference: pure marshalling, no algorithm. The tested
-// equivalent of this layer is zlib.ts_b200/api.py over the same C ABI.
+// NOT RUN IN THIS IMAGE: there is no Node binary and no node_api.h here or on the GPU boxes;
+// tests/test_abi.py type-checks this file against a stub of the N-API declarations it uses (tests/napi_stub/). It is
+// the binding a maintainer adds to the reference: pure marshalling, no algorithm. The tested equivalent of this layer
+// is zlib.ts_b200/api.py over the same C ABI.
+//
+// Memory: everything the GPU copies from or to is page-locked (zlb_host_alloc). Outputs are handed to JS as views into
+// ONE external ArrayBuffer over the page-locked result buffer (no copy; freed when the last view is collected). Inputs
+// that live in the JS heap are gathered into a page-locked blob (one memcpy); an input that already lives in memory
+// from hostAlloc() (exported below) is passed as it is.
 //
 // Exports (all synchronous, like the reference's API):
 //   deflateBatch(inputs: Uint8Array[], compressionType, chunkBytes, flags, mode?) -> {outputs: Uint8Array[], crc32: number[], adler32: number[]}
@@ -10,6 +16,7 @@
 //                                                          -> {outputs, status: number[], inUsed: number[], crc32, adler32}
 //   checksumBatch(inputs: Uint8Array[], kinds)             -> {crc32: number[], adler32: number[]}
 //   crc32Combine(a, b, lenB), adler32Combine(a, b, lenB)
+//   hostAlloc(bytes) -> Uint8Array over page-locked memory (build inputs in it: they then travel without a copy)
 //   archive(kind, inputs: Uint8Array[], heads: Uint8Array[], cdirs: Uint8Array[] | null, methods: number[] | null,
 //           tail: Uint8Array, compressionType, chunkBytes, mode)
 //                                   -> {output: Uint8Array, crc32, adler32, offsets: number[], lengths: number[]}
@@ -54,7 +61,48 @@ static bool get_u8(napi_env env, napi_value v, Bytes* out)
     return true;
 }
 
-static napi_value make_u8(napi_env env, const uint8_t* src, size_t n)
+// page-locked host memory for the duration of a call
+struct HostBuf {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    explicit HostBuf(size_t bytes) : n(bytes ? bytes : 1)
+    {
+        void* q = nullptr;
+        if (zlb_host_alloc(n, &q) == ZLB_OK) p = (uint8_t*)q;
+    }
+    ~HostBuf()
+    {
+        if (p) zlb_host_free(p);
+    }
+    uint8_t* release()
+    {
+        uint8_t* q = p;
+        p = nullptr;
+        return q;
+    }
+    HostBuf(const HostBuf&) = delete;
+    HostBuf& operator=(const HostBuf&) = delete;
+};
+
+static void free_host(napi_env, void* data, void*) { zlb_host_free(data); }
+
+// An external ArrayBuffer that takes over a page-locked buffer (freed by the finalizer), and views into it
+static napi_value adopt_buffer(napi_env env, uint8_t* p, size_t n)
+{
+    napi_value ab;
+    if (napi_create_external_arraybuffer(env, p, n, free_host, nullptr, &ab) != napi_ok) {
+        zlb_host_free(p);  // (runtimes that forbid external buffers: the caller falls back to a copy)
+        return nullptr;
+    }
+    return ab;
+}
+static napi_value view_u8(napi_env env, napi_value ab, size_t off, size_t n)
+{
+    napi_value ta;
+    napi_create_typedarray(env, napi_uint8_array, n, ab, off, &ta);
+    return ta;
+}
+static napi_value copy_u8(napi_env env, const uint8_t* src, size_t n)
 {
     void* data;
     napi_value ab, ta;
@@ -63,6 +111,22 @@ static napi_value make_u8(napi_env env, const uint8_t* src, size_t n)
     napi_create_typedarray(env, napi_uint8_array, n, ab, 0, &ta);
     return ta;
 }
+// the outputs of a batch: views into the adopted result buffer, or copies where that is not possible
+struct Outputs {
+    napi_env env;
+    napi_value ab = nullptr;
+    uint8_t* base;
+    Outputs(napi_env e, HostBuf& out) : env(e), base(out.p)
+    {
+        const size_t n = out.n;
+        ab = adopt_buffer(env, out.release(), n);
+        if (!ab) base = nullptr;
+    }
+    napi_value at(const uint8_t* fallback_base, size_t off, size_t n) const
+    {
+        return ab ? view_u8(env, ab, off, n) : copy_u8(env, fallback_base + off, n);
+    }
+};
 
 static napi_value num_array(napi_env env, const std::vector<double>& v)
 {
@@ -121,10 +185,17 @@ static napi_value DeflateBatch(napi_env env, napi_callback_info info)
         in_total += in[i].n;
         out_total += items[i].out_cap;
     }
-    std::vector<uint8_t> blob(in_total ? in_total : 1), out(out_total ? out_total : 1);
-    for (uint32_t i = 0; i < n; ++i)
-        if (in[i].n) memcpy(blob.data() + items[i].in_off, in[i].p, in[i].n);
-    int rc = zlb_deflate_batch_host(g_ctx, blob.data(), blob.size(), out.data(), out.size(), items.data(), res.data(), n,
+    // one input that already lives in page-locked memory (hostAlloc) travels as it is; anything else is gathered
+    const bool direct = n == 1 && in[0].n && zlb_host_is_pinned(in[0].p);
+    HostBuf blob(direct ? 1 : in_total), out(out_total);
+    if (!blob.p || !out.p) {
+        napi_throw_error(env, nullptr, "zlib.ts-b200: out of host memory");
+        return nullptr;
+    }
+    if (!direct)
+        for (uint32_t i = 0; i < n; ++i)
+            if (in[i].n) memcpy(blob.p + items[i].in_off, in[i].p, in[i].n);
+    int rc = zlb_deflate_batch_host(g_ctx, direct ? in[0].p : blob.p, in_total, out.p, out_total, items.data(), res.data(), n,
                                     (int)mode, (int)ctype, chunk, flags);
     if (rc != ZLB_OK) {
         napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
@@ -134,8 +205,10 @@ static napi_value DeflateBatch(napi_env env, napi_callback_info info)
     napi_create_object(env, &result);
     napi_create_array_with_length(env, n, &outs);
     std::vector<double> crc(n), adler(n);
+    const uint8_t* out_base = out.p;
+    Outputs views(env, out);  // the result buffer now belongs to the ArrayBuffer the outputs are views of
     for (uint32_t i = 0; i < n; ++i) {
-        napi_set_element(env, outs, i, make_u8(env, out.data() + items[i].out_off, (size_t)res[i].out_len));
+        napi_set_element(env, outs, i, views.at(out_base, items[i].out_off, (size_t)res[i].out_len));
         crc[i] = res[i].crc32;
         adler[i] = res[i].adler32;
     }
@@ -171,8 +244,14 @@ static napi_value InflateBatch(napi_env env, napi_callback_info info)
         items[i].out_cap = (uint64_t)caps[i];
         out_total += items[i].out_cap;
     }
-    std::vector<uint8_t> out(out_total ? out_total : 1);
-    int rc = zlb_inflate_batch_host(g_ctx, in.p, in.n, out.data(), out.size(), items.data(), res.data(), n, flags);
+    // the input is one Uint8Array already: page-locked if it came from hostAlloc(), otherwise the library stages it
+    // through its own page-locked shadow (copy threads, overlapped with the transfers)
+    HostBuf out(out_total);
+    if (!out.p) {
+        napi_throw_error(env, nullptr, "zlib.ts-b200: out of host memory");
+        return nullptr;
+    }
+    int rc = zlb_inflate_batch_host(g_ctx, in.p, in.n, out.p, out_total, items.data(), res.data(), n, flags);
     if (rc != ZLB_OK) {
         napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
         return nullptr;
@@ -181,8 +260,10 @@ static napi_value InflateBatch(napi_env env, napi_callback_info info)
     napi_create_object(env, &result);
     napi_create_array_with_length(env, n, &outs);
     std::vector<double> st(n), used(n), crc(n), adler(n);
+    const uint8_t* out_base = out.p;
+    Outputs views(env, out);
     for (size_t i = 0; i < n; ++i) {
-        napi_set_element(env, outs, (uint32_t)i, make_u8(env, out.data() + items[i].out_off, (size_t)res[i].out_len));
+        napi_set_element(env, outs, (uint32_t)i, views.at(out_base, items[i].out_off, (size_t)res[i].out_len));
         st[i] = res[i].status;
         used[i] = (double)res[i].in_used;
         crc[i] = res[i].crc32;
@@ -221,10 +302,16 @@ static napi_value ChecksumBatch(napi_env env, napi_callback_info info)
         items[i].in_len = in[i].n;
         total += in[i].n;
     }
-    std::vector<uint8_t> blob(total ? total : 1);
-    for (uint32_t i = 0; i < n; ++i)
-        if (in[i].n) memcpy(blob.data() + items[i].in_off, in[i].p, in[i].n);
-    if (zlb_checksum_batch_host(g_ctx, blob.data(), blob.size(), items.data(), res.data(), n, kinds) != ZLB_OK) {
+    const bool direct = n == 1 && in[0].n && zlb_host_is_pinned(in[0].p);
+    HostBuf blob(direct ? 1 : total);
+    if (!blob.p) {
+        napi_throw_error(env, nullptr, "zlib.ts-b200: out of host memory");
+        return nullptr;
+    }
+    if (!direct)
+        for (uint32_t i = 0; i < n; ++i)
+            if (in[i].n) memcpy(blob.p + items[i].in_off, in[i].p, in[i].n);
+    if (zlb_checksum_batch_host(g_ctx, direct ? in[0].p : blob.p, total, items.data(), res.data(), n, kinds) != ZLB_OK) {
         napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
         return nullptr;
     }
@@ -294,18 +381,21 @@ static napi_value Archive(napi_env env, napi_callback_info info)
     }
     const uint64_t tail_off = meta_total;
     meta_total += tail.n;
-    std::vector<uint8_t> blob(in_total ? in_total : 1), meta(meta_total ? meta_total : 1);
-    for (uint32_t i = 0; i < n; ++i) {
-        if (in[i].n) memcpy(blob.data() + ent[i].in_off, in[i].p, in[i].n);
-        if (head[i].n) memcpy(meta.data() + ent[i].head_off, head[i].p, head[i].n);
-        if (cdir[i].n) memcpy(meta.data() + ent[i].cdir_off, cdir[i].p, cdir[i].n);
-    }
-    if (tail.n) memcpy(meta.data() + tail_off, tail.p, tail.n);
     const uint32_t cb = (mode & ZLB_MODE_PRIMED) && (chunk == 0 || chunk > ZLB_PRIMED_CHUNK) ? ZLB_PRIMED_CHUNK : chunk;
-    std::vector<uint8_t> out(zlb_archive_bound((int)kind, ent.data(), n, tail.n, cb, (int)ctype) + 1);
+    HostBuf blob(in_total), meta(meta_total), out(zlb_archive_bound((int)kind, ent.data(), n, tail.n, cb, (int)ctype) + 1);
+    if (!blob.p || !meta.p || !out.p) {
+        napi_throw_error(env, nullptr, "zlib.ts-b200: out of host memory");
+        return nullptr;
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (in[i].n) memcpy(blob.p + ent[i].in_off, in[i].p, in[i].n);
+        if (head[i].n) memcpy(meta.p + ent[i].head_off, head[i].p, head[i].n);
+        if (cdir[i].n) memcpy(meta.p + ent[i].cdir_off, cdir[i].p, cdir[i].n);
+    }
+    if (tail.n) memcpy(meta.p + tail_off, tail.p, tail.n);
     uint64_t total = 0;
-    int rc = zlb_archive_host(g_ctx, (int)kind, blob.data(), in_total, meta.data(), meta_total, ent.data(), n, tail_off,
-                              tail.n, out.data(), out.size(), &total, res.data(), (int)mode, (int)ctype, chunk);
+    int rc = zlb_archive_host(g_ctx, (int)kind, blob.p, in_total, meta.p, meta_total, ent.data(), n, tail_off,
+                              tail.n, out.p, out.n, &total, res.data(), (int)mode, (int)ctype, chunk);
     if (rc != ZLB_OK) {
         napi_throw_error(env, nullptr, zlb_last_error(g_ctx));
         return nullptr;
@@ -319,7 +409,9 @@ static napi_value Archive(napi_env env, napi_callback_info info)
     }
     napi_value result;
     napi_create_object(env, &result);
-    napi_set_named_property(env, result, "output", make_u8(env, out.data(), (size_t)total));
+    const uint8_t* out_base = out.p;
+    Outputs views(env, out);  // the archive is a view of the page-locked result buffer: no copy
+    napi_set_named_property(env, result, "output", views.at(out_base, 0, (size_t)total));
     napi_set_named_property(env, result, "crc32", num_array(env, crc));
     napi_set_named_property(env, result, "adler32", num_array(env, adler));
     napi_set_named_property(env, result, "offsets", num_array(env, offs));
@@ -345,6 +437,29 @@ static napi_value Combine(napi_env env, napi_callback_info info, bool crc)
 static napi_value Crc32Combine(napi_env env, napi_callback_info info) { return Combine(env, info, true); }
 static napi_value Adler32Combine(napi_env env, napi_callback_info info) { return Combine(env, info, false); }
 
+// hostAlloc(bytes) -> Uint8Array over page-locked memory (zlb_host_alloc): what a caller fills instead of
+// `new Uint8Array(n)` (src/RawDeflate.ts:58) when the data should travel without a staging copy
+static napi_value HostAlloc(napi_env env, napi_callback_info info)
+{
+    size_t argc = 1;
+    napi_value argv[1];
+    napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr);
+    double bytes = 0;
+    napi_get_value_double(env, argv[0], &bytes);
+    const size_t n = bytes > 0 ? (size_t)bytes : 0;
+    void* p = nullptr;
+    if (zlb_host_alloc(n ? n : 1, &p) != ZLB_OK) {
+        napi_throw_error(env, nullptr, "zlib.ts-b200: out of host memory");
+        return nullptr;
+    }
+    napi_value ab = adopt_buffer(env, (uint8_t*)p, n ? n : 1);
+    if (!ab) {
+        napi_throw_error(env, nullptr, "zlib.ts-b200: this runtime does not allow external ArrayBuffers");
+        return nullptr;
+    }
+    return view_u8(env, ab, 0, n);
+}
+
 static napi_value Init(napi_env env, napi_value exports)
 {
     napi_property_descriptor d[] = {
@@ -354,6 +469,7 @@ static napi_value Init(napi_env env, napi_value exports)
         {"archive", nullptr, Archive, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"crc32Combine", nullptr, Crc32Combine, nullptr, nullptr, nullptr, napi_default, nullptr},
         {"adler32Combine", nullptr, Adler32Combine, nullptr, nullptr, nullptr, napi_default, nullptr},
+        {"hostAlloc", nullptr, HostAlloc, nullptr, nullptr, nullptr, napi_default, nullptr},
     };
     napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
     return exports;

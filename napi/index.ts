@@ -8,10 +8,11 @@ export enum CompressionType { NONE = 0, FIXED = 1, DYNAMIC = 2, RESERVED = 3 }  
 export enum BufferType { BLOCK = 0, ADAPTIVE = 1 }                                   // src/RawInflate.ts:5-8
 export interface RawDeflateOptions { lazy?: number; compressionType?: CompressionType;
     outputBuffer?: number[] | Uint8Array; outputIndex?: number;
-    b200?: { chunkBytes?: number; mode?: 'compat' | 'fast' | 'primed' | 'fast-primed'; depth?: number; smallest?: boolean } }
+    b200?: { chunkBytes?: number; mode?: 'compat' | 'fast' | 'primed' | 'fast-primed'; depth?: number; smallest?: boolean; lazy?: boolean } }
 // engine-only knob -> ZLB_MODE_* (include/zlibts_b200.h); the default is the reference-compatible mode
 const modeOf = (o: RawDeflateOptions = {}) => { const b = o.b200 ?? {}; const m = b.mode ?? 'compat';
-    return (m.startsWith('fast') ? 1 | ((b.depth ?? 0) << 8) : 0) | (m.endsWith('primed') ? 2 : 0) | (b.smallest ? 4 : 0); };
+    return (m.startsWith('fast') ? 1 | ((b.depth ?? 0) << 8) : 0) | (m.endsWith('primed') ? 2 : 0) | (b.smallest ? 4 : 0) |
+        (b.lazy && m.startsWith('fast') ? 8 : 0); };   // lazy: ZLB_MODE_LAZY, a fast-mode option
 export interface RawInflateOptions { index?: number; bufferSize?: number; bufferType?: BufferType; resize?: boolean }
 
 const STATUS_TEXT: { [k: number]: string } = {                                       // include/zlibts_b200.h

@@ -4,6 +4,8 @@ import re
 
 import zlib
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 
 def test_exports_match_header():
     import zlibts_b200 as z
@@ -39,3 +41,17 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(z.EngineError):
         z.Engine(0)
+
+
+def test_napi_addon_type_checks_against_the_napi_declarations():
+    """napi/addon.cc cannot be built or run here (no Node, no node_api.h): it is at least type-checked, against a stub
+    of the N-API declarations it uses (tests/napi_stub/node_api.h) and the real C-ABI header."""
+    import shutil
+    import subprocess
+    import pytest
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("no g++")
+    r = subprocess.run([gxx, "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "tests", "napi_stub"),
+                        os.path.join(ROOT, "napi", "addon.cc")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
