@@ -19,6 +19,9 @@ const STATUS_TEXT: { [k: number]: string } = {                                  
     1: 'input buffer is broken', 2: 'unknown BTYPE: 3', 3: 'invalid code length',
     5: 'invalid uncompressed block header: LEN', 6: 'invalid deflate stream: undefined code or distance',
     7: 'invalid deflate stream: over-subscribed code lengths' };
+// the reference's message for a zlb_result.status: N of 'invalid code length: N' and LEN / NLEN ride above bit 7
+const statusText = (st: number) => (st & 0xFF) === 3 ? 'invalid code length: ' + (st >>> 8) :
+    (st & 0xFF) === 5 && (st >>> 8) ? 'invalid uncompressed block header: NLEN' : (STATUS_TEXT[st & 0xFF] ?? 'inflate failed');
 const u8 = (x: number[] | Uint8Array) => x instanceof Uint8Array ? x : new Uint8Array(x);
 
 export class RawDeflate {                                                            // src/RawDeflate.ts:50-114
@@ -55,7 +58,7 @@ export class RawInflate {                                                       
         for (;;) {                                                                   // the reference grows its buffer
             const r = native.inflateBatch(this.input, [this.ip], [this.input.length - this.ip], [cap], flags);
             if (r.status[0] === 4) { cap *= 4; continue; }
-            if (r.status[0] !== 0) throw new Error(STATUS_TEXT[r.status[0]] ?? 'inflate failed');
+            if (r.status[0] !== 0) throw new Error(statusText(r.status[0]));
             this.ip += r.inUsed[0]; this.buffer = r.outputs[0]; this.op = r.outputs[0].length;
             (this as any).crc32 = r.crc32[0]; (this as any).adler32 = r.adler32[0];
             return r.outputs[0];

@@ -105,6 +105,21 @@ int zts_copy_back(zlb_ctx* ctx, ZtsHostStage* st, cudaStream_t s, const uint8_t*
 void zts_prof_begin(zlb_ctx* ctx, int slot);
 void zts_prof_end(zlb_ctx* ctx, int slot);
 
+// -DZTS_CHECK: bounds asserts on the kernels' table / token / bitmap indices (compute-sanitizer is not available on
+// the GPU pool; the checked build runs the GPU test suite once per round, see profiles/). Off in the product build.
+#ifdef ZTS_CHECK
+#include <stdio.h>
+#define ZTS_ASSERT(c)                                                        \
+    do {                                                                     \
+        if (!(c)) {                                                          \
+            printf("ZTS_ASSERT %s:%d %s\n", __FILE__, __LINE__, #c);         \
+            __trap();                                                        \
+        }                                                                    \
+    } while (0)
+#else
+#define ZTS_ASSERT(c) ((void)0)
+#endif
+
 #define ZTS_CUDA(ctx, call)                                                                       \
     do {                                                                                          \
         cudaError_t _e = (call);                                                                  \

@@ -211,6 +211,7 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
     for (uint32_t i = tid; i < (hdr_bits + 7) / 8; i += PACK_THREADS) {
         const uint32_t b = codes[c].hdr[i];
         const uint32_t bit = base_bit + i * 8;
+        ZTS_ASSERT((bit >> 5) < stage_words);
         if (b) atomicOr(&stage[bit >> 5], b << (bit & 31));  // byte-aligned inside a word: never straddles
     }
     const uint32_t* list = tok_list + (size_t)c * LZ_LIST_PER_CHUNK;
@@ -254,6 +255,7 @@ bitpack_kernel(const ZtsChunk* __restrict__ chunks, const ZtsChunkInfo* __restri
                 const uint32_t w0 = (uint32_t)(bp >> 5), sh = (uint32_t)(bp & 31);
                 // up to 48 + 31 bits -> three words
                 const unsigned long long lo64 = t.bits << sh;
+                ZTS_ASSERT(w0 + 2u < stage_words + 2u && w0 < stage_words);
                 atomicOr(&stage[w0], (uint32_t)lo64);
                 const uint32_t mid = (uint32_t)(lo64 >> 32);
                 if (mid) atomicOr(&stage[w0 + 1], mid);

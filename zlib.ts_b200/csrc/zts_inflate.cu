@@ -587,6 +587,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             }
             const bool live = lane < nvalid;
             // -- literals: one store
+            ZTS_ASSERT(!live || (pos + len <= cap && (!is_match || dist <= pos)));
             if (live && !is_match) dst[pos] = (uint8_t)(mytok >> 16);
             // -- matches, sub-batch by sub-batch
             uint32_t start = 0;

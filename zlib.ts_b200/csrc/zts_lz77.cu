@@ -307,6 +307,7 @@ __device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __re
                     }
                 }
             }
+            ZTS_ASSERT(p < n && lo <= i && i < m);
             st_u32_hint(&P[p], i | ((i - lo) << 16), keep);
         }
         // inside a long bucket consecutive slots are consecutive positions (runs of one byte): one atomic per warp then
@@ -358,6 +359,7 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
     while (cur > lo && best_len < 3u) {
         const uint32_t cnt = min(32u, cur - lo);
         const bool act = lane < cnt;
+        ZTS_ASSERT(cur >= cnt && cur <= LZ_MAX_CHUNK);
         const uint32_t q = act ? sorted[cur - 1 - lane] : 0u;  // lane 0 = newest candidate
         const bool inwin = act && (p - q <= LZ_WINDOW);
         uint32_t key = 0;
@@ -384,8 +386,10 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
             const uint32_t o = k * 32u + lane;
             hitq[k] = 0;
             if (o < cnt) {
+                ZTS_ASSERT(cur >= 1u + o && cur <= LZ_MAX_CHUNK);
                 const uint32_t q = sorted[cur - 1u - o];
                 hitq[k] = q;
+                ZTS_ASSERT(q < p);
                 if (p - q > LZ_WINDOW)
                     out = true;
                 else if (S[q + best_len] == pt)
@@ -631,6 +635,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                         __syncwarp();
                         if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
                         if (v) {
+                            ZTS_ASSERT(dst < m);
                             st_u32_hint(&T[dst], i | (hh << 16), keep);
                             atomicAdd(&cntB[(dst >> 11) * 256u + (hh >> 8)], 1u);
                         }
@@ -682,6 +687,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                 if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
                 __syncwarp();
                 if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                ZTS_ASSERT(!v || dst < m);
                 if (v) sorted[dst] = (uint16_t)e;
                 __syncwarp();
             }
@@ -867,6 +873,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                             bool end;
                             if (bl < 3u) {
                                 // nothing found yet: the newest candidate not yet looked at, exact test
+                                ZTS_ASSERT(s_cur >= 1u && s_cur <= m && s_left >= 1u);
                                 const uint32_t q = sorted[--s_cur];
                                 --s_left;
                                 end = s_left == 0u;
@@ -885,6 +892,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                                 // best_len must match. Four candidates per step through that test alone; the nearest
                                 // that passes gets the exact comparison
                                 const uint32_t c4 = min(4u, s_left);
+                                ZTS_ASSERT(c4 >= 1u && s_cur >= c4 && s_cur <= m);
                                 const uint32_t q0 = sorted[s_cur - 1u], q1 = c4 > 1u ? sorted[s_cur - 2u] : 0u,
                                                q2 = c4 > 2u ? sorted[s_cur - 3u] : 0u, q3 = c4 > 3u ? sorted[s_cur - 4u] : 0u;
                                 const bool h0 = SV[q0 + bl] == ptail, h1 = c4 > 1u && SV[q1 + bl] == ptail,
@@ -907,6 +915,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                                 s_cur -= used;
                                 s_left -= used;
                                 end = s_left == 0u || p - qo > LZ_WINDOW;
+                                ZTS_ASSERT(q == 0xFFFFFFFFu || (q < p && q + bl < n + 32u));
                                 if (q != 0xFFFFFFFFu && p - q <= LZ_WINDOW) {
                                     const uint32_t len = lz_match_len(SV, q, p, pw, pw1, maxlen);
                                     if (len > bl) {
@@ -978,6 +987,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                             tok = SV[at];  // the bit was a "maybe" (hash collisions), or everything lies outside the window
                             np = at + 1u;
                         }
+                        ZTS_ASSERT(tok_i < tok_0 + LZ_TILE_POS + 8u && at < n && (resync || at / LZ_TILE_POS == t));
                         tbuf[tok_i++] = tok;
                         if (!resync) visited[at >> 5] |= 1u << (at & 31u);
                         p = np;
@@ -1027,6 +1037,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                         const uint32_t k = mm ? min((uint32_t)__ffs((int)mm) - 1u, avail) : avail;
                         if (k) {
                             // k positions without any candidate: k literals (src/LZ77.ts:267-272)
+                            ZTS_ASSERT(tok_i + k <= tok_0 + LZ_TILE_POS + 8u && p + k <= t_end && t_end <= n);
                             {
                                 uint32_t o = 0;  // single tokens up to a 16-byte boundary of the token slots, then four per store
                                 for (; o < k && ((tok_i + o) & 3u); ++o) tbuf[tok_i + o] = SV[p + o];
@@ -1049,6 +1060,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                         if (k < avail) {  // p has candidates
                             const uint32_t rank = pinfo >> 16;  // earlier entries of the bucket: the slots in front of p's own
                             s_cur = pinfo & 0xFFFFu;
+                            ZTS_ASSERT(p + 3u < n && rank <= s_cur && s_cur < m && sorted[s_cur] == p);
                             maxlen = min(LZ_MAXLEN, n - p);
                             best = 0;
                             if (rank > LZ_PRIV_CAP && depth > LZ_PRIV_CAP) {
@@ -1171,6 +1183,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 const uint32_t* fx = fix_c + lz_tok_off(w);
                 const uint32_t* sp = spec_c + lz_tok_off(w) + from;
                 const uint32_t ns = sc - from;
+                ZTS_ASSERT(tok_off[w] + nf + ns <= n && from <= sc && nf <= LZ_TILE_POS && sc <= LZ_TILE_POS);
                 for (uint32_t k = lane; k < nf + ns; k += 32) {
                     const uint32_t tok = k < nf ? fx[k] : sp[k - nf];
                     st_u32_hint(&dst[k], tok, stream);
