@@ -869,60 +869,44 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                     uint32_t it = 0;
                     while (busy) {
                         if (st == ST_SRCH) {
+                            // One code path for every searching lane. Behind a known match only a strictly longer one
+                            // counts (:183): its byte at best_len must match -- four candidates per step go through that
+                            // test alone and the nearest that passes gets the exact comparison. Before a match is known
+                            // the step looks at one candidate, which "passes" unconditionally.
                             const uint32_t bl = best >> 16;
-                            bool end;
-                            if (bl < 3u) {
-                                // nothing found yet: the newest candidate not yet looked at, exact test
-                                ZTS_ASSERT(s_cur >= 1u && s_cur <= m && s_left >= 1u);
-                                const uint32_t q = sorted[--s_cur];
-                                --s_left;
-                                end = s_left == 0u;
-                                if (p - q > LZ_WINDOW) {
-                                    end = true;  // older ones are outside the window too (src/LZ77.ts:223)
-                                } else {
-                                    const uint32_t len = lz_match_len(SV, q, p, pw, pw1, maxlen);
-                                    if (len) {
-                                        best = (len << 16) | q;
-                                        ptail = SV[p + len];
-                                        end = end || len >= maxlen;  // :189 (258) or capped by the input end
-                                    }
-                                }
-                            } else {
-                                // only a strictly longer match replaces the best of the nearer ones (:183): its byte at
-                                // best_len must match. Four candidates per step through that test alone; the nearest
-                                // that passes gets the exact comparison
-                                const uint32_t c4 = min(4u, s_left);
-                                ZTS_ASSERT(c4 >= 1u && s_cur >= c4 && s_cur <= m);
-                                const uint32_t q0 = sorted[s_cur - 1u], q1 = c4 > 1u ? sorted[s_cur - 2u] : 0u,
-                                               q2 = c4 > 2u ? sorted[s_cur - 3u] : 0u, q3 = c4 > 3u ? sorted[s_cur - 4u] : 0u;
-                                const bool h0 = SV[q0 + bl] == ptail, h1 = c4 > 1u && SV[q1 + bl] == ptail,
-                                           h2 = c4 > 2u && SV[q2 + bl] == ptail, h3 = c4 > 3u && SV[q3 + bl] == ptail;
-                                uint32_t used = c4, q = 0xFFFFFFFFu;
-                                if (h0) {
-                                    used = 1u;
-                                    q = q0;
-                                } else if (h1) {
-                                    used = 2u;
-                                    q = q1;
-                                } else if (h2) {
-                                    used = 3u;
-                                    q = q2;
-                                } else if (h3) {
-                                    q = q3;
-                                }
-                                // the oldest candidate looked at decides about the window (ascending positions)
-                                const uint32_t qo = used == 1u ? q0 : used == 2u ? q1 : used == 3u ? q2 : q3;
-                                s_cur -= used;
-                                s_left -= used;
-                                end = s_left == 0u || p - qo > LZ_WINDOW;
-                                ZTS_ASSERT(q == 0xFFFFFFFFu || (q < p && q + bl < n + 32u));
-                                if (q != 0xFFFFFFFFu && p - q <= LZ_WINDOW) {
-                                    const uint32_t len = lz_match_len(SV, q, p, pw, pw1, maxlen);
-                                    if (len > bl) {
-                                        best = (len << 16) | q;
-                                        ptail = SV[p + len];
-                                        end = end || len >= maxlen;
-                                    }
+                            const bool known = bl >= 3u;
+                            const uint32_t c4 = known ? min(4u, s_left) : 1u;
+                            ZTS_ASSERT(s_left >= 1u && s_cur >= c4 && s_cur <= m);
+                            const uint32_t q0 = sorted[s_cur - 1u], q1 = c4 > 1u ? sorted[s_cur - 2u] : 0u,
+                                           q2 = c4 > 2u ? sorted[s_cur - 3u] : 0u, q3 = c4 > 3u ? sorted[s_cur - 4u] : 0u;
+                            const bool h0 = !known || SV[q0 + bl] == ptail, h1 = c4 > 1u && SV[q1 + bl] == ptail,
+                                       h2 = c4 > 2u && SV[q2 + bl] == ptail, h3 = c4 > 3u && SV[q3 + bl] == ptail;
+                            uint32_t used = c4, q = 0xFFFFFFFFu;
+                            if (h0) {
+                                used = 1u;
+                                q = q0;
+                            } else if (h1) {
+                                used = 2u;
+                                q = q1;
+                            } else if (h2) {
+                                used = 3u;
+                                q = q2;
+                            } else if (h3) {
+                                q = q3;
+                            }
+                            // the oldest candidate looked at decides about the window (ascending positions): older ones
+                            // are outside it too (src/LZ77.ts:223)
+                            const uint32_t qo = used == 1u ? q0 : used == 2u ? q1 : used == 3u ? q2 : q3;
+                            s_cur -= used;
+                            s_left -= used;
+                            bool end = s_left == 0u || p - qo > LZ_WINDOW;
+                            ZTS_ASSERT(q == 0xFFFFFFFFu || (q < p && q + bl < n + 32u));
+                            if (q != 0xFFFFFFFFu && p - q <= LZ_WINDOW) {
+                                const uint32_t len = lz_match_len(SV, q, p, pw, pw1, maxlen);
+                                if (len > bl) {
+                                    best = (len << 16) | q;
+                                    ptail = SV[p + len];
+                                    end = end || len >= maxlen;  // :189 (258) or capped by the input end
                                 }
                             }
                             if (end) st = ST_RES;
