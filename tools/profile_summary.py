@@ -30,9 +30,10 @@ def rows_of(rep):
 
 def main():
     tag = sys.argv[1]
-    units_per_launch = int(sys.argv[2]) if len(sys.argv) > 2 else 2048  # chunks (streams) one captured launch processed
+    units_per_launch = int(sys.argv[2]) if len(sys.argv) > 2 else 4096  # chunks (streams) one captured launch processed
     out = {}
     traffic = {}
+    inst = {}
     for leg in ("deflate", "fast", "inflate", "frame"):
         rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (leg, tag))
         if not os.path.exists(rep):
@@ -53,6 +54,8 @@ def main():
             out.setdefault(name, []).append(d)
             if leg == "frame":   # captured on another workload (C4 sample): not part of the bench step's traffic table
                 continue
+            if "smsp__inst_executed.sum" in d and name not in inst:
+                inst[name] = d["smsp__inst_executed.sum"]["value"]
             try:
                 rd, wr = d["dram__bytes_read.sum"], d["dram__bytes_write.sum"]
                 traffic[name] = rd["value"] * UNIT_SCALE.get(rd["unit"], 1) + wr["value"] * UNIT_SCALE.get(wr["unit"], 1)
@@ -60,10 +63,10 @@ def main():
                 pass
     json.dump(out, open(os.path.join(ROOT, "profiles", "%s_ncu_summary.json" % tag), "w"), indent=1)
     json.dump({"_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (bytes), ncu --set full, tag " + tag,
-               "_units_per_launch": units_per_launch, **traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
+               "_units_per_launch": units_per_launch, "_inst_executed": inst, **traffic}, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
     with open(os.path.join(ROOT, "profiles", "%s_source_hotspots.txt" % tag), "w") as f:
         for leg, pat, stem in (("deflate", "lz77_chunk", "zts_lz77"), ("deflate", "huffman_build", "zts_huffman"),
-                               ("deflate", "bitpack", "zts_deflate"), ("fast", "lz77_fast", "zts_lz77"),
+                               ("deflate", "bitpack", "zts_deflate"),
                                ("inflate", "inflate_warp", "zts_inflate")):
             rep = os.path.join(ROOT, "gpurun_out", "prof_%s_%s.ncu-rep" % (leg, tag))
             if os.path.exists(rep):
