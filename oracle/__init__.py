@@ -22,7 +22,15 @@ _lib = None
 
 
 def build():
+    """The C restatement, and -- where the reference is present (this container, not the GPU box) -- the interpreter
+    that executes it (oracle/_ref/minijs)."""
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
+    try:
+        from . import refjs
+        if refjs.available():
+            refjs.build()
+    except Exception:  # the interpreter only serves the CPU tests; they say so themselves if it is missing
+        pass
 
 
 def lib():
