@@ -228,7 +228,9 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
 //               candidates of p are the `rank` slots in front of its own). L2-resident scratch, 4 bytes per position.
 //   hasbits   = one bit per position in shared memory: "may have a candidate" -- an earlier position with the same
 //               3 bytes inside the window, found by walking back over the hash collisions in front of the slot.
+#ifndef LZ_HAS_WALK
 #define LZ_HAS_WALK 16u        // collisions walked over before a position is declared "may have a candidate"
+#endif
 #ifndef LZ_PRIV_CAP
 #define LZ_PRIV_CAP 64u        // a search over more earlier bucket entries than this is handed to the whole warp
 #endif
