@@ -7,28 +7,34 @@
 // per-key JS arrays newest-first; here the same function is evaluated as:
 //
 //   1. the chunk is staged in shared memory by a TMA bulk copy (cp.async.bulk + mbarrier);
-//   2. all positions are radix-sorted (stable, 2 LSD passes, ballot-based ranking inside a warp, no atomics)
-//      by a 13-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous;
-//   3. every position gets a 16-bit info word (L2-resident scratch): its rank inside its bucket (how many earlier
-//      positions the bucket holds) and a "may have a candidate" bit -- an earlier position with the same 3 bytes
-//      inside the window, found by walking back over the few hash collisions in front of the position's slot;
+//   2. all positions are radix-sorted (stable, 2 LSD passes of 8 bits, ballot-based ranking inside a warp)
+//      by a 16-bit hash of their 3-byte key -> per-bucket position lists, ascending, contiguous; there is no table of
+//      bucket starts;
+//   3. one pass over the sorted index: a slot whose hash differs from its predecessor's starts a bucket, a position's
+//      rank is its distance to the last start; every position gets an info word (L2-resident scratch): its slot and
+//      its rank (how many earlier positions the bucket holds), and one bit in shared memory, "may have a candidate"
+//      -- an earlier position with the same 3 bytes inside the window, found by walking back over the few hash
+//      collisions in front of the position's slot;
 //   4a. the chunk is cut into 1024 tiles of 64 positions and EVERY THREAD OWNS ONE: it parses its tile speculatively
 //      from the tile's start, all by itself -- runs of positions without a candidate are literals and are emitted
 //      together; at a position with candidates the thread walks the `rank` slots in front of the position's own slot,
-//      newest first: window test, tail-byte filter against the best so far, exact key, word-wise extension; strictly
-//      longer wins, so ties stay with the nearest. A warp iterates "a few candidate steps for every lane that is
-//      searching, then one token / next-position step for the lanes that are not", so lanes with short and long
-//      candidate lists do not wait for each other. Positions behind long candidate lists (ends of runs, low-entropy
-//      records) are handed to the whole warp, 32 (or 128) candidates per step;
+//      newest first: one candidate per step with the exact comparison until a match is known, then four per step
+//      through the tail-byte test (only a strictly longer match counts) with the exact comparison for the nearest
+//      that passes; strictly longer wins, so ties stay with the nearest. A warp iterates "candidate steps for the
+//      lanes that are searching, then one token / next-position step for the lanes that are not", so lanes with short
+//      and long candidate lists do not wait for each other. Positions behind long candidate lists (ends of runs,
+//      low-entropy records) are handed to the whole warp, 32 (then 128) candidates per step. A bounded search depth
+//      (fast mode) and one-step lazy evaluation (ZLB_MODE_LAZY) are options of the same loop;
 //   4b. the greedy parse is memoryless in p, so the true parse re-enters each tile at the true exit of the previous
 //      one and only has to be re-parsed until it meets a speculatively parsed position (a visited-bit per
 //      position); the remainder of the speculative tokens is reused. The owner of tile t does this for tile t + 1
 //      as soon as its own tile is done, assuming tile t exits where its speculative parse did; the few tiles whose
 //      predecessor exits elsewhere (a match that jumps a whole tile, chains inside long runs) are redone chain by
 //      chain, one warp per chain, and a final check over the true exits verifies every splice;
-//   5. litlen / dist histograms are taken over the surviving tokens.
+//   5. the surviving tokens are copied into the chunk's contiguous token list and histogrammed (litlen / dist).
 //
-// Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB bucket starts + 14 KiB scratch.
+// Shared memory: 64 KiB chunk + 128 KiB sorted positions + 16 KiB radix offsets / visited bits + tile table, 8 KiB
+// candidate bits, 8 KiB tile tables and counters.
 #include <stddef.h>
 
 #include "zts_deflate.cuh"
@@ -43,7 +49,7 @@ struct LzSmem {
     static constexpr uint32_t SORTED_BYTES = LZ_MAX_CHUNK * 2;
     static constexpr uint32_t BSTART_OFF = SORTED_OFF + SORTED_BYTES;  // 16 KiB: radix running offsets | visited bits + tile table
     static constexpr uint32_t BSTART_BYTES = 16384 + 16;
-    static constexpr uint32_t AUX_OFF = BSTART_OFF + BSTART_BYTES;     // 8 KiB: radix counters | visited bits
+    static constexpr uint32_t AUX_OFF = BSTART_OFF + BSTART_BYTES;     // 8 KiB: may-have-a-candidate bits
     static constexpr uint32_t AUX_BYTES = 8192;
     static constexpr uint32_t MISC_OFF = AUX_OFF + AUX_BYTES;
     static constexpr uint32_t MISC_BYTES = 8192;
