@@ -861,6 +861,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             uint32_t tok_i = 0, tok_0 = 0;   // next / first token slot of the parse in hand
             uint32_t* tbuf = spec_c;
             uint32_t pinfo = 0;       // P[p], requested as soon as p is known
+            bool have_info = true;    // pinfo belongs to p
             uint32_t s_cur = 0, s_left = 0, best = 0, ptail = 0, pw = 0, pw1 = 0, maxlen = 0;
             uint32_t saved = 0;  // lazy evaluation: the match (len << 16 | q) found at p - 1, waiting for the search at p
             if (t >= t0 && t < n_tiles) {
@@ -984,6 +985,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                         if (!resync) visited[at >> 5] |= 1u << (at & 31u);
                         p = np;
                         if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                        have_info = true;
                         st = ST_ADV;
                     }
                 }
@@ -1047,9 +1049,11 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                                 if (bits >> 32) visited[w + 1] |= (uint32_t)(bits >> 32);
                             }
                             p += k;
-                            if (p < n) pinfo = ld_u32_hint(&P[p], keep);
+                            have_info = false;  // (fetched below if a search follows at once: literal-only stretches never ask)
                         }
                         if (k < avail) {  // p has candidates
+                            if (!have_info) pinfo = ld_u32_hint(&P[p], keep);
+                            have_info = true;
                             const uint32_t rank = pinfo >> 16;  // earlier entries of the bucket: the slots in front of p's own
                             s_cur = pinfo & 0xFFFFu;
                             ZTS_ASSERT(p + 3u < n && rank <= s_cur && s_cur < m && sorted[s_cur] == p);
