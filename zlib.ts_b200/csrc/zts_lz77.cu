@@ -1173,18 +1173,41 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
         __syncthreads();
         {
             const unsigned long long stream = l2_policy_stream();
-            for (uint32_t w = t0 + warp; w < n_tiles; w += LZ_WARPS) {
+            // a warp takes 32 consecutive tiles (their tokens are consecutive in the list); the first 64 tokens of the
+            // next tile are requested before the current tile's are stored, so the trip to the L2 scratch overlaps
+            const uint32_t NONE = 0xFFFFFFFFu;  // (no token has all bits set)
+            auto fetch = [&](uint32_t w, uint32_t k) -> uint32_t {  // token k of tile w, NONE behind its end
+                if (w >= n_tiles) return NONE;
                 const uint32_t nf = M->fix_count[w], from = M2->spec_from[w], sc = M->spec_count[w];
+                if (k >= nf + (sc - from)) return NONE;
+                return k < nf ? fix_c[lz_tok_off(w) + k] : spec_c[lz_tok_off(w) + from + (k - nf)];
+            };
+            const uint32_t w_first = t0 + warp * 32u;
+            uint32_t a0 = fetch(w_first, lane), a1 = fetch(w_first, lane + 32u);
+            for (uint32_t w = w_first; w < min(n_tiles, w_first + 32u); ++w) {
+                const uint32_t b0 = fetch(w + 1u < w_first + 32u ? w + 1u : n_tiles, lane),
+                               b1 = fetch(w + 1u < w_first + 32u ? w + 1u : n_tiles, lane + 32u);
                 uint32_t* dst = list_c + tok_off[w];
-                const uint32_t* fx = fix_c + lz_tok_off(w);
-                const uint32_t* sp = spec_c + lz_tok_off(w) + from;
-                const uint32_t ns = sc - from;
-                ZTS_ASSERT(tok_off[w] + nf + ns <= n && from <= sc && nf <= LZ_TILE_POS && sc <= LZ_TILE_POS);
-                for (uint32_t k = lane; k < nf + ns; k += 32) {
-                    const uint32_t tok = k < nf ? fx[k] : sp[k - nf];
-                    st_u32_hint(&dst[k], tok, stream);
-                    hist_token(tok, M->hist);
+                ZTS_ASSERT(tok_off[w] <= n);
+                if (a0 != NONE) {
+                    st_u32_hint(&dst[lane], a0, stream);
+                    hist_token(a0, M->hist);
                 }
+                if (a1 != NONE) {
+                    st_u32_hint(&dst[lane + 32u], a1, stream);
+                    hist_token(a1, M->hist);
+                }
+                if (__any_sync(0xFFFFFFFFu, a1 != NONE)) {  // a tile holds up to 64 re-parsed + 64 speculative tokens
+                    for (uint32_t k = lane + 64u; k < 2u * LZ_TILE_POS; k += 32u) {
+                        const uint32_t tok = fetch(w, k);
+                        if (tok != NONE) {
+                            st_u32_hint(&dst[k], tok, stream);
+                            hist_token(tok, M->hist);
+                        }
+                    }
+                }
+                a0 = b0;
+                a1 = b1;
             }
         }
         __syncthreads();
