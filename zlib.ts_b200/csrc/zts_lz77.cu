@@ -241,10 +241,10 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
 #define LZ_PRIV_CAP 64u        // a search over more earlier bucket entries than this is handed to the whole warp
 #endif
 #ifndef LZ_WAIT_MUL
-#define LZ_WAIT_MUL 1u         // ... which happens when LZ_WAIT_MUL x (lanes waiting) >= lanes searching
+#define LZ_WAIT_MUL 0u         // ... or, if not 0, as soon as LZ_WAIT_MUL x (lanes waiting) >= lanes searching (measured: 0 is best)
 #endif
 #ifndef LZ_KMAX
-#define LZ_KMAX 16u            // candidate steps in a row before the lanes that wait for their next position are served
+#define LZ_KMAX 8u             // candidate steps in a row before the lanes that wait for their next position are served
 #endif
 
 // Every warp walks the 2048 slots of the sorted index it ranked in the last radix sweep, 32 per step. Bucket starts
@@ -363,22 +363,34 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
     const uint32_t pw1 = ld_u32(S, p + 4);
     uint32_t best = 0, best_len = 0;
     if (depth < cur - lo) lo = cur - depth;  // candidate budget
+    // Positions ascend with the slot, so the candidates inside the window are the upper part of [lo, cur): it is cut
+    // off once (binary search, every lane the same), and no step has to look at distances again (src/LZ77.ts:223)
+    if (cur > lo && p - sorted[lo] > LZ_WINDOW) {
+        uint32_t a = lo, b = cur;  // first slot inside the window lies in (a, b]
+        while (b - a > 1u) {
+            const uint32_t mid = (a + b) >> 1;
+            if (p - sorted[mid] > LZ_WINDOW)
+                a = mid;
+            else
+                b = mid;
+        }
+        lo = b;
+    }
     // until a match is known: 32 candidates per step, exact comparison
     while (cur > lo && best_len < 3u) {
         const uint32_t cnt = min(32u, cur - lo);
-        const bool act = lane < cnt;
         ZTS_ASSERT(cur >= cnt && cur <= LZ_MAX_CHUNK);
-        const uint32_t q = act ? sorted[cur - 1 - lane] : 0u;  // lane 0 = newest candidate
-        const bool inwin = act && (p - q <= LZ_WINDOW);
         uint32_t key = 0;
-        if (inwin) key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
+        if (lane < cnt) {
+            const uint32_t q = sorted[cur - 1 - lane];  // lane 0 = newest candidate
+            key = (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q;
+        }
         const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);  // longest, then nearest
         if (m >> 16) {
             best_len = m >> 16;
             best = m;
         }
         cur -= cnt;
-        if (__any_sync(0xFFFFFFFFu, act && !inwin)) cur = lo;  // older ones are outside the window (:223)
     }
     // behind a known match only a strictly longer one counts (:183): its byte at best_len must match, which is the
     // cheapest test and rejects nearly everything. 128 candidates per step through that test (four independent
@@ -388,7 +400,6 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
         const uint8_t pt = S[p + best_len];
         uint32_t key = 0, hitq[4];
         unsigned hm = 0;  // which of this lane's four candidates passed the test
-        bool out = false;
 #pragma unroll
         for (uint32_t k = 0; k < 4u; ++k) {
             const uint32_t o = k * 32u + lane;
@@ -397,11 +408,8 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
                 ZTS_ASSERT(cur >= 1u + o && cur <= LZ_MAX_CHUNK);
                 const uint32_t q = sorted[cur - 1u - o];
                 hitq[k] = q;
-                ZTS_ASSERT(q < p);
-                if (p - q > LZ_WINDOW)
-                    out = true;
-                else if (S[q + best_len] == pt)
-                    hm |= 1u << k;
+                ZTS_ASSERT(q < p && p - q <= LZ_WINDOW);
+                if (S[q + best_len] == pt) hm |= 1u << k;
             }
         }
         while (hm) {
@@ -410,8 +418,7 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
             const uint32_t q = k == 0u ? hitq[0] : k == 1u ? hitq[1] : k == 2u ? hitq[2] : hitq[3];
             key = max(key, (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q);
         }
-        const unsigned hits = __ballot_sync(0xFFFFFFFFu, key != 0u);
-        if (hits) {
+        if (__any_sync(0xFFFFFFFFu, key != 0u)) {
             const uint32_t m = __reduce_max_sync(0xFFFFFFFFu, key);
             if ((m >> 16) > best_len) {
                 best_len = m >> 16;
@@ -419,7 +426,6 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
             }
         }
         cur -= cnt;
-        if (__any_sync(0xFFFFFFFFu, out)) break;  // older ones are outside the window (:223)
     }
     if (best_len < 3) return 0;
     return (best_len << 16) | (p - (best & 0xFFFFu));
@@ -872,7 +878,7 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                 st = ST_ADV;
             }
             for (;;) {
-                // -- candidate steps of the searching lanes; left when a quarter of the lanes in work wait to be served
+                // -- candidate steps of the searching lanes: up to LZ_KMAX in a row, then the lanes that wait are served
                 {
                     unsigned busy = __ballot_sync(0xFFFFFFFFu, st == ST_SRCH);
                     uint32_t it = 0;
