@@ -276,11 +276,13 @@ def test_fast_mode_valid_streams_and_ratio_within_tolerance(engine):
     items = z.make_items(len(datas))
     items["in_off"], items["in_len"], items["out_off"], items["out_cap"] = offs, lens, ooffs[:-1], caps
     d_out = torch.zeros(int(ooffs[-1]), dtype=torch.uint8, device="cuda")
-    res = engine.deflate_batch(torch.from_numpy(blob).cuda(), d_out, items, mode=z.MODE_FAST)
-    h = d_out.cpu().numpy()
-    for d, o, r in zip(datas, ooffs[:-1], res):
-        assert int(r["status"]) == 0
-        assert zlib.decompress(h[int(o):int(o) + int(r["out_len"])].tobytes(), -15) == d
+    for mode in (z.MODE_FAST, z.MODE_FAST | z.MODE_LAZY, z.mode_fast(3) | z.MODE_LAZY | z.MODE_PRIMED):
+        d_out.zero_()
+        res = engine.deflate_batch(torch.from_numpy(blob).cuda(), d_out, items, mode=mode)
+        h = d_out.cpu().numpy()
+        for d, o, r in zip(datas, ooffs[:-1], res):
+            assert int(r["status"]) == 0
+            assert zlib.decompress(h[int(o):int(o) + int(r["out_len"])].tobytes(), -15) == d, (mode, len(d))
 
 
 def _fuzz_inputs(rng, count, big_every=50, small_max=6000):
