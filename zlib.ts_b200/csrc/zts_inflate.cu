@@ -26,6 +26,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <chrono>
 
 #include "zts_common.cuh"
@@ -39,6 +40,7 @@
 #define KIND_BASE 1u   // length or distance base + extra bits
 #define KIND_EOB 2u
 #define KIND_INVALID 3u
+#define ROOT_UNRESOLVED (KIND_INVALID << 8)  // root-table entry of a bit pattern whose code is longer than the root (0 bits)
 
 struct HuffTab {
     uint16_t first_code[16];  // canonical (MSB-first) first code of each length
@@ -56,6 +58,9 @@ struct InfWarpSmem {
     HuffTab lit, dist, cl;
     uint8_t lens[32 + 288 + 32 + 16];  // [0,19) code-length code; [32, 32+hlit+hdist) litlen ++ dist
 };
+
+static_assert(offsetof(InfWarpSmem, lens) % 4 == 0 && sizeof(InfWarpSmem::lens) >= 128,
+              "the token slots of a batch alias the code-length staging area");
 
 // LengthCodeTable / LengthExtraTable (src/RawInflate.ts:17-28; symbols 286/287 decode as 258 there)
 __constant__ uint16_t c_len_base[31] = {3,  4,  5,  6,  7,  8,  9,  10, 11,  13,  15,  17,  19,  23,  27, 31,
@@ -126,8 +131,9 @@ __device__ bool build_table(int which, const uint8_t* lens, int n, int root_bits
         kraft += c << (15 - L);
     }
     if (kraft > (1u << 15)) return false;
-    // root table: 0 = "not resolved here" (long code or unused pattern)
-    for (int i = (int)lane; i < (1 << root_bits); i += 32) root[i] = 0;
+    // root table: 0 bits = "not resolved here" (long code or unused pattern); the kind field of such an entry says
+    // "not a literal", so the symbol loop meets it behind the one test it makes anyway
+    for (int i = (int)lane; i < (1 << root_bits); i += 32) root[i] = ROOT_UNRESOLVED;
     __syncwarp();
     // assign codes in (length, symbol) order; running offset per length kept uniformly in registers
     uint32_t offs[16];
@@ -477,6 +483,10 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                 unsigned long long buf = br.buf;
                 int cnt = br.cnt;
                 uint32_t wpos = br.win_pos, wtaken = 0;
+                // the batch's tokens go through shared memory (one store per symbol instead of a compare + select into the
+                // lane that owns the slot); the code-length staging area is dead while symbols are decoded
+                const uint32_t tok_s = __shfl_sync(0xFFFFFFFFu, (uint32_t)__cvta_generic_to_shared(S->lens), 0);
+                uint32_t ta = tok_s;
                 do {
                     if (cnt <= 32) {
                         if (wpos == 32) {
@@ -491,64 +501,64 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                     }
                     uint32_t e;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_s + (((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)) << 2)) : "memory");
-                    if ((e & 15u) == 0) {
-                        e = slow_decode(TAB_LITLEN, (uint32_t)buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit);
-                        if (e == 0) {
-                            stop = 2;
-                            break;
-                        }
-                    }
-                    buf >>= (e & 15u);
+                    buf >>= (e & 15u);  // (0 bits for a code the root table does not resolve)
                     cnt -= (int)(e & 15u);
                     uint32_t tokv = e & 0x00FF0000u;  // literal
                     if (e & 0x300u) {
-                        if (!(e & 0x100u)) {  // KIND_EOB (2); KIND_INVALID is 3
-                            stop = 1;
-                            break;
-                        }
-                        if (e & 0x200u) {
-                            stop = 2;
-                            break;
-                        }
-                        const uint32_t xb = (e >> 4) & 15u;
-                        const uint32_t len = (e >> 16) + ((uint32_t)buf & ((1u << xb) - 1u));
-                        buf >>= xb;
-                        cnt -= (int)xb;
-                        if (cnt <= 32) {
-                            if (wpos == 32) {
-                                br_advance_window(br);
-                                wpos = 0;
-                            }
-                            const uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, (int)wpos);
-                            wpos++;
-                            wtaken++;
-                            buf |= (unsigned long long)w << cnt;
-                            cnt += 32;
-                        }
-                        uint32_t d;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(dist_s + (((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)) << 2)) : "memory");
-                        if ((d & 15u) == 0) {
-                            d = slow_decode(TAB_DIST, (uint32_t)buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist);
-                            if (d == 0) {
+                        if ((e & 15u) == 0) {
+                            e = slow_decode(TAB_LITLEN, (uint32_t)buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit);
+                            if (e == 0) {
                                 stop = 2;
                                 break;
                             }
+                            buf >>= (e & 15u);
+                            cnt -= (int)(e & 15u);
+                            tokv = e & 0x00FF0000u;
                         }
-                        buf >>= (d & 15u);
-                        cnt -= (int)(d & 15u);
-                        if ((d & 0x300u) != (KIND_BASE << 8)) {
-                            stop = 2;
-                            break;
+                        if (e & 0x300u) {
+                            if ((e & 0x300u) != (KIND_BASE << 8)) {
+                                stop = (e & 0x100u) ? 2u : 1u;  // KIND_INVALID (3) / KIND_EOB (2)
+                                break;
+                            }
+                            const uint32_t xb = (e >> 4) & 15u;
+                            const uint32_t len = (e >> 16) + ((uint32_t)buf & ((1u << xb) - 1u));
+                            buf >>= xb;
+                            cnt -= (int)xb;
+                            if (cnt <= 32) {
+                                if (wpos == 32) {
+                                    br_advance_window(br);
+                                    wpos = 0;
+                                }
+                                const uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, (int)wpos);
+                                wpos++;
+                                wtaken++;
+                                buf |= (unsigned long long)w << cnt;
+                                cnt += 32;
+                            }
+                            uint32_t d;
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(dist_s + (((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)) << 2)) : "memory");
+                            if ((d & 0x300u) != (KIND_BASE << 8)) {
+                                if ((d & 15u) == 0) d = slow_decode(TAB_DIST, (uint32_t)buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist);
+                                if ((d & 0x300u) != (KIND_BASE << 8)) {  // undefined code (0) or DistCodeTable[30..31]
+                                    stop = 2;
+                                    break;
+                                }
+                            }
+                            buf >>= (d & 15u);
+                            cnt -= (int)(d & 15u);
+                            const uint32_t db = (d >> 4) & 15u;
+                            const uint32_t dist = (d >> 16) + ((uint32_t)buf & ((1u << db) - 1u));
+                            buf >>= db;
+                            cnt -= (int)db;
+                            tokv = (len << 16) | dist;
                         }
-                        const uint32_t db = (d >> 4) & 15u;
-                        const uint32_t dist = (d >> 16) + ((uint32_t)buf & ((1u << db) - 1u));
-                        buf >>= db;
-                        cnt -= (int)db;
-                        tokv = (len << 16) | dist;
                     }
-                    mytok = lane == ntok ? tokv : mytok;
-                    ntok++;
-                } while (ntok < 32);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(ta), "r"(tokv) : "memory");
+                    ta += 4u;
+                } while (ta != tok_s + 128u);
+                ntok = (ta - tok_s) >> 2;
+                __syncwarp();
+                if (lane < ntok) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mytok) : "r"(tok_s + 4u * lane) : "memory");
                 br.buf = buf;
                 br.cnt = cnt;
                 br.win_pos = wpos;

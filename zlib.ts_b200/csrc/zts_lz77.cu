@@ -870,6 +870,11 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
             bool have_info = true;    // pinfo belongs to p
             uint32_t s_cur = 0, s_left = 0, best = 0, ptail = 0, pw = 0, pw1 = 0, maxlen = 0;
             uint32_t saved = 0;  // lazy evaluation: the match (len << 16 | q) found at p - 1, waiting for the search at p
+#ifdef LZ_DEBUG_COUNTS
+            uint32_t dbg_s[2] = {0, 0}, dbg_steps[2] = {0, 0}, dbg_coop[2] = {0, 0}, dbg_tok[2] = {0, 0}, dbg_iter = 0;
+            if (tid < 16) M->hist[tid] = 0;
+            __syncthreads();
+#endif
             if (t >= t0 && t < n_tiles) {
                 p = t_begin + M->tile_start[t];
                 t_end = min(n, t_begin + LZ_TILE_POS);
@@ -884,6 +889,9 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                     uint32_t it = 0;
                     while (busy) {
                         if (st == ST_SRCH) {
+#ifdef LZ_DEBUG_COUNTS
+                            dbg_steps[resync]++;
+#endif
                             // One code path for every searching lane. Behind a known match only a strictly longer one
                             // counts (:183): its byte at best_len must match -- four candidates per step go through that
                             // test alone and the nearest that passes gets the exact comparison. Before a match is known
@@ -987,6 +995,9 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                             np = at + 1u;
                         }
                         ZTS_ASSERT(tok_i < tok_0 + LZ_TILE_POS + 8u && at < n && (resync || at / LZ_TILE_POS == t));
+#ifdef LZ_DEBUG_COUNTS
+                        dbg_tok[resync]++;
+#endif
                         tbuf[tok_i++] = tok;
                         if (!resync) visited[at >> 5] |= 1u << (at & 31u);
                         p = np;
@@ -1065,6 +1076,10 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                             ZTS_ASSERT(p + 3u < n && rank <= s_cur && s_cur < m && sorted[s_cur] == p);
                             maxlen = min(LZ_MAXLEN, n - p);
                             best = 0;
+#ifdef LZ_DEBUG_COUNTS
+                            dbg_s[resync]++;
+                            if (rank > LZ_PRIV_CAP && depth > LZ_PRIV_CAP) dbg_coop[resync]++;
+#endif
                             if (rank > LZ_PRIV_CAP && depth > LZ_PRIV_CAP) {
                                 s_left = rank;
                                 st = ST_COOP;
@@ -1077,8 +1092,30 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                         }
                     }
                 }
+#ifdef LZ_DEBUG_COUNTS
+                dbg_iter++;
+#endif
                 if (__all_sync(0xFFFFFFFFu, st == ST_DONE)) break;
             }
+#ifdef LZ_DEBUG_COUNTS
+            if (blockIdx.x < 4) {
+                for (int k = 0; k < 2; ++k) {
+                    atomicAdd(&M->hist[k * 4 + 0], dbg_s[k]);
+                    atomicAdd(&M->hist[k * 4 + 1], dbg_steps[k]);
+                    atomicAdd(&M->hist[k * 4 + 2], dbg_coop[k]);
+                    atomicAdd(&M->hist[k * 4 + 3], dbg_tok[k]);
+                }
+                if (lane == 0) atomicAdd(&M->hist[8], dbg_iter);
+                if (lane == 0) atomicMax(&M->hist[9], dbg_iter);
+                __syncthreads();
+                if (tid == 0)
+                    printf("chunk %u: spec srch %u steps %u coop %u tok %u | fix srch %u steps %u coop %u tok %u | warp iters sum %u max %u\n", c,
+                           M->hist[0], M->hist[1], M->hist[2], M->hist[3], M->hist[4], M->hist[5], M->hist[6], M->hist[7], M->hist[8], M->hist[9]);
+                __syncthreads();
+                if (tid < 16) M->hist[tid] = 0;
+                __syncthreads();
+            }
+#endif
         }
         __threadfence_block();
         __syncthreads();
