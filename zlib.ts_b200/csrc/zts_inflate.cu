@@ -33,7 +33,12 @@
 
 #define INF_WARPS_PER_CTA 4
 #define LIT_ROOT_BITS 10
-#define DIST_ROOT_BITS 8
+#ifndef DIST_ROOT_BITS
+#define DIST_ROOT_BITS 7
+#endif
+#ifndef INF_MIN_CTAS
+#define INF_MIN_CTAS 8   // 64 registers: eight CTAs of four warps per SM (their tables: 8 x 28 KB)
+#endif
 #define CL_ROOT_BITS 7
 
 #define KIND_LITERAL 0u
@@ -57,6 +62,7 @@ struct InfWarpSmem {
     uint16_t cl_sorted[20];
     HuffTab lit, dist, cl;
     uint8_t lens[32 + 288 + 32 + 16];  // [0,19) code-length code; [32, 32+hlit+hdist) litlen ++ dist
+    uint32_t ring[128];                // input words on their way into the bit buffer (BitReader)
 };
 
 static_assert(offsetof(InfWarpSmem, lens) % 4 == 0 && sizeof(InfWarpSmem::lens) >= 128,
@@ -177,17 +183,22 @@ __device__ __forceinline__ uint32_t slow_decode(int which, uint32_t bits, int ro
     return 0;  // undefined code
 }
 
+// Input words reach the bit buffer through a ring of 128 words in shared memory: a window of 32 words (one per lane,
+// requested a window ahead) is appended whenever fewer than INF_RING_MIN unread words are left, which the symbol loop
+// checks once per batch -- a batch of 32 symbols takes at most 32 x 48 bits, i.e. at most 50 words -- so that its refills are one shared-memory
+// load at a running address.
+#define INF_RING_WORDS 128u
+#define INF_RING_MIN 52u
 struct BitReader {
-    const uint32_t* win_base;  // aligned address of the current 128-byte window
-    const uint8_t* end;        // one past the last readable input byte
-    uint32_t win;              // this lane's word of the window
-    uint32_t win_next;         // this lane's word of the following window (prefetched)
-    uint32_t win_pos;          // next word of the window to consume (0..32)
+    const uint32_t* next_base;  // aligned address of the window behind the prefetched one
+    const uint8_t* end;         // one past the last readable input byte
+    uint32_t win_next;          // this lane's word of the next window to append (prefetched)
+    uint32_t ring_s;            // shared-window address of this warp's ring
+    uint32_t rd, wr;            // words consumed / appended since the last (re)start
     unsigned long long buf;
-    int cnt;                   // valid bits in buf
-    unsigned long long words_taken;  // words moved into buf since the last (re)start
+    int cnt;                    // valid bits in buf
     unsigned long long base_bits;    // stream bits consumed before the last (re)start
-    uint32_t skip_bits;        // bits of the first word that precede the (re)start point
+    uint32_t skip_bits;         // bits of the first word that precede the (re)start point
 };
 
 __device__ __forceinline__ uint32_t br_fetch(const BitReader& br, const uint32_t* base)
@@ -198,39 +209,42 @@ __device__ __forceinline__ uint32_t br_fetch(const BitReader& br, const uint32_t
     return ((const uint8_t*)p < br.end) ? __ldg(p) : 0u;
 }
 
-__device__ __forceinline__ void br_load_window(BitReader& br)
+// appends the prefetched window and requests the one behind it (all lanes; the slots it overwrites were read at
+// least INF_RING_WORDS - 32 - INF_RING_MIN words ago)
+__device__ __forceinline__ void br_append(BitReader& br)
 {
-    br.win = br_fetch(br, br.win_base);
-    br.win_next = br_fetch(br, br.win_base + 32);
-    br.win_pos = 0;
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(br.ring_s + (((br.wr + zts_lane()) & (INF_RING_WORDS - 1u)) << 2)), "r"(br.win_next)
+                 : "memory");
+    br.wr += 32u;
+    br.win_next = br_fetch(br, br.next_base);
+    br.next_base += 32;
+    __syncwarp();
 }
 
-// next window: the prefetched words become current, the one after is requested now and is not
-// needed before another 128 bytes have been consumed
-__device__ __forceinline__ void br_advance_window(BitReader& br)
+__device__ __forceinline__ uint32_t br_ring_word(const BitReader& br, uint32_t i)
 {
-    br.win_base += 32;
-    br.win = br.win_next;
-    br.win_next = br_fetch(br, br.win_base + 32);
-    br.win_pos = 0;
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(br.ring_s + ((i & (INF_RING_WORDS - 1u)) << 2)) : "memory");
+    return w;
 }
 
 __device__ __forceinline__ void br_init(BitReader& br, const uint8_t* src, const uint8_t* end,
                                         unsigned long long base_bits)
 {
     uintptr_t a = (uintptr_t)src;
-    br.win_base = (const uint32_t*)(a & ~(uintptr_t)3);
+    const uint32_t* base = (const uint32_t*)(a & ~(uintptr_t)3);
     br.end = end;
     br.base_bits = base_bits;
     br.skip_bits = (uint32_t)(a & 3) * 8;
-    br.buf = 0;
-    br.cnt = 0;
-    br.words_taken = 0;
-    br_load_window(br);
+    br.rd = br.wr = 0;
+    __syncwarp();  // (a restart: every lane is done with the ring)
+    br.win_next = br_fetch(br, base);
+    br.next_base = base + 32;
+    br_append(br);
+    br_append(br);
     // first word: drop the bytes before the stream
-    uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, 0);
-    br.win_pos = 1;
-    br.words_taken = 1;
+    const uint32_t w = br_ring_word(br, 0);
+    br.rd = 1;
     br.buf = (unsigned long long)(w >> br.skip_bits);
     br.cnt = 32 - (int)br.skip_bits;
 }
@@ -238,10 +252,9 @@ __device__ __forceinline__ void br_init(BitReader& br, const uint8_t* src, const
 __device__ __forceinline__ void br_refill(BitReader& br)
 {
     if (br.cnt <= 32) {
-        if (br.win_pos == 32) br_advance_window(br);
-        uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, br.win_pos);
-        br.win_pos++;
-        br.words_taken++;
+        if (br.rd == br.wr) br_append(br);
+        const uint32_t w = br_ring_word(br, br.rd);
+        br.rd++;
         br.buf |= (unsigned long long)w << br.cnt;
         br.cnt += 32;
     }
@@ -258,7 +271,7 @@ __device__ __forceinline__ uint32_t br_take(BitReader& br, int n)
 // stream bits consumed so far
 __device__ __forceinline__ unsigned long long br_bits_used(const BitReader& br)
 {
-    return br.base_bits + br.words_taken * 32ull - br.skip_bits - (unsigned long long)br.cnt;
+    return br.base_bits + (unsigned long long)br.rd * 32ull - br.skip_bits - (unsigned long long)br.cnt;
 }
 
 // ---- which error does the reference raise when the input ends early? ---------------------------------------------
@@ -310,7 +323,7 @@ __device__ uint32_t inf_classify_symbols(const InfWarpSmem* S, const uint8_t* sr
     return ZLB_ST_INPUT_BROKEN;
 }
 
-__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(INF_WARPS_PER_CTA * 32, INF_MIN_CTAS)
 inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const zlb_item* __restrict__ items,
                     zlb_result* __restrict__ results, uint32_t n_items, uint32_t flags)
 {
@@ -328,6 +341,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
     const unsigned long long cap = it.out_cap;
 
     BitReader br;
+    br.ring_s = (uint32_t)__cvta_generic_to_shared(S->ring);
     br_init(br, src, src + it.in_len, 0);
 
     unsigned long long op = 0;
@@ -480,25 +494,31 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                 dist_s = __shfl_sync(0xFFFFFFFFu, dist_s, 0);
                 // same for the end-of-input pointer of the bit reader (recomputed from the item table otherwise)
                 br.end = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)br.end, 0));
+                // with a whole batch worth of words in the ring the refills below need no test
+                while (br.wr - br.rd < INF_RING_MIN) br_append(br);
                 unsigned long long buf = br.buf;
                 int cnt = br.cnt;
-                uint32_t wpos = br.win_pos, wtaken = 0;
+                const uint32_t ring_s = __shfl_sync(0xFFFFFFFFu, br.ring_s, 0), ring_e = ring_s + 4u * INF_RING_WORDS;
+                const uint32_t ra0 = ring_s + ((br.rd & (INF_RING_WORDS - 1u)) << 2);
+                uint32_t ra = ra0;  // address of the next word
                 // the batch's tokens go through shared memory (one store per symbol instead of a compare + select into the
                 // lane that owns the slot); the code-length staging area is dead while symbols are decoded
                 const uint32_t tok_s = __shfl_sync(0xFFFFFFFFu, (uint32_t)__cvta_generic_to_shared(S->lens), 0);
                 uint32_t ta = tok_s;
+                const uint32_t tok_e = tok_s + 128u;
+                // a word from the ring if 32 more bits fit (a length code: before it reads on, which is enough for its
+                // extra bits and the distance, 5 + 15 + 13 bits)
+#define INF_TAKE_WORD()                                                                       \
+    if (cnt <= 32) {                                                                          \
+        uint32_t w_;                                                                          \
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w_) : "r"(ra) : "memory");              \
+        ra += 4u;                                                                             \
+        ra = ra == ring_e ? ring_s : ra;                                                      \
+        buf |= (unsigned long long)w_ << cnt;                                                 \
+        cnt += 32;                                                                            \
+    }
                 do {
-                    if (cnt <= 32) {
-                        if (wpos == 32) {
-                            br_advance_window(br);
-                            wpos = 0;
-                        }
-                        const uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, (int)wpos);
-                        wpos++;
-                        wtaken++;
-                        buf |= (unsigned long long)w << cnt;
-                        cnt += 32;
-                    }
+                    INF_TAKE_WORD()
                     uint32_t e;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_s + (((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)) << 2)) : "memory");
                     buf >>= (e & 15u);  // (0 bits for a code the root table does not resolve)
@@ -520,21 +540,11 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                                 stop = (e & 0x100u) ? 2u : 1u;  // KIND_INVALID (3) / KIND_EOB (2)
                                 break;
                             }
+                            INF_TAKE_WORD()
                             const uint32_t xb = (e >> 4) & 15u;
                             const uint32_t len = (e >> 16) + ((uint32_t)buf & ((1u << xb) - 1u));
                             buf >>= xb;
                             cnt -= (int)xb;
-                            if (cnt <= 32) {
-                                if (wpos == 32) {
-                                    br_advance_window(br);
-                                    wpos = 0;
-                                }
-                                const uint32_t w = __shfl_sync(0xFFFFFFFFu, br.win, (int)wpos);
-                                wpos++;
-                                wtaken++;
-                                buf |= (unsigned long long)w << cnt;
-                                cnt += 32;
-                            }
                             uint32_t d;
                             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(dist_s + (((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)) << 2)) : "memory");
                             if ((d & 0x300u) != (KIND_BASE << 8)) {
@@ -555,14 +565,14 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                     }
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(ta), "r"(tokv) : "memory");
                     ta += 4u;
-                } while (ta != tok_s + 128u);
+                } while (ta != tok_e);
+#undef INF_TAKE_WORD
                 ntok = (ta - tok_s) >> 2;
                 __syncwarp();
                 if (lane < ntok) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mytok) : "r"(tok_s + 4u * lane) : "memory");
                 br.buf = buf;
                 br.cnt = cnt;
-                br.win_pos = wpos;
-                br.words_taken += wtaken;
+                br.rd += ((ra - ra0) & (4u * INF_RING_WORDS - 1u)) >> 2;  // (fewer than INF_RING_WORDS words per batch)
             }
             if (stop == 1) eob = true;
             if (stop == 2) status = ZLB_ST_BAD_CODE;
