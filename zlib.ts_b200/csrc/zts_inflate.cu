@@ -989,7 +989,7 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
     // waves only pay when the items are laid out in order on both sides (then a wave is one contiguous copy each way)
     size_t n_waves = 1;
     if (hio && n >= 1024) {
-        n_waves = n >= 16384 ? 8 : 4;
+        n_waves = n >= 32768 ? 16 : n >= 16384 ? 8 : 4;  // (the last wave's output travels alone: keep it small)
         for (size_t i = 1; i < n && n_waves > 1; ++i)
             if (h_items[i].in_off < h_items[i - 1].in_off + h_items[i - 1].in_len ||
                 h_items[i].out_off < h_items[i - 1].out_off + h_items[i - 1].out_cap)
@@ -1083,9 +1083,12 @@ static int inflate_device(zlb_ctx* ctx, const uint8_t* d_in, uint8_t* d_out, con
             }
         }
         ZTS_CUDA(ctx, cudaEventRecord(zts_sync_event(ctx, 2 + 2 * k), st));
-        if (st != ctx->stream) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 + 2 * k), 0));  // the call ends on ctx->stream
         if (k + 1 < n_waves && (rc = wave_in(k + 1))) return rc;  // behind the launches: may wait for the copy threads
     }
+    // the call ends on ctx->stream -- joined only here: a join inside the loop would make the next wave queued on
+    // ctx->stream wait for the waves in flight on the other streams
+    for (size_t k = 0; k < n_waves; ++k)
+        if (!(kinds || k % 4 == 0)) ZTS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, zts_sync_event(ctx, 2 + 2 * k), 0));
     // every wave is queued (none waits for the host): their outputs leave in order, each as soon as its wave is done
     for (size_t k = 0; k < n_waves; ++k)
         if ((rc = wave_out(k))) return rc;
