@@ -900,31 +900,25 @@ lz77_chunk_kernel(const uint8_t* __restrict__ in, const ZtsChunk* __restrict__ c
                             const bool known = bl >= 3u;
                             const uint32_t c4 = known ? min(4u, s_left) : 1u;
                             ZTS_ASSERT(s_left >= 1u && s_cur >= c4 && s_cur <= m);
-                            const uint32_t q0 = sorted[s_cur - 1u], q1 = c4 > 1u ? sorted[s_cur - 2u] : 0u,
-                                           q2 = c4 > 2u ? sorted[s_cur - 3u] : 0u, q3 = c4 > 3u ? sorted[s_cur - 4u] : 0u;
-                            const bool h0 = !known || SV[q0 + bl] == ptail, h1 = c4 > 1u && SV[q1 + bl] == ptail,
-                                       h2 = c4 > 2u && SV[q2 + bl] == ptail, h3 = c4 > 3u && SV[q3 + bl] == ptail;
-                            uint32_t used = c4, q = 0xFFFFFFFFu;
-                            if (h0) {
-                                used = 1u;
-                                q = q0;
-                            } else if (h1) {
-                                used = 2u;
-                                q = q1;
-                            } else if (h2) {
-                                used = 3u;
-                                q = q2;
-                            } else if (h3) {
-                                q = q3;
-                            }
-                            // the oldest candidate looked at decides about the window (ascending positions): older ones
-                            // are outside it too (src/LZ77.ts:223)
-                            const uint32_t qo = used == 1u ? q0 : used == 2u ? q1 : used == 3u ? q2 : q3;
-                            s_cur -= used;
-                            s_left -= used;
-                            bool end = s_left == 0u || p - qo > LZ_WINDOW;
-                            ZTS_ASSERT(q == 0xFFFFFFFFu || (q < p && q + bl < n + 32u));
-                            if (q != 0xFFFFFFFFu && p - q <= LZ_WINDOW) {
+                            // the four slots in front of the cursor and their tail bytes, whatever c4 is: slots in front
+                            // of the list (down to three u16 in front of `sorted`: the chunk buffer's slack) are read and
+                            // masked out -- no branch in the step
+                            const uint16_t* sp = sorted + s_cur;
+                            const uint32_t q0 = sp[-1], q1 = sp[-2], q2 = sp[-3], q3 = sp[-4];
+                            uint32_t hm = (SV[q0 + bl] == ptail ? 1u : 0u) | (SV[q1 + bl] == ptail ? 2u : 0u) |
+                                          (SV[q2 + bl] == ptail ? 4u : 0u) | (SV[q3 + bl] == ptail ? 8u : 0u);
+                            hm = known ? hm & ((1u << c4) - 1u) : 1u;
+                            // the candidate that decides: the nearest that passed, else the oldest looked at -- it tells
+                            // whether the window ends here (ascending positions: older ones are outside it too,
+                            // src/LZ77.ts:223)
+                            const uint32_t j = hm ? (uint32_t)__ffs((int)hm) - 1u : c4 - 1u;
+                            const uint32_t q = j == 0u ? q0 : j == 1u ? q1 : j == 2u ? q2 : q3;
+                            s_cur -= j + 1u;
+                            s_left -= j + 1u;
+                            const bool inside = p - q <= LZ_WINDOW;
+                            bool end = s_left == 0u || !inside;
+                            ZTS_ASSERT(q < p && q + bl < n + 32u);
+                            if (hm && inside) {
                                 const uint32_t len = lz_match_len(SV, q, p, pw, pw1, maxlen);
                                 if (len > bl) {
                                     best = (len << 16) | q;
