@@ -156,9 +156,16 @@ __device__ __forceinline__ unsigned peers_of(uint32_t d, bool valid)
     unsigned peers = valid ? m : ~m;
 #pragma unroll
     for (int b = 0; b < NBITS; ++b) {
-        const bool bit = (d >> b) & 1u;
-        m = __ballot_sync(0xFFFFFFFFu, bit);
-        peers &= bit ? m : ~m;
+        // test, vote, select, AND-XOR: the C++ form of this costs six instructions per bit
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 t, m, s;\n\t"
+            "and.b32 t, %1, %2;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+            "selp.b32 s, 0, 0xffffffff, p;\n\t"
+            "lop3.b32 %0, %0, m, s, 0x60;\n\t}"   // peers & (m ^ s): m where the bit is set, ~m where it is not
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
     }
     return peers;
 #endif
