@@ -286,15 +286,20 @@ __device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __re
             carry = at;
         }
     }
+    // the position of a slot is fetched two steps ahead, its key bytes one step ahead (two dependent shared-memory
+    // round trips that would otherwise stand in front of every step)
+    const uint32_t NOPOS = 0xFFFFFFFFu;
+    uint32_t p_n1 = i0 + lane < m ? (uint32_t)sorted[i0 + lane] : NOPOS;
+    uint32_t p_n2 = i0 + 32u + lane < m ? (uint32_t)sorted[i0 + 32u + lane] : NOPOS;
+    uint32_t key_n1 = p_n1 != NOPOS ? ld_u32(S, p_n1) & 0xFFFFFFu : 0u;
     for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {  // whole warps stay in the loop (warp votes below)
         const uint32_t i = i0 + it * 32 + lane;
         const bool valid = i < m;
-        uint32_t p = 0xFFFFFFFFu, key = 0, h = 0xFFFFFFFEu;
-        if (valid) {
-            p = sorted[i];
-            key = ld_u32(S, p) & 0xFFFFFFu;
-            h = lz_hash(key);
-        }
+        const uint32_t p = p_n1, key = key_n1;
+        p_n1 = p_n2;
+        key_n1 = p_n1 != NOPOS ? ld_u32(S, p_n1) & 0xFFFFFFu : 0u;
+        p_n2 = (it + 2u < LZ_SORT_TILE / 32 && i + 64u < m) ? (uint32_t)sorted[i + 64u] : NOPOS;
+        const uint32_t h = valid ? lz_hash(key) : 0xFFFFFFFEu;
         uint32_t hprev = __shfl_up_sync(0xFFFFFFFFu, h, 1);
         if (lane == 0) hprev = hlast;
         hlast = __shfl_sync(0xFFFFFFFFu, h, 31);
@@ -644,17 +649,21 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                 // sweep B
                 if (w_begin < m) {
                     uint16_t* wc = cnt16 + warp * 256u;
+                    // the key bytes of the next step are fetched while this one is ranked (the ranking is a chain of
+                    // shared-memory round trips through wc[])
+                    uint32_t key_next = w_begin + lane < m ? ld_u32(SV, w_begin + lane) : 0u;
                     for (uint32_t it = 0; it < LZ_SORT_TILE / 32; ++it) {
                         const uint32_t i = w_begin + it * 32 + lane;
                         const bool v = i < m;
-                        uint32_t hh = 0xFFFFu;
-                        if (v) hh = lz_hash(ld_u32(SV, i) & 0xFFFFFFu);
+                        const uint32_t hh = v ? lz_hash(key_next & 0xFFFFFFu) : 0xFFFFu;
+                        key_next = (it + 1 < LZ_SORT_TILE / 32 && i + 32u < m) ? ld_u32(SV, i + 32u) : 0u;
                         const uint32_t d = hh & 255u;
                         const unsigned peers = peers_of<8>(d, v);
                         uint32_t dst = 0;
                         if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
                         __syncwarp();
-                        if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                        // (the first lane of a group has read the group's offset itself)
+                        if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(dst + __popc(peers));
                         if (v) {
                             ZTS_ASSERT(dst < m);
                             st_u32_hint(&T[dst], i | (hh << 16), keep);
@@ -707,7 +716,7 @@ __device__ __forceinline__ LzIndexed lz_stage_and_index(const uint8_t* __restric
                 uint32_t dst = 0;
                 if (v) dst = (uint32_t)wc[d] + __popc(peers & zts_lanemask_lt());
                 __syncwarp();
-                if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(wc[d] + __popc(peers));
+                if (v && lane == (unsigned)(__ffs((int)peers) - 1)) wc[d] = (uint16_t)(dst + __popc(peers));
                 ZTS_ASSERT(!v || dst < m);
                 if (v) sorted[dst] = (uint16_t)e;
                 __syncwarp();
