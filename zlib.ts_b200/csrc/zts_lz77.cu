@@ -328,7 +328,7 @@ __device__ __forceinline__ void lz_build_info(const LzS& S, const uint16_t* __re
                 }
             }
             ZTS_ASSERT(p < n && lo <= i && i < m);
-            st_u32_hint(&P[p], i | ((i - lo) << 16), keep);
+            if (has) st_u32_hint(&P[p], i | ((i - lo) << 16), keep);  // (only read where the bit is set; a scattered store)
         }
         // inside a long bucket consecutive slots are consecutive positions (runs of one byte): one atomic per warp then
         const uint32_t w = p >> 5, w0 = __shfl_sync(0xFFFFFFFFu, w, 0);
