@@ -517,55 +517,60 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
         buf |= (unsigned long long)w_ << cnt;                                                 \
         cnt += 32;                                                                            \
     }
+#define INF_SYMBOL(SLOT) { \
+                    INF_TAKE_WORD() \
+                    uint32_t e; \
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_s + (((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)) << 2)) : "memory"); \
+                    buf >>= (e & 15u); \
+                    cnt -= (int)(e & 15u); \
+                    uint32_t tokv = e & 0x00FF0000u; \
+                    if (e & 0x300u) { \
+                        if ((e & 15u) == 0) { \
+                            e = slow_decode(TAB_LITLEN, (uint32_t)buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit); \
+                            if (e == 0) { \
+                                stop = 2; \
+                                { ta += 4u * (SLOT); break; } \
+                            } \
+                            buf >>= (e & 15u); \
+                            cnt -= (int)(e & 15u); \
+                            tokv = e & 0x00FF0000u; \
+                        } \
+                        if (e & 0x300u) { \
+                            if ((e & 0x300u) != (KIND_BASE << 8)) { \
+                                stop = (e & 0x100u) ? 2u : 1u; \
+                                { ta += 4u * (SLOT); break; } \
+                            } \
+                            INF_TAKE_WORD() \
+                            const uint32_t xb = (e >> 4) & 15u; \
+                            const uint32_t len = (e >> 16) + ((uint32_t)buf & ((1u << xb) - 1u)); \
+                            buf >>= xb; \
+                            cnt -= (int)xb; \
+                            uint32_t d; \
+                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(dist_s + (((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)) << 2)) : "memory"); \
+                            if ((d & 0x300u) != (KIND_BASE << 8)) { \
+                                if ((d & 15u) == 0) d = slow_decode(TAB_DIST, (uint32_t)buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist); \
+                                if ((d & 0x300u) != (KIND_BASE << 8)) { \
+                                    stop = 2; \
+                                    { ta += 4u * (SLOT); break; } \
+                                } \
+                            } \
+                            buf >>= (d & 15u); \
+                            cnt -= (int)(d & 15u); \
+                            const uint32_t db = (d >> 4) & 15u; \
+                            const uint32_t dist = (d >> 16) + ((uint32_t)buf & ((1u << db) - 1u)); \
+                            buf >>= db; \
+                            cnt -= (int)db; \
+                            tokv = (len << 16) | dist; \
+                        } \
+                    } \
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(ta + 4u * (SLOT)), "r"(tokv) : "memory"); }
+                // two symbols per trip (the token slots of a batch are an even number): one loop test for both
                 do {
-                    INF_TAKE_WORD()
-                    uint32_t e;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_s + (((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)) << 2)) : "memory");
-                    buf >>= (e & 15u);  // (0 bits for a code the root table does not resolve)
-                    cnt -= (int)(e & 15u);
-                    uint32_t tokv = e & 0x00FF0000u;  // literal
-                    if (e & 0x300u) {
-                        if ((e & 15u) == 0) {
-                            e = slow_decode(TAB_LITLEN, (uint32_t)buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit);
-                            if (e == 0) {
-                                stop = 2;
-                                break;
-                            }
-                            buf >>= (e & 15u);
-                            cnt -= (int)(e & 15u);
-                            tokv = e & 0x00FF0000u;
-                        }
-                        if (e & 0x300u) {
-                            if ((e & 0x300u) != (KIND_BASE << 8)) {
-                                stop = (e & 0x100u) ? 2u : 1u;  // KIND_INVALID (3) / KIND_EOB (2)
-                                break;
-                            }
-                            INF_TAKE_WORD()
-                            const uint32_t xb = (e >> 4) & 15u;
-                            const uint32_t len = (e >> 16) + ((uint32_t)buf & ((1u << xb) - 1u));
-                            buf >>= xb;
-                            cnt -= (int)xb;
-                            uint32_t d;
-                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(dist_s + (((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)) << 2)) : "memory");
-                            if ((d & 0x300u) != (KIND_BASE << 8)) {
-                                if ((d & 15u) == 0) d = slow_decode(TAB_DIST, (uint32_t)buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist);
-                                if ((d & 0x300u) != (KIND_BASE << 8)) {  // undefined code (0) or DistCodeTable[30..31]
-                                    stop = 2;
-                                    break;
-                                }
-                            }
-                            buf >>= (d & 15u);
-                            cnt -= (int)(d & 15u);
-                            const uint32_t db = (d >> 4) & 15u;
-                            const uint32_t dist = (d >> 16) + ((uint32_t)buf & ((1u << db) - 1u));
-                            buf >>= db;
-                            cnt -= (int)db;
-                            tokv = (len << 16) | dist;
-                        }
-                    }
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(ta), "r"(tokv) : "memory");
-                    ta += 4u;
+                    INF_SYMBOL(0u)
+                    INF_SYMBOL(1u)
+                    ta += 8u;
                 } while (ta != tok_e);
+#undef INF_SYMBOL
 #undef INF_TAKE_WORD
                 ntok = (ta - tok_s) >> 2;
                 __syncwarp();
