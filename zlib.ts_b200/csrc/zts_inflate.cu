@@ -525,21 +525,26 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                     cnt -= (int)(e & 15u); \
                     uint32_t tokv = e & 0x00FF0000u; \
                     if (e & 0x300u) { \
-                        if ((e & 15u) == 0) { \
-                            e = slow_decode(TAB_LITLEN, (uint32_t)buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit); \
-                            if (e == 0) { \
-                                stop = 2; \
+                        bool is_match = (e & 0x300u) == (KIND_BASE << 8); \
+                        if (!is_match) { /* unresolved by the root table, end of block or an undefined symbol */ \
+                            if ((e & 15u) == 0) { \
+                                e = slow_decode(TAB_LITLEN, (uint32_t)buf, LIT_ROOT_BITS, S->lit_sorted, &S->lit); \
+                                if (e == 0) { \
+                                    stop = 2; \
+                                    { ta += 4u * (SLOT); break; } \
+                                } \
+                                buf >>= (e & 15u); \
+                                cnt -= (int)(e & 15u); \
+                                tokv = e & 0x00FF0000u; \
+                            } \
+                            const uint32_t kind = e & 0x300u; \
+                            if (kind > (KIND_BASE << 8)) { \
+                                stop = (e & 0x100u) ? 2u : 1u; /* KIND_INVALID (3) / KIND_EOB (2) */ \
                                 { ta += 4u * (SLOT); break; } \
                             } \
-                            buf >>= (e & 15u); \
-                            cnt -= (int)(e & 15u); \
-                            tokv = e & 0x00FF0000u; \
+                            is_match = kind != 0u; \
                         } \
-                        if (e & 0x300u) { \
-                            if ((e & 0x300u) != (KIND_BASE << 8)) { \
-                                stop = (e & 0x100u) ? 2u : 1u; \
-                                { ta += 4u * (SLOT); break; } \
-                            } \
+                        if (is_match) { \
                             INF_TAKE_WORD() \
                             const uint32_t xb = (e >> 4) & 15u; \
                             const uint32_t len = (e >> 16) + ((uint32_t)buf & ((1u << xb) - 1u)); \
