@@ -486,24 +486,24 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             uint32_t stop = 0;  // 1 = end of block, 2 = undefined code / symbol
             const unsigned long long batch_pos = br_bits_used(br);  // (only looked at when the input ends inside the batch)
             {
-                uint32_t lit_s = (uint32_t)__cvta_generic_to_shared(S->lit_root);
-                uint32_t dist_s = (uint32_t)__cvta_generic_to_shared(S->dist_root);
-                // the addresses are warp-uniform; routing them through a shuffle keeps them in registers (ptxas
-                // otherwise recomputes them from %tid and %cluster_ctaid in front of every look-up: 9 instructions)
-                lit_s = __shfl_sync(0xFFFFFFFFu, lit_s, 0);
-                dist_s = __shfl_sync(0xFFFFFFFFu, dist_s, 0);
+                // the address of the warp's slice is warp-uniform; routing it through a shuffle keeps it in a register
+                // (ptxas otherwise recomputes it from %tid and %cluster_ctaid in front of every look-up: 9 instructions),
+                // and everything in the slice is that register plus a constant
+                const uint32_t smem_s = __shfl_sync(0xFFFFFFFFu, (uint32_t)__cvta_generic_to_shared(S), 0);
+                const uint32_t lit_s = smem_s + (uint32_t)offsetof(InfWarpSmem, lit_root);
+                const uint32_t dist_s = smem_s + (uint32_t)offsetof(InfWarpSmem, dist_root);
                 // same for the end-of-input pointer of the bit reader (recomputed from the item table otherwise)
                 br.end = reinterpret_cast<const uint8_t*>(__shfl_sync(0xFFFFFFFFu, (unsigned long long)br.end, 0));
                 // with a whole batch worth of words in the ring the refills below need no test
                 while (br.wr - br.rd < INF_RING_MIN) br_append(br);
                 unsigned long long buf = br.buf;
                 int cnt = br.cnt;
-                const uint32_t ring_s = __shfl_sync(0xFFFFFFFFu, br.ring_s, 0), ring_e = ring_s + 4u * INF_RING_WORDS;
+                const uint32_t ring_s = smem_s + (uint32_t)offsetof(InfWarpSmem, ring), ring_e = ring_s + 4u * INF_RING_WORDS;
                 const uint32_t ra0 = ring_s + ((br.rd & (INF_RING_WORDS - 1u)) << 2);
                 uint32_t ra = ra0;  // address of the next word
                 // the batch's tokens go through shared memory (one store per symbol instead of a compare + select into the
                 // lane that owns the slot); the code-length staging area is dead while symbols are decoded
-                const uint32_t tok_s = __shfl_sync(0xFFFFFFFFu, (uint32_t)__cvta_generic_to_shared(S->lens), 0);
+                const uint32_t tok_s = smem_s + (uint32_t)offsetof(InfWarpSmem, lens);
                 uint32_t ta = tok_s;
                 const uint32_t tok_e = tok_s + 128u;
                 // a word from the ring if 32 more bits fit (a length code: before it reads on, which is enough for its
