@@ -517,8 +517,8 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
         buf |= (unsigned long long)w_ << cnt;                                                 \
         cnt += 32;                                                                            \
     }
-#define INF_SYMBOL(SLOT) { \
-                    INF_TAKE_WORD() \
+#define INF_SYMBOL(SLOT, TOP, TAIL) { \
+                    if (TOP) INF_TAKE_WORD() \
                     uint32_t e; \
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_s + (((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)) << 2)) : "memory"); \
                     buf >>= (e & 15u); \
@@ -566,13 +566,16 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                             buf >>= db; \
                             cnt -= (int)db; \
                             tokv = (len << 16) | dist; \
+                            if (TAIL) INF_TAKE_WORD() \
                         } \
                     } \
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(ta + 4u * (SLOT)), "r"(tokv) : "memory"); }
-                // two symbols per trip (the token slots of a batch are an even number): one loop test for both
+                // Two symbols per trip (the token slots of a batch are an even number): one loop test for both, and the
+                // second one does not ask for a word: behind a literal that was read right after that test at least 17
+                // bits are left, enough for any code, and a match of the first symbol takes a word when it is done.
                 do {
-                    INF_SYMBOL(0u)
-                    INF_SYMBOL(1u)
+                    INF_SYMBOL(0u, true, true)
+                    INF_SYMBOL(1u, false, false)
                     ta += 8u;
                 } while (ta != tok_e);
 #undef INF_SYMBOL
