@@ -520,7 +520,8 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
 #define INF_SYMBOL(SLOT, TOP, TAIL) { \
                     if (TOP) INF_TAKE_WORD() \
                     uint32_t e; \
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(lit_s + (((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)) << 2)) : "memory"); \
+                    asm volatile("{\n\t.reg .b32 a;\n\tmad.lo.u32 a, %1, 4, %2;\n\tld.shared.u32 %0, [a];\n\t}" /* (index * 4 + base in one instruction) */ \
+                                 : "=r"(e) : "r"((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)), "r"(lit_s) : "memory"); \
                     buf >>= (e & 15u); \
                     cnt -= (int)(e & 15u); \
                     uint32_t tokv = e & 0x00FF0000u; \
@@ -551,7 +552,8 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                             buf >>= xb; \
                             cnt -= (int)xb; \
                             uint32_t d; \
-                            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(d) : "r"(dist_s + (((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)) << 2)) : "memory"); \
+                            asm volatile("{\n\t.reg .b32 a;\n\tmad.lo.u32 a, %1, 4, %2;\n\tld.shared.u32 %0, [a];\n\t}" \
+                                         : "=r"(d) : "r"((uint32_t)buf & ((1u << DIST_ROOT_BITS) - 1u)), "r"(dist_s) : "memory"); \
                             if ((d & 0x300u) != (KIND_BASE << 8)) { \
                                 if ((d & 15u) == 0) d = slow_decode(TAB_DIST, (uint32_t)buf, DIST_ROOT_BITS, S->dist_sorted, &S->dist); \
                                 if ((d & 0x300u) != (KIND_BASE << 8)) { \
