@@ -37,14 +37,24 @@ def lcg_sizes(n, seed=4):
 def c1(eng):
     d = synth.text(1 << 20, 1).tobytes()
     z.api.set_engine(eng)
-    t0 = time.perf_counter()
+    # the first call of each kind pays for scratch and page-locked staging allocations: one untimed call, then the
+    # median of three
     c = z.Deflate(d).compress()
-    t1 = time.perf_counter()
     out = z.Inflate(c, {"verify": True}).decompress()
-    t2 = time.perf_counter()
     assert out.tobytes() == d and zlib.decompress(c.tobytes()) == d
+    td, ti = [], []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        c = z.Deflate(d).compress()
+        t1 = time.perf_counter()
+        out = z.Inflate(c, {"verify": True}).decompress()
+        t2 = time.perf_counter()
+        td.append((t1 - t0) * 1e3)
+        ti.append((t2 - t1) * 1e3)
+    assert out.tobytes() == d
     return {"config": "C1", "bytes": len(d), "compressed": int(c.size), "ratio": c.size / len(d),
-            "deflate_ms_host_api": (t1 - t0) * 1e3, "inflate_ms_host_api": (t2 - t1) * 1e3, "roundtrip_ok": True}
+            "deflate_ms_host_api": sorted(td)[1], "inflate_ms_host_api": sorted(ti)[1],
+            "timing": "median of 3 calls after one untimed call", "roundtrip_ok": True}
 
 
 def c3(eng, n_streams=65536, host_leg=True):
