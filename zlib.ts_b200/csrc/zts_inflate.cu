@@ -608,11 +608,17 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                 const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, sft);
                 if (lane >= (unsigned)sft) inc += t;
             }
-            const unsigned long long pos = op + (inc - len);  // where this token's bytes start
+            // Everything below works with 32-bit offsets from the batch's first byte (a batch is at most 32 x 258 bytes):
+            // `rel` = where this token's bytes start; the output written so far and the room left are clamped to
+            // values that decide the same (a distance is at most 32768, a batch at most 8256 bytes).
+            const uint32_t rel = inc - len;
+            uint8_t* const bdst = dst + op;  // first byte of the batch
+            const uint32_t behind = op > 0x00FFFFFFull ? 0x00FFFFFFu : (uint32_t)op;         // bytes in front of the batch
+            const uint32_t room = cap - op > 0x00FFFFFFull ? 0x00FFFFFFu : (uint32_t)(cap - op);  // (op <= cap always)
             // a distance beyond the start of the output (the reference would copy `undefined` -> 0) or an
             // output slot that is too small ends the batch before the offending token
-            const bool bad_dist = is_match && (unsigned long long)dist > pos;
-            const bool over = mine && pos + len > cap;
+            const bool bad_dist = is_match && dist > behind + rel;
+            const bool over = mine && rel + len > room;
             const unsigned bad_mask = __ballot_sync(0xFFFFFFFFu, bad_dist || over);
             uint32_t nvalid = ntok;
             if (bad_mask) {
@@ -622,16 +628,18 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             }
             const bool live = lane < nvalid;
             // -- literals: one store
-            ZTS_ASSERT(!live || (pos + len <= cap && (!is_match || dist <= pos)));
-            if (live && !is_match) dst[pos] = (uint8_t)(mytok >> 16);
+            ZTS_ASSERT(!live || (op + rel + len <= cap && (!is_match || dist <= op + rel)));
+            if (live && !is_match) bdst[rel] = (uint8_t)(mytok >> 16);
             // -- matches, sub-batch by sub-batch
             uint32_t start = 0;
             unsigned match_mask = __ballot_sync(0xFFFFFFFFu, live && is_match);
+            // where this match's source ends (exclusive), as an offset from the batch's first byte: negative when it
+            // lies in front of the batch
+            const int src_end = (int)rel - (int)dist + (int)(len < dist ? len : dist);
             while (match_mask) {
-                const unsigned long long sub_start = __shfl_sync(0xFFFFFFFFu, pos, (int)start);
+                const int sub_start = (int)__shfl_sync(0xFFFFFFFFu, rel, (int)start);
                 // reads bytes written by this very sub-batch? (source end beyond its first byte)
-                const bool dep = live && is_match && lane >= start &&
-                                 pos - dist + (len < dist ? len : dist) > sub_start;
+                const bool dep = live && is_match && lane >= start && src_end > sub_start;
                 const unsigned dep_mask = __ballot_sync(0xFFFFFFFFu, dep);
                 const uint32_t cut = dep_mask ? (uint32_t)__ffs((int)dep_mask) - 1u : 32u;  // > start always
                 const bool in_sub = live && is_match && lane >= start && lane < cut;
@@ -639,10 +647,10 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                 if (__any_sync(0xFFFFFFFFu, small)) {
                     // short non-overlapping matches: every lane copies its own, loads first, then stores
                     uint8_t v[8];
-                    const uint8_t* sp = dst + (pos - dist);
+                    uint8_t* dp = bdst + rel;
+                    const uint8_t* sp = dp - dist;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) v[k] = (small && (uint32_t)k < len) ? sp[k] : (uint8_t)0;
-                    uint8_t* dp = dst + pos;
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         if (small && (uint32_t)k < len) dp[k] = v[k];
@@ -653,8 +661,8 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                     big_mask &= big_mask - 1;
                     const uint32_t jl = __shfl_sync(0xFFFFFFFFu, len, j);
                     const uint32_t jd = __shfl_sync(0xFFFFFFFFu, dist, j);
-                    const unsigned long long jp = __shfl_sync(0xFFFFFFFFu, pos, j);
-                    uint8_t* o = dst + jp;
+                    const uint32_t jr = __shfl_sync(0xFFFFFFFFu, rel, j);
+                    uint8_t* o = bdst + jr;
                     const uint8_t* s0 = o - jd;
                     if (jd >= jl) {
                         for (uint32_t k = lane; k < jl; k += 32) o[k] = s0[k];
