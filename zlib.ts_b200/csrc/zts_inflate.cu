@@ -630,18 +630,21 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             // -- literals: one store
             ZTS_ASSERT(!live || (op + rel + len <= cap && (!is_match || dist <= op + rel)));
             if (live && !is_match) bdst[rel] = (uint8_t)(mytok >> 16);
-            // -- matches, sub-batch by sub-batch
+            __syncwarp();  // (a match may read the literals of its own batch)
+            // -- matches, sub-batch by sub-batch: a sub-batch ends in front of the first match that reads what a match
+            //    of the same sub-batch writes
             uint32_t start = 0;
             unsigned match_mask = __ballot_sync(0xFFFFFFFFu, live && is_match);
             // where this match's source ends (exclusive), as an offset from the batch's first byte: negative when it
             // lies in front of the batch
             const int src_end = (int)rel - (int)dist + (int)(len < dist ? len : dist);
             while (match_mask) {
-                const int sub_start = (int)__shfl_sync(0xFFFFFFFFu, rel, (int)start);
-                // reads bytes written by this very sub-batch? (source end beyond its first byte)
+                // first byte the matches of this sub-batch write (its first match's: match_mask holds lanes >= start)
+                const int sub_start = (int)__shfl_sync(0xFFFFFFFFu, rel, __ffs((int)match_mask) - 1);
+                // reads bytes written by this very sub-batch? (source end beyond that byte)
                 const bool dep = live && is_match && lane >= start && src_end > sub_start;
                 const unsigned dep_mask = __ballot_sync(0xFFFFFFFFu, dep);
-                const uint32_t cut = dep_mask ? (uint32_t)__ffs((int)dep_mask) - 1u : 32u;  // > start always
+                const uint32_t cut = dep_mask ? (uint32_t)__ffs((int)dep_mask) - 1u : 32u;  // behind the first match always
                 const bool in_sub = live && is_match && lane >= start && lane < cut;
                 const bool small = in_sub && len <= 8u && dist >= len;
                 if (__any_sync(0xFFFFFFFFu, small)) {
