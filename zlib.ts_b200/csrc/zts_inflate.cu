@@ -45,6 +45,7 @@
 #define KIND_BASE 1u   // length or distance base + extra bits
 #define KIND_EOB 2u
 #define KIND_INVALID 3u
+#define INF_TOK_MATCH 0x80000000u  // token of a match: INF_TOK_MATCH | len << 16 | dist; a literal: byte << 16 | (ignored) < 256
 #define ROOT_UNRESOLVED (KIND_INVALID << 8)  // root-table entry of a bit pattern whose code is longer than the root (0 bits)
 
 struct HuffTab {
@@ -89,7 +90,9 @@ __device__ __forceinline__ uint32_t make_entry(int which, uint32_t sym, uint32_t
     if (which == TAB_LITLEN) {
         if (sym < 256) return (sym << 16) | (KIND_LITERAL << 8) | nbits;
         if (sym == 256) return (KIND_EOB << 8) | nbits;
-        if (sym < 288) return ((uint32_t)c_len_base[sym - 257] << 16) | (KIND_BASE << 8) |
+        // (bit 31 marks a match token: it travels with the length base into `len << 16 | dist`, so that a literal's
+        // token is its table entry as it is -- byte << 16, code length below -- without a mask in the symbol loop)
+        if (sym < 288) return INF_TOK_MATCH | ((uint32_t)c_len_base[sym - 257] << 16) | (KIND_BASE << 8) |
                               ((uint32_t)c_len_extra[sym - 257] << 4) | nbits;
         return (KIND_INVALID << 8) | nbits;
     }
@@ -479,7 +482,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
         // ---- symbol loop (src/RawInflate.ts:466-516), 32 symbols per batch
         bool eob = false;
         while (!eob && status == ZLB_ST_OK) {
-            // -- decode: token of symbol i ends up in lane i: literal = byte << 16, match = len << 16 | dist.
+            // -- decode: token of symbol i ends up in lane i: literal = byte << 16 | junk < 256, match = INF_TOK_MATCH | len << 16 | dist.
             //    The tables are addressed through 32-bit shared-window addresses held in registers (a generic
             //    pointer to the per-warp slice gets rematerialised from %tid on every look-up otherwise).
             uint32_t mytok = 0, ntok = 0;
@@ -524,7 +527,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                                  : "=r"(e) : "r"((uint32_t)buf & ((1u << LIT_ROOT_BITS) - 1u)), "r"(lit_s) : "memory"); \
                     buf >>= (e & 15u); \
                     cnt -= (int)(e & 15u); \
-                    uint32_t tokv = e & 0x00FF0000u; \
+                    uint32_t tokv = e; /* (a literal's entry is its token) */ \
                     if (e & 0x300u) { \
                         bool is_match = (e & 0x300u) == (KIND_BASE << 8); \
                         if (!is_match) { /* unresolved by the root table, end of block or an undefined symbol */ \
@@ -536,7 +539,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                                 } \
                                 buf >>= (e & 15u); \
                                 cnt -= (int)(e & 15u); \
-                                tokv = e & 0x00FF0000u; \
+                                tokv = e; \
                             } \
                             const uint32_t kind = e & 0x300u; \
                             if (kind > (KIND_BASE << 8)) { \
@@ -599,9 +602,9 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             }
             // -- output positions: exclusive prefix sum of the token lengths
             const bool mine = lane < ntok;
-            const uint32_t dist = mytok & 0xFFFFu;
-            const bool is_match = mine && dist != 0;
-            const uint32_t len = !mine ? 0u : (dist ? (mytok >> 16) : 1u);
+            const uint32_t dist = mytok & 0xFFFFu;  // (of a match)
+            const bool is_match = mine && (mytok & INF_TOK_MATCH);
+            const uint32_t len = !mine ? 0u : (is_match ? (mytok >> 16) & 0x7FFFu : 1u);
             uint32_t inc = len;
 #pragma unroll
             for (int sft = 1; sft < 32; sft <<= 1) {
