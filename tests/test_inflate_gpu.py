@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import gpu_inflate_many, rand_bytes, zlib_raw
+from helpers import gpu_inflate_many, long_code_match_stream, rand_bytes, zlib_raw
 
 pytestmark = pytest.mark.gpu
 
@@ -218,3 +218,18 @@ def test_truncated_input_statuses_follow_the_reference(engine):
         elif ref.startswith("ERR invalid code length"):
             assert False, (k, got, ref)   # a code cut short is never anything else here
     assert same_as_reference > 0.85 * len(streams)   # 1147 of 1279; the rest is the B-7 end check
+
+
+def test_matches_of_48_bits_each(engine):
+    """Hand-built streams in which every symbol takes the most bits a symbol can take (15-bit length code + 5 extra
+    bits + 15-bit distance code + 13 extra bits): the bound the decoder's input ring is sized for (a batch of 32
+    symbols reads 48 words), long codes on both slow paths, and matches that reach up to 32768 bytes back."""
+    rng = np.random.default_rng(11)
+    datas, streams = [], []
+    for n_hist, n_matches in ((32768, 1), (32768, 31), (40000, 33), (65536, 1000), (50000, 4000)):
+        hist = rng.integers(0, 256, n_hist, dtype=np.uint8).tobytes()
+        s, expect = long_code_match_stream(hist, n_matches, seed=n_matches)
+        assert zlib.decompressobj(-15).decompress(s) == expect
+        datas.append(expect)
+        streams.append(s)
+    _check(engine, datas, streams)

@@ -303,3 +303,16 @@ def test_truncated_input_errors_equal_the_executed_reference():
             assert got == want, (v["name"], cut, got, want)
             n += 1
     assert n > 1200
+
+
+def test_inflate_of_hand_built_48_bit_symbols():
+    """the stream builder of tests/test_inflate_gpu.py::test_matches_of_48_bits_each, CPU side: CPython zlib and the
+    oracle's RawInflate read it alike"""
+    import zlib
+    import numpy as np
+    from helpers import long_code_match_stream
+    hist = np.random.default_rng(2).integers(0, 256, 40000, dtype=np.uint8).tobytes()
+    s, expect = long_code_match_stream(hist, 500)
+    assert zlib.decompressobj(-15).decompress(s) == expect
+    out, ip = oracle.raw_inflate(s + b"\0\0\0\0", 0, out_cap=len(expect))
+    assert out == expect and ip == len(s)
