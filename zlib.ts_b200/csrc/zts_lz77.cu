@@ -250,6 +250,9 @@ __device__ __forceinline__ uint32_t lz_match_len(const LzS& S, uint32_t q, uint3
 #ifndef LZ_WAIT_MUL
 #define LZ_WAIT_MUL 0u         // ... or, if not 0, as soon as LZ_WAIT_MUL x (lanes waiting) >= lanes searching (measured: 0 is best)
 #endif
+#ifndef LZ_COOP_PER_LANE
+#define LZ_COOP_PER_LANE 8u    // candidates per lane and step of the warp search's tail-byte filter
+#endif
 #ifndef LZ_KMAX
 #define LZ_KMAX 8u             // candidate steps in a row before the lanes that wait for their next position are served
 #endif
@@ -408,26 +411,25 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
     // cheapest test and rejects nearly everything. 128 candidates per step through that test (four independent
     // look-ups per lane in flight); the few that pass get the exact comparison
     while (cur > lo && best_len < maxlen) {  // :189 (258) or capped by the input end
-        const uint32_t cnt = min(128u, cur - lo);
+        const uint32_t cnt = min(32u * LZ_COOP_PER_LANE, cur - lo);
         const uint8_t pt = S[p + best_len];
-        uint32_t key = 0, hitq[4];
-        unsigned hm = 0;  // which of this lane's four candidates passed the test
+        uint32_t key = 0;
+        unsigned hm = 0;  // which of this lane's candidates passed the test
+        const uint16_t* sp = sorted + cur - 1u - lane;  // candidate k of this lane: sp[-32 k]
 #pragma unroll
-        for (uint32_t k = 0; k < 4u; ++k) {
+        for (uint32_t k = 0; k < LZ_COOP_PER_LANE; ++k) {
             const uint32_t o = k * 32u + lane;
-            hitq[k] = 0;
             if (o < cnt) {
                 ZTS_ASSERT(cur >= 1u + o && cur <= LZ_MAX_CHUNK);
-                const uint32_t q = sorted[cur - 1u - o];
-                hitq[k] = q;
+                const uint32_t q = sp[-32 * (int)k];
                 ZTS_ASSERT(q < p && p - q <= LZ_WINDOW);
                 if (S[q + best_len] == pt) hm |= 1u << k;
             }
         }
-        while (hm) {
+        while (hm) {  // (rare: the position is read again)
             const uint32_t k = (uint32_t)__ffs((int)hm) - 1u;
             hm &= hm - 1u;
-            const uint32_t q = k == 0u ? hitq[0] : k == 1u ? hitq[1] : k == 2u ? hitq[2] : hitq[3];
+            const uint32_t q = sp[-32 * (int)k];
             key = max(key, (lz_match_len(S, q, p, pw, pw1, maxlen) << 16) | q);
         }
         if (__any_sync(0xFFFFFFFFu, key != 0u)) {
