@@ -408,7 +408,7 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
         cur -= cnt;
     }
     // behind a known match only a strictly longer one counts (:183): its byte at best_len must match, which is the
-    // cheapest test and rejects nearly everything. 128 candidates per step through that test (four independent
+    // cheapest test and rejects nearly everything. 256 candidates per step through that test (eight independent
     // look-ups per lane in flight); the few that pass get the exact comparison
     while (cur > lo && best_len < maxlen) {  // :189 (258) or capped by the input end
         const uint32_t cnt = min(32u * LZ_COOP_PER_LANE, cur - lo);
