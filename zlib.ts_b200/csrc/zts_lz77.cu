@@ -117,6 +117,14 @@ struct LzS {
     const uint8_t* S;
     uint32_t sa;  // shared-space address of S
     __device__ __forceinline__ uint8_t operator[](uint32_t i) const { return S[i]; }
+    // the same through the 32-bit shared-window address: in the warp search a load through the generic pointer makes
+    // ptxas rebuild the window base (S2UR, UMOV, ULEA, two adds) in front of every byte it reads
+    __device__ __forceinline__ uint8_t at(uint32_t i) const
+    {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa + i));
+        return (uint8_t)v;
+    }
 };
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
 {
@@ -359,7 +367,7 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
     // is longer, so that is the reference's answer (it stops at the first candidate there, :189 / end of input)
     {
         const uint32_t b0 = pw & 0xFFu;
-        if (((pw ^ (pw >> 8)) & 0xFFFFu) == 0 && p > 0 && S[p - 1] == b0) {  // bytes 0..2 equal, and the one before
+        if (((pw ^ (pw >> 8)) & 0xFFFFu) == 0 && p > 0 && S.at(p - 1) == b0) {  // bytes 0..2 equal, and the one before
             const uint32_t splat = b0 * 0x01010101u;
             bool same = true;
 #pragma unroll
@@ -412,7 +420,7 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
     // look-ups per lane in flight); the few that pass get the exact comparison
     while (cur > lo && best_len < maxlen) {  // :189 (258) or capped by the input end
         const uint32_t cnt = min(32u * LZ_COOP_PER_LANE, cur - lo);
-        const uint8_t pt = S[p + best_len];
+        const uint8_t pt = S.at(p + best_len);
         uint32_t key = 0;
         unsigned hm = 0;  // which of this lane's candidates passed the test
         const uint16_t* sp = sorted + cur - 1u - lane;  // candidate k of this lane: sp[-32 k]
@@ -423,7 +431,7 @@ __device__ __forceinline__ uint32_t lz_search_from(const LzS& S, const uint16_t*
                 ZTS_ASSERT(cur >= 1u + o && cur <= LZ_MAX_CHUNK);
                 const uint32_t q = sp[-32 * (int)k];
                 ZTS_ASSERT(q < p && p - q <= LZ_WINDOW);
-                if (S[q + best_len] == pt) hm |= 1u << k;
+                if (S.at(q + best_len) == pt) hm |= 1u << k;
             }
         }
         while (hm) {  // (rare: the position is read again)
