@@ -31,13 +31,15 @@
 
 #include "zts_common.cuh"
 
-#define INF_WARPS_PER_CTA 4
+#ifndef INF_WARPS_PER_CTA
+#define INF_WARPS_PER_CTA 1  // a CTA holds its shared memory until its slowest stream is done: one stream per CTA wastes none
+#endif
 #define LIT_ROOT_BITS 10
 #ifndef DIST_ROOT_BITS
 #define DIST_ROOT_BITS 7
 #endif
 #ifndef INF_MIN_CTAS
-#define INF_MIN_CTAS 8   // 64 registers: eight CTAs of four warps per SM (their tables: 8 x 28 KB)
+#define INF_MIN_CTAS 29  // 64 registers; 29 one-warp CTAs per SM (7 KB of tables + 1 KB the system reserves per CTA)
 #endif
 #define CL_ROOT_BITS 7
 
