@@ -39,7 +39,7 @@
 #define DIST_ROOT_BITS 7
 #endif
 #ifndef INF_MIN_CTAS
-#define INF_MIN_CTAS 29  // 64 registers; 29 one-warp CTAs per SM (7 KB of tables + 1 KB the system reserves per CTA)
+#define INF_MIN_CTAS 32  // 64 registers; 32 one-warp CTAs per SM (6272 B of tables + 1 KB the system reserves per CTA)
 #endif
 #define CL_ROOT_BITS 7
 
@@ -56,19 +56,22 @@ struct HuffTab {
     uint16_t count[16];
 };
 
+// 6272 bytes per stream: with the 1 KB the system reserves per CTA, 32 one-warp CTAs fill the 228 KB of an SM. What a
+// dynamic block header needs only while it is read lives where the tables it leads to are built afterwards: the
+// code-length code's root table in the distance root, its sorted symbols and counts in the distance code's, its 19
+// lengths in the first bytes of the literal / length code's sorted symbols.
 struct InfWarpSmem {
     uint32_t lit_root[1 << LIT_ROOT_BITS];
-    uint32_t dist_root[1 << DIST_ROOT_BITS];
-    uint32_t cl_root[1 << CL_ROOT_BITS];
-    uint16_t lit_sorted[288];
-    uint16_t dist_sorted[32];
-    uint16_t cl_sorted[20];
-    HuffTab lit, dist, cl;
-    uint8_t lens[32 + 288 + 32 + 16];  // [0,19) code-length code; [32, 32+hlit+hdist) litlen ++ dist
-    uint32_t ring[128];                // input words on their way into the bit buffer (BitReader)
+    uint32_t dist_root[1 << DIST_ROOT_BITS];  // (+ the code-length code's root table)
+    uint16_t lit_sorted[288];                  // (+ the code-length code's lengths, 32 bytes)
+    uint16_t dist_sorted[32];                  // (+ the code-length code's sorted symbols)
+    HuffTab lit, dist;                         // (dist: + the code-length code's)
+    uint8_t stage[320];                        // litlen ++ dist code lengths of a header; the token slots of a batch
+    uint32_t ring[128];                        // input words on their way into the bit buffer (BitReader)
 };
-
-static_assert(offsetof(InfWarpSmem, lens) % 4 == 0 && sizeof(InfWarpSmem::lens) >= 128,
+static_assert(CL_ROOT_BITS <= DIST_ROOT_BITS, "the code-length root table lives in the distance root table");
+static_assert(sizeof(InfWarpSmem) == 6272, "32 x (sizeof + 1 KB) fills an SM");
+static_assert(offsetof(InfWarpSmem, stage) % 4 == 0 && sizeof(InfWarpSmem::stage) >= 128,
               "the token slots of a batch alias the code-length staging area");
 
 // LengthCodeTable / LengthExtraTable (src/RawInflate.ts:17-28; symbols 286/287 decode as 258 there)
@@ -296,7 +299,7 @@ __device__ uint32_t inf_peek(const uint8_t* src, unsigned long long in_len, unsi
 // status of a Huffman code of the code-length alphabet read at `pos` (dynamic block header)
 __device__ uint32_t inf_classify_cl(const InfWarpSmem* S, const uint8_t* src, unsigned long long in_len, unsigned long long pos)
 {
-    const uint32_t e = S->cl_root[inf_peek(src, in_len, pos) & ((1u << CL_ROOT_BITS) - 1u)];
+    const uint32_t e = S->dist_root[inf_peek(src, in_len, pos) & ((1u << CL_ROOT_BITS) - 1u)];
     const uint32_t nb = e & 15u;
     if (nb && pos + nb > in_len * 8ull) return ZLB_ST_CODE_LENGTH | (nb << 8);
     return ZLB_ST_INPUT_BROKEN;  // the code was there: its repeat count was not
@@ -407,11 +410,11 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
         if (btype == 1) {
             // ---- fixed Huffman tables (src/RawInflate.ts:45-61)
             if (have_fixed != 1) {
-                for (int i = (int)lane; i < 288; i += 32) S->lens[32 + i] = i <= 143 ? 8 : i <= 255 ? 9 : i <= 279 ? 7 : 8;
-                for (int i = (int)lane; i < 30; i += 32) S->lens[32 + 288 + i] = 5;
+                for (int i = (int)lane; i < 288; i += 32) S->stage[i] = i <= 143 ? 8 : i <= 255 ? 9 : i <= 279 ? 7 : 8;
+                for (int i = (int)lane; i < 30; i += 32) S->stage[288 + i] = 5;
                 __syncwarp();
-                build_table(TAB_LITLEN, S->lens + 32, 288, LIT_ROOT_BITS, S->lit_root, S->lit_sorted, &S->lit);
-                build_table(TAB_DIST, S->lens + 32 + 288, 30, DIST_ROOT_BITS, S->dist_root, S->dist_sorted, &S->dist);
+                build_table(TAB_LITLEN, S->stage, 288, LIT_ROOT_BITS, S->lit_root, S->lit_sorted, &S->lit);
+                build_table(TAB_DIST, S->stage + 288, 30, DIST_ROOT_BITS, S->dist_root, S->dist_sorted, &S->dist);
                 have_fixed = 1;
             }
         } else {
@@ -421,19 +424,20 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             uint32_t hlit = br_take(br, 5) + 257;
             uint32_t hdist = br_take(br, 5) + 1;
             uint32_t hclen = br_take(br, 4) + 4;
-            if (lane < 19) S->lens[lane] = 0;
+            uint8_t* const cl_lens = reinterpret_cast<uint8_t*>(S->lit_sorted);  // (dead before that table is built)
+            if (lane < 19) cl_lens[lane] = 0;
             __syncwarp();
             for (uint32_t i = 0; i < hclen; ++i) {
                 br_refill(br);
                 uint32_t v = br_take(br, 3);
-                if (lane == 0) S->lens[c_huff_order[i]] = (uint8_t)v;
+                if (lane == 0) cl_lens[c_huff_order[i]] = (uint8_t)v;
             }
             __syncwarp();
             if (br_bits_used(br) > in_bits) {
                 status = ZLB_ST_INPUT_BROKEN;
                 break;
             }
-            if (!build_table(TAB_CL, S->lens, 19, CL_ROOT_BITS, S->cl_root, S->cl_sorted, &S->cl)) {
+            if (!build_table(TAB_CL, cl_lens, 19, CL_ROOT_BITS, S->dist_root, S->dist_sorted, &S->dist)) {
                 status = ZLB_ST_BAD_LENGTHS;
                 break;
             }
@@ -444,7 +448,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
             while (i < total && status == ZLB_ST_OK) {
                 br_refill(br);
                 const unsigned long long cl_pos = br_bits_used(br);
-                uint32_t e = S->cl_root[(uint32_t)br.buf & ((1u << CL_ROOT_BITS) - 1u)];
+                uint32_t e = S->dist_root[(uint32_t)br.buf & ((1u << CL_ROOT_BITS) - 1u)];  // (the code-length code's table)
                 uint32_t nb = e & 15u;
                 if (nb == 0) {
                     status = ZLB_ST_BAD_CODE;
@@ -465,16 +469,16 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                 }
                 // lanes store the run cooperatively (rep <= 138)
                 for (uint32_t k = lane; k < rep; k += 32)
-                    if (i + k < total) S->lens[32 + i + k] = (uint8_t)val;  // staging above the CL lengths
+                    if (i + k < total) S->stage[i + k] = (uint8_t)val;
                 i += rep;
                 prev = val;
                 if (br_bits_used(br) > in_bits) status = inf_classify_cl(S, src, it.in_len, cl_pos);
             }
             if (status != ZLB_ST_OK) break;
             __syncwarp();
-            // lens[32 .. 32+total) holds litlen then dist lengths
-            if (!build_table(TAB_LITLEN, S->lens + 32, (int)hlit, LIT_ROOT_BITS, S->lit_root, S->lit_sorted, &S->lit) ||
-                !build_table(TAB_DIST, S->lens + 32 + hlit, (int)hdist, DIST_ROOT_BITS, S->dist_root, S->dist_sorted,
+            // stage[0 .. total) holds litlen then dist lengths
+            if (!build_table(TAB_LITLEN, S->stage, (int)hlit, LIT_ROOT_BITS, S->lit_root, S->lit_sorted, &S->lit) ||
+                !build_table(TAB_DIST, S->stage + hlit, (int)hdist, DIST_ROOT_BITS, S->dist_root, S->dist_sorted,
                              &S->dist)) {
                 status = ZLB_ST_BAD_LENGTHS;
                 break;
@@ -508,7 +512,7 @@ inflate_warp_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, c
                 uint32_t ra = ra0;  // address of the next word
                 // the batch's tokens go through shared memory (one store per symbol instead of a compare + select into the
                 // lane that owns the slot); the code-length staging area is dead while symbols are decoded
-                const uint32_t tok_s = smem_s + (uint32_t)offsetof(InfWarpSmem, lens);
+                const uint32_t tok_s = smem_s + (uint32_t)offsetof(InfWarpSmem, stage);
                 uint32_t ta = tok_s;
                 const uint32_t tok_e = tok_s + 128u;
                 // a word from the ring if 32 more bits fit (a length code: before it reads on, which is enough for its
